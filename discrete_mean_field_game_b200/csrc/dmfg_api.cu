@@ -1,0 +1,473 @@
+// extern "C" entry points of libdmfg (see include/dmfg.h): argument checking,
+// kernel selection, launch geometry, workspace carving.  No torch, no hidden
+// state: every call works on caller-owned device pointers and a caller stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "dmfg_rollout.cuh"
+
+using namespace dmfg;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define DMFG_CUDA(call)                                                                    \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(DMFG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                               \
+    } while (0)
+
+constexpr int kMaxPartialCtas = 148 * 8;     // upper bound on the persistent grids below
+constexpr int kTdChunk = 64;                 // transitions staged per CTA iteration in td_gw_kernel
+
+inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a * a; }
+inline size_t esize(int dtype) { return dtype == DMFG_F64 ? 8 : 4; }
+inline bool fast_d(int d) { return d == 4 || d == 15 || d == 16; }
+
+int sm_count(int* out) {
+    int dev = 0;
+    DMFG_CUDA(cudaGetDevice(&dev));
+    DMFG_CUDA(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+    return DMFG_OK;
+}
+
+bool use_fast(const dmfg_rollout_args* a) {
+    if (a->variant == DMFG_VARIANT_GENERIC) return false;
+    return fast_d(a->d);
+}
+
+// workspace map of one dmfg_rollout call
+struct RolloutWs {
+    uint64_t partials = 0, states = 0, rewards = 0, grads = 0, delta_buf = 0, total = 0;
+    bool need_states = false, need_rewards = false, need_grads = false;
+};
+RolloutWs rollout_ws(const dmfg_rollout_args* a) {
+    RolloutWs w;
+    const uint64_t F = (uint64_t)num_features_c(a->d);
+    const bool td = a->w != nullptr;
+    const bool accum = td && a->acc != nullptr;
+    uint64_t off = 0;
+    if (accum) { w.partials = off; off += align_up((uint64_t)kMaxPartialCtas * (2 + F) * 8); }
+    if (!use_fast(a) && td) {
+        const uint64_t TB = (uint64_t)a->T * (uint64_t)a->B, es = esize(a->dtype);
+        if (!a->states) { w.need_states = true; w.states = off; off += align_up((TB + a->B) * a->d * es); }
+        if (!a->rewards && !a->rewards_in) { w.need_rewards = true; w.rewards = off; off += align_up(TB * es); }
+        if (!a->grads) { w.need_grads = true; w.grads = off; off += align_up(TB * es); }
+        w.delta_buf = off; off += align_up(TB * 8);
+    }
+    w.total = off;
+    return w;
+}
+
+int check_rollout(const dmfg_rollout_args* a) {
+    if (!a) return fail(DMFG_ERR_INVALID, "args is NULL");
+    if (a->struct_size != sizeof(dmfg_rollout_args))
+        return fail(DMFG_ERR_INVALID, "dmfg_rollout_args.struct_size %u != %zu (header mismatch)",
+                    a->struct_size, sizeof(dmfg_rollout_args));
+    if (a->dtype != DMFG_F32 && a->dtype != DMFG_F64) return fail(DMFG_ERR_INVALID, "dtype %d", a->dtype);
+    if (a->d < 1 || a->d > DMFG_MAX_D) return fail(DMFG_ERR_INVALID, "d=%d outside [1,%d]", a->d, DMFG_MAX_D);
+    if (a->T < 0) return fail(DMFG_ERR_INVALID, "T=%d < 0", a->T);
+    if (a->B < 0) return fail(DMFG_ERR_INVALID, "B=%lld < 0", (long long)a->B);
+    if (a->reward_kind < DMFG_REWARD_NONE || a->reward_kind > DMFG_REWARD_SYNTHETIC)
+        return fail(DMFG_ERR_INVALID, "reward_kind %d", a->reward_kind);
+    if (a->discount_kind != DMFG_DISCOUNT_STEP && a->discount_kind != DMFG_DISCOUNT_CUMULATIVE)
+        return fail(DMFG_ERR_INVALID, "discount_kind %d", a->discount_kind);
+    if (a->noise_kind != DMFG_NOISE_INJECTED && a->noise_kind != DMFG_NOISE_PHILOX)
+        return fail(DMFG_ERR_INVALID, "noise_kind %d", a->noise_kind);
+    if (a->variant < DMFG_VARIANT_AUTO || a->variant > DMFG_VARIANT_FAST)
+        return fail(DMFG_ERR_INVALID, "variant %d", a->variant);
+    if (a->variant == DMFG_VARIANT_FAST && !fast_d(a->d))
+        return fail(DMFG_ERR_UNSUPPORTED, "fast variant is built for d in {4,15,16}, not d=%d", a->d);
+    if (a->B > 0 && !a->pi0) return fail(DMFG_ERR_INVALID, "pi0 is NULL");
+    if (a->B > 0 && a->T > 0 && a->noise_kind == DMFG_NOISE_INJECTED && !a->noise_y)
+        return fail(DMFG_ERR_INVALID, "noise_kind=INJECTED needs noise_y");
+    if ((a->deltas || a->acc) && !a->w) return fail(DMFG_ERR_INVALID, "deltas/acc need critic weights w");
+    if ((a->alpha == nullptr) != (a->alpha_deriv == nullptr))
+        return fail(DMFG_ERR_INVALID, "alpha and alpha_deriv must be requested together");
+    if (!(a->alpha_scale > 0.0)) return fail(DMFG_ERR_INVALID, "alpha_scale must be > 0");
+    return DMFG_OK;
+}
+
+template <typename R>
+RolloutParams<R> make_params(const dmfg_rollout_args* a) {
+    RolloutParams<R> p;
+    p.d = a->d; p.T = a->T; p.B = a->B; p.pop_offset = a->pop_offset;
+    p.theta = a->theta; p.theta_dev = a->theta_dev;
+    p.shift = a->shift; p.alpha_scale = a->alpha_scale; p.gamma = a->gamma;
+    p.reward_kind = a->reward_kind; p.discount_kind = a->discount_kind;
+    p.noise_y = (const R*)a->noise_y; p.seed = a->seed; p.step_offset = a->step_offset;
+    p.pi0 = (const R*)a->pi0; p.w = a->w; p.rewards_in = (const R*)a->rewards_in;
+    p.states = (R*)a->states; p.actions = (R*)a->actions; p.alpha = (R*)a->alpha;
+    p.alpha_deriv = (R*)a->alpha_deriv; p.rewards = (R*)a->rewards; p.deltas = (R*)a->deltas;
+    p.grads = (R*)a->grads; p.pi_final = (R*)a->pi_final; p.partials = nullptr;
+    return p;
+}
+
+template <int D, int G, typename R, int NOISE>
+int launch_fast(RolloutParams<R> p, bool td, int* grid_out, cudaStream_t st) {
+    auto kern = rollout_fast_kernel<D, G, R, NOISE>;
+    const size_t smem = td ? (size_t)2 * (D + 2) * kFastThreads * sizeof(double) : 0;
+    DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0, sms = 0;
+    DMFG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFastThreads, smem));
+    if (int rc = sm_count(&sms)) return rc;
+    if (occ < 1) return fail(DMFG_ERR_CUDA, "rollout_fast_kernel<%d> does not fit an SM", D);
+    const long long gpb = kFastThreads / G;
+    const long long ntiles = (p.B + gpb - 1) / gpb;
+    long long grid = (long long)sms * occ;
+    if (grid > kMaxPartialCtas) grid = kMaxPartialCtas;
+    if (grid > ntiles) grid = ntiles;
+    *grid_out = (int)grid;
+    kern<<<(unsigned)grid, kFastThreads, smem, st>>>(p);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
+template <typename R, int NOISE>
+int dispatch_fast(const RolloutParams<R>& p, bool td, int* grid, cudaStream_t st) {
+    switch (p.d) {
+        case 4: return launch_fast<4, 4, R, NOISE>(p, td, grid, st);
+        case 15: return launch_fast<15, 16, R, NOISE>(p, td, grid, st);
+        case 16: return launch_fast<16, 16, R, NOISE>(p, td, grid, st);
+    }
+    return fail(DMFG_ERR_UNSUPPORTED, "no fast kernel for d=%d", p.d);
+}
+
+template <typename R, int NOISE>
+int launch_generic(const RolloutParams<R>& p, cudaStream_t st) {
+    auto kern = rollout_generic_kernel<R, NOISE>;
+    constexpr int WPB = kGenericThreads / 32;
+    const size_t smem = (size_t)WPB * 2 * p.d * (sizeof(double) + sizeof(R));
+    DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0, sms = 0;
+    DMFG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kGenericThreads, smem));
+    if (int rc = sm_count(&sms)) return rc;
+    if (occ < 1) return fail(DMFG_ERR_CUDA, "rollout_generic_kernel does not fit an SM at d=%d", p.d);
+    long long grid = (long long)sms * occ;
+    const long long need = (p.B + WPB - 1) / WPB;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, kGenericThreads, smem, st>>>(p);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
+template <typename R>
+int run_td(const TdParams<R>& p0, double* acc, double* partials, cudaStream_t st) {
+    TdParams<R> p = p0;
+    const int F = num_features_c(p.d);
+    int sms = 0;
+    if (int rc = sm_count(&sms)) return rc;
+    {
+        const long long warps_needed = p.B;
+        long long grid = (warps_needed + 3) / 4;
+        if (grid > (long long)sms * 16) grid = (long long)sms * 16;
+        td_delta_kernel<R><<<(unsigned)grid, 128, 0, st>>>(p);
+        DMFG_CUDA(cudaGetLastError());
+    }
+    if (acc) {
+        const long long N = (long long)p.T * p.B;
+        long long grid = (N + kTdChunk - 1) / kTdChunk;
+        if (grid > kMaxPartialCtas) grid = kMaxPartialCtas;
+        p.partials = partials;
+        const size_t smem = (size_t)kTdChunk * (p.d + 3) * sizeof(double);
+        DMFG_CUDA(cudaFuncSetAttribute(td_gw_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        td_gw_kernel<R><<<(unsigned)grid, 256, smem, st>>>(p, kTdChunk);
+        DMFG_CUDA(cudaGetLastError());
+        reduce_partials_kernel<<<(F + 2 + 127) / 128, 128, 0, st>>>(partials, (int)grid, F + 2, acc);
+        DMFG_CUDA(cudaGetLastError());
+    }
+    return DMFG_OK;
+}
+
+template <typename R>
+int rollout_typed(const dmfg_rollout_args* a, cudaStream_t st) {
+    const RolloutWs ws = rollout_ws(a);
+    if (ws.total > 0 && (!a->workspace || a->workspace_bytes < ws.total))
+        return fail(DMFG_ERR_WORKSPACE, "workspace of %llu bytes needed, %llu given",
+                    (unsigned long long)ws.total, (unsigned long long)(a->workspace ? a->workspace_bytes : 0));
+    char* wsp = (char*)a->workspace;
+    RolloutParams<R> p = make_params<R>(a);
+    const bool td = a->w != nullptr;
+    const bool accum = td && a->acc != nullptr;
+    const int F = num_features_c(a->d);
+    if (a->B == 0 || (a->T == 0 && !a->states && !a->pi_final)) {
+        if (accum) DMFG_CUDA(cudaMemsetAsync(a->acc, 0, (size_t)(2 + F) * 8, st));
+        return DMFG_OK;
+    }
+    if (use_fast(a)) {
+        if (accum) p.partials = (double*)(wsp + ws.partials);
+        int grid = 0, rc;
+        if (a->noise_kind == DMFG_NOISE_PHILOX) rc = dispatch_fast<R, DMFG_NOISE_PHILOX>(p, td, &grid, st);
+        else rc = dispatch_fast<R, DMFG_NOISE_INJECTED>(p, td, &grid, st);
+        if (rc) return rc;
+        if (accum) {
+            reduce_partials_kernel<<<(F + 2 + 127) / 128, 128, 0, st>>>(p.partials, grid, F + 2, a->acc);
+            DMFG_CUDA(cudaGetLastError());
+        }
+        return DMFG_OK;
+    }
+    // generic: rollout (recording what the TD pass needs), then TD from the record
+    if (td) {
+        if (ws.need_states) p.states = (R*)(wsp + ws.states);
+        if (ws.need_rewards) p.rewards = (R*)(wsp + ws.rewards);
+        if (ws.need_grads) p.grads = (R*)(wsp + ws.grads);
+    }
+    p.deltas = nullptr;
+    int rc;
+    if (a->noise_kind == DMFG_NOISE_PHILOX) rc = launch_generic<R, DMFG_NOISE_PHILOX>(p, st);
+    else rc = launch_generic<R, DMFG_NOISE_INJECTED>(p, st);
+    if (rc) return rc;
+    if (td) {
+        TdParams<R> t;
+        t.d = a->d; t.T = a->T; t.B = a->B; t.gamma = a->gamma; t.discount_kind = a->discount_kind;
+        t.states = p.states; t.rewards = a->rewards_in ? (const R*)a->rewards_in : p.rewards;
+        t.grads = p.grads; t.w = a->w; t.deltas = (R*)a->deltas;
+        t.delta_buf = (double*)(wsp + ws.delta_buf); t.partials = nullptr;
+        return run_td<R>(t, accum ? a->acc : nullptr, accum ? (double*)(wsp + ws.partials) : nullptr, st);
+    }
+    return DMFG_OK;
+}
+
+// ---- learners --------------------------------------------------------------
+template <int D, int G, typename R, int NOISE>
+int launch_learners(const LearnerParams<R>& p, cudaStream_t st) {
+    auto kern = learners_fast_kernel<D, G, R, NOISE>;
+    const size_t smem = (size_t)(D + 2) * kFastThreads * sizeof(double);
+    DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long gpb = kFastThreads / G;
+    const long long grid = (p.L + gpb - 1) / gpb;
+    kern<<<(unsigned)grid, kFastThreads, smem, st>>>(p);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+template <typename R, int NOISE>
+int dispatch_learners(const LearnerParams<R>& p, cudaStream_t st) {
+    switch (p.d) {
+        case 4: return launch_learners<4, 4, R, NOISE>(p, st);
+        case 15: return launch_learners<15, 16, R, NOISE>(p, st);
+        case 16: return launch_learners<16, 16, R, NOISE>(p, st);
+    }
+    return fail(DMFG_ERR_UNSUPPORTED, "dmfg_ac_learners is built for d in {4,15,16}, not d=%d", p.d);
+}
+template <typename R>
+int learners_typed(const dmfg_learners_args* a, cudaStream_t st) {
+    LearnerParams<R> p;
+    p.d = a->d; p.T = a->T; p.E = a->E; p.episode0 = a->episode0; p.S = a->S;
+    p.L = a->L; p.learner_offset = a->learner_offset;
+    p.theta = a->theta; p.w = a->w; p.shift = a->shift; p.alpha_scale = a->alpha_scale;
+    p.shift_scalar = a->shift_scalar; p.alpha_scale_scalar = a->alpha_scale_scalar;
+    p.gamma = a->gamma; p.lr_critic = a->lr_critic; p.lr_actor = a->lr_actor;
+    p.constant_lr = a->constant_lr; p.reward_kind = a->reward_kind; p.discount_kind = a->discount_kind;
+    p.mat_pi0 = (const R*)a->mat_pi0; p.start_rows = a->start_rows; p.noise_y = (const R*)a->noise_y;
+    p.seed = a->seed; p.theta_trace = a->theta_trace; p.delta_trace = a->delta_trace;
+    p.total_reward = a->total_reward; p.pi_final = (R*)a->pi_final;
+    if (a->noise_kind == DMFG_NOISE_PHILOX) return dispatch_learners<R, DMFG_NOISE_PHILOX>(p, st);
+    return dispatch_learners<R, DMFG_NOISE_INJECTED>(p, st);
+}
+
+// ---- testing aids ------------------------------------------------------------
+__global__ void gamma_sample_kernel(const float* __restrict__ shape, long long n, NoiseKey nk, float* out) {
+    const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = 2 * pair;
+    if (i >= n) return;
+    const float a0 = shape[i], a1 = (i + 1 < n) ? shape[i + 1] : 1.0f;
+    float y0, y1;
+    gamma_pair(nk, (uint32_t)pair, a0, a1, y0, y1);
+    out[i] = y0;
+    if (i + 1 < n) out[i + 1] = y1;
+}
+template <typename R>
+__global__ void digamma_kernel(const R* __restrict__ x, long long n, R* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = digamma(x[i]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dmfg_version(void) { return DMFG_VERSION; }
+const char* dmfg_last_error(void) { return g_last_error.c_str(); }
+int64_t dmfg_num_features(int32_t d) { return num_features_c(d); }
+int64_t dmfg_acc_len(int32_t d) { return 2 + (int64_t)num_features_c(d); }
+
+uint64_t dmfg_rollout_workspace_bytes(const dmfg_rollout_args* a) {
+    if (!a || a->struct_size != sizeof(dmfg_rollout_args) || a->d < 1 || a->d > DMFG_MAX_D) return 0;
+    return rollout_ws(a).total;
+}
+
+int dmfg_rollout(const dmfg_rollout_args* a, void* stream) {
+    if (int rc = check_rollout(a)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return a->dtype == DMFG_F64 ? rollout_typed<double>(a, st) : rollout_typed<float>(a, st);
+}
+
+uint64_t dmfg_td_workspace_bytes(const dmfg_td_args* a) {
+    if (!a || a->struct_size != sizeof(dmfg_td_args) || a->d < 1 || a->d > DMFG_MAX_D) return 0;
+    const uint64_t F = (uint64_t)num_features_c(a->d);
+    uint64_t off = align_up((uint64_t)a->T * (uint64_t)a->B * 8);
+    if (a->acc) off += align_up((uint64_t)kMaxPartialCtas * (2 + F) * 8);
+    return off;
+}
+
+int dmfg_td_accumulate(const dmfg_td_args* a, void* stream) {
+    if (!a) return fail(DMFG_ERR_INVALID, "args is NULL");
+    if (a->struct_size != sizeof(dmfg_td_args)) return fail(DMFG_ERR_INVALID, "dmfg_td_args.struct_size mismatch");
+    if (a->dtype != DMFG_F32 && a->dtype != DMFG_F64) return fail(DMFG_ERR_INVALID, "dtype %d", a->dtype);
+    if (a->d < 1 || a->d > DMFG_MAX_D || a->T < 0 || a->B < 0) return fail(DMFG_ERR_INVALID, "bad d/T/B");
+    if (!a->states || !a->rewards || !a->w) return fail(DMFG_ERR_INVALID, "states, rewards and w are required");
+    if (a->acc && !a->grads) return fail(DMFG_ERR_INVALID, "acc needs grads");
+    const uint64_t need = dmfg_td_workspace_bytes(a);
+    if (!a->workspace || a->workspace_bytes < need)
+        return fail(DMFG_ERR_WORKSPACE, "workspace of %llu bytes needed", (unsigned long long)need);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = num_features_c(a->d);
+    if (a->B == 0 || a->T == 0) {
+        if (a->acc) DMFG_CUDA(cudaMemsetAsync(a->acc, 0, (size_t)(2 + F) * 8, st));
+        return DMFG_OK;
+    }
+    char* wsp = (char*)a->workspace;
+    double* delta_buf = (double*)wsp;
+    double* partials = (double*)(wsp + align_up((uint64_t)a->T * (uint64_t)a->B * 8));
+    if (a->dtype == DMFG_F64) {
+        TdParams<double> t{a->d, a->T, a->B, a->gamma, a->discount_kind, (const double*)a->states,
+                           (const double*)a->rewards, (const double*)a->grads, a->w, (double*)a->deltas,
+                           delta_buf, nullptr};
+        return run_td<double>(t, a->acc, partials, st);
+    }
+    TdParams<float> t{a->d, a->T, a->B, a->gamma, a->discount_kind, (const float*)a->states,
+                      (const float*)a->rewards, (const float*)a->grads, a->w, (float*)a->deltas,
+                      delta_buf, nullptr};
+    return run_td<float>(t, a->acc, partials, st);
+}
+
+int dmfg_ac_apply_update(int32_t d, double* theta_dev, double* w, const double* acc, double lr_critic_eff,
+                         double lr_actor_eff, double scale, void* stream) {
+    if (d < 1 || d > DMFG_MAX_D || !w || !acc) return fail(DMFG_ERR_INVALID, "dmfg_ac_apply_update: bad argument");
+    const int F = num_features_c(d);
+    ac_apply_update_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(F, theta_dev, w, acc, lr_critic_eff,
+                                                                            lr_actor_eff, scale);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
+int dmfg_ac_learners(const dmfg_learners_args* a, void* stream) {
+    if (!a) return fail(DMFG_ERR_INVALID, "args is NULL");
+    if (a->struct_size != sizeof(dmfg_learners_args))
+        return fail(DMFG_ERR_INVALID, "dmfg_learners_args.struct_size mismatch");
+    if (a->dtype != DMFG_F32 && a->dtype != DMFG_F64) return fail(DMFG_ERR_INVALID, "dtype %d", a->dtype);
+    if (a->L < 0 || a->E < 0 || a->T < 0 || a->S < 1) return fail(DMFG_ERR_INVALID, "bad L/E/T/S");
+    if (!a->theta || !a->w || !a->mat_pi0) return fail(DMFG_ERR_INVALID, "theta, w and mat_pi0 are required");
+    if (a->noise_kind == DMFG_NOISE_INJECTED && (!a->noise_y || !a->start_rows))
+        return fail(DMFG_ERR_INVALID, "noise_kind=INJECTED needs noise_y and start_rows");
+    if (a->reward_kind < DMFG_REWARD_NONE || a->reward_kind > DMFG_REWARD_SYNTHETIC)
+        return fail(DMFG_ERR_INVALID, "reward_kind %d", a->reward_kind);
+    if (a->L == 0 || a->E == 0) return DMFG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    return a->dtype == DMFG_F64 ? learners_typed<double>(a, st) : learners_typed<float>(a, st);
+}
+
+int dmfg_rollout_host(const dmfg_rollout_args* h, void* stream) {
+    if (int rc = check_rollout(h)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    dmfg_rollout_args a = *h;
+    const size_t es = esize(a.dtype);
+    const size_t B = (size_t)a.B, T = (size_t)a.T, d = (size_t)a.d, F = (size_t)num_features_c(a.d);
+    struct Buf { void** dev; const void* host_in; void* host_out; size_t bytes; };
+    void *pi0 = nullptr, *y = nullptr, *w = nullptr, *rin = nullptr, *states = nullptr, *actions = nullptr,
+         *alpha = nullptr, *deriv = nullptr, *rewards = nullptr, *deltas = nullptr, *grads = nullptr,
+         *pif = nullptr, *acc = nullptr, *ws = nullptr;
+    Buf bufs[] = {
+        {&pi0, h->pi0, nullptr, B * d * es},
+        {&y, h->noise_kind == DMFG_NOISE_INJECTED ? h->noise_y : nullptr, nullptr, T * B * d * d * es},
+        {&w, h->w, nullptr, F * 8},
+        {&rin, h->rewards_in, nullptr, T * B * es},
+        {&states, nullptr, h->states, (T + 1) * B * d * es},
+        {&actions, nullptr, h->actions, T * B * d * d * es},
+        {&alpha, nullptr, h->alpha, T * B * d * d * es},
+        {&deriv, nullptr, h->alpha_deriv, T * B * d * d * es},
+        {&rewards, nullptr, h->rewards, T * B * es},
+        {&deltas, nullptr, h->deltas, T * B * es},
+        {&grads, nullptr, h->grads, T * B * es},
+        {&pif, nullptr, h->pi_final, B * d * es},
+        {&acc, nullptr, h->acc, (2 + F) * 8},
+    };
+    int rc = DMFG_OK;
+    auto cleanup = [&]() {
+        for (auto& b : bufs) if (*b.dev) cudaFreeAsync(*b.dev, st);
+        if (ws) cudaFreeAsync(ws, st);
+    };
+    for (auto& b : bufs) {
+        if ((b.host_in || b.host_out) && b.bytes > 0) {
+            cudaError_t e = cudaMallocAsync(b.dev, b.bytes, st);
+            if (e == cudaSuccess && b.host_in) e = cudaMemcpyAsync(*b.dev, b.host_in, b.bytes, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) { cleanup(); return fail(DMFG_ERR_CUDA, "dmfg_rollout_host: %s", cudaGetErrorString(e)); }
+        }
+    }
+    a.pi0 = pi0; a.noise_y = y; a.w = (const double*)w; a.rewards_in = rin; a.states = states; a.actions = actions;
+    a.alpha = alpha; a.alpha_deriv = deriv; a.rewards = rewards; a.deltas = deltas; a.grads = grads;
+    a.pi_final = pif; a.acc = (double*)acc; a.theta_dev = nullptr;
+    a.workspace = nullptr; a.workspace_bytes = 0;
+    const uint64_t need = rollout_ws(&a).total;
+    if (need) {
+        cudaError_t e = cudaMallocAsync(&ws, need, st);
+        if (e != cudaSuccess) { cleanup(); return fail(DMFG_ERR_CUDA, "dmfg_rollout_host: %s", cudaGetErrorString(e)); }
+        a.workspace = ws; a.workspace_bytes = need;
+    }
+    rc = dmfg_rollout(&a, stream);
+    if (rc == DMFG_OK) {
+        for (auto& b : bufs) {
+            if (b.host_out && b.bytes > 0) {
+                cudaError_t e = cudaMemcpyAsync(b.host_out, *b.dev, b.bytes, cudaMemcpyDeviceToHost, st);
+                if (e != cudaSuccess) { rc = fail(DMFG_ERR_CUDA, "dmfg_rollout_host: %s", cudaGetErrorString(e)); break; }
+            }
+        }
+    }
+    cleanup();
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == DMFG_OK && e != cudaSuccess) rc = fail(DMFG_ERR_CUDA, "dmfg_rollout_host: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+void dmfg_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    const uint4 r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+int dmfg_gamma_sample(const float* shape, int64_t n, uint64_t seed, uint64_t pop, float* out, void* stream) {
+    if (n < 0 || (n > 0 && (!shape || !out))) return fail(DMFG_ERR_INVALID, "dmfg_gamma_sample: bad argument");
+    if (n == 0) return DMFG_OK;
+    const long long pairs = (n + 1) / 2;
+    gamma_sample_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        shape, n, make_noise_key(seed, pop), out);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
+int dmfg_digamma(int32_t dtype, const void* x, int64_t n, void* out, void* stream) {
+    if (n < 0 || (n > 0 && (!x || !out))) return fail(DMFG_ERR_INVALID, "dmfg_digamma: bad argument");
+    if (n == 0) return DMFG_OK;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (dtype == DMFG_F64) digamma_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x, n, (double*)out);
+    else if (dtype == DMFG_F32) digamma_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, n, (float*)out);
+    else return fail(DMFG_ERR_INVALID, "dtype %d", dtype);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
+}  // extern "C"

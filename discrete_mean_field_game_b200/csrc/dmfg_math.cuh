@@ -1,0 +1,239 @@
+// Device math shared by the dmfg kernels (sm_100a).
+//
+//   * Philox4x32-10 counter-based generator (Salmon et al., SC'11) -- counters are
+//     (population id, slot, attempt) so a draw never depends on the GPU count,
+//     the grid shape or the kernel variant.
+//   * Box-Muller normals + Marsaglia-Tsang Gamma(shape,1) with the U^(1/a) boost
+//     for shape < 1 -- the in-kernel replacement of np.random.gamma
+//     (mfg_ac2.py:242); validated statistically, not bit-for-bit.
+//   * softplus concentration alpha / d alpha / d theta (mfg_ac2.py:228-234)
+//   * digamma (scipy.special.digamma at mfg_ac2.py:364-367)
+//
+// Tm is the "math type": float for the throughput path, double for the
+// float64 parity path.  All REDUCTIONS are done in double by the callers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dmfg {
+
+// ------------------------------------------------------------------ Philox
+#define DMFG_PHILOX_M0 0xD2511F53u
+#define DMFG_PHILOX_M1 0xCD9E8D57u
+#define DMFG_PHILOX_W0 0x9E3779B9u
+#define DMFG_PHILOX_W1 0xBB67AE85u
+
+__host__ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2,
+                                                      uint32_t& c3, uint32_t k0, uint32_t k1) {
+#ifdef __CUDA_ARCH__
+    const uint32_t hi0 = __umulhi(DMFG_PHILOX_M0, c0);
+    const uint32_t hi1 = __umulhi(DMFG_PHILOX_M1, c2);
+#else
+    const uint32_t hi0 = (uint32_t)(((uint64_t)DMFG_PHILOX_M0 * c0) >> 32);
+    const uint32_t hi1 = (uint32_t)(((uint64_t)DMFG_PHILOX_M1 * c2) >> 32);
+#endif
+    const uint32_t lo0 = DMFG_PHILOX_M0 * c0;
+    const uint32_t lo1 = DMFG_PHILOX_M1 * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+}
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                        uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += DMFG_PHILOX_W0;
+        k1 += DMFG_PHILOX_W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// Identifies one stream of draws: key = seed, counter words 0/1 = global population id.
+struct NoiseKey {
+    uint32_t k0, k1;     // seed
+    uint32_t p0, p1;     // population (or learner) id
+};
+__host__ __device__ __forceinline__ NoiseKey make_noise_key(uint64_t seed, uint64_t pop) {
+    NoiseKey k;
+    k.k0 = (uint32_t)seed; k.k1 = (uint32_t)(seed >> 32);
+    k.p0 = (uint32_t)pop;  k.p1 = (uint32_t)(pop >> 32);
+    return k;
+}
+
+// Slot of the Gamma pair (columns 2p, 2p+1) of row i at (global) step t.
+__host__ __device__ __forceinline__ uint32_t gamma_slot(uint32_t t, int d, int i, int p) {
+    const uint32_t pd = (uint32_t)((d + 1) >> 1);
+    return (t * (uint32_t)d + (uint32_t)i) * pd + (uint32_t)p;
+}
+#define DMFG_CTR_BOOST 0x80000000u   // counter word 3 of the boost uniforms (attempts count from 0)
+#define DMFG_CTR_START 0xC0000000u   // counter word 3 of the start-row draw of the learners
+
+// uniform in (0,1), never 0 or 1
+__device__ __forceinline__ float u01(uint32_t w) {
+    return fmaf(__uint2float_rz(w), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
+
+__device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& n0, float& n1) {
+    const float r = sqrtf(-2.0f * __logf(u01(w0)));
+    float s, c;
+    sincospif(2.0f * u01(w1), &s, &c);
+    n0 = r * c;
+    n1 = r * s;
+}
+
+// One Marsaglia-Tsang proposal for Gamma(dd + 1/3, 1).  cc = 1/sqrt(9 dd).
+// The log test is evaluated in a cancellation-free form: with e = cc*x,
+//   x^2/2 + dd(1 - v + ln v),  v = (1+e)^3
+// equals  dd * 3 * sum_{k>=4} (-1)^(k+1) e^k / k  because dd*cc^2 = 1/9 cancels the
+// x^2/2 term exactly; the series is used for |e| < 1/4, the direct form otherwise.
+__device__ __forceinline__ bool mt_propose(float dd, float cc, float x, float u, float& y) {
+    const float e = cc * x;
+    const float v1 = 1.0f + e;
+    if (v1 <= 0.0f) return false;
+    const float v = v1 * v1 * v1;
+    const float x2 = x * x;
+    y = dd * v;
+    if (u < 1.0f - 0.0331f * x2 * x2) return true;
+    float rhs;
+    if (fabsf(e) < 0.25f) {
+        // sum_{k>=4} (-1)^(k+1) e^k/k = -e^4 * h,  h = sum_{m=0..9} (-e)^m/(m+4)  (|e|<1/4: rel. err < 2e-7)
+        float h = 1.0f / 13.0f;
+        h = fmaf(h, -e, 1.0f / 12.0f);
+        h = fmaf(h, -e, 1.0f / 11.0f);
+        h = fmaf(h, -e, 1.0f / 10.0f);
+        h = fmaf(h, -e, 1.0f / 9.0f);
+        h = fmaf(h, -e, 1.0f / 8.0f);
+        h = fmaf(h, -e, 1.0f / 7.0f);
+        h = fmaf(h, -e, 1.0f / 6.0f);
+        h = fmaf(h, -e, 1.0f / 5.0f);
+        h = fmaf(h, -e, 1.0f / 4.0f);
+        const float e2 = e * e;
+        rhs = -3.0f * dd * e2 * e2 * h;
+    } else {
+        rhs = 0.5f * x2 + dd * (1.0f - v + __logf(v));
+    }
+    return __logf(u) < rhs;
+}
+
+struct GammaSetup {
+    float dd, cc, inv_a;
+    bool boost;
+};
+__device__ __forceinline__ GammaSetup gamma_setup(float a) {
+    GammaSetup g;
+    g.boost = a < 1.0f;
+    g.inv_a = 1.0f / a;                   // inf for a == 0 -> boost factor 0 -> y = 0 (np.random.gamma(0) == 0)
+    const float a1 = g.boost ? a + 1.0f : a;
+    g.dd = a1 - (1.0f / 3.0f);
+    g.cc = rsqrtf(9.0f * g.dd);
+    return g;
+}
+
+// Gamma(a0,1), Gamma(a1,1) for the pair in `slot`.  One Philox call feeds both
+// elements (two Box-Muller normals + two acceptance uniforms); rejected elements
+// move on to attempt+1.  Shapes < 1 take one more call for the boost uniforms.
+__device__ __forceinline__ void gamma_pair(const NoiseKey& nk, uint32_t slot, float a0, float a1,
+                                           float& y0, float& y1) {
+    const GammaSetup g0 = gamma_setup(a0), g1 = gamma_setup(a1);
+    bool done0 = false, done1 = false;
+    uint32_t attempt = 0;
+    y0 = 0.0f; y1 = 0.0f;
+    do {
+        const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, attempt, nk.k0, nk.k1);
+        float n0, n1;
+        box_muller(w.x, w.y, n0, n1);
+        if (!done0) done0 = mt_propose(g0.dd, g0.cc, n0, u01(w.z), y0);
+        if (!done1) done1 = mt_propose(g1.dd, g1.cc, n1, u01(w.w), y1);
+        ++attempt;
+    } while (!(done0 && done1) && attempt < 64u);
+    if (g0.boost || g1.boost) {
+        const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, DMFG_CTR_BOOST, nk.k0, nk.k1);
+        if (g0.boost) y0 *= exp2f(__log2f(u01(w.x)) * g0.inv_a);
+        if (g1.boost) y1 *= exp2f(__log2f(u01(w.y)) * g1.inv_a);
+    }
+}
+
+// ------------------------------------------------------------ policy alpha
+// x = pi_j - pi_i - shift;  alpha = ln(1+exp(theta x));  alpha' = x / (1+exp(-theta x))
+// (mfg_ac2.py:228-234), evaluated in the overflow-free form.
+template <typename Tm> struct Math;
+template <> struct Math<float> {
+    static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+    static __device__ __forceinline__ float log_(float x) { return logf(x); }
+    static __device__ __forceinline__ float log1p_(float x) { return log1pf(x); }
+    static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+};
+template <> struct Math<double> {
+    static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+    static __device__ __forceinline__ double log_(double x) { return log(x); }
+    static __device__ __forceinline__ double log1p_(double x) { return log1p(x); }
+    static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+};
+
+template <typename Tm>
+__device__ __forceinline__ void policy_alpha(Tm theta, Tm x, Tm& alpha, Tm& alpha_deriv) {
+    const Tm t = theta * x;
+    const Tm e = Math<Tm>::exp_(-Math<Tm>::abs_(t));       // in (0,1]
+    const Tm l = Math<Tm>::log1p_(e);
+    const Tm inv = Tm(1) / (Tm(1) + e);
+    const bool pos = t >= Tm(0);
+    alpha = pos ? t + l : l;
+    alpha_deriv = x * (pos ? inv : e * inv);
+}
+
+// ----------------------------------------------------------------- digamma
+// psi(x), x > 0.  Recurrence psi(x) = psi(x+n) - sum_{k<n} 1/(x+k), then the
+// asymptotic series.  float: n = 6 folded into ONE division via
+//   x(x+5) = q, (x+1)(x+4) = q+4, (x+2)(x+3) = q+6,  sum = q'(3q^2+20q+24) / (q(q+4)(q+6)),
+// every term positive, so small x (psi ~ -1/x, alpha down to 1e-5) keeps full
+// relative accuracy.
+__device__ __forceinline__ float digamma(float x) {
+    float s = 0.0f, z = x;
+    if (x < 1.0e4f) {
+        const float q = fmaf(x, x, 5.0f * x);
+        const float num = fmaf(2.0f, x, 5.0f) * fmaf(fmaf(3.0f, q, 20.0f), q, 24.0f);
+        const float den = q * (q + 4.0f) * (q + 6.0f);
+        s = num / den;
+        z = x + 6.0f;
+    }
+    const float rz = 1.0f / z;
+    const float r2 = rz * rz;
+    // 1/12 - r2/120 + r2^2/252 - r2^3/240
+    float p = fmaf(r2, -1.0f / 240.0f, 1.0f / 252.0f);
+    p = fmaf(r2, p, -1.0f / 120.0f);
+    p = fmaf(r2, p, 1.0f / 12.0f);
+    return logf(z) - 0.5f * rz - r2 * p - s;
+}
+
+__device__ __forceinline__ double digamma(double x) {
+    double s = 0.0;
+    while (x < 10.0) { s += 1.0 / x; x += 1.0; }
+    const double rz = 1.0 / x;
+    const double r2 = rz * rz;
+    // Bernoulli series: 1/12, 1/120, 1/252, 1/240, 1/132, 691/32760, 1/12
+    double p = 1.0 / 12.0;
+    p = fma(r2, -p, 691.0 / 32760.0);
+    p = fma(r2, -p, 1.0 / 132.0);
+    p = fma(r2, -p, 1.0 / 240.0);
+    p = fma(r2, -p, 1.0 / 252.0);
+    p = fma(r2, -p, 1.0 / 120.0);
+    p = fma(r2, -p, 1.0 / 12.0);
+    return log(x) - 0.5 * rz - r2 * p - s;
+}
+
+// ln(P) with the reference's P == 0 -> 1e-100 substitution (mfg_ac2.py:369).
+__device__ __forceinline__ float log_prob(float p) { return p > 0.0f ? logf(p) : -230.25850929940458f; }
+__device__ __forceinline__ double log_prob(double p) { return p > 0.0 ? log(p) : -230.25850929940458; }
+
+// ------------------------------------------------------- sub-warp reductions
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+    return v;
+}
+
+}  // namespace dmfg

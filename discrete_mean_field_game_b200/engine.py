@@ -1,0 +1,261 @@
+"""Thin device-side plumbing over libdmfg: torch owns device memory and streams,
+the C ABI does the work.  Every function here takes/returns CUDA tensors in the
+library's time-major layouts (states [T+1,B,d], actions [T,B,d,d], per-step
+scalars [T,B]); nothing falls back to the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (DISCOUNT_CUMULATIVE, DISCOUNT_STEP, F32, F64, NOISE_INJECTED, NOISE_PHILOX,
+                   REWARD_KINDS, VARIANTS, LearnersArgs, RolloutArgs, TdArgs, check, num_features)
+
+ROLLOUT_OUTPUTS = ("states", "actions", "alpha", "alpha_deriv", "rewards", "deltas", "grads", "pi_final")
+
+_workspaces = {}
+
+
+def _dtype_code(dtype):
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.float64:
+        return F64
+    raise TypeError("stream dtype must be torch.float32 or torch.float64, got %r" % (dtype,))
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _require(t, name, device, dtype, shape):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor" % name)
+    if t.device != device:
+        raise ValueError("%s is on %s, expected %s" % (name, t.device, device))
+    if t.dtype != dtype:
+        raise TypeError("%s has dtype %s, expected %s" % (name, t.dtype, dtype))
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def _workspace(device, nbytes):
+    """Grow-only scratch per (device, stream)."""
+    if nbytes == 0:
+        return None
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("discrete_mean_field_game_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU fallback")
+    _lib.load()
+
+
+def rollout(pi0, theta, shift, alpha_scale, T, *, w=None, gamma=1.0, reward="ac2", discount="step",
+            noise_y=None, seed=0, pop_offset=0, step_offset=0, outputs=("states",), want_acc=False,
+            rewards_in=None, theta_dev=None, variant="auto", out=None):
+    """dmfg_rollout on CUDA tensors.
+
+    pi0 [B,d] (float32/float64 selects the stream dtype); noise_y [T,B,d,d] selects
+    injected noise, otherwise in-kernel Philox keyed by (seed, pop_offset + b).
+    Returns a dict with the requested `outputs` (time-major tensors) and, with
+    want_acc, 'acc' = [sum delta*g, sum delta*phi (F), sum r] as float64.
+    `out` may carry preallocated tensors for any output (reused across calls).
+    """
+    lib = _lib.load()
+    if not pi0.is_cuda:
+        raise TypeError("pi0 must be a CUDA tensor")
+    device, dtype = pi0.device, pi0.dtype
+    B, d = pi0.shape
+    F = num_features(d)
+    pi0 = _require(pi0, "pi0", device, dtype, (B, d))
+    a = RolloutArgs()
+    a.struct_size = C.sizeof(RolloutArgs)
+    a.dtype, a.d, a.T, a.B, a.pop_offset = _dtype_code(dtype), d, int(T), B, int(pop_offset)
+    a.theta, a.shift, a.alpha_scale, a.gamma = float(theta), float(shift), float(alpha_scale), float(gamma)
+    a.theta_dev = _ptr(_require(theta_dev, "theta_dev", device, torch.float64, (1,))) if theta_dev is not None else None
+    a.reward_kind = REWARD_KINDS[reward]
+    a.discount_kind = DISCOUNT_STEP if discount == "step" else DISCOUNT_CUMULATIVE
+    a.variant = VARIANTS[variant]
+    a.seed, a.step_offset = int(seed) & (2 ** 64 - 1), int(step_offset)
+    if noise_y is not None:
+        a.noise_kind = NOISE_INJECTED
+        a.noise_y = _ptr(_require(noise_y, "noise_y", device, dtype, (T, B, d, d)))
+    else:
+        a.noise_kind = NOISE_PHILOX
+    a.pi0 = _ptr(pi0)
+    if w is not None:
+        a.w = _ptr(_require(w, "w", device, torch.float64, (F,)))
+    if rewards_in is not None:
+        a.rewards_in = _ptr(_require(rewards_in, "rewards_in", device, dtype, (T, B)))
+    shapes = dict(states=(T + 1, B, d), actions=(T, B, d, d), alpha=(T, B, d, d), alpha_deriv=(T, B, d, d),
+                  rewards=(T, B), deltas=(T, B), grads=(T, B), pi_final=(B, d))
+    res = {}
+    with torch.cuda.device(device):
+        for name in outputs:
+            if name not in shapes:
+                raise ValueError("unknown output %r" % name)
+            t = out.get(name) if out else None
+            if t is None:
+                t = torch.empty(shapes[name], dtype=dtype, device=device)
+            else:
+                _require(t, name, device, dtype, shapes[name])
+            res[name] = t
+            setattr(a, name, _ptr(t))
+        if want_acc:
+            acc = out.get("acc") if out else None
+            if acc is None:
+                acc = torch.empty(2 + F, dtype=torch.float64, device=device)
+            res["acc"] = _require(acc, "acc", device, torch.float64, (2 + F,))
+            a.acc = _ptr(acc)
+        need = lib.dmfg_rollout_workspace_bytes(C.byref(a))
+        ws = _workspace(device, need)
+        if ws is not None:
+            a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        check(lib.dmfg_rollout(C.byref(a), _stream_ptr(device)))
+    return res
+
+
+def td_accumulate(states, rewards, grads, w, *, gamma=1.0, discount="step", want_deltas=True, want_acc=True):
+    """dmfg_td_accumulate: TD errors / accumulators from a recorded batch of trajectories."""
+    lib = _lib.load()
+    device, dtype = states.device, states.dtype
+    T1, B, d = states.shape
+    T = T1 - 1
+    F = num_features(d)
+    a = TdArgs()
+    a.struct_size = C.sizeof(TdArgs)
+    a.dtype, a.d, a.T, a.B = _dtype_code(dtype), d, T, B
+    a.gamma = float(gamma)
+    a.discount_kind = DISCOUNT_STEP if discount == "step" else DISCOUNT_CUMULATIVE
+    a.states = _ptr(_require(states, "states", device, dtype, (T + 1, B, d)))
+    a.rewards = _ptr(_require(rewards, "rewards", device, dtype, (T, B)))
+    if grads is not None:
+        a.grads = _ptr(_require(grads, "grads", device, dtype, (T, B)))
+    a.w = _ptr(_require(w, "w", device, torch.float64, (F,)))
+    res = {}
+    with torch.cuda.device(device):
+        if want_deltas:
+            res["deltas"] = torch.empty((T, B), dtype=dtype, device=device)
+            a.deltas = _ptr(res["deltas"])
+        if want_acc:
+            res["acc"] = torch.empty(2 + F, dtype=torch.float64, device=device)
+            a.acc = _ptr(res["acc"])
+        ws = _workspace(device, lib.dmfg_td_workspace_bytes(C.byref(a)))
+        if ws is not None:
+            a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        check(lib.dmfg_td_accumulate(C.byref(a), _stream_ptr(device)))
+    return res
+
+
+def apply_update(d, theta_dev, w, acc, lr_critic_eff, lr_actor_eff, scale):
+    """theta += lr_a*scale*acc[0]; w += lr_c*scale*acc[1:1+F]  (mfg_ac2.py:511-522), on device."""
+    lib = _lib.load()
+    device = w.device
+    with torch.cuda.device(device):
+        check(lib.dmfg_ac_apply_update(int(d), _ptr(theta_dev), _ptr(w), _ptr(acc), float(lr_critic_eff),
+                                       float(lr_actor_eff), float(scale), _stream_ptr(device)))
+
+
+def learners(theta, w, mat_pi0, E, T, *, shift, alpha_scale, episode0=0, gamma=1.0, lr_critic=0.1,
+             lr_actor=0.001, constant=False, reward="ac2", discount="step", start_rows=None, noise_y=None,
+             seed=0, learner_offset=0, trace=False, want_total_reward=True):
+    """dmfg_ac_learners: L independent serial learners with per-step updates.
+
+    theta [L] float64 and w [L,F] float64 are updated IN PLACE.  shift / alpha_scale may be
+    floats or [L] float64 tensors.  mat_pi0 [S,d] selects the stream dtype.
+    """
+    lib = _lib.load()
+    device, dtype = mat_pi0.device, mat_pi0.dtype
+    S, d = mat_pi0.shape
+    L = theta.shape[0]
+    F = num_features(d)
+    a = LearnersArgs()
+    a.struct_size = C.sizeof(LearnersArgs)
+    a.dtype, a.d, a.T, a.L, a.E = _dtype_code(dtype), d, int(T), L, int(E)
+    a.learner_offset, a.episode0 = int(learner_offset), int(episode0)
+    a.theta = _ptr(_require(theta, "theta", device, torch.float64, (L,)))
+    a.w = _ptr(_require(w, "w", device, torch.float64, (L, F)))
+    if isinstance(shift, torch.Tensor):
+        a.shift = _ptr(_require(shift, "shift", device, torch.float64, (L,)))
+    else:
+        a.shift_scalar = float(shift)
+    if isinstance(alpha_scale, torch.Tensor):
+        a.alpha_scale = _ptr(_require(alpha_scale, "alpha_scale", device, torch.float64, (L,)))
+    else:
+        a.alpha_scale_scalar = float(alpha_scale)
+    a.gamma, a.lr_critic, a.lr_actor = float(gamma), float(lr_critic), float(lr_actor)
+    a.constant_lr = 1 if constant else 0
+    a.reward_kind = REWARD_KINDS[reward]
+    a.discount_kind = DISCOUNT_STEP if discount == "step" else DISCOUNT_CUMULATIVE
+    a.mat_pi0, a.S = _ptr(_require(mat_pi0, "mat_pi0", device, dtype, (S, d))), S
+    a.seed = int(seed) & (2 ** 64 - 1)
+    if noise_y is not None:
+        a.noise_kind = NOISE_INJECTED
+        a.noise_y = _ptr(_require(noise_y, "noise_y", device, dtype, (L, E, T, d, d)))
+        if start_rows is None:
+            raise ValueError("injected noise needs start_rows [L,E]")
+    else:
+        a.noise_kind = NOISE_PHILOX
+    if start_rows is not None:
+        a.start_rows = _ptr(_require(start_rows, "start_rows", device, torch.int32, (L, E)))
+    res = {}
+    with torch.cuda.device(device):
+        if trace:
+            res["theta_trace"] = torch.empty((L, E, T), dtype=torch.float64, device=device)
+            res["delta_trace"] = torch.empty((L, E, T), dtype=torch.float64, device=device)
+            a.theta_trace, a.delta_trace = _ptr(res["theta_trace"]), _ptr(res["delta_trace"])
+        if want_total_reward:
+            res["total_reward"] = torch.empty((L, E), dtype=torch.float64, device=device)
+            a.total_reward = _ptr(res["total_reward"])
+        res["pi_final"] = torch.empty((L, d), dtype=dtype, device=device)
+        a.pi_final = _ptr(res["pi_final"])
+        check(lib.dmfg_ac_learners(C.byref(a), _stream_ptr(device)))
+    return res
+
+
+def gamma_sample(shape, seed=0, pop=0):
+    """Gamma(shape,1) variates from the kernels' own sampler (testing aid)."""
+    lib = _lib.load()
+    shape = shape.contiguous().to(torch.float32)
+    out = torch.empty_like(shape)
+    with torch.cuda.device(shape.device):
+        check(lib.dmfg_gamma_sample(_ptr(shape), shape.numel(), int(seed), int(pop), _ptr(out),
+                                    _stream_ptr(shape.device)))
+    return out
+
+
+def digamma(x):
+    """Device digamma of the library for float32/float64 tensors (testing aid)."""
+    lib = _lib.load()
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.dmfg_digamma(_dtype_code(x.dtype), _ptr(x), x.numel(), _ptr(out), _stream_ptr(x.device)))
+    return out
+
+
+def philox(ctr, key):
+    """Host evaluation of the library's Philox4x32-10 (known-answer tests)."""
+    lib = _lib.load()
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib.dmfg_philox4x32_10(c, k, o)
+    return tuple(int(v) for v in o)

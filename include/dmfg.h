@@ -1,0 +1,224 @@
+/*
+ * dmfg.h -- C ABI of the B200 (sm_100a) population-dynamics hot path.
+ *
+ * The reference (011235813/discrete_mean_field_game) has no FFI / plugin
+ * boundary: its only interface is the Python method surface of the solver
+ * classes.  This header therefore DEFINES the boundary; each entry point cites
+ * the reference method(s) it replaces.  A maintainer binds it with ctypes
+ * (INTEGRATION.md shows the stub) -- no torch types cross this interface.
+ *
+ * Conventions
+ *   - every function returns an int status: DMFG_OK (0) or a negative error;
+ *     nothing throws across the ABI; dmfg_last_error() gives the message of
+ *     the calling thread's last failure.
+ *   - pointers are DEVICE pointers owned by the caller unless the name ends
+ *     in _host; `stream` is a cudaStream_t passed as void* (NULL = default).
+ *     All work is enqueued on that stream and nothing synchronises unless
+ *     stated; there is no hidden global state, calls are re-entrant per stream.
+ *   - "streams" (states, actions, noise, per-step scalars) have the element
+ *     type selected by `dtype`; PARAMETERS and REDUCED SUMS (theta, w, the
+ *     gradient accumulators) are always double.
+ *   - bulk layouts are TIME-MAJOR so that one CTA's populations are contiguous
+ *     at every step:  states [T+1][B][d], actions / noise [T][B][d][d],
+ *     per-step scalars [T][B].
+ *   - F = d(d+1)/2 + d + 1 critic features, ordered as the reference's code
+ *     builds them (mfg_ac2.py:333-344): pi_i*pi_j for i<=j row-major, pi, 1.
+ */
+#ifndef DMFG_H
+#define DMFG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMFG_VERSION 1
+
+/* status codes */
+#define DMFG_OK               0
+#define DMFG_ERR_INVALID     -1   /* bad argument (NULL, size, enum)          */
+#define DMFG_ERR_UNSUPPORTED -2   /* valid request this build cannot serve    */
+#define DMFG_ERR_CUDA        -3   /* CUDA runtime error (see dmfg_last_error) */
+#define DMFG_ERR_WORKSPACE   -4   /* workspace missing or too small           */
+
+/* dtype of stream buffers */
+#define DMFG_F32 0
+#define DMFG_F64 1
+
+/* reward functor */
+#define DMFG_REWARD_NONE      0   /* rollout only (generate_trajectory)                     */
+#define DMFG_REWARD_AC2       1   /* mfg_ac2.py:257-287  sum_i pi_i sum_j P_ij^2 (pi_j-pi_i) */
+#define DMFG_REWARD_SYNTHETIC 2   /* mfg_synthetic.py:249-265  -1/2 sum_i pi_i |P_i|^2       */
+
+/* factor on V(pi') in the TD error */
+#define DMFG_DISCOUNT_STEP       0   /* gamma           (mfg_ac2.py:505) */
+#define DMFG_DISCOUNT_CUMULATIVE 1   /* gamma^t running (ac_irl.py:691)  */
+
+/* noise source for the Gamma variates of sample_action */
+#define DMFG_NOISE_INJECTED 0   /* caller supplies y[T][B][d][d] (parity with the reference's draws) */
+#define DMFG_NOISE_PHILOX   1   /* in-kernel Philox4x32-10 + Marsaglia-Tsang, keyed by (seed, population id) */
+
+/* kernel selection (testing aid) */
+#define DMFG_VARIANT_AUTO    0
+#define DMFG_VARIANT_GENERIC 1   /* warp per population, any d <= DMFG_MAX_D         */
+#define DMFG_VARIANT_FAST    2   /* half-warp per population, compile-time d (4/15/16) */
+
+#define DMFG_MAX_D 256
+
+/* ---- library ---------------------------------------------------------- */
+int         dmfg_version(void);
+const char* dmfg_last_error(void);
+/* number of critic features for d topics (mfg_ac2.py:175) */
+int64_t     dmfg_num_features(int32_t d);
+/* length of the reduced accumulator written by dmfg_rollout / dmfg_td_accumulate: 2 + F doubles
+ *   acc[0] = sum_{t,b} delta*g   acc[1..F] = sum_{t,b} delta*phi(pi_t)   acc[1+F] = sum_{t,b} r   */
+int64_t     dmfg_acc_len(int32_t d);
+
+/* ---- a1..a7, a9: batched rollout with frozen parameters ---------------- *
+ * Replaces, for B populations at once and T transitions each:
+ *   sample_action            mfg_ac2.py:211-254, ac_irl.py:509-548
+ *   pi' = P^T pi             mfg_ac2.py:497
+ *   calc_reward              mfg_ac2.py:257-287 / mfg_synthetic.py:249-265
+ *   calc_features, TD error  mfg_ac2.py:325-344, 505
+ *   calc_gradient_vectorized mfg_ac2.py:347-381, ac_irl.py:573-624
+ *   generate_trajectory(ies) mfg_ac2.py:566-592, ac_irl.py:735-767
+ * Every output pointer is optional (NULL = not produced).                  */
+typedef struct dmfg_rollout_args {
+    uint32_t struct_size;       /* sizeof(dmfg_rollout_args) */
+    int32_t  dtype;             /* DMFG_F32 | DMFG_F64 */
+    int32_t  d;                 /* topics */
+    int32_t  T;                 /* transitions per episode (reference: 15) */
+    int64_t  B;                 /* populations in this call */
+    int64_t  pop_offset;        /* global id of population 0 (Philox subsequence = pop_offset + b) */
+
+    double   theta;             /* policy parameter, used when theta_dev == NULL */
+    const double* theta_dev;    /* optional device scalar overriding `theta` */
+    double   shift;
+    double   alpha_scale;
+    double   gamma;
+    int32_t  reward_kind;       /* DMFG_REWARD_* */
+    int32_t  discount_kind;     /* DMFG_DISCOUNT_* */
+
+    int32_t  noise_kind;        /* DMFG_NOISE_* */
+    int32_t  variant;           /* DMFG_VARIANT_* */
+    const void* noise_y;        /* [T][B][d][d] Gamma(alpha*alpha_scale,1) variates (INJECTED) */
+    uint64_t seed;              /* PHILOX key */
+    uint64_t step_offset;       /* PHILOX: added to t so that successive calls do not reuse draws */
+
+    const void*   pi0;          /* [B][d] start states */
+    const double* w;            /* [F] critic weights; NULL = no TD error / accumulators */
+    const void*   rewards_in;   /* optional [T][B]: externally supplied rewards (overrides reward_kind in delta) */
+
+    void* states;               /* [T+1][B][d] */
+    void* actions;              /* [T][B][d][d] */
+    void* alpha;                /* [T][B][d][d]  mat_alpha       (mfg_ac2.py:228) */
+    void* alpha_deriv;          /* [T][B][d][d]  mat_alpha_deriv (mfg_ac2.py:232-234) */
+    void* rewards;              /* [T][B] */
+    void* deltas;               /* [T][B] TD errors (needs w) */
+    void* grads;                /* [T][B] d log F / d theta */
+    void* pi_final;             /* [B][d] */
+    double* acc;                /* [2+F] reduced sums, OVERWRITTEN (needs w and workspace) */
+
+    void*    workspace;         /* scratch: per-CTA partial sums (deterministic two-stage reduction) and,
+                                   for the generic variant with w != NULL, unrequested intermediates */
+    uint64_t workspace_bytes;   /* >= dmfg_rollout_workspace_bytes(args) */
+} dmfg_rollout_args;
+
+/* exact scratch need of this call (0 when none); looks at d, T, B, dtype, variant, w, acc and
+ * which outputs are requested -- never at buffer contents */
+uint64_t dmfg_rollout_workspace_bytes(const dmfg_rollout_args* args);
+int dmfg_rollout(const dmfg_rollout_args* args, void* stream);
+
+/* ---- a4, a5: TD errors + accumulators from recorded trajectories -------- *
+ * delta_t = r_t + g_t V(pi_{t+1}) - V(pi_t) with external rewards (the IRL
+ * reward net, ac_irl.py:683-691); sums delta*g and delta*phi like dmfg_rollout. */
+typedef struct dmfg_td_args {
+    uint32_t struct_size;
+    int32_t  dtype;
+    int32_t  d, T;
+    int64_t  B;
+    double   gamma;
+    int32_t  discount_kind;
+    int32_t  reserved;
+    const void*   states;       /* [T+1][B][d] */
+    const void*   rewards;      /* [T][B] */
+    const void*   grads;        /* [T][B] */
+    const double* w;            /* [F] */
+    void*    deltas;            /* [T][B] optional */
+    double*  acc;               /* [2+F] optional */
+    void*    workspace;
+    uint64_t workspace_bytes;   /* >= dmfg_td_workspace_bytes(args) */
+} dmfg_td_args;
+uint64_t dmfg_td_workspace_bytes(const dmfg_td_args* args);
+int dmfg_td_accumulate(const dmfg_td_args* args, void* stream);
+
+/* ---- a5, a7: apply one actor-critic update on device --------------------- *
+ * theta += lr_actor_eff * scale * acc[0];  w += lr_critic_eff * scale * acc[1..F]
+ * (mfg_ac2.py:511-522).  lr_*_eff are the already-decayed step sizes; scale is
+ * 1/B for the batch-mean update.  theta_dev and w are updated in place.     */
+int dmfg_ac_apply_update(int32_t d, double* theta_dev, double* w, const double* acc,
+                         double lr_critic_eff, double lr_actor_eff, double scale, void* stream);
+
+/* ---- a8: independent serial learners (exact reference semantics) -------- *
+ * L learners, each with its OWN (theta, w) and per-step online updates, run E
+ * episodes of T transitions: mfg_ac2.actor_critic.train (mfg_ac2.py:448-539),
+ * AC_IRL.train with a closed-form reward (ac_irl.py:634-732) and the
+ * (shift, theta0) sweep of mfg_synthetic.py:902-925.  L = 1 is config 1.    */
+typedef struct dmfg_learners_args {
+    uint32_t struct_size;
+    int32_t  dtype;
+    int32_t  d, T;
+    int64_t  L;                 /* learners */
+    int64_t  learner_offset;    /* global id of learner 0 (Philox subsequence) */
+    int32_t  E;                 /* episodes in this call */
+    int32_t  episode0;          /* index of the first episode: 0 (mfg_ac2.py:460) or 1 (ac_irl.py:649), or a resume point */
+
+    double*  theta;             /* [L] in/out */
+    double*  w;                 /* [L][F] in/out */
+    const double* shift;        /* [L] or NULL -> shift_scalar */
+    const double* alpha_scale;  /* [L] or NULL -> alpha_scale_scalar */
+    double   shift_scalar;
+    double   alpha_scale_scalar;
+    double   gamma;
+    double   lr_critic;
+    double   lr_actor;
+    int32_t  constant_lr;       /* 1 = constant step sizes (mfg_ac2.py:511,519) */
+    int32_t  reward_kind;
+    int32_t  discount_kind;
+    int32_t  noise_kind;
+
+    const void*    mat_pi0;     /* [S][d] start-state table (init_pi0, mfg_ac2.py:179-208) */
+    int32_t        S;
+    int32_t        reserved;
+    const int32_t* start_rows;  /* [L][E] injected start rows, or NULL -> Philox randint */
+    const void*    noise_y;     /* [L][E][T][d][d] (INJECTED) */
+    uint64_t       seed;
+
+    double*  theta_trace;       /* [L][E][T] theta after each step, optional */
+    double*  delta_trace;       /* [L][E][T] optional */
+    double*  total_reward;      /* [L][E] optional */
+    void*    pi_final;          /* [L][d] optional: last state of the last episode */
+} dmfg_learners_args;
+int dmfg_ac_learners(const dmfg_learners_args* args, void* stream);
+
+/* ---- host-buffer convenience wrapper (the end-to-end path) --------------- *
+ * Same as dmfg_rollout but pi0 / noise_y / w and every output are HOST
+ * pointers; the call allocates device buffers, copies in, runs, copies out
+ * and synchronises `stream` before returning.  workspace is ignored.       */
+int dmfg_rollout_host(const dmfg_rollout_args* args_with_host_pointers, void* stream);
+
+/* ---- testing aids: direct access to the device math ---------------------- */
+/* Philox4x32-10 on the host (same code the kernels run): out[4] = philox(ctr[4], key[2]) */
+void dmfg_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out);
+/* n Gamma(shape[i],1) variates (float, device pointers) drawn exactly as the rollout kernels
+ * draw them: element i uses pair slot i/2 of population `pop` */
+int dmfg_gamma_sample(const float* shape, int64_t n, uint64_t seed, uint64_t pop, float* out, void* stream);
+/* out[i] = digamma(x[i]) with the device implementation of the given dtype */
+int dmfg_digamma(int32_t dtype, const void* x, int64_t n, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMFG_H */
