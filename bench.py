@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Headline benchmark: population-steps/s of the batched actor-critic train step at d = 15.
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on; it fits one GPU):
+2^20 independent populations per GPU x d = 15 topics x 16-step episodes, synthetic Dirichlet(1)
+start states, in-kernel Philox noise.  One "step" of this benchmark = ONE EPISODE of the batched
+trainer: every population runs 16 transitions of (sample P, pi' = P^T pi, closed-form reward,
+TD error, policy-gradient and critic-gradient contributions) with frozen (theta, w), followed by
+the reduction of the [2+F] gradient buffer, (N > 1: one NCCL all-reduce of it) and the update
+of (theta, w) on the device.  population-steps per step = B * T per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2-pops 20]
+
+Prints ONE JSON line (rank 0).  `value` is timed on the device with inputs resident in HBM;
+`e2e` goes through the public NumPy-in/NumPy-out API (`actor_critic.train_batch`) with the
+start states copied from pinned host memory every step and theta/w read back every step.
+`--impl reference` times the CPU restatement of the reference's train() loop (oracle port:
+the reference is Python and does not exist on the GPU box) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, T = 15, 16
+THETA, SHIFT, ALPHA_SCALE = 8.86349, 0.16, 12000.0
+LR_CRITIC, LR_ACTOR = 0.1, 0.1
+METRIC, UNIT = "population-steps/sec (d=15)", "population-steps/s"
+ALGO_BYTES_TRAIN = 16.0        # train, no recording: 2*4d/T + 8 B per population-step
+ALGO_BYTES_RECORD = 4.0 * (D + D * D) + 4.0 * D / T   # rollout + record: 963.75 B per population-step
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_profile_constants():
+    """Instructions per population-step of the dominant kernel, from the committed ncu summary."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_constants.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_pi0(B, seed):
+    rng = np.random.RandomState(seed)
+    g = rng.standard_gamma(1.0, size=(B, D)).astype(np.float64)
+    return (g / g.sum(1, keepdims=True)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    seed, episodes = args
+    from oracle import mfg_oracle as O
+    np.random.seed(seed)
+    mat = O.synthetic_start_states(n_rows=21, n_cols=20, d=D, seed=0)
+    w0 = np.random.rand(O.num_features(D))
+    t0 = time.perf_counter()
+    O.train_serial(mat, THETA, w0, SHIFT, ALPHA_SCALE, episodes, lr_critic=LR_CRITIC, lr_actor=LR_ACTOR,
+                   flavour="mfg_ac2", num_steps=T)
+    return time.perf_counter() - t0
+
+
+def cpu_throughput(episodes_per_worker, cores, pool):
+    t0 = time.perf_counter()
+    pool.map(_cpu_worker, [(100 + i, episodes_per_worker) for i in range(cores)])
+    dt = time.perf_counter() - t0
+    return cores * episodes_per_worker * T / dt, dt
+
+
+def make_pool(cores):
+    import multiprocessing as mp
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    return mp.get_context("fork").Pool(cores)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    budget = 150.0 / (args.steps + args.warmup)                    # whole run within a few minutes
+    episodes = max(1, int(1400.0 * min(budget, 20.0) / T))         # ~1.4 k steps/s/core
+    pool = make_pool(cores)
+    for _ in range(args.warmup):
+        cpu_throughput(max(1, episodes // 8), cores, pool)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_throughput(episodes, cores, pool)
+    dt = time.perf_counter() - t0
+    pool.close()
+    value = args.steps * cores * episodes * T / dt
+    sample = "%d processes x %d episodes x %d steps of mfg_ac2.train per bench step (oracle port)" % (
+        cores, episodes, T)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "mfg_ac2.train per-step actor-critic, d=15, T=16, single population per process",
+                   "d": D, "T": T},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from discrete_mean_field_game_b200 import engine
+    from discrete_mean_field_game_b200.mfg_ac2 import actor_critic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    engine.require_cuda()
+
+    B = 1 << args.log2_pops
+    F = D * (D + 1) // 2 + D + 1
+    pi0_host = torch.from_numpy(synthetic_pi0(B, seed=3 + rank)).pin_memory()
+    pi0 = pi0_host.to(dev)
+    rng = np.random.RandomState(0)
+    w = torch.as_tensor(rng.rand(F), dtype=torch.float64, device=dev)
+    theta = torch.tensor([THETA], dtype=torch.float64, device=dev)
+    out = {"acc": torch.empty(2 + F, dtype=torch.float64, device=dev)}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    pop_offset = rank * B
+
+    def step(episode, ev=None):
+        lr_c = LR_CRITIC / (episode + 1.0)
+        lr_a = LR_ACTOR / ((episode + 1.0) * math.log(math.log(episode + 20.0)))
+        if ev:
+            ev[0].record()
+        r = engine.rollout(pi0, 0.0, SHIFT, ALPHA_SCALE, T, w=w, theta_dev=theta, gamma=1.0, reward="ac2",
+                           seed=1234, pop_offset=pop_offset, step_offset=episode * T, outputs=(),
+                           want_acc=True, out=out)
+        if ev:
+            ev[1].record()
+        if world > 1:
+            dist.all_reduce(r["acc"])
+        engine.apply_update(D, theta, w, r["acc"], lr_c, lr_a, 1.0 / (B * world))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for e in range(args.warmup):
+        step(e)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                                     # L2 flush between timed iterations (untimed)
+        step_ev[k][0].record()
+        step(args.warmup + k, kern_ev[k])
+        step_ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+    ms_steps = sum(a.elapsed_time(b) for a, b in step_ev)
+    ms_kern = sum(a.elapsed_time(b) for a, b in kern_ev) / args.steps
+    t = torch.tensor([ms_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t[0]) / args.steps
+    value = B * T * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API: host start states in, theta / w out, every step
+    ac = actor_critic(theta=THETA, shift=SHIFT, alpha_scale=ALPHA_SCALE, d=D,
+                      mat_pi0=np.full((1, D), 1.0 / D), device=dev, dtype="float32", seed=1234)
+    ac.w = rng.rand(F, 1)
+    e2e_steps = max(3, min(args.steps, 10))
+    ac.train_batch(pi0_host, num_episodes=1, T=T, lr_critic=LR_CRITIC, lr_actor=LR_ACTOR, pop_offset=pop_offset)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        ac.train_batch(pi0_host, num_episodes=1, T=T, lr_critic=LR_CRITIC, lr_actor=LR_ACTOR,
+                       pop_offset=pop_offset, first_episode=k + 1)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = B * T * world * e2e_steps / float(te[0])
+
+    # ---- the other two modes of config 3 (single GPU numbers, for the roofline discussion)
+    modes = {}
+    if rank == 0:
+        def timed(fn, n=3):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tot = 0.0
+            for _ in range(n):
+                flush.zero_()
+                a.record(); fn(); b.record(); torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+            return tot / n
+        Br = min(B, 1 << 18)                                  # actions of 2^18 x 16 steps = 3.8 GB
+        rec_out = {"states": torch.empty((T + 1, Br, D), device=dev), "actions": torch.empty((T, Br, D, D), device=dev)}
+        ms_roll = timed(lambda: engine.rollout(pi0, THETA, SHIFT, ALPHA_SCALE, T, reward="none", seed=7,
+                                               outputs=("pi_final",)))
+        ms_rec = timed(lambda: engine.rollout(pi0[:Br], THETA, SHIFT, ALPHA_SCALE, T, reward="none", seed=7,
+                                              outputs=("states", "actions"), out=rec_out))
+        modes = {"rollout_only": {"value": B * T / (ms_roll * 1e-3), "unit": UNIT, "populations": B},
+                 "rollout_record": {"value": Br * T / (ms_rec * 1e-3), "unit": UNIT, "populations": Br,
+                                    "hbm_gbs": Br * T * ALGO_BYTES_RECORD / (ms_rec * 1e-3) / 1e9}}
+        del rec_out
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_peaks()
+    achieved = B * T * ALGO_BYTES_TRAIN / (ms_kern * 1e-3) / 1e9
+    consts = load_profile_constants()
+    roofline = {"bound": "hbm", "kernel": "rollout_fast_kernel<15,16,float,PHILOX>", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": consts.get("train_dram_bytes_per_launch"),
+                "peak_source": peak_src, "kernel_ms": ms_kern,
+                "algorithmic_bytes_per_population_step": ALGO_BYTES_TRAIN,
+                "note": "train step without recording moves 16 B per population-step: the kernel is "
+                        "instruction-issue bound (Gamma sampling, digamma), not HBM bound -- see `issue`"}
+    ipp = consts.get("train_inst_per_population_step")
+    if ipp and clocks and clocks.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        ipc = ipp * (B * T / (ms_kern * 1e-3)) / (sms * clocks["sm_mhz"] * 1e6)
+        roofline["issue"] = {"warp_inst_per_population_step": ipp, "achieved_ipc_per_sm": ipc,
+                             "peak_ipc_per_sm": 4.0, "frac": ipc / 4.0}
+    if "rollout_record" in modes:
+        modes["rollout_record"]["hbm_frac"] = modes["rollout_record"]["hbm_gbs"] / peak
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        pool = make_pool(cores)
+        cpu_throughput(20, cores, pool)
+        episodes = 900                                         # ~10 s per core at ~1.4 k steps/s
+        v, dt = cpu_throughput(episodes, cores, pool)
+        pool.close()
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+                        "sample": "%d processes x %d episodes x %d steps of the oracle port of mfg_ac2.train "
+                                  "(per-step updates, one population per process), d=15" % (cores, episodes, T)}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (transcendentals) + f64 (state, reductions)", "data": "synthetic",
+        "config": {"workload": "configs[2]: batched actor-critic train step (a1-a7), %d populations/GPU x d=15 x "
+                               "16-step episodes, per-episode batch-mean update" % B,
+                   "populations_per_gpu": B, "d": D, "T": T, "update": "per_episode", "noise": "philox4x32-10",
+                   "l2": "flushed between timed iterations (256 MiB write)", "parallelism": "dp%d" % world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 4,
+                "d2h_bytes_per_step": (F + 1) * 8 + 8, "steps": e2e_steps},
+        "gpu_launches": 3 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "modes": modes, "wall_s": t_wall,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2-pops", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,7 +17,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
 F32, F64 = 0, 1
 REWARD_NONE, REWARD_AC2, REWARD_SYNTHETIC = 0, 1, 2
 DISCOUNT_STEP, DISCOUNT_CUMULATIVE = 0, 1
-NOISE_INJECTED, NOISE_PHILOX = 0, 1
+NOISE_INJECTED, NOISE_PHILOX, NOISE_ACTIONS = 0, 1, 2
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_FAST = 0, 1, 2
 MAX_D = 256
 
@@ -69,6 +69,7 @@ class LearnersArgs(C.Structure):
         ("noise_kind", C.c_int32),
         ("mat_pi0", C.c_void_p), ("S", C.c_int32), ("reserved", C.c_int32),
         ("start_rows", C.c_void_p), ("noise_y", C.c_void_p), ("seed", C.c_uint64),
+        ("noise_episode_offset", C.c_int64),
         ("theta_trace", C.c_void_p), ("delta_trace", C.c_void_p), ("total_reward", C.c_void_p),
         ("pi_final", C.c_void_p),
     ]
@@ -85,6 +86,8 @@ SYMBOLS = [
     ("dmfg_rollout_host", C.c_int, [C.POINTER(RolloutArgs), C.c_void_p]),
     ("dmfg_td_workspace_bytes", C.c_uint64, [C.POINTER(TdArgs)]),
     ("dmfg_td_accumulate", C.c_int, [C.POINTER(TdArgs), C.c_void_p]),
+    ("dmfg_critic_eval", C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
     ("dmfg_ac_apply_update", C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_double, C.c_double, C.c_void_p]),
     ("dmfg_ac_learners", C.c_int, [C.POINTER(LearnersArgs), C.c_void_p]),

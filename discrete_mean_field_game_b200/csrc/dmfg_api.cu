@@ -87,15 +87,17 @@ int check_rollout(const dmfg_rollout_args* a) {
         return fail(DMFG_ERR_INVALID, "reward_kind %d", a->reward_kind);
     if (a->discount_kind != DMFG_DISCOUNT_STEP && a->discount_kind != DMFG_DISCOUNT_CUMULATIVE)
         return fail(DMFG_ERR_INVALID, "discount_kind %d", a->discount_kind);
-    if (a->noise_kind != DMFG_NOISE_INJECTED && a->noise_kind != DMFG_NOISE_PHILOX)
+    if (a->noise_kind < DMFG_NOISE_INJECTED || a->noise_kind > DMFG_NOISE_ACTIONS)
         return fail(DMFG_ERR_INVALID, "noise_kind %d", a->noise_kind);
+    if (a->noise_kind == DMFG_NOISE_ACTIONS && a->T > 1)
+        return fail(DMFG_ERR_INVALID, "noise_kind=ACTIONS evaluates single transitions (T must be <= 1)");
     if (a->variant < DMFG_VARIANT_AUTO || a->variant > DMFG_VARIANT_FAST)
         return fail(DMFG_ERR_INVALID, "variant %d", a->variant);
     if (a->variant == DMFG_VARIANT_FAST && !fast_d(a->d))
         return fail(DMFG_ERR_UNSUPPORTED, "fast variant is built for d in {4,15,16}, not d=%d", a->d);
     if (a->B > 0 && !a->pi0) return fail(DMFG_ERR_INVALID, "pi0 is NULL");
-    if (a->B > 0 && a->T > 0 && a->noise_kind == DMFG_NOISE_INJECTED && !a->noise_y)
-        return fail(DMFG_ERR_INVALID, "noise_kind=INJECTED needs noise_y");
+    if (a->B > 0 && a->T > 0 && a->noise_kind != DMFG_NOISE_PHILOX && !a->noise_y)
+        return fail(DMFG_ERR_INVALID, "noise_kind=INJECTED/ACTIONS needs noise_y");
     if ((a->deltas || a->acc) && !a->w) return fail(DMFG_ERR_INVALID, "deltas/acc need critic weights w");
     if ((a->alpha == nullptr) != (a->alpha_deriv == nullptr))
         return fail(DMFG_ERR_INVALID, "alpha and alpha_deriv must be requested together");
@@ -213,6 +215,7 @@ int rollout_typed(const dmfg_rollout_args* a, cudaStream_t st) {
         if (accum) p.partials = (double*)(wsp + ws.partials);
         int grid = 0, rc;
         if (a->noise_kind == DMFG_NOISE_PHILOX) rc = dispatch_fast<R, DMFG_NOISE_PHILOX>(p, td, &grid, st);
+        else if (a->noise_kind == DMFG_NOISE_ACTIONS) rc = dispatch_fast<R, DMFG_NOISE_ACTIONS>(p, td, &grid, st);
         else rc = dispatch_fast<R, DMFG_NOISE_INJECTED>(p, td, &grid, st);
         if (rc) return rc;
         if (accum) {
@@ -230,6 +233,7 @@ int rollout_typed(const dmfg_rollout_args* a, cudaStream_t st) {
     p.deltas = nullptr;
     int rc;
     if (a->noise_kind == DMFG_NOISE_PHILOX) rc = launch_generic<R, DMFG_NOISE_PHILOX>(p, st);
+    else if (a->noise_kind == DMFG_NOISE_ACTIONS) rc = launch_generic<R, DMFG_NOISE_ACTIONS>(p, st);
     else rc = launch_generic<R, DMFG_NOISE_INJECTED>(p, st);
     if (rc) return rc;
     if (td) {
@@ -274,7 +278,7 @@ int learners_typed(const dmfg_learners_args* a, cudaStream_t st) {
     p.gamma = a->gamma; p.lr_critic = a->lr_critic; p.lr_actor = a->lr_actor;
     p.constant_lr = a->constant_lr; p.reward_kind = a->reward_kind; p.discount_kind = a->discount_kind;
     p.mat_pi0 = (const R*)a->mat_pi0; p.start_rows = a->start_rows; p.noise_y = (const R*)a->noise_y;
-    p.seed = a->seed; p.theta_trace = a->theta_trace; p.delta_trace = a->delta_trace;
+    p.seed = a->seed; p.noise_episode_offset = a->noise_episode_offset; p.theta_trace = a->theta_trace; p.delta_trace = a->delta_trace;
     p.total_reward = a->total_reward; p.pi_final = (R*)a->pi_final;
     if (a->noise_kind == DMFG_NOISE_PHILOX) return dispatch_learners<R, DMFG_NOISE_PHILOX>(p, st);
     return dispatch_learners<R, DMFG_NOISE_INJECTED>(p, st);
@@ -356,6 +360,30 @@ int dmfg_td_accumulate(const dmfg_td_args* a, void* stream) {
     return run_td<float>(t, a->acc, partials, st);
 }
 
+int dmfg_critic_eval(int32_t dtype, int32_t d, int64_t N, const void* states, const double* w, void* features,
+                     void* values, void* stream) {
+    if (dtype != DMFG_F32 && dtype != DMFG_F64) return fail(DMFG_ERR_INVALID, "dtype %d", dtype);
+    if (d < 1 || d > DMFG_MAX_D || N < 0) return fail(DMFG_ERR_INVALID, "dmfg_critic_eval: bad d/N");
+    if (N > 0 && !states) return fail(DMFG_ERR_INVALID, "dmfg_critic_eval: states is NULL");
+    if (values && !w) return fail(DMFG_ERR_INVALID, "dmfg_critic_eval: values need w");
+    if (N == 0) return DMFG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long F = num_features_c(d);
+    if (features) {
+        const unsigned grid = (unsigned)((N * F + 255) / 256);
+        if (dtype == DMFG_F64) critic_features_kernel<double><<<grid, 256, 0, st>>>(d, N, (const double*)states, (double*)features);
+        else critic_features_kernel<float><<<grid, 256, 0, st>>>(d, N, (const float*)states, (float*)features);
+        DMFG_CUDA(cudaGetLastError());
+    }
+    if (values) {
+        const unsigned grid = (unsigned)((N + 3) / 4);
+        if (dtype == DMFG_F64) critic_value_kernel<double><<<grid, 128, 0, st>>>(d, N, (const double*)states, w, (double*)values);
+        else critic_value_kernel<float><<<grid, 128, 0, st>>>(d, N, (const float*)states, w, (float*)values);
+        DMFG_CUDA(cudaGetLastError());
+    }
+    return DMFG_OK;
+}
+
 int dmfg_ac_apply_update(int32_t d, double* theta_dev, double* w, const double* acc, double lr_critic_eff,
                          double lr_actor_eff, double scale, void* stream) {
     if (d < 1 || d > DMFG_MAX_D || !w || !acc) return fail(DMFG_ERR_INVALID, "dmfg_ac_apply_update: bad argument");
@@ -394,7 +422,7 @@ int dmfg_rollout_host(const dmfg_rollout_args* h, void* stream) {
          *pif = nullptr, *acc = nullptr, *ws = nullptr;
     Buf bufs[] = {
         {&pi0, h->pi0, nullptr, B * d * es},
-        {&y, h->noise_kind == DMFG_NOISE_INJECTED ? h->noise_y : nullptr, nullptr, T * B * d * d * es},
+        {&y, h->noise_kind != DMFG_NOISE_PHILOX ? h->noise_y : nullptr, nullptr, T * B * d * d * es},
         {&w, h->w, nullptr, F * 8},
         {&rin, h->rewards_in, nullptr, T * B * es},
         {&states, nullptr, h->states, (T + 1) * B * d * es},

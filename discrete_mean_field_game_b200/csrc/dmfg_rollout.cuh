@@ -130,12 +130,12 @@ struct StepCore {
             for (int e = 0; e < 2; ++e) {
                 const int j = 2 * p + e;
                 if (j < D) {
-                    if (yv[j] == R(0)) yv[j] = R(1e-20);           // mfg_ac2.py:244
+                    if (NOISE != DMFG_NOISE_ACTIONS && yv[j] == R(0)) yv[j] = R(1e-20);   // mfg_ac2.py:244
                     ysum += (double)yv[j];
                 }
             }
         }
-        const double inv = 1.0 / ysum;
+        const double inv = NOISE == DMFG_NOISE_ACTIONS ? 1.0 : 1.0 / ysum;
         const R psi_row = digamma((R)asum);
         double c[G];
         double racc = 0.0, g2 = 0.0;
@@ -230,7 +230,7 @@ rollout_fast_kernel(const RolloutParams<R> p) {
             double pi_next[G], next_self, rew, grad;
             StepCore<D, G, R, NOISE>::run(
                 pi, pi_self, r, theta, shift, scale, p.reward_kind,
-                NOISE == DMFG_NOISE_INJECTED ? p.noise_y + row : nullptr, nk,
+                NOISE != DMFG_NOISE_PHILOX ? p.noise_y + row : nullptr, nk,
                 (uint32_t)(p.step_offset + t),
                 (p.actions && live) ? p.actions + row : nullptr,
                 (p.alpha && live) ? p.alpha + row : nullptr,
@@ -382,7 +382,7 @@ rollout_generic_kernel(const RolloutParams<R> p) {
                     for (int e = 0; e < 2; ++e) {
                         const int j = 2 * pp + e;
                         if (j < d) {
-                            if (yv[e] == R(0)) yv[e] = R(1e-20);
+                            if (NOISE != DMFG_NOISE_ACTIONS && yv[e] == R(0)) yv[e] = R(1e-20);
                             ysum += (double)yv[e];
                             y_s[j] = yv[e];
                             dv_s[j] = dv[e];
@@ -392,7 +392,7 @@ rollout_generic_kernel(const RolloutParams<R> p) {
                 ysum = group_sum<32>(ysum);
                 asum = group_sum<32>(asum);
                 dsum = group_sum<32>(dsum);
-                const double inv = 1.0 / ysum;
+                const double inv = NOISE == DMFG_NOISE_ACTIONS ? 1.0 : 1.0 / ysum;
                 if (lane == 0) gacc += (double)digamma((R)asum) * dsum;
                 for (int pp = lane; pp < pd; pp += 32) {
 #pragma unroll
@@ -528,6 +528,46 @@ __global__ void __launch_bounds__(256) td_gw_kernel(const TdParams<R> p, int chu
     }
 }
 
+// calc_features / calc_value for N states: thread per (state, feature)
+template <typename R>
+__global__ void critic_features_kernel(int d, long long N, const R* __restrict__ states, R* __restrict__ features) {
+    const int F = num_features_c(d), Q = d * (d + 1) / 2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * F) return;
+    const long long n = idx / F;
+    const int f = (int)(idx - n * F);
+    const R* s = states + n * d;
+    R v;
+    if (f < Q) {
+        int i = 0, rem = f;
+        while (rem >= d - i) { rem -= d - i; ++i; }
+        v = s[i] * s[i + rem];
+    } else if (f < Q + d) {
+        v = s[f - Q];
+    } else {
+        v = R(1);
+    }
+    features[idx] = v;
+}
+// warp per state: V = phi(pi) . w accumulated in double
+template <typename R>
+__global__ void critic_value_kernel(int d, long long N, const R* __restrict__ states, const double* __restrict__ w,
+                                    R* __restrict__ values) {
+    const int lane = threadIdx.x & 31, Q = d * (d + 1) / 2;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= N) return;
+    const R* s = states + warp * d;
+    double v = 0.0;
+    for (int i = lane; i < d; i += 32) {
+        const double* wq = w + quad_index(d, i, i);
+        double a = w[Q + i];
+        for (int j = i; j < d; ++j) a = fma(wq[j - i], (double)s[j], a);
+        v = fma(a, (double)s[i], v);
+    }
+    v = group_sum<32>(v) + w[Q + d];
+    if (lane == 0) values[warp] = (R)v;
+}
+
 // theta += lr_a*scale*acc[0];  w[f] += lr_c*scale*acc[1+f]   (mfg_ac2.py:511-522)
 __global__ void ac_apply_update_kernel(int F, double* theta, double* w, const double* __restrict__ acc,
                                        double lr_c, double lr_a, double scale) {
@@ -552,6 +592,7 @@ struct LearnerParams {
     const int* start_rows;
     const R* noise_y;
     unsigned long long seed;
+    long long noise_episode_offset;
     double *theta_trace, *delta_trace, *total_reward;
     R* pi_final;
 };
@@ -583,7 +624,8 @@ learners_fast_kernel(const LearnerParams<R> p) {
         if (p.start_rows != nullptr) {
             start = p.start_rows[l * p.E + e];
         } else {
-            const uint4 wv = philox4x32_10(nk.p0, nk.p1, (uint32_t)episode, DMFG_CTR_START, nk.k0, nk.k1);
+            const uint4 wv = philox4x32_10(nk.p0, nk.p1, (uint32_t)(episode + p.noise_episode_offset),
+                                           DMFG_CTR_START, nk.k0, nk.k1);
             start = (int)__umulhi(wv.x, (uint32_t)p.S);          // randint(S), mfg_ac2.py:466
         }
         pi_self = row_ok ? (double)p.mat_pi0[(long long)start * D + r] : 0.0;
@@ -599,7 +641,7 @@ learners_fast_kernel(const LearnerParams<R> p) {
             StepCore<D, G, R, NOISE>::run(
                 pi, pi_self, r, (R)theta, shift, scale, p.reward_kind,
                 NOISE == DMFG_NOISE_INJECTED ? p.noise_y + (et * D + r) * D : nullptr, nk,
-                (uint32_t)((long long)episode * p.T + t), nullptr, nullptr, nullptr,
+                (uint32_t)((episode + p.noise_episode_offset) * p.T + t), nullptr, nullptr, nullptr,
                 pi_next, next_self, rew, grad);
             const double v_next = critic_value<D, G>(wl, NT, pi_next, next_self);
             const double v_cur = critic_value<D, G>(wl, NT, pi, pi_self);

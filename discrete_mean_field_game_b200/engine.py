@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (DISCOUNT_CUMULATIVE, DISCOUNT_STEP, F32, F64, NOISE_INJECTED, NOISE_PHILOX,
+from ._lib import (DISCOUNT_CUMULATIVE, DISCOUNT_STEP, F32, F64, NOISE_ACTIONS, NOISE_INJECTED, NOISE_PHILOX,
                    REWARD_KINDS, VARIANTS, LearnersArgs, RolloutArgs, TdArgs, check, num_features)
 
 ROLLOUT_OUTPUTS = ("states", "actions", "alpha", "alpha_deriv", "rewards", "deltas", "grads", "pi_final")
@@ -69,7 +69,7 @@ def require_cuda():
 
 def rollout(pi0, theta, shift, alpha_scale, T, *, w=None, gamma=1.0, reward="ac2", discount="step",
             noise_y=None, seed=0, pop_offset=0, step_offset=0, outputs=("states",), want_acc=False,
-            rewards_in=None, theta_dev=None, variant="auto", out=None):
+            rewards_in=None, theta_dev=None, variant="auto", out=None, actions_in=None):
     """dmfg_rollout on CUDA tensors.
 
     pi0 [B,d] (float32/float64 selects the stream dtype); noise_y [T,B,d,d] selects
@@ -77,6 +77,7 @@ def rollout(pi0, theta, shift, alpha_scale, T, *, w=None, gamma=1.0, reward="ac2
     Returns a dict with the requested `outputs` (time-major tensors) and, with
     want_acc, 'acc' = [sum delta*g, sum delta*phi (F), sum r] as float64.
     `out` may carry preallocated tensors for any output (reused across calls).
+    actions_in [1,B,d,d] (with T == 1) evaluates GIVEN transition matrices instead of sampling.
     """
     lib = _lib.load()
     if not pi0.is_cuda:
@@ -94,7 +95,10 @@ def rollout(pi0, theta, shift, alpha_scale, T, *, w=None, gamma=1.0, reward="ac2
     a.discount_kind = DISCOUNT_STEP if discount == "step" else DISCOUNT_CUMULATIVE
     a.variant = VARIANTS[variant]
     a.seed, a.step_offset = int(seed) & (2 ** 64 - 1), int(step_offset)
-    if noise_y is not None:
+    if actions_in is not None:
+        a.noise_kind = NOISE_ACTIONS
+        a.noise_y = _ptr(_require(actions_in, "actions_in", device, dtype, (T, B, d, d)))
+    elif noise_y is not None:
         a.noise_kind = NOISE_INJECTED
         a.noise_y = _ptr(_require(noise_y, "noise_y", device, dtype, (T, B, d, d)))
     else:
@@ -164,6 +168,25 @@ def td_accumulate(states, rewards, grads, w, *, gamma=1.0, discount="step", want
     return res
 
 
+def critic_eval(states, w=None, want_features=True, want_values=False):
+    """calc_features / calc_value (mfg_ac2.py:290-344) for states [N,d] on device."""
+    lib = _lib.load()
+    device, dtype = states.device, states.dtype
+    N, d = states.shape
+    F = num_features(d)
+    states = _require(states, "states", device, dtype, (N, d))
+    res = {}
+    with torch.cuda.device(device):
+        if want_features:
+            res["features"] = torch.empty((N, F), dtype=dtype, device=device)
+        if want_values:
+            res["values"] = torch.empty((N,), dtype=dtype, device=device)
+            w = _require(w, "w", device, torch.float64, (F,))
+        check(lib.dmfg_critic_eval(_dtype_code(dtype), d, N, _ptr(states), _ptr(w) if want_values else None,
+                                   _ptr(res.get("features")), _ptr(res.get("values")), _stream_ptr(device)))
+    return res
+
+
 def apply_update(d, theta_dev, w, acc, lr_critic_eff, lr_actor_eff, scale):
     """theta += lr_a*scale*acc[0]; w += lr_c*scale*acc[1:1+F]  (mfg_ac2.py:511-522), on device."""
     lib = _lib.load()
@@ -175,7 +198,7 @@ def apply_update(d, theta_dev, w, acc, lr_critic_eff, lr_actor_eff, scale):
 
 def learners(theta, w, mat_pi0, E, T, *, shift, alpha_scale, episode0=0, gamma=1.0, lr_critic=0.1,
              lr_actor=0.001, constant=False, reward="ac2", discount="step", start_rows=None, noise_y=None,
-             seed=0, learner_offset=0, trace=False, want_total_reward=True):
+             seed=0, learner_offset=0, noise_episode_offset=0, trace=False, want_total_reward=True):
     """dmfg_ac_learners: L independent serial learners with per-step updates.
 
     theta [L] float64 and w [L,F] float64 are updated IN PLACE.  shift / alpha_scale may be
@@ -206,6 +229,7 @@ def learners(theta, w, mat_pi0, E, T, *, shift, alpha_scale, episode0=0, gamma=1
     a.discount_kind = DISCOUNT_STEP if discount == "step" else DISCOUNT_CUMULATIVE
     a.mat_pi0, a.S = _ptr(_require(mat_pi0, "mat_pi0", device, dtype, (S, d))), S
     a.seed = int(seed) & (2 ** 64 - 1)
+    a.noise_episode_offset = int(noise_episode_offset)
     if noise_y is not None:
         a.noise_kind = NOISE_INJECTED
         a.noise_y = _ptr(_require(noise_y, "noise_y", device, dtype, (L, E, T, d, d)))

@@ -59,6 +59,9 @@ extern "C" {
 /* noise source for the Gamma variates of sample_action */
 #define DMFG_NOISE_INJECTED 0   /* caller supplies y[T][B][d][d] (parity with the reference's draws) */
 #define DMFG_NOISE_PHILOX   1   /* in-kernel Philox4x32-10 + Marsaglia-Tsang, keyed by (seed, population id) */
+#define DMFG_NOISE_ACTIONS  2   /* noise_y holds the transition matrices P themselves (no normalisation):
+                                   evaluates reward / gradient / pi' of GIVEN (state, action) pairs, e.g.
+                                   calc_reward(P, pi) and calc_gradient_vectorized(P, pi) on caller data */
 
 /* kernel selection (testing aid) */
 #define DMFG_VARIANT_AUTO    0
@@ -154,6 +157,12 @@ typedef struct dmfg_td_args {
 uint64_t dmfg_td_workspace_bytes(const dmfg_td_args* args);
 int dmfg_td_accumulate(const dmfg_td_args* args, void* stream);
 
+/* ---- a4: critic features and values -------------------------------------- *
+ * calc_features / calc_value (mfg_ac2.py:290-344) for N states [N][d]:
+ * features [N][F] and/or values [N] = phi(pi) . w (either output may be NULL). */
+int dmfg_critic_eval(int32_t dtype, int32_t d, int64_t N, const void* states, const double* w,
+                     void* features, void* values, void* stream);
+
 /* ---- a5, a7: apply one actor-critic update on device --------------------- *
  * theta += lr_actor_eff * scale * acc[0];  w += lr_critic_eff * scale * acc[1..F]
  * (mfg_ac2.py:511-522).  lr_*_eff are the already-decayed step sizes; scale is
@@ -195,6 +204,9 @@ typedef struct dmfg_learners_args {
     const int32_t* start_rows;  /* [L][E] injected start rows, or NULL -> Philox randint */
     const void*    noise_y;     /* [L][E][T][d][d] (INJECTED) */
     uint64_t       seed;
+    int64_t        noise_episode_offset; /* PHILOX: stream position = episode + this, so that repeated train()
+                                            calls (which restart the step-size schedule at episode0) never
+                                            reuse draws */
 
     double*  theta_trace;       /* [L][E][T] theta after each step, optional */
     double*  delta_trace;       /* [L][E][T] optional */

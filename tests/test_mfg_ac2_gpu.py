@@ -1,0 +1,218 @@
+"""The drop-in ``mfg_ac2.actor_critic`` class: the reference's hand tests (test2.py) turned into
+assertions, run through the public NumPy-in / NumPy-out API on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mfg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+mfg_ac2 = pytest.importorskip("discrete_mean_field_game_b200.mfg_ac2")
+
+
+@pytest.fixture(scope="module")
+def start_states():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return O.synthetic_start_states(n_rows=21, n_cols=20, d=20, seed=0)
+
+
+def make(start_states, **kw):
+    kw.setdefault("dtype", "float64")
+    kw.setdefault("seed", 1)
+    return mfg_ac2.actor_critic(mat_pi0=start_states, **kw)
+
+
+def test_constructor_surface(start_states):
+    ac = make(start_states)                                   # mfg_ac2.py:25 defaults
+    assert (ac.theta, ac.shift, ac.alpha_scale, ac.d) == (8.86349, 0.16, 12000, 21)
+    assert ac.w.shape == (21 * 22 // 2 + 21 + 1, 1) and ac.w.min() >= 0 and ac.w.max() < 1
+    assert ac.mat_pi0.shape == (21, 20) and ac.num_start_samples == 21
+    assert ac.mat_alpha.shape == (21, 21) and ac.mat_alpha_deriv.shape == (21, 21)
+
+
+def test_init_pi0_reads_reference_format(tmp_path, start_states):
+    d = tmp_path / "train_normalized_round2"
+    d.mkdir()
+    for k, row in enumerate(start_states, start=1):
+        lines = [" ".join("%.3e" % v for v in row)] + [" ".join("%.3e" % v for v in row[::-1])] * 15
+        (d / ("trend_distribution_day%d.csv" % k)).write_text("\n".join(lines) + "\n")
+    ac = mfg_ac2.actor_critic(d=15, path_to_dir=str(d), dtype="float64", seed=0)
+    np.testing.assert_array_equal(ac.mat_pi0, start_states[:, :15])
+
+
+def test_action(start_states, kat):
+    """test2.py:14-32: rows of P and the new state keep their mass; with the reference's draws
+    injected the reference's P comes back."""
+    ac = make(start_states, theta=10, shift=0.4, d=4)
+    pi = np.array([0.7, 0.09, 0.01, 0.2])
+    P = ac.sample_action(pi)
+    assert P.shape == (4, 4) and np.all(P > 0)
+    np.testing.assert_allclose(P.sum(1), 1.0, rtol=1e-12)
+    np.testing.assert_allclose(P.T.dot(pi).sum(), 1.0, rtol=1e-12)
+    P2 = ac.sample_action(pi)
+    assert not np.allclose(P, P2)                              # the stream advances
+    Pg = ac.sample_action(pi, y=kat["d4_y"])
+    np.testing.assert_allclose(Pg, kat["d4_P"], rtol=1e-12)
+    np.testing.assert_allclose(ac.mat_alpha, kat["d4_alpha"], rtol=1e-10)
+    np.testing.assert_allclose(ac.mat_alpha_deriv, kat["d4_alpha_deriv"], rtol=1e-10)
+    np.testing.assert_allclose(ac.step(Pg, pi), kat["d4_pi_next"], rtol=1e-12)
+
+
+def test_reward(start_states, kat):
+    """test2.py:46-56: the fixed (non-stochastic) 3x3 input -> -39.07."""
+    ac = make(start_states)
+    P = np.array([[1, 3, 3], [4, 5, 6], [7, 8, 9]])
+    r = ac.calc_reward(P, np.array([0.1, 0.2, 0.7]), 3)
+    assert r.shape == (1,)
+    np.testing.assert_allclose(r[0], -39.07, rtol=1e-12)
+    np.testing.assert_allclose(r[0], kat["reward3"], rtol=1e-12)
+    ac32 = make(start_states, dtype="float32")
+    np.testing.assert_allclose(ac32.calc_reward(P, np.array([0.1, 0.2, 0.7]), 3)[0], -39.07, rtol=1e-6)
+
+
+def test_value_and_features(start_states, kat):
+    """test2.py:73-88: d=3, w=1 -> 2.77; feature order of the code, not of the docstring."""
+    ac = make(start_states, d=3)
+    ac.w = np.ones(10)
+    np.testing.assert_allclose(ac.calc_value(np.array([0.1, 0.2, 0.7])), 2.77, rtol=1e-13)
+    np.testing.assert_array_equal(ac.calc_features(np.array([2.0, 3.0, 5.0])), kat["features_235"])
+    ac4 = make(start_states, d=4)
+    np.testing.assert_allclose(ac4.calc_features(kat["d4_pi"]), kat["d4_features"], rtol=1e-15)
+
+
+def test_gradient_first(start_states, kat):
+    """test2.py:105-121: the three gradient entry points agree (and equal the reference's value)."""
+    ac = make(start_states, theta=10, shift=0.4, d=4)
+    pi = kat["d4_pi"]
+    P = ac.sample_action(pi, y=kat["d4_y"])
+    P_before = P.copy()
+    g1, g2, g3 = ac.calc_gradient_basic(P, pi), ac.calc_gradient(P, pi), ac.calc_gradient_vectorized(P, pi)
+    assert g1 == g2 == g3
+    np.testing.assert_allclose(g3, kat["d4_grad_vectorized"], rtol=1e-10)
+    np.testing.assert_array_equal(P, P_before)                 # inputs are not mutated (quirk A.11)
+    np.testing.assert_allclose(ac.calc_reward(P, pi, 4)[0], kat["d4_reward"], rtol=1e-10)
+
+
+def test_forward_d47(start_states, fwd47):
+    """test2.py:203-224: multi-step rollout at d = 47 (generic kernel)."""
+    ac = make(start_states, d=4)
+    ac.d = 47
+    pi = fwd47["states"][0]
+    for t in range(3):
+        P = ac.sample_action(pi, y=fwd47["y"][t])
+        np.testing.assert_allclose(P, fwd47["actions"][t], rtol=1e-11)
+        pi = np.transpose(P).dot(pi)
+    np.testing.assert_allclose(pi, fwd47["states"][3], rtol=1e-11)
+    traj = ac.generate_trajectory(fwd47["states"][0], 4, y=fwd47["y"])
+    np.testing.assert_allclose(traj, fwd47["states"], rtol=1e-11)
+    free = ac.generate_trajectory(fwd47["states"][0], 16)
+    assert free.shape == (16, 47)
+    np.testing.assert_allclose(free.sum(1), 1.0, rtol=1e-10)
+
+
+def test_generate_trajectory_d15(start_states, traj15):
+    ac = make(start_states, d=15)
+    out = ac.generate_trajectory(traj15["pi0"], 16, y=traj15["y"])
+    np.testing.assert_allclose(out, traj15["trajectory"], rtol=1e-11)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_train_replays_reference(start_states, trace, dtype, capsys):
+    """Config 1 through the class: mfg_ac2.py:831-836 with the reference's recorded draws."""
+    ac = mfg_ac2.actor_critic(theta=float(trace["theta0"]), shift=0.16, alpha_scale=12000, d=15,
+                              mat_pi0=trace["mat_pi0"], dtype=dtype, seed=0)
+    ac.w = trace["w0"].reshape(-1, 1).copy()
+    ac.train(num_episodes=3, gamma=1, constant=0, lr_critic=0.1, lr_actor=0.1,
+             start_rows=trace["start_rows"], noise_y=trace["y"])
+    rt = 1e-11 if dtype == "float64" else 1e-6
+    np.testing.assert_allclose(ac.theta, float(trace["theta_final"]), rtol=rt)
+    np.testing.assert_allclose(ac.w.ravel(), trace["w_final"], rtol=10 * rt, atol=1e-7 if dtype == "float32" else 0)
+    assert ac.w.shape == (136, 1)
+    assert "Average reward during previous 100 episodes" in capsys.readouterr().out
+
+
+def test_train_generic_d_matches_oracle(start_states):
+    """d = 21 (the reference's default) has no fused learner kernel: host-driven per-step path."""
+    rng = np.random.RandomState(2)
+    d, E, T = 21, 2, 15
+    mat = O.synthetic_start_states(n_rows=21, n_cols=30, d=21, seed=4)
+    ac = mfg_ac2.actor_critic(d=d, mat_pi0=mat, dtype="float64", seed=3)
+    w0 = ac.w.ravel().copy()
+    start = rng.randint(0, 21, size=E)
+    y = rng.gamma(shape=200.0, size=(E, T, d, d))
+    ac.train(num_episodes=E, lr_critic=0.1, lr_actor=0.001, start_rows=start, noise_y=y, verbose=False)
+    th, w, _ = O.train_serial(mat, 8.86349, w0, 0.16, 12000, E, lr_critic=0.1, lr_actor=0.001,
+                              flavour="mfg_ac2", noise=O.InjectedNoise(start, y))
+    np.testing.assert_allclose(ac.theta, th, rtol=1e-11)
+    np.testing.assert_allclose(ac.w.ravel(), w, rtol=1e-10)
+
+
+def test_train_philox_is_reproducible_and_learns_something(start_states):
+    a = mfg_ac2.actor_critic(d=15, mat_pi0=start_states, dtype="float32", seed=42)
+    b = mfg_ac2.actor_critic(d=15, mat_pi0=start_states, dtype="float32", seed=42)
+    b.w = a.w.copy()
+    a.train(num_episodes=30, lr_critic=0.1, lr_actor=0.1, consecutive=10, verbose=False)
+    b.train(num_episodes=30, lr_critic=0.1, lr_actor=0.1, consecutive=7, verbose=False)   # chunking is invisible
+    assert a.theta == b.theta and np.array_equal(a.w, b.w)
+    assert a.theta != 8.86349 and np.isfinite(a.theta)
+    th1 = a.theta
+    a.train(num_episodes=5, verbose=False)                      # a second call continues the noise stream
+    assert a.theta != th1
+
+
+def test_train_batch_per_step_reduces_to_train_at_B1(start_states, trace):
+    """SURVEY 7 hard part 1: the per_step batched update IS the reference's update at B = 1."""
+    ac = mfg_ac2.actor_critic(d=15, mat_pi0=trace["mat_pi0"], dtype="float64", seed=9)
+    w0 = ac.w.copy()
+    pi0 = trace["mat_pi0"][4:5]
+    ac.train_batch(pi0, num_episodes=2, T=15, lr_critic=0.1, lr_actor=0.1, update="per_step")
+    th_b, w_b = ac.theta, ac.w.ravel().copy()
+    # replay through the serial learner with the same Philox draws: record them via rollout_batch
+    ref = mfg_ac2.actor_critic(d=15, mat_pi0=trace["mat_pi0"], dtype="float64", seed=9)
+    ref.w = w0.copy()
+    theta, w = 8.86349, w0.ravel().copy()
+    import math
+    from discrete_mean_field_game_b200 import engine
+    for e in range(2):
+        pi = pi0[0]
+        for t in range(15):
+            ref.theta = theta
+            out = engine.rollout(ref._dev(pi[None]), theta, 0.16, 12000, 1, seed=9, step_offset=e * 15 + t,
+                                 reward="none", outputs=("actions",))
+            P = out["actions"][0, 0].cpu().numpy()
+            alpha, deriv = O.policy_alpha(pi, theta, 0.16)
+            pn = O.mean_field_step(P, pi)
+            delta = O.reward_ac2(P, pi) + O.features(pn) @ w - O.features(pi) @ w
+            g = O.log_policy_gradient(alpha, deriv, P)
+            w = w + O.critic_lr(e, 0.1, False) * delta * O.features(pi)
+            theta = theta + O.actor_lr(e, 0.1, False) * delta * g
+            pi = pn
+    np.testing.assert_allclose(th_b, theta, rtol=1e-10)
+    np.testing.assert_allclose(w_b, w, rtol=1e-10)
+
+
+def test_train_batch_per_episode_matches_oracle(start_states):
+    """per_episode: frozen parameters, one batch-mean update per episode."""
+    rng = np.random.RandomState(0)
+    B, T, d = 64, 15, 15
+    pi0 = rng.dirichlet(np.ones(d), size=B)
+    ac = mfg_ac2.actor_critic(d=d, mat_pi0=start_states, dtype="float64", seed=5)
+    w0 = ac.w.ravel().copy()
+    rec = ac.rollout_batch(pi0, T=T, record=True, seed=5)           # same draws as episode 0 of train_batch
+    res = ac.train_batch(pi0, num_episodes=1, T=T, lr_critic=0.1, lr_actor=0.01, update="per_episode", seed=5)
+    alpha, deriv = O.policy_alpha(rec["states"][:-1], 8.86349, 0.16)
+    g = O.log_policy_gradient(alpha, deriv, rec["actions"])
+    r = O.reward_ac2(rec["actions"], rec["states"][:-1])
+    phi = O.features(rec["states"])
+    v = phi @ w0
+    delta = r + v[1:] - v[:-1]
+    np.testing.assert_allclose(rec["rewards"], r, rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(rec["deltas"], delta, rtol=1e-8, atol=1e-14)
+    np.testing.assert_allclose(rec["grads"], g, rtol=1e-9)
+    th = 8.86349 + O.actor_lr(0, 0.01, False) / B * np.sum(delta * g)
+    w = w0 + O.critic_lr(0, 0.1, False) / B * np.einsum("tb,tbf->f", delta, phi[:-1])
+    np.testing.assert_allclose(res["theta"], th, rtol=1e-11)
+    np.testing.assert_allclose(ac.w.ravel(), w, rtol=1e-10)
+    np.testing.assert_allclose(res["mean_reward"][0], r.sum() / B, rtol=1e-9)
