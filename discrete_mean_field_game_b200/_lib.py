@@ -19,6 +19,7 @@ REWARD_NONE, REWARD_AC2, REWARD_SYNTHETIC = 0, 1, 2
 DISCOUNT_STEP, DISCOUNT_CUMULATIVE = 0, 1
 NOISE_INJECTED, NOISE_PHILOX, NOISE_ACTIONS = 0, 1, 2
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_FAST = 0, 1, 2
+DROPOUT_NONE, DROPOUT_MASKS, DROPOUT_PHILOX = 0, 1, 2
 MAX_D = 256
 
 REWARD_KINDS = {"none": REWARD_NONE, "ac2": REWARD_AC2, "synthetic": REWARD_SYNTHETIC}
@@ -75,6 +76,27 @@ class LearnersArgs(C.Structure):
     ]
 
 
+class RnetArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("d", C.c_int32), ("n_fc3", C.c_int32), ("n_fc4", C.c_int32),
+        ("N", C.c_int64), ("params", C.c_void_p), ("states", C.c_void_p), ("actions", C.c_void_p),
+        ("dropout", C.c_int32), ("keep_prob", C.c_float), ("mask3", C.c_void_p), ("mask4", C.c_void_p),
+        ("seed", C.c_uint64), ("sample_offset", C.c_uint64), ("rewards", C.c_void_p),
+        ("drewards", C.c_void_p), ("grad", C.c_void_p), ("accumulate", C.c_int32), ("reserved", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+    ]
+
+
+class IrlLossArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("T", C.c_int32), ("n_demo", C.c_int64), ("M", C.c_int64),
+        ("gen_t_stride", C.c_int64), ("gen_j_stride", C.c_int64), ("num_demo_traj", C.c_double),
+        ("r_demo", C.c_void_p), ("r_gen", C.c_void_p), ("log_z", C.c_void_p),
+        ("d_demo", C.c_void_p), ("d_gen", C.c_void_p), ("loss_out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+    ]
+
+
 # every symbol include/dmfg.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("dmfg_version", C.c_int, []),
@@ -91,6 +113,20 @@ SYMBOLS = [
     ("dmfg_ac_apply_update", C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_double, C.c_double, C.c_void_p]),
     ("dmfg_ac_learners", C.c_int, [C.POINTER(LearnersArgs), C.c_void_p]),
+    ("dmfg_rnet_param_count", C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    ("dmfg_rnet_param_offsets", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
+    ("dmfg_rnet_workspace_bytes", C.c_uint64, [C.POINTER(RnetArgs)]),
+    ("dmfg_rnet_forward", C.c_int, [C.POINTER(RnetArgs), C.c_void_p]),
+    ("dmfg_rnet_backward", C.c_int, [C.POINTER(RnetArgs), C.c_void_p]),
+    ("dmfg_irl_loss_workspace_bytes", C.c_uint64, [C.c_int64]),
+    ("dmfg_irl_loss_grad", C.c_int, [C.POINTER(IrlLossArgs), C.c_void_p]),
+    ("dmfg_adam_tf", C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64,
+                               C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_int32, C.c_void_p, C.c_void_p]),
+    ("dmfg_dirichlet_logq", C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_double, C.c_void_p, C.c_void_p]),
+    ("dmfg_irl_log_z", C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_double,
+                                 C.c_void_p, C.c_void_p]),
     ("dmfg_philox4x32_10", None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("dmfg_gamma_sample", C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     ("dmfg_digamma", C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -6,14 +6,16 @@
 #include <cstring>
 #include <string>
 
+#include "dmfg_error.h"
 #include "dmfg_rollout.cuh"
 
 using namespace dmfg;
 
 namespace {
-
 thread_local std::string g_last_error;
+}
 
+namespace dmfg {
 int fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -23,14 +25,15 @@ int fail(int code, const char* fmt, ...) {
     g_last_error = buf;
     return code;
 }
+int sm_count(int* out) {
+    int dev = 0;
+    DMFG_CUDA(cudaGetDevice(&dev));
+    DMFG_CUDA(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+    return DMFG_OK;
+}
+}  // namespace dmfg
 
-#define DMFG_CUDA(call)                                                                    \
-    do {                                                                                   \
-        cudaError_t e_ = (call);                                                           \
-        if (e_ != cudaSuccess)                                                             \
-            return fail(DMFG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
-                        __FILE__, __LINE__);                                               \
-    } while (0)
+namespace {
 
 constexpr int kMaxPartialCtas = 148 * 8;     // upper bound on the persistent grids below
 constexpr int kTdChunk = 64;                 // transitions staged per CTA iteration in td_gw_kernel
@@ -39,12 +42,6 @@ inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a 
 inline size_t esize(int dtype) { return dtype == DMFG_F64 ? 8 : 4; }
 inline bool fast_d(int d) { return d == 4 || d == 15 || d == 16; }
 
-int sm_count(int* out) {
-    int dev = 0;
-    DMFG_CUDA(cudaGetDevice(&dev));
-    DMFG_CUDA(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
-    return DMFG_OK;
-}
 
 bool use_fast(const dmfg_rollout_args* a) {
     if (a->variant == DMFG_VARIANT_GENERIC) return false;

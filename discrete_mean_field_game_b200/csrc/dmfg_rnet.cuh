@@ -1,0 +1,745 @@
+// Reward network r_net(state, action) of the MaxEnt-IRL path (networks.py:13-157), fused forward and
+// backward for N transitions, plus the IRL loss, TF-style Adam and the Dirichlet log-density of calc_z.
+//
+//   conv 5x5 (1->1) + ReLU -> conv 3x3 (1->2) + ReLU -> NHWC flatten -> fc3 (2d^2 -> n3) + ReLU [dropout]
+//   -> concat state -> fc4 (n3+d -> n4) + ReLU [dropout] -> out (n4 -> 1) + tanh
+//
+// Mapping: a group of G lanes (16 for d <= 16) owns one transition; lane h owns ROW h of the d x d action:
+// it evaluates row h of conv1 and of both conv2 channels with the outputs in registers (the 5 / 3 input
+// rows come from a zero-haloed shared-memory tile, odd row stride => conflict free), multiplies its 2d
+// conv2 activations into fc3 from a per-row block of W3 (row-block stride = 4 mod 8 words => the LDS.128
+// of a quarter warp hit 8 distinct bank quads), and the group all-reduces the n3 partial sums with
+// shuffles.  Nothing intermediate leaves the SM.  The packed parameter vector (15 KB at d = 15) is staged
+// ONCE per persistent CTA by a TMA bulk copy (cp.async.bulk + mbarrier).
+//
+// Backward recomputes the forward in the same kernel (activations are 2.7 KB per transition against a
+// 960 B input: recomputing beats caching), backpropagates through every layer and accumulates parameter
+// gradients without atomics: conv / fc4 gradients in per-thread slots, the fc3 gradient -- the only big
+// one, [2d^2, n3] -- as a CTA-wide outer-product over a tile of 16 transitions with thread-owned (k, n)
+// accumulators in registers.  Per-CTA partials are then summed in fixed order (deterministic).
+#pragma once
+#include "dmfg_math.cuh"
+#include "../../include/dmfg.h"
+
+namespace dmfg {
+
+constexpr int kRnetThreads = 256;
+constexpr int kK1 = 5, kK2 = 3;
+#define DMFG_CTR_DROPOUT 0xA0000000u   // Philox counter word 3 of the dropout uniforms
+
+struct RnetLayout {
+    int d, n3, n4;
+    int k1, b1, k2, b2, w3, b3, w4, b4, w5, b5, total;
+};
+__host__ __device__ inline RnetLayout rnet_layout(int d, int n3, int n4) {
+    RnetLayout L;
+    L.d = d; L.n3 = n3; L.n4 = n4;
+    int o = 0;
+    L.k1 = o; o += kK1 * kK1;
+    L.b1 = o; o += 1;
+    L.k2 = o; o += kK2 * kK2 * 2;
+    L.b2 = o; o += 2;
+    L.w3 = o; o += 2 * d * d * n3;
+    L.b3 = o; o += n3;
+    L.w4 = o; o += (n3 + d) * n4;
+    L.b4 = o; o += n4;
+    L.w5 = o; o += n4;
+    L.b5 = o; o += 1;
+    L.total = o;
+    return L;
+}
+
+struct RnetParams {
+    int d, n3, n4;
+    long long N;
+    const float* params;
+    const float* states;      // [N][d]
+    const float* actions;     // [N][d][d]
+    int dropout;              // DMFG_DROPOUT_*
+    float keep_prob;
+    const unsigned char* mask3;   // [N][n3]
+    const unsigned char* mask4;   // [N][n4]
+    unsigned long long seed, sample_offset;
+    float* rewards;           // [N] or null
+    const float* drewards;    // [N] (backward)
+    float* partials;          // [grid][total] (backward)
+};
+
+// shared-memory map (in floats), identical on host and device
+template <int G, int NP, bool BWD>
+struct RnetSmem {
+    static constexpr int GPB = kRnetThreads / G;
+    static constexpr int RA = G + 4, SA = (G + 4) | 1;
+    static constexpr int RC = G + 2, SC = (G + 2) | 1;
+    static constexpr int NSLOT = 25 + 1 + 18 + 2 + 2 * NP;     // per-thread gradient slots
+    static constexpr int NSMALL = 3 * NP + 1;                  // per-group: gW5[NP] gb4[NP] gb3[NP] gb5
+    int wflat, w3s, w3stride, tiles, tile_stride, flat, flat_stride, dz3, gacc, gsmall, total;
+    __host__ __device__ RnetSmem(int d, int ptotal) {
+        int o = 0;
+        wflat = o; o += (ptotal + 3) / 4 * 4;
+        w3stride = 2 * d * NP;
+        if (((w3stride / 4) & 1) == 0) w3stride += 4;
+        w3s = o; o += G * w3stride;
+        tile_stride = RA * SA + RC * SC + (BWD ? 2 * RC * SC : 0);
+        tiles = o; o += GPB * tile_stride;
+        flat = dz3 = gacc = gsmall = 0; flat_stride = 0;
+        if (BWD) {
+            flat_stride = 2 * d * d;
+            flat_stride += flat_stride & 1;
+            flat = o; o += GPB * flat_stride;
+            dz3 = o; o += GPB * NP;
+            gacc = o; o += NSLOT * kRnetThreads;
+            gsmall = o; o += GPB * NSMALL;
+        }
+        total = o;
+    }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// TMA bulk copy global -> shared of `bytes` (multiple of 16, both sides 16-byte aligned), completion on mbar
+__device__ __forceinline__ void tma_bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* mbar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+    }
+}
+
+template <int G>
+__device__ __forceinline__ float group_sum_f(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+    return v;
+}
+
+// keep masks of the two dropout layers for transition `sample` (Philox mode): unit j of layer l keeps
+// iff u01(word) < keep_prob, words drawn 4 at a time from counter (sample, l*64 + j/4, DROPOUT)
+template <int NP>
+__device__ __forceinline__ void dropout_masks_philox(unsigned long long seed, unsigned long long sample, float keep,
+                                                     float (&m3)[NP], float (&m4)[NP]) {
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint32_t s0 = (uint32_t)sample, s1 = (uint32_t)(sample >> 32);
+#pragma unroll
+    for (int q = 0; q < NP / 4; ++q) {
+        const uint4 a = philox4x32_10(s0, s1, (uint32_t)q, DMFG_CTR_DROPOUT, k0, k1);
+        const uint4 b = philox4x32_10(s0, s1, 64u + (uint32_t)q, DMFG_CTR_DROPOUT, k0, k1);
+        m3[4 * q + 0] = u01(a.x) < keep ? 1.f : 0.f; m3[4 * q + 1] = u01(a.y) < keep ? 1.f : 0.f;
+        m3[4 * q + 2] = u01(a.z) < keep ? 1.f : 0.f; m3[4 * q + 3] = u01(a.w) < keep ? 1.f : 0.f;
+        m4[4 * q + 0] = u01(b.x) < keep ? 1.f : 0.f; m4[4 * q + 1] = u01(b.y) < keep ? 1.f : 0.f;
+        m4[4 * q + 2] = u01(b.z) < keep ? 1.f : 0.f; m4[4 * q + 3] = u01(b.w) < keep ? 1.f : 0.f;
+    }
+}
+
+template <int G, int NP, bool BWD>
+__global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const RnetParams p) {
+    using SM = RnetSmem<G, NP, BWD>;
+    constexpr int GPB = SM::GPB, SA = SM::SA, SC = SM::SC, RA = SM::RA, RC = SM::RC;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int d = p.d, n3 = p.n3, n4 = p.n4;
+    const RnetLayout L = rnet_layout(d, n3, n4);
+    const SM S(d, L.total);
+    const int tid = threadIdx.x, h = tid % G, grp = tid / G;
+    float* wf = smem + S.wflat;
+    float* w3s = smem + S.w3s;
+    float* At = smem + S.tiles + grp * S.tile_stride;
+    float* Ct = At + RA * SA;
+
+    // ---- stage the parameters: one TMA bulk copy (+ <= 3 tail floats) ----------------------------
+    const uint32_t bulk_floats = ((uintptr_t)p.params & 15) == 0 ? (uint32_t)(L.total / 4 * 4) : 0u;
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0 && bulk_floats) tma_bulk_load(wf, p.params, bulk_floats * 4u, &mbar);
+    for (int i = bulk_floats + tid; i < L.total; i += kRnetThreads) wf[i] = p.params[i];
+    for (int i = tid; i < GPB * S.tile_stride; i += kRnetThreads) smem[S.tiles + i] = 0.f;    // zero halos
+    if (BWD) {
+        for (int i = tid; i < GPB * S.flat_stride; i += kRnetThreads) smem[S.flat + i] = 0.f;
+        for (int i = tid; i < SM::NSLOT * kRnetThreads; i += kRnetThreads) smem[S.gacc + i] = 0.f;
+        for (int i = tid; i < GPB * SM::NSMALL; i += kRnetThreads) smem[S.gsmall + i] = 0.f;
+    }
+    if (bulk_floats) mbar_wait(&mbar, 0);
+    __syncthreads();
+    // fc3 weights into per-row blocks [h][2d][NP] (zero padded columns), conflict-free stride
+    for (int i = tid; i < G * S.w3stride; i += kRnetThreads) w3s[i] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < 2 * d * d * n3; i += kRnetThreads) {
+        const int k = i / n3, n = i - k * n3;
+        const int row = k / (2 * d), kk = k - row * 2 * d;
+        w3s[row * S.w3stride + kk * NP + n] = wf[L.w3 + i];
+    }
+    __syncthreads();
+
+    const bool row_ok = h < d;
+    const float inv_keep = p.dropout ? 1.0f / p.keep_prob : 1.0f;
+    // persistent register accumulators (backward)
+    float gw3[2][NP], gw4pi[NP], gw4h[NP];
+    if (BWD) {
+#pragma unroll
+        for (int n = 0; n < NP; ++n) { gw3[0][n] = gw3[1][n] = 0.f; gw4pi[n] = gw4h[n] = 0.f; }
+    }
+    const long long ntiles = (p.N + GPB - 1) / GPB;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        long long n = tile * GPB + grp;
+        const bool live = n < p.N;           // dead groups shadow the last transition (warp-wide syncs stay
+        if (!live) n = p.N - 1;              // convergent); their writes are masked and their dr is 0
+        float dz3[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) dz3[j] = 0.f;
+        float c2[2][G];
+        {
+            // ---- action tile -> shared (interior of the zero-haloed tile) ------------------------
+            const float* a = p.actions + n * d * d;
+            if (row_ok)
+                for (int i = 0; i < d; ++i) At[(i + 2) * SA + h + 2] = a[i * d + h];
+            const float pi_h = row_ok ? p.states[n * d + h] : 0.f;
+            __syncwarp();
+            // ---- conv1 row h ----------------------------------------------------------------------
+            float c1[G];
+            {
+                const float b1 = wf[L.b1];
+#pragma unroll
+                for (int w = 0; w < G; ++w) c1[w] = b1;
+#pragma unroll
+                for (int dh = 0; dh < kK1; ++dh) {
+                    const float* row = At + (h + dh) * SA;
+                    float k[kK1];
+#pragma unroll
+                    for (int dw = 0; dw < kK1; ++dw) k[dw] = wf[L.k1 + dh * kK1 + dw];
+#pragma unroll
+                    for (int wp = 0; wp < G + 4; ++wp) {
+                        const float v = row[wp];
+#pragma unroll
+                        for (int dw = 0; dw < kK1; ++dw) {
+                            const int w = wp - dw;
+                            if (w >= 0 && w < G) c1[w] = fmaf(v, k[dw], c1[w]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < G; ++w) {
+                    c1[w] = (row_ok && w < d) ? fmaxf(c1[w], 0.f) : 0.f;
+                    Ct[(h + 1) * SC + w + 1] = c1[w];
+                }
+            }
+            __syncwarp();
+            // ---- conv2 row h, both channels -------------------------------------------------------
+            {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float b2 = wf[L.b2 + c];
+#pragma unroll
+                    for (int w = 0; w < G; ++w) c2[c][w] = b2;
+                }
+#pragma unroll
+                for (int dh = 0; dh < kK2; ++dh) {
+                    const float* row = Ct + (h + dh) * SC;
+                    float k[kK2][2];
+#pragma unroll
+                    for (int dw = 0; dw < kK2; ++dw) {
+                        k[dw][0] = wf[L.k2 + (dh * kK2 + dw) * 2];
+                        k[dw][1] = wf[L.k2 + (dh * kK2 + dw) * 2 + 1];
+                    }
+#pragma unroll
+                    for (int wp = 0; wp < G + 2; ++wp) {
+                        const float v = row[wp];
+#pragma unroll
+                        for (int dw = 0; dw < kK2; ++dw) {
+                            const int w = wp - dw;
+                            if (w >= 0 && w < G) {
+                                c2[0][w] = fmaf(v, k[dw][0], c2[0][w]);
+                                c2[1][w] = fmaf(v, k[dw][1], c2[1][w]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int w = 0; w < G; ++w) c2[c][w] = (row_ok && w < d) ? fmaxf(c2[c][w], 0.f) : 0.f;
+            }
+            // ---- fc3: this row's 2d activations x W3 row block, then all-reduce over the group ----
+            float z3[NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) z3[j] = 0.f;
+            const float* wrow = w3s + (row_ok ? h : 0) * S.w3stride;
+#pragma unroll
+            for (int w = 0; w < G; ++w) {
+                if (w < d) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float4* wq = reinterpret_cast<const float4*>(wrow + (w * 2 + c) * NP);
+#pragma unroll
+                        for (int q = 0; q < NP / 4; ++q) {
+                            const float4 ww = wq[q];
+                            z3[4 * q + 0] = fmaf(c2[c][w], ww.x, z3[4 * q + 0]);
+                            z3[4 * q + 1] = fmaf(c2[c][w], ww.y, z3[4 * q + 1]);
+                            z3[4 * q + 2] = fmaf(c2[c][w], ww.z, z3[4 * q + 2]);
+                            z3[4 * q + 3] = fmaf(c2[c][w], ww.w, z3[4 * q + 3]);
+                        }
+                    }
+                }
+            }
+            float m3[NP], m4[NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) { m3[j] = 1.f; m4[j] = 1.f; }
+            if (p.dropout == DMFG_DROPOUT_MASKS) {
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    if (j < n3) m3[j] = p.mask3[n * n3 + j] ? 1.f : 0.f;
+                    if (j < n4) m4[j] = p.mask4[n * n4 + j] ? 1.f : 0.f;
+                }
+            } else if (p.dropout == DMFG_DROPOUT_PHILOX) {
+                dropout_masks_philox<NP>(p.seed, p.sample_offset + (unsigned long long)n, p.keep_prob, m3, m4);
+            }
+            float h3[NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                z3[j] = group_sum_f<G>(z3[j]) + (j < n3 ? wf[L.b3 + j] : 0.f);
+                h3[j] = j < n3 ? fmaxf(z3[j], 0.f) * m3[j] * inv_keep : 0.f;
+            }
+            // ---- fc4 over [h3, pi] ----------------------------------------------------------------
+            float z4[NP], h4[NP];
+#pragma unroll
+            for (int m = 0; m < NP; ++m) {
+                float part = (row_ok && m < n4) ? pi_h * wf[L.w4 + (n3 + h) * n4 + m] : 0.f;
+                part = group_sum_f<G>(part);
+                if (m < n4) {
+                    float z = wf[L.b4 + m] + part;
+#pragma unroll
+                    for (int j = 0; j < NP; ++j)
+                        if (j < n3) z = fmaf(h3[j], wf[L.w4 + j * n4 + m], z);
+                    z4[m] = z;
+                    h4[m] = fmaxf(z, 0.f) * m4[m] * inv_keep;
+                } else {
+                    z4[m] = 0.f; h4[m] = 0.f;
+                }
+            }
+            // ---- out + tanh -----------------------------------------------------------------------
+            float z5 = wf[L.b5];
+#pragma unroll
+            for (int m = 0; m < NP; ++m)
+                if (m < n4) z5 = fmaf(h4[m], wf[L.w5 + m], z5);
+            const float r = tanhf(z5);
+            if (p.rewards != nullptr && h == 0 && live) p.rewards[n] = r;
+
+            if (BWD) {
+                float* Dt = Ct + RC * SC;                    // dz2 tile, 2 channels
+                float* gs = smem + S.gsmall + grp * SM::NSMALL;
+                const float dz5 = live ? p.drewards[n] * (1.f - r * r) : 0.f;
+                float dz4[NP];
+#pragma unroll
+                for (int m = 0; m < NP; ++m)
+                    dz4[m] = (m < n4 && z4[m] > 0.f) ? dz5 * wf[L.w5 + m] * m4[m] * inv_keep : 0.f;
+                if (h == 0) {
+#pragma unroll
+                    for (int m = 0; m < NP; ++m) {
+                        gs[m] = fmaf(h4[m], dz5, gs[m]);                    // d out/weights
+                        gs[NP + m] += dz4[m];                               // d fc4/biases
+                    }
+                    gs[3 * NP] += dz5;                                      // d out/biases
+                }
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int m = 0; m < NP; ++m)
+                        if (m < n4 && j < n3) s = fmaf(dz4[m], wf[L.w4 + j * n4 + m], s);
+                    dz3[j] = (j < n3 && z3[j] > 0.f) ? s * m3[j] * inv_keep : 0.f;
+                }
+                if (h == 0) {
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) gs[2 * NP + j] += dz3[j];   // d fc3/biases
+                }
+                // d fc4/weights: row n3+h (state part) on every lane, row h (h3 part) on lanes h < n3
+#pragma unroll
+                for (int m = 0; m < NP; ++m) gw4pi[m] = fmaf(pi_h, dz4[m], gw4pi[m]);
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    if (j == h) {
+#pragma unroll
+                        for (int m = 0; m < NP; ++m) gw4h[m] = fmaf(h3[j], dz4[m], gw4h[m]);
+                    }
+                }
+                // conv2 activations of this transition -> flat tile (consumed by the CTA-wide fc3 gradient)
+                float* fl = smem + S.flat + grp * S.flat_stride;
+                if (row_ok) {
+#pragma unroll
+                    for (int w = 0; w < G; ++w)
+                        if (w < d) *reinterpret_cast<float2*>(fl + (h * d + w) * 2) = make_float2(c2[0][w], c2[1][w]);
+                }
+                // d conv2 pre-activation: dz2 = (W3 row block . dz3) masked by relu
+                float dz2[2][G];
+#pragma unroll
+                for (int w = 0; w < G; ++w) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        float s = 0.f;
+                        if (w < d) {
+                            const float4* wq = reinterpret_cast<const float4*>(wrow + (w * 2 + c) * NP);
+#pragma unroll
+                            for (int q = 0; q < NP / 4; ++q) {
+                                const float4 ww = wq[q];
+                                s = fmaf(dz3[4 * q + 0], ww.x, s); s = fmaf(dz3[4 * q + 1], ww.y, s);
+                                s = fmaf(dz3[4 * q + 2], ww.z, s); s = fmaf(dz3[4 * q + 3], ww.w, s);
+                            }
+                        }
+                        dz2[c][w] = c2[c][w] > 0.f ? s : 0.f;
+                        Dt[c * RC * SC + (h + 1) * SC + w + 1] = dz2[c][w];
+                    }
+                }
+                float* ga = smem + S.gacc + tid;
+                // d conv2/weights [dh][dw][c] and biases
+                {
+                    float gk[kK2 * kK2 * 2];
+#pragma unroll
+                    for (int i = 0; i < kK2 * kK2 * 2; ++i) gk[i] = 0.f;
+#pragma unroll
+                    for (int dh = 0; dh < kK2; ++dh) {
+                        const float* row = Ct + (h + dh) * SC;
+#pragma unroll
+                        for (int wp = 0; wp < G + 2; ++wp) {
+                            const float v = row[wp];
+#pragma unroll
+                            for (int dw = 0; dw < kK2; ++dw) {
+                                const int w = wp - dw;
+                                if (w >= 0 && w < G) {
+                                    gk[(dh * kK2 + dw) * 2] = fmaf(v, dz2[0][w], gk[(dh * kK2 + dw) * 2]);
+                                    gk[(dh * kK2 + dw) * 2 + 1] = fmaf(v, dz2[1][w], gk[(dh * kK2 + dw) * 2 + 1]);
+                                }
+                            }
+                        }
+                    }
+                    float sb0 = 0.f, sb1 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < G; ++w) { sb0 += dz2[0][w]; sb1 += dz2[1][w]; }
+#pragma unroll
+                    for (int i = 0; i < 18; ++i) ga[(26 + i) * kRnetThreads] += gk[i];
+                    ga[44 * kRnetThreads] += sb0;
+                    ga[45 * kRnetThreads] += sb1;
+                }
+                __syncwarp();
+                // d conv1 output row h: full correlation of dz2 with the flipped conv2 kernel
+                float dz1[G];
+#pragma unroll
+                for (int w = 0; w < G; ++w) dz1[w] = 0.f;
+#pragma unroll
+                for (int e = 0; e < kK2; ++e) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float* row = Dt + c * RC * SC + (h + e) * SC;
+                        float k[kK2];
+#pragma unroll
+                        for (int f = 0; f < kK2; ++f) k[f] = wf[L.k2 + ((2 - e) * kK2 + (2 - f)) * 2 + c];
+#pragma unroll
+                        for (int wp = 0; wp < G + 2; ++wp) {
+                            const float v = row[wp];
+#pragma unroll
+                            for (int f = 0; f < kK2; ++f) {
+                                const int w = wp - f;
+                                if (w >= 0 && w < G) dz1[w] = fmaf(v, k[f], dz1[w]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < G; ++w) dz1[w] = c1[w] > 0.f ? dz1[w] : 0.f;
+                // d conv1/weights [dh][dw] and bias
+                {
+                    float gk[kK1 * kK1];
+#pragma unroll
+                    for (int i = 0; i < kK1 * kK1; ++i) gk[i] = 0.f;
+#pragma unroll
+                    for (int dh = 0; dh < kK1; ++dh) {
+                        const float* row = At + (h + dh) * SA;
+#pragma unroll
+                        for (int wp = 0; wp < G + 4; ++wp) {
+                            const float v = row[wp];
+#pragma unroll
+                            for (int dw = 0; dw < kK1; ++dw) {
+                                const int w = wp - dw;
+                                if (w >= 0 && w < G) gk[dh * kK1 + dw] = fmaf(v, dz1[w], gk[dh * kK1 + dw]);
+                            }
+                        }
+                    }
+                    float sb = 0.f;
+#pragma unroll
+                    for (int w = 0; w < G; ++w) sb += dz1[w];
+#pragma unroll
+                    for (int i = 0; i < 25; ++i) ga[i * kRnetThreads] += gk[i];
+                    ga[25 * kRnetThreads] += sb;
+                }
+            }
+            __syncwarp();      // tiles are rewritten by the next transition of this group
+        }
+        if (BWD) {
+            // ---- fc3 gradient: CTA-wide outer product flat^T . dz3 over this tile's transitions ----
+            if (h == 0) {
+                float* dzt = smem + S.dz3 + grp * NP;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) dzt[j] = dz3[j];          // zero for dead groups
+            }
+            __syncthreads();
+            const int K = 2 * d * d;
+            const int k0 = tid, k1 = tid + kRnetThreads;
+            for (int t = 0; t < GPB; ++t) {
+                const float* fl = smem + S.flat + t * S.flat_stride;
+                const float* dzt = smem + S.dz3 + t * NP;
+                const float f0 = k0 < K ? fl[k0] : 0.f;
+                const float f1 = k1 < K ? fl[k1] : 0.f;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    const float dzj = dzt[j];
+                    gw3[0][j] = fmaf(f0, dzj, gw3[0][j]);
+                    gw3[1][j] = fmaf(f1, dzj, gw3[1][j]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (!BWD) return;
+    // ---- per-CTA partial gradient, fixed summation order ---------------------------------------------
+    float* out = p.partials + (long long)blockIdx.x * L.total;
+    {
+        const int K = 2 * d * d;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int k = tid + s * kRnetThreads;
+            if (k < K) {
+#pragma unroll
+                for (int j = 0; j < NP; ++j)
+                    if (j < n3) out[L.w3 + k * n3 + j] = gw3[s][j];
+            }
+        }
+    }
+    float* ga = smem + S.gacc;
+#pragma unroll
+    for (int m = 0; m < NP; ++m) {
+        ga[(46 + m) * kRnetThreads + tid] = gw4pi[m];
+        ga[(46 + NP + m) * kRnetThreads + tid] = gw4h[m];
+    }
+    __syncthreads();
+    // conv slots: sum over all threads (warp w takes slots w, w+8, ...)
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int s = warp; s < 46; s += kRnetThreads / 32) {
+            float v = 0.f;
+            for (int j = 0; j < kRnetThreads / 32; ++j) v += ga[s * kRnetThreads + lane + 32 * j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) {
+                int dst;
+                if (s < 25) dst = L.k1 + s;
+                else if (s == 25) dst = L.b1;
+                else if (s < 44) dst = L.k2 + (s - 26);
+                else dst = L.b2 + (s - 44);
+                out[dst] = v;
+            }
+        }
+    }
+    // fc4 weights: rows n3+h (all lanes) and rows h < n3, summed over groups
+    for (int i = tid; i < (n3 + d) * n4; i += kRnetThreads) {
+        const int row = i / n4, m = i - row * n4;
+        const int slot = row < n3 ? 46 + NP + m : 46 + m;
+        const int lane_h = row < n3 ? row : row - n3;
+        float v = 0.f;
+        for (int g = 0; g < GPB; ++g) v += ga[slot * kRnetThreads + g * G + lane_h];
+        out[L.w4 + i] = v;
+    }
+    // small per-group sums
+    for (int i = tid; i < SM::NSMALL; i += kRnetThreads) {
+        float v = 0.f;
+        for (int g = 0; g < GPB; ++g) v += smem[S.gsmall + g * SM::NSMALL + i];
+        const int which = i / NP, m = i - which * NP;
+        if (i == 3 * NP) out[L.b5] = v;
+        else if (which == 0 && m < n4) out[L.w5 + m] = v;
+        else if (which == 1 && m < n4) out[L.b4 + m] = v;
+        else if (which == 2 && m < n3) out[L.b3 + m] = v;
+    }
+}
+
+// grad[i] = (accumulate ? grad[i] : 0) + sum over CTAs of partials[cta][i]
+__global__ void rnet_reduce_partials_kernel(const float* __restrict__ partials, int ncta, int n, int accumulate,
+                                            float* __restrict__ grad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int c = 0; c < ncta; ++c) s += partials[(long long)c * n + i];
+    grad[i] = accumulate ? grad[i] + s : s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// IRL loss (ac_irl.py:390-406).  r_gen is indexed [t * gen_t_stride + j * gen_j_stride]: time-major
+// rollout records use (M, 1), the reference's trajectory-major feed uses (1, T).
+//   first  = -(1/num_demo_traj) sum r_demo;  second = ln((1/M) sum_j z_j exp(sum_t r_gen[j,t]))
+//   d_demo[n] = -1/num_demo_traj;  d_gen[j,t] = softmax_j(R_j + ln z_j)
+// Stage 1: per-trajectory E_j = exp(R_j + lnz_j) and per-block partial sums (double);
+// stage 2 (one block): totals -> out[0..3] = {loss, first, second, sum E}; stage 3: d_gen.
+// ---------------------------------------------------------------------------------------------------
+struct IrlLossParams {
+    long long n_demo, M;
+    int T;
+    long long gen_t_stride, gen_j_stride;
+    double num_demo_traj;
+    const float *r_demo, *r_gen, *log_z;
+    float *d_demo, *d_gen;
+    double* traj_e;       // [M]
+    double* partials;     // [nblocks][2]
+    double* out;          // [4]
+    double reg_loss_scale;
+};
+
+__device__ __forceinline__ double block_sum_double(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
+    __syncthreads();
+    return s;   // valid on thread 0
+}
+
+__global__ void __launch_bounds__(256) irl_loss_stage1_kernel(const IrlLossParams p) {
+    __shared__ double sh[8];
+    double se = 0.0, sd = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < p.M; j += stride) {
+        double R = 0.0;
+        for (int t = 0; t < p.T; ++t) R += (double)p.r_gen[t * p.gen_t_stride + j * p.gen_j_stride];
+        if (p.log_z) R += (double)p.log_z[j];
+        const double e = exp(R);
+        p.traj_e[j] = e;
+        se += e;
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_demo; i += stride) {
+        sd += (double)p.r_demo[i];
+        if (p.d_demo) p.d_demo[i] = (float)(-1.0 / p.num_demo_traj);
+    }
+    se = block_sum_double(se, sh);
+    sd = block_sum_double(sd, sh);
+    if (threadIdx.x == 0) { p.partials[2 * blockIdx.x] = se; p.partials[2 * blockIdx.x + 1] = sd; }
+}
+__global__ void irl_loss_stage2_kernel(const IrlLossParams p, int nblocks) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double se = 0.0, sd = 0.0;
+    for (int b = 0; b < nblocks; ++b) { se += p.partials[2 * b]; sd += p.partials[2 * b + 1]; }
+    const double first = -sd / p.num_demo_traj;
+    const double second = log(se / (double)p.M);
+    p.out[0] = first + second;
+    p.out[1] = first;
+    p.out[2] = second;
+    p.out[3] = se;
+}
+__global__ void __launch_bounds__(256) irl_loss_stage3_kernel(const IrlLossParams p) {
+    const double inv = 1.0 / p.out[3];
+    const long long total = p.M * p.T;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        // iterate in memory order of the faster-varying index
+        long long j; int t;
+        if (p.gen_j_stride == 1) { t = (int)(i / p.M); j = i - (long long)t * p.M; }
+        else { j = i / p.T; t = (int)(i - j * p.T); }
+        p.d_gen[t * p.gen_t_stride + j * p.gen_j_stride] = (float)(p.traj_e[j] * inv);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TF-style Adam on a flat f32 vector (tf.train.AdamOptimizer, ac_irl.py:417): lr_t is computed by the
+// caller from the step count; optional l1_l2 regulariser gradient sign(w) + w on [reg_begin, reg_end)
+// ranges (fc3 and fc4 weights, networks.py:69,74); grad_scale folds the 1/world of a data-parallel mean.
+// ---------------------------------------------------------------------------------------------------
+__global__ void adam_tf_kernel(int n, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                               const float* __restrict__ g, float grad_scale, float lr_t, float beta1, float beta2,
+                               float omb1, float omb2, float eps, int reg0_begin, int reg0_end, int reg1_begin, int reg1_end) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float w = p[i];
+    float gi = g[i] * grad_scale;
+    if ((i >= reg0_begin && i < reg0_end) || (i >= reg1_begin && i < reg1_end))
+        gi += (w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f)) + w;
+    const float mi = beta1 * m[i] + omb1 * gi;       // omb = 1 - beta rounded once from double
+    const float vi = beta2 * v[i] + omb2 * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = w - lr_t * mi / (sqrtf(vi) + eps);
+}
+// sum |w| + w^2/2 over the two regularised ranges -> out[0] (double); single block
+__global__ void __launch_bounds__(256) reg_loss_kernel(const float* __restrict__ p, int b0, int e0, int b1, int e1,
+                                                       double* out) {
+    __shared__ double sh[8];
+    double s = 0.0;
+    for (int i = b0 + threadIdx.x; i < e0; i += blockDim.x) { const double w = p[i]; s += fabs(w) + 0.5 * w * w; }
+    for (int i = b1 + threadIdx.x; i < e1; i += blockDim.x) { const double w = p[i]; s += fabs(w) + 0.5 * w * w; }
+    s = block_sum_double(s, sh);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// calc_z (ac_irl.py:324-379): log q_k(tau_j) = sum_t sum_i ln Dir(a_t[i,:]; max(alpha_k(s_t)[i,:], 1+1e-6)).
+// One warp per (transition n, policy k): lanes stride the rows, each lane walks its row's d columns.
+// logq_tk [N][K] per transition; the host-side caller sums over t per trajectory (tiny) -- or use
+// dmfg_irl_log_z which does it on the device.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) dirichlet_logq_kernel(int d, long long N, int K, const float* __restrict__ states,
+                                                             const float* __restrict__ actions,
+                                                             const double* __restrict__ thetas, double shift,
+                                                             double* __restrict__ logq) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= N * K) return;
+    const long long n = warp / K;
+    const int k = (int)(warp - n * K);
+    const double theta = thetas[k];
+    const float* s = states + n * d;
+    const float* a = actions + n * d * d;
+    double acc = 0.0;
+    for (int i = lane; i < d; i += 32) {
+        const double si = (double)s[i];
+        double asum = 0.0, lsum = 0.0, psum = 0.0;
+        for (int j = 0; j < d; ++j) {
+            const double x = ((double)s[j] - si - shift) * theta;
+            double al = x > 0.0 ? x + log1p(exp(-x)) : log1p(exp(x));
+            al = fmax(al, 1.0 + 1e-6);
+            asum += al;
+            lsum += lgamma(al);
+            psum += (al - 1.0) * log((double)a[i * d + j]);
+        }
+        acc += lgamma(asum) - lsum + psum;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) logq[n * K + k] = acc;
+}
+
+// ln z_j = ln K - ln N_start - logsumexp_k( sum_t logq[(t*t_stride + j*j_stride)][k] ); thread per trajectory
+__global__ void irl_log_z_kernel(long long M, int T, int K, long long t_stride, long long j_stride,
+                                 const double* __restrict__ logq, double num_start, float* __restrict__ log_z) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    double mx = -1e300;
+    for (int k = 0; k < K; ++k) {
+        double s = 0.0;
+        for (int t = 0; t < T; ++t) s += logq[(t * t_stride + j * j_stride) * K + k];
+        mx = fmax(mx, s);
+    }
+    double se = 0.0;
+    for (int k = 0; k < K; ++k) {
+        double s = 0.0;
+        for (int t = 0; t < T; ++t) s += logq[(t * t_stride + j * j_stride) * K + k];
+        se += exp(s - mx);
+    }
+    log_z[j] = (float)(log((double)K) - log(num_start) - (mx + log(se)));
+}
+
+}  // namespace dmfg

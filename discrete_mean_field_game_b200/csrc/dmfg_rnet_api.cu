@@ -1,0 +1,233 @@
+// extern "C" entry points of the IRL half of libdmfg (include/dmfg.h): reward network forward /
+// backward, IRL loss, TF-style Adam, Dirichlet log-density for calc_z.
+#include <cmath>
+#include <cstdint>
+
+#include "dmfg_error.h"
+#include "dmfg_rnet.cuh"
+
+using namespace dmfg;
+
+namespace {
+
+constexpr int kG = 16;           // lanes per transition: d <= 16
+constexpr int kNP = 8;           // padded width of fc3 / fc4: n_fc3, n_fc4 <= 8
+constexpr int kMaxRnetCtas = 148 * 2;
+constexpr int kLossBlocks = 148 * 4;
+
+inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a * a; }
+
+int check_rnet(const dmfg_rnet_args* a, bool bwd) {
+    if (!a) return fail(DMFG_ERR_INVALID, "args is NULL");
+    if (a->struct_size != sizeof(dmfg_rnet_args))
+        return fail(DMFG_ERR_INVALID, "dmfg_rnet_args.struct_size %u != %zu (header mismatch)", a->struct_size,
+                    sizeof(dmfg_rnet_args));
+    if (a->d < 1 || a->n_fc3 < 1 || a->n_fc4 < 1 || a->N < 0) return fail(DMFG_ERR_INVALID, "bad d/n_fc3/n_fc4/N");
+    if (a->d > kG || a->n_fc3 > kNP || a->n_fc4 > kNP)
+        return fail(DMFG_ERR_UNSUPPORTED, "reward-net kernels are built for d <= %d, n_fc3, n_fc4 <= %d (got %d, %d, %d)",
+                    kG, kNP, a->d, a->n_fc3, a->n_fc4);
+    if (!a->params) return fail(DMFG_ERR_INVALID, "params is NULL");
+    if (a->N > 0 && (!a->states || !a->actions)) return fail(DMFG_ERR_INVALID, "states/actions are NULL");
+    if (a->dropout < DMFG_DROPOUT_NONE || a->dropout > DMFG_DROPOUT_PHILOX) return fail(DMFG_ERR_INVALID, "dropout %d", a->dropout);
+    if (a->dropout != DMFG_DROPOUT_NONE && !(a->keep_prob > 0.f && a->keep_prob <= 1.f))
+        return fail(DMFG_ERR_INVALID, "keep_prob must be in (0,1]");
+    if (a->dropout == DMFG_DROPOUT_MASKS && a->N > 0 && (!a->mask3 || !a->mask4))
+        return fail(DMFG_ERR_INVALID, "dropout=MASKS needs mask3 and mask4");
+    if (!bwd && a->N > 0 && !a->rewards) return fail(DMFG_ERR_INVALID, "rewards is NULL");
+    if (bwd) {
+        if (!a->grad) return fail(DMFG_ERR_INVALID, "grad is NULL");
+        if (a->N > 0 && !a->drewards) return fail(DMFG_ERR_INVALID, "drewards is NULL");
+    }
+    return DMFG_OK;
+}
+
+RnetParams make_params(const dmfg_rnet_args* a) {
+    RnetParams p;
+    p.d = a->d; p.n3 = a->n_fc3; p.n4 = a->n_fc4; p.N = a->N;
+    p.params = a->params; p.states = a->states; p.actions = a->actions;
+    p.dropout = a->dropout; p.keep_prob = a->keep_prob; p.mask3 = a->mask3; p.mask4 = a->mask4;
+    p.seed = a->seed; p.sample_offset = a->sample_offset;
+    p.rewards = a->rewards; p.drewards = a->drewards; p.partials = nullptr;
+    return p;
+}
+
+template <bool BWD>
+int rnet_grid(const dmfg_rnet_args* a, int* grid, size_t* smem_bytes) {
+    auto kern = rnet_kernel<kG, kNP, BWD>;
+    const RnetLayout L = rnet_layout(a->d, a->n_fc3, a->n_fc4);
+    const RnetSmem<kG, kNP, BWD> S(a->d, L.total);
+    const size_t smem = (size_t)S.total * sizeof(float);
+    DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0, sms = 0;
+    DMFG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRnetThreads, smem));
+    if (int rc = sm_count(&sms)) return rc;
+    if (occ < 1) return fail(DMFG_ERR_CUDA, "rnet_kernel needs %zu bytes of shared memory: does not fit an SM", smem);
+    long long g = (long long)sms * occ;
+    if (g > kMaxRnetCtas) g = kMaxRnetCtas;
+    const long long ntiles = (a->N + kRnetThreads / kG - 1) / (kRnetThreads / kG);
+    if (g > ntiles) g = ntiles;
+    if (g < 1) g = 1;
+    *grid = (int)g;
+    *smem_bytes = smem;
+    return DMFG_OK;
+}
+
+void reg_ranges(int l1l2, int d, int n3, int n4, int* b0, int* e0, int* b1, int* e1) {
+    *b0 = *e0 = *b1 = *e1 = 0;
+    if (!l1l2) return;
+    const RnetLayout L = rnet_layout(d, n3, n4);
+    *b0 = L.w3; *e0 = L.b3;
+    *b1 = L.w4; *e1 = L.b4;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t dmfg_rnet_param_count(int32_t d, int32_t n_fc3, int32_t n_fc4) {
+    if (d < 1 || n_fc3 < 1 || n_fc4 < 1) return 0;
+    return rnet_layout(d, n_fc3, n_fc4).total;
+}
+
+int dmfg_rnet_param_offsets(int32_t d, int32_t n_fc3, int32_t n_fc4, int64_t* o) {
+    if (d < 1 || n_fc3 < 1 || n_fc4 < 1 || !o) return fail(DMFG_ERR_INVALID, "dmfg_rnet_param_offsets: bad argument");
+    const RnetLayout L = rnet_layout(d, n_fc3, n_fc4);
+    o[0] = L.k1; o[1] = L.b1; o[2] = L.k2; o[3] = L.b2; o[4] = L.w3; o[5] = L.b3; o[6] = L.w4; o[7] = L.b4;
+    o[8] = L.w5; o[9] = L.b5;
+    return DMFG_OK;
+}
+
+uint64_t dmfg_rnet_workspace_bytes(const dmfg_rnet_args* a) {
+    if (!a || a->struct_size != sizeof(dmfg_rnet_args) || a->d < 1 || a->n_fc3 < 1 || a->n_fc4 < 1) return 0;
+    if (!a->grad) return 0;
+    return align_up((uint64_t)kMaxRnetCtas * (uint64_t)rnet_layout(a->d, a->n_fc3, a->n_fc4).total * sizeof(float));
+}
+
+int dmfg_rnet_forward(const dmfg_rnet_args* a, void* stream) {
+    if (int rc = check_rnet(a, false)) return rc;
+    if (a->N == 0) return DMFG_OK;
+    int grid = 0;
+    size_t smem = 0;
+    if (int rc = rnet_grid<false>(a, &grid, &smem)) return rc;
+    rnet_kernel<kG, kNP, false><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
+int dmfg_rnet_backward(const dmfg_rnet_args* a, void* stream) {
+    if (int rc = check_rnet(a, true)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int total = rnet_layout(a->d, a->n_fc3, a->n_fc4).total;
+    if (a->N == 0) {
+        if (!a->accumulate) DMFG_CUDA(cudaMemsetAsync(a->grad, 0, (size_t)total * sizeof(float), st));
+        return DMFG_OK;
+    }
+    const uint64_t need = dmfg_rnet_workspace_bytes(a);
+    if (!a->workspace || a->workspace_bytes < need)
+        return fail(DMFG_ERR_WORKSPACE, "workspace of %llu bytes needed, %llu given", (unsigned long long)need,
+                    (unsigned long long)(a->workspace ? a->workspace_bytes : 0));
+    int grid = 0;
+    size_t smem = 0;
+    if (int rc = rnet_grid<true>(a, &grid, &smem)) return rc;
+    RnetParams p = make_params(a);
+    p.partials = (float*)a->workspace;
+    rnet_kernel<kG, kNP, true><<<grid, kRnetThreads, smem, st>>>(p);
+    DMFG_CUDA(cudaGetLastError());
+    rnet_reduce_partials_kernel<<<(total + 127) / 128, 128, 0, st>>>(p.partials, grid, total, a->accumulate, a->grad);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
+uint64_t dmfg_irl_loss_workspace_bytes(int64_t M) {
+    if (M < 0) return 0;
+    return align_up((uint64_t)M * 8) + align_up((uint64_t)kLossBlocks * 2 * 8);
+}
+
+int dmfg_irl_loss_grad(const dmfg_irl_loss_args* a, void* stream) {
+    if (!a) return fail(DMFG_ERR_INVALID, "args is NULL");
+    if (a->struct_size != sizeof(dmfg_irl_loss_args)) return fail(DMFG_ERR_INVALID, "dmfg_irl_loss_args.struct_size mismatch");
+    if (a->T < 1 || a->M < 1 || a->n_demo < 0) return fail(DMFG_ERR_INVALID, "bad T/M/n_demo");
+    if (!a->r_gen || (a->n_demo > 0 && !a->r_demo) || !a->loss_out) return fail(DMFG_ERR_INVALID, "r_demo, r_gen and loss_out are required");
+    if (!(a->num_demo_traj > 0)) return fail(DMFG_ERR_INVALID, "num_demo_traj must be > 0");
+    if (!((a->gen_t_stride == a->M && a->gen_j_stride == 1) || (a->gen_t_stride == 1 && a->gen_j_stride == a->T)))
+        return fail(DMFG_ERR_INVALID, "r_gen strides must be (M,1) time-major or (1,T) trajectory-major");
+    const uint64_t need = dmfg_irl_loss_workspace_bytes(a->M);
+    if (!a->workspace || a->workspace_bytes < need)
+        return fail(DMFG_ERR_WORKSPACE, "workspace of %llu bytes needed", (unsigned long long)need);
+    cudaStream_t st = (cudaStream_t)stream;
+    IrlLossParams p;
+    p.n_demo = a->n_demo; p.M = a->M; p.T = a->T; p.gen_t_stride = a->gen_t_stride; p.gen_j_stride = a->gen_j_stride;
+    p.num_demo_traj = a->num_demo_traj; p.r_demo = a->r_demo; p.r_gen = a->r_gen; p.log_z = a->log_z;
+    p.d_demo = a->d_demo; p.d_gen = a->d_gen;
+    p.traj_e = (double*)a->workspace;
+    p.partials = (double*)((char*)a->workspace + align_up((uint64_t)a->M * 8));
+    p.out = a->loss_out;
+    p.reg_loss_scale = 0.0;
+    const long long work = a->M > a->n_demo ? a->M : a->n_demo;
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > kLossBlocks) blocks = kLossBlocks;
+    if (blocks < 1) blocks = 1;
+    irl_loss_stage1_kernel<<<blocks, 256, 0, st>>>(p);
+    DMFG_CUDA(cudaGetLastError());
+    irl_loss_stage2_kernel<<<1, 32, 0, st>>>(p, blocks);
+    DMFG_CUDA(cudaGetLastError());
+    if (a->d_gen) {
+        long long b3 = (a->M * a->T + 255) / 256;
+        if (b3 > kLossBlocks) b3 = kLossBlocks;
+        irl_loss_stage3_kernel<<<(int)b3, 256, 0, st>>>(p);
+        DMFG_CUDA(cudaGetLastError());
+    }
+    return DMFG_OK;
+}
+
+int dmfg_adam_tf(int64_t n, float* params, float* m, float* v, const float* grad, double grad_scale, int64_t step,
+                 double lr, double beta1, double beta2, double eps, int32_t l1l2, int32_t d, int32_t n_fc3,
+                 int32_t n_fc4, double* reg_loss_out, void* stream) {
+    if (n < 0 || (n > 0 && (!params || !m || !v || !grad))) return fail(DMFG_ERR_INVALID, "dmfg_adam_tf: bad argument");
+    if (step < 1) return fail(DMFG_ERR_INVALID, "dmfg_adam_tf: step counts from 1");
+    if (n > INT32_MAX) return fail(DMFG_ERR_UNSUPPORTED, "dmfg_adam_tf: n too large");
+    int b0, e0, b1, e1;
+    if (l1l2 || reg_loss_out) {
+        if (d < 1 || n_fc3 < 1 || n_fc4 < 1 || rnet_layout(d, n_fc3, n_fc4).total != n)
+            return fail(DMFG_ERR_INVALID, "dmfg_adam_tf: l1l2 needs (d, n_fc3, n_fc4) matching n");
+    }
+    reg_ranges(l1l2 || reg_loss_out, d, n_fc3, n_fc4, &b0, &e0, &b1, &e1);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (reg_loss_out) {
+        reg_loss_kernel<<<1, 256, 0, st>>>(params, b0, e0, b1, e1, reg_loss_out);
+        DMFG_CUDA(cudaGetLastError());
+    }
+    if (!l1l2) b0 = e0 = b1 = e1 = 0;
+    if (n == 0) return DMFG_OK;
+    const double lr_t = lr * std::sqrt(1.0 - std::pow(beta2, (double)step)) / (1.0 - std::pow(beta1, (double)step));
+    adam_tf_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>((int)n, params, m, v, grad, (float)grad_scale, (float)lr_t,
+                                                        (float)beta1, (float)beta2, (float)(1.0 - beta1),
+                                                        (float)(1.0 - beta2), (float)eps, b0, e0, b1, e1);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
+int dmfg_dirichlet_logq(int32_t d, int64_t N, int32_t K, const float* states, const float* actions,
+                        const double* thetas, double shift, double* logq, void* stream) {
+    if (d < 1 || d > DMFG_MAX_D || N < 0 || K < 1) return fail(DMFG_ERR_INVALID, "dmfg_dirichlet_logq: bad d/N/K");
+    if (N > 0 && (!states || !actions || !thetas || !logq)) return fail(DMFG_ERR_INVALID, "dmfg_dirichlet_logq: NULL argument");
+    if (N == 0) return DMFG_OK;
+    const long long warps = N * K;
+    dirichlet_logq_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, (cudaStream_t)stream>>>(d, N, K, states, actions, thetas,
+                                                                                        shift, logq);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
+int dmfg_irl_log_z(int64_t M, int32_t T, int32_t K, int64_t t_stride, int64_t j_stride, const double* logq,
+                   double num_start_samples, float* log_z, void* stream) {
+    if (M < 0 || T < 1 || K < 1 || !(num_start_samples > 0)) return fail(DMFG_ERR_INVALID, "dmfg_irl_log_z: bad argument");
+    if (M > 0 && (!logq || !log_z)) return fail(DMFG_ERR_INVALID, "dmfg_irl_log_z: NULL argument");
+    if (M == 0) return DMFG_OK;
+    irl_log_z_kernel<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(M, T, K, t_stride, j_stride, logq,
+                                                                                  num_start_samples, log_z);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
+}  // extern "C"

@@ -283,3 +283,167 @@ def philox(ctr, key):
     o = (C.c_uint32 * 4)()
     lib.dmfg_philox4x32_10(c, k, o)
     return tuple(int(v) for v in o)
+
+
+# ----------------------------------------------------------------------------- IRL path (a10-a13)
+def rnet_param_count(d, n_fc3, n_fc4):
+    return int(_lib.load().dmfg_rnet_param_count(int(d), int(n_fc3), int(n_fc4)))
+
+
+def rnet_param_offsets(d, n_fc3, n_fc4):
+    """Offsets of conv1/w, conv1/b, conv2/w, conv2/b, fc3/w, fc3/b, fc4/w, fc4/b, out/w, out/b."""
+    o = (C.c_int64 * 10)()
+    check(_lib.load().dmfg_rnet_param_offsets(int(d), int(n_fc3), int(n_fc4), o))
+    return [int(x) for x in o]
+
+
+def _rnet_args(params, states, actions, n_fc3, n_fc4, mask3, mask4, keep_prob, seed, sample_offset):
+    from ._lib import DROPOUT_MASKS, DROPOUT_NONE, DROPOUT_PHILOX, RnetArgs
+    device = states.device
+    N, d = states.shape
+    P = rnet_param_count(d, n_fc3, n_fc4)
+    a = RnetArgs()
+    a.struct_size = C.sizeof(RnetArgs)
+    a.d, a.n_fc3, a.n_fc4, a.N = d, int(n_fc3), int(n_fc4), N
+    a.params = _ptr(_require(params, "params", device, torch.float32, (P,)))
+    a.states = _ptr(_require(states, "states", device, torch.float32, (N, d)))
+    a.actions = _ptr(_require(actions, "actions", device, torch.float32, (N, d, d)))
+    if mask3 is not None or mask4 is not None:
+        a.dropout = DROPOUT_MASKS
+        a.mask3 = _ptr(_require(mask3, "mask3", device, torch.uint8, (N, n_fc3)))
+        a.mask4 = _ptr(_require(mask4, "mask4", device, torch.uint8, (N, n_fc4)))
+    elif seed is not None:
+        a.dropout = DROPOUT_PHILOX
+        a.seed, a.sample_offset = int(seed) & (2 ** 64 - 1), int(sample_offset)
+    else:
+        a.dropout = DROPOUT_NONE
+    a.keep_prob = float(keep_prob)
+    return a, P
+
+
+def rnet_forward(params, states, actions, n_fc3, n_fc4, *, mask3=None, mask4=None, keep_prob=0.4, seed=None,
+                 sample_offset=0, out=None):
+    """r_net(state, action) for N transitions (networks.py:13-157).  states [N,d], actions [N,d,d] float32.
+    Dropout: mask3/mask4 uint8 keep masks (parity), or `seed` for in-kernel Philox masks, or neither."""
+    lib = _lib.load()
+    a, _ = _rnet_args(params, states, actions, n_fc3, n_fc4, mask3, mask4, keep_prob, seed, sample_offset)
+    device = states.device
+    N = states.shape[0]
+    with torch.cuda.device(device):
+        r = out if out is not None else torch.empty(N, dtype=torch.float32, device=device)
+        a.rewards = _ptr(_require(r, "rewards", device, torch.float32, (N,)))
+        check(lib.dmfg_rnet_forward(C.byref(a), _stream_ptr(device)))
+    return r
+
+
+def rnet_backward(params, states, actions, drewards, n_fc3, n_fc4, *, grad=None, accumulate=False, mask3=None,
+                  mask4=None, keep_prob=0.4, seed=None, sample_offset=0, want_rewards=False):
+    """Flat gradient of sum_n drewards[n]*r[n] w.r.t. the parameters (forward recomputed in-kernel)."""
+    lib = _lib.load()
+    a, P = _rnet_args(params, states, actions, n_fc3, n_fc4, mask3, mask4, keep_prob, seed, sample_offset)
+    device = states.device
+    N = states.shape[0]
+    with torch.cuda.device(device):
+        if grad is None:
+            grad = torch.zeros(P, dtype=torch.float32, device=device)
+        a.grad = _ptr(_require(grad, "grad", device, torch.float32, (P,)))
+        a.drewards = _ptr(_require(drewards, "drewards", device, torch.float32, (N,)))
+        a.accumulate = 1 if accumulate else 0
+        r = None
+        if want_rewards:
+            r = torch.empty(N, dtype=torch.float32, device=device)
+            a.rewards = _ptr(r)
+        ws = _workspace(device, lib.dmfg_rnet_workspace_bytes(C.byref(a)))
+        if ws is not None:
+            a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        check(lib.dmfg_rnet_backward(C.byref(a), _stream_ptr(device)))
+    return (grad, r) if want_rewards else grad
+
+
+def irl_loss_grad(r_demo, r_gen, T, num_demo_traj, *, layout="time_major", log_z=None, want_grads=True):
+    """IRL loss terms and dL/dr (ac_irl.py:390-406).  r_gen holds M*T rewards, time-major [T,M] (rollout
+    record) or trajectory-major [M,T] (the reference's feed).  Returns dict(loss [4] float64 device =
+    {first+second, first, second, sum_j z_j e^{R_j}}, d_demo, d_gen)."""
+    from ._lib import IrlLossArgs
+    lib = _lib.load()
+    device = r_gen.device
+    n_gen = r_gen.numel()
+    M = n_gen // int(T)
+    if M * int(T) != n_gen:
+        raise ValueError("r_gen has %d elements, not a multiple of T=%d" % (n_gen, T))
+    a = IrlLossArgs()
+    a.struct_size = C.sizeof(IrlLossArgs)
+    a.T, a.n_demo, a.M = int(T), r_demo.numel(), M
+    if layout == "time_major":
+        a.gen_t_stride, a.gen_j_stride = M, 1
+    elif layout == "trajectory_major":
+        a.gen_t_stride, a.gen_j_stride = 1, int(T)
+    else:
+        raise ValueError("layout must be 'time_major' or 'trajectory_major'")
+    a.num_demo_traj = float(num_demo_traj)
+    a.r_demo = _ptr(_require(r_demo, "r_demo", device, torch.float32, tuple(r_demo.shape)))
+    a.r_gen = _ptr(_require(r_gen, "r_gen", device, torch.float32, tuple(r_gen.shape)))
+    if log_z is not None:
+        a.log_z = _ptr(_require(log_z, "log_z", device, torch.float32, (M,)))
+    res = {}
+    with torch.cuda.device(device):
+        res["loss"] = torch.empty(4, dtype=torch.float64, device=device)
+        a.loss_out = _ptr(res["loss"])
+        if want_grads:
+            res["d_demo"] = torch.empty_like(r_demo)
+            res["d_gen"] = torch.empty_like(r_gen)
+            a.d_demo, a.d_gen = _ptr(res["d_demo"]), _ptr(res["d_gen"])
+        ws = _workspace(device, lib.dmfg_irl_loss_workspace_bytes(M))
+        a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        check(lib.dmfg_irl_loss_grad(C.byref(a), _stream_ptr(device)))
+    return res
+
+
+def adam_tf(params, m, v, grad, step, lr, *, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, l1l2=False,
+            net=None, want_reg_loss=False):
+    """One TF-style Adam step in place (ac_irl.py:417-418); net=(d,n_fc3,n_fc4) is needed for l1l2."""
+    lib = _lib.load()
+    device = params.device
+    n = params.numel()
+    for name, t in (("params", params), ("m", m), ("v", v), ("grad", grad)):
+        _require(t, name, device, torch.float32, (n,))
+    d, n3, n4 = net if net is not None else (0, 0, 0)
+    reg = None
+    with torch.cuda.device(device):
+        if want_reg_loss:
+            reg = torch.empty(1, dtype=torch.float64, device=device)
+        check(lib.dmfg_adam_tf(n, _ptr(params), _ptr(m), _ptr(v), _ptr(grad), float(grad_scale), int(step), float(lr),
+                               float(beta1), float(beta2), float(eps), 1 if l1l2 else 0, int(d), int(n3), int(n4),
+                               _ptr(reg), _stream_ptr(device)))
+    return reg
+
+
+def dirichlet_logq(states, actions, thetas, shift):
+    """logq[n,k] = sum_i ln Dir(a_n[i,:]; max(alpha_{theta_k}(s_n)[i,:], 1+1e-6))  (ac_irl.py:344-361)."""
+    lib = _lib.load()
+    device = states.device
+    N, d = states.shape
+    K = thetas.numel()
+    _require(states, "states", device, torch.float32, (N, d))
+    _require(actions, "actions", device, torch.float32, (N, d, d))
+    _require(thetas, "thetas", device, torch.float64, (K,))
+    with torch.cuda.device(device):
+        out = torch.empty((N, K), dtype=torch.float64, device=device)
+        check(lib.dmfg_dirichlet_logq(d, N, K, _ptr(states), _ptr(actions), _ptr(thetas), float(shift), _ptr(out),
+                                      _stream_ptr(device)))
+    return out
+
+
+def irl_log_z(logq, T, num_start_samples, layout="time_major"):
+    """ln z_j (ac_irl.py:377-379) from per-transition logq [M*T, K]."""
+    lib = _lib.load()
+    device = logq.device
+    NT, K = logq.shape
+    M = NT // int(T)
+    ts, js = (M, 1) if layout == "time_major" else (1, int(T))
+    _require(logq, "logq", device, torch.float64, (NT, K))
+    with torch.cuda.device(device):
+        out = torch.empty(M, dtype=torch.float32, device=device)
+        check(lib.dmfg_irl_log_z(M, int(T), K, ts, js, _ptr(logq), float(num_start_samples), _ptr(out),
+                                 _stream_ptr(device)))
+    return out

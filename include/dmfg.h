@@ -221,6 +221,99 @@ int dmfg_ac_learners(const dmfg_learners_args* args, void* stream);
  * and synchronises `stream` before returning.  workspace is ignored.       */
 int dmfg_rollout_host(const dmfg_rollout_args* args_with_host_pointers, void* stream);
 
+/* ---- a10: reward network r_net(state, action) ----------------------------- *
+ * networks.py:13-157 (r_net, r_net_dropout, r_net_l1l2, r_net_dropout_l1l2) as
+ * instantiated by AC_IRL.create_network (ac_irl.py:232-267: f1=1, k1=5, f2=2,
+ * k2=3): conv5x5+ReLU -> conv3x3(2ch)+ReLU -> NHWC flatten -> fc3+ReLU [dropout]
+ * -> concat state -> fc4+ReLU [dropout] -> out+tanh.   float32 like the TF graph
+ * (ac_irl.py:239-246).  Parameters are ONE flat vector in TF variable order:
+ *   conv1/weights[5,5,1,1] conv1/biases[1] conv2/weights[3,3,1,2] conv2/biases[2]
+ *   fc3/weights[2d^2,n3] fc3/biases[n3] fc4/weights[n3+d,n4] fc4/biases[n4]
+ *   out/weights[n4,1] out/biases[1]
+ * Transitions are rows of states [N][d] / actions [N][d][d]; a time-major rollout
+ * record [T][B].. is such an array with N = T*B.  Built for d <= 16, n3,n4 <= 8. */
+#define DMFG_DROPOUT_NONE   0   /* reg = 'none' | 'l1l2'                                       */
+#define DMFG_DROPOUT_MASKS  1   /* caller supplies 0/1 keep masks (parity)                     */
+#define DMFG_DROPOUT_PHILOX 2   /* in-kernel Philox keep masks keyed by (seed, sample_offset+n) */
+
+int64_t dmfg_rnet_param_count(int32_t d, int32_t n_fc3, int32_t n_fc4);
+/* offsets[10] of the ten tensors above inside the flat vector */
+int dmfg_rnet_param_offsets(int32_t d, int32_t n_fc3, int32_t n_fc4, int64_t* offsets10);
+
+typedef struct dmfg_rnet_args {
+    uint32_t struct_size;
+    int32_t  d, n_fc3, n_fc4;
+    int64_t  N;                   /* transitions */
+    const float* params;          /* [dmfg_rnet_param_count] */
+    const float* states;          /* [N][d] */
+    const float* actions;         /* [N][d][d] */
+    int32_t  dropout;             /* DMFG_DROPOUT_* */
+    float    keep_prob;           /* 0.4 in the reference (networks.py:70,75) */
+    const uint8_t* mask3;         /* [N][n_fc3] keep masks (MASKS) */
+    const uint8_t* mask4;         /* [N][n_fc4] */
+    uint64_t seed;                /* PHILOX */
+    uint64_t sample_offset;       /* PHILOX: global id of transition 0 */
+    float*   rewards;             /* [N] out (forward: required; backward: optional) */
+    /* backward only */
+    const float* drewards;        /* [N] dL/dr */
+    float*   grad;                /* [param_count] dL/dparams */
+    int32_t  accumulate;          /* 0: grad is overwritten, 1: added to */
+    int32_t  reserved;
+    void*    workspace;           /* backward: per-CTA partial gradients */
+    uint64_t workspace_bytes;     /* >= dmfg_rnet_workspace_bytes(args) */
+} dmfg_rnet_args;
+uint64_t dmfg_rnet_workspace_bytes(const dmfg_rnet_args* args);
+/* sess.run(reward_gen / reward_demo) (ac_irl.py:683,882) */
+int dmfg_rnet_forward(const dmfg_rnet_args* args, void* stream);
+/* d(sum_n drewards[n] * r[n]) / dparams: the reward-net part of optimizer.minimize (ac_irl.py:417-418) */
+int dmfg_rnet_backward(const dmfg_rnet_args* args, void* stream);
+
+/* ---- a11: MaxEnt IRL loss and its derivative w.r.t. the rewards ----------- *
+ * create_training_method (ac_irl.py:382-413):
+ *   first  = -(1/num_demo_traj) * sum(r_demo)
+ *   second = ln((1/M) * sum_j z_j * exp(sum_t r_gen[j,t]))     (z_j = 1 when log_z == NULL, as upstream :406)
+ * r_gen[j,t] lives at r_gen[t*gen_t_stride + j*gen_j_stride] (time-major record: (M,1); the reference's
+ * trajectory-major feed: (1,T)); d_gen uses the same indexing.
+ * loss_out[4] (double, device) = {first+second, first, second, sum_j z_j exp(R_j)}.   */
+typedef struct dmfg_irl_loss_args {
+    uint32_t struct_size;
+    int32_t  T;
+    int64_t  n_demo;              /* demo transitions */
+    int64_t  M;                   /* generated trajectories */
+    int64_t  gen_t_stride, gen_j_stride;
+    double   num_demo_traj;       /* quirk: the demo sum is divided by TRAJECTORIES (ac_irl.py:390) */
+    const float* r_demo;          /* [n_demo] */
+    const float* r_gen;           /* [M*T] */
+    const float* log_z;           /* [M] or NULL */
+    float*   d_demo;              /* [n_demo] out, optional */
+    float*   d_gen;               /* [M*T] out, optional */
+    double*  loss_out;            /* [4] out */
+    void*    workspace;
+    uint64_t workspace_bytes;     /* >= dmfg_irl_loss_workspace_bytes(M) */
+} dmfg_irl_loss_args;
+uint64_t dmfg_irl_loss_workspace_bytes(int64_t M);
+int dmfg_irl_loss_grad(const dmfg_irl_loss_args* args, void* stream);
+
+/* ---- a11: one TF-style Adam step on the flat parameter vector -------------- *
+ * tf.train.AdamOptimizer(lr).minimize (ac_irl.py:417-418): step counts from 1,
+ * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t), p -= lr_t*m/(sqrt(v)+eps).  With l1l2 != 0
+ * the gradient of l1_l2_regularizer() (sum|w| + sum w^2/2, networks.py:69,74) on the fc3
+ * and fc4 weight ranges of an r_net(d,n3,n4) vector is added; reg_loss_out (optional,
+ * device double) receives the regulariser value BEFORE the step.  grad_scale multiplies
+ * grad first (1/world for a data-parallel mean).                                  */
+int dmfg_adam_tf(int64_t n, float* params, float* m, float* v, const float* grad, double grad_scale,
+                 int64_t step, double lr, double beta1, double beta2, double eps,
+                 int32_t l1l2, int32_t d, int32_t n_fc3, int32_t n_fc4, double* reg_loss_out, void* stream);
+
+/* ---- a13: Dirichlet log-density of recorded actions under K policies ------ *
+ * calc_pdf_action / calc_z (ac_irl.py:270-379), in log space and without the `c`
+ * normaliser: logq[n][k] = sum_i ln Dir(a_n[i,:]; max(alpha_{theta_k}(s_n)[i,:], 1+1e-6)).  */
+int dmfg_dirichlet_logq(int32_t d, int64_t N, int32_t K, const float* states, const float* actions,
+                        const double* thetas, double shift, double* logq, void* stream);
+/* ln z_j = ln K - ln num_start - logsumexp_k sum_t logq[t*t_stride + j*j_stride][k]   (ac_irl.py:377-379) */
+int dmfg_irl_log_z(int64_t M, int32_t T, int32_t K, int64_t t_stride, int64_t j_stride, const double* logq,
+                   double num_start_samples, float* log_z, void* stream);
+
 /* ---- testing aids: direct access to the device math ---------------------- */
 /* Philox4x32-10 on the host (same code the kernels run): out[4] = philox(ctr[4], key[2]) */
 void dmfg_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out);
