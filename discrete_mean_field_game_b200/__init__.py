@@ -9,5 +9,5 @@ underneath: hand-written sm_100a kernels behind the C ABI of include/dmfg.h
 """
 from . import _lib  # noqa: F401
 
-__all__ = ["_lib", "engine", "mfg_ac2"]
+__all__ = ["_lib", "engine", "mfg_ac2", "ac_irl", "networks", "layers"]
 __version__ = "0.1.0"

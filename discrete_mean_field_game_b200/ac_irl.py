@@ -1,0 +1,484 @@
+"""Drop-in for the reference's ``ac_irl.AC_IRL`` (ac_irl.py:31-954) on B200: maximum-entropy IRL
+(guided-cost-learning style) with the forward actor-critic in the loop.
+
+Same constructor, method names, argument order and attributes as the reference.  The numeric work
+runs on the GPU through libdmfg (include/dmfg.h): ``dmfg_rollout`` (sample_action, P^T pi,
+gradient), ``dmfg_rnet_forward/backward`` (networks.r_net*), ``dmfg_irl_loss_grad`` (the loss of
+create_training_method), ``dmfg_adam_tf`` (AdamOptimizer.minimize), ``dmfg_td_accumulate`` +
+``dmfg_ac_apply_update`` (TD error and the w / theta updates), ``dmfg_dirichlet_logq`` (calc_z).
+
+Differences, on purpose:
+  * data can be given in memory (``mat_pi0=``, ``mat_pi0_test=``, ``demonstrations=``, ...) instead of
+    being read from ``./train_normalized_round2`` etc.; the file readers are kept (and work on Linux:
+    upstream needs pandas behind a Windows-only import, ac_irl.py:16-22,186);
+  * noise is an explicit Philox key (``seed``), not the global NumPy / TF state;
+  * ``use_z=True`` turns on the importance weights z_j that upstream implements but leaves commented
+    out (ac_irl.py:404-405), evaluated in log space (no ``c`` normaliser needed);
+  * ``update_reward_batch`` / ``generate_batch`` are the batched device-resident versions of
+    update_reward / generate_trajectories (thousands of trajectories per update).
+There is no TensorFlow: ``self.sess.run(fetches, feed_dict)`` is a small shim that evaluates the
+reward net for the fed arrays (what test_acirl.py:60-70 and train() at :683 do).
+"""
+from __future__ import annotations
+
+import math
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import engine, networks
+from .mfg_ac2 import actor_critic as _actor_critic
+from .networks import Placeholder
+
+T_STEPS = 15          # ac_irl.py:664,749
+
+
+class Session:
+    """Just enough of tf.Session for the reference's call sites: run(fetch | [fetches], feed_dict)."""
+
+    def __init__(self, owner):
+        self.owner = owner
+
+    def run(self, fetches, feed_dict=None):
+        single = not isinstance(fetches, (list, tuple))
+        outs = [self.owner._fetch(f, feed_dict or {}) for f in ([fetches] if single else fetches)]
+        return outs[0] if single else outs
+
+
+class AC_IRL(_actor_critic):
+    reward_kind = "none"              # the reward is the network (ac_irl.py:683)
+    discount_kind = "cumulative"      # ac_irl.py:691 multiplies V(s') by the running discount
+    first_episode = 1                 # ac_irl.py:649
+
+    def __init__(self, theta=8.64, shift=0, alpha_scale=1e4, d=15, lr_reward=1e-4, num_policies=10, c=2e11,
+                 reg='dropout_l1l2', n_fc3=8, n_fc4=4, saved_network=None, use_tf=True, summarize=False,
+                 mat_pi0=None, mat_pi0_test=None, demonstrations=None, demonstrations_test=None,
+                 device=None, seed=None, net_seed=None, use_z=False):
+        """reg - 'none', 'dropout', 'l1l2', 'dropout_l1l2'; use_tf=False skips the reward net (ac_irl.py:33-37).
+        In-memory data: mat_pi0 [n,d], demonstrations = list of trajectories, each a list of 15
+        (state[d], action[d,d]) pairs -- the structure read_demonstrations returns."""
+        engine.require_cuda()
+        self.summarize = summarize
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.dtype = torch.float32                       # the TF graph is float32 (ac_irl.py:239-246)
+        self.theta = theta
+        self.theta_initial = theta
+        self.shift = shift
+        self.alpha_scale = alpha_scale
+        self.w = self.init_w(d)
+        self.d = d
+        self.lr_reward = lr_reward
+        self.num_policies = num_policies
+        self.c = c
+        if reg not in ('none', 'dropout', 'l1l2', 'dropout_l1l2'):
+            raise ValueError("reg must be 'none', 'dropout', 'l1l2' or 'dropout_l1l2'")
+        self.reg = reg
+        self.n_fc3 = n_fc3
+        self.n_fc4 = n_fc4
+        self.use_z = bool(use_z)
+        self.seed = int(np.random.randint(2 ** 31 - 1)) if seed is None else int(seed)
+        self.net_seed = net_seed
+        self._draws = 0
+        self._episodes = 0
+        self._dropout_calls = 0
+        self.mat_alpha = np.zeros([d, d])
+        self.mat_alpha_deriv = np.zeros([d, d])
+
+        cwd = os.getcwd()
+        if mat_pi0 is not None:
+            self.mat_pi0 = np.array(mat_pi0, dtype=np.float64)[:, :d].copy()
+        else:
+            self.init_pi0(path_to_dir=cwd + '/train_normalized_round2')
+        self.num_start_samples = self.mat_pi0.shape[0]
+        if mat_pi0_test is not None:
+            self.mat_pi0_test = np.array(mat_pi0_test, dtype=np.float64)[:, :d].copy()
+        elif mat_pi0 is None:
+            self.init_pi0_test(path_to_dir=cwd + '/test_normalized_round2', day_start=22)
+        else:
+            self.mat_pi0_test = self.mat_pi0.copy()
+        self.num_start_samples_test = self.mat_pi0_test.shape[0]
+
+        if demonstrations is not None:
+            self.list_demonstrations = list(demonstrations)
+        elif mat_pi0 is None:
+            self.list_demonstrations = self.read_demonstrations(state_dir='./train_normalized_round2',
+                                                                action_dir='./actions_2', dim_action=20, start_day=1)
+        else:
+            self.list_demonstrations = []
+        if demonstrations_test is not None:
+            self.list_demonstrations_test = list(demonstrations_test)
+        elif mat_pi0 is None:
+            self.list_demonstrations_test = self.read_demonstrations(state_dir='./test_normalized_round2',
+                                                                     action_dir='./actions_test_2', dim_action=20,
+                                                                     start_day=22)
+        else:
+            self.list_demonstrations_test = []
+        self.list_eval_demo_transitions = [pair for traj in self.list_demonstrations for pair in traj]
+        self.list_generated = []
+        self.list_eval_gen_transitions = []
+
+        if use_tf:
+            self.create_network()
+        self.num_demo_samples = 5
+        self.num_gen_samples = 5
+        self.num_sampled_trajectories = self.num_gen_samples
+        self.list_policies = [theta] * self.num_policies
+        self.reward_update_count = 0
+        self.loss_val = self.first_term_val = self.second_term_val = float("nan")
+        if use_tf:
+            self.create_training_method()
+            self.sess = Session(self)
+            if saved_network:
+                self.restore("saved/" + saved_network)
+
+    # ------------------------------------------------------------- file formats
+    def init_pi0_test(self, path_to_dir, day_start=22, verbose=0):
+        """First line of trend_distribution_day<k>.csv for k = day_start.. (ac_irl.py:477-506)."""
+        rows = []
+        for k in range(day_start, day_start + len(os.listdir(path_to_dir))):
+            name = "trend_distribution_day%d.csv" % k
+            with open(os.path.join(path_to_dir, name)) as f:
+                rows.append([float(v) for v in f.readline().split()][: self.d])
+            if verbose:
+                print(name)
+        self.mat_pi0_test = np.array(rows, dtype=np.float64)
+
+    def read_demonstrations(self, state_dir, action_dir, dim_action=20, start_day=1):
+        """List of trajectories, each 15 (state[d], action[d,d]) pairs (ac_irl.py:164-200).
+        trend_distribution_day<k>.csv: 16 space-separated rows; action_day<k>.txt: 15 blocks of
+        dim_action rows (blank lines between blocks are skipped), top-left d x d is used."""
+        print("Inside read_demonstrations")
+        num_file_action = len(os.listdir(action_dir))
+        if num_file_action != len(os.listdir(state_dir)):
+            print("Weird")
+        out = []
+        for idx_day in range(start_day, start_day + num_file_action):
+            states = np.loadtxt(os.path.join(state_dir, "trend_distribution_day%d.csv" % idx_day), ndmin=2)
+            actions = np.loadtxt(os.path.join(action_dir, "action_day%d.txt" % idx_day), ndmin=2)
+            traj = []
+            for hour in range(T_STEPS):
+                state = states[hour, 0:self.d]
+                action = actions[hour * dim_action:(hour * dim_action + self.d), 0:self.d]
+                traj.append((state, action))
+            out.append(traj)
+        return out
+
+    def get_eval_transitions(self, list_trajectories):
+        """One (s, a) per trajectory: index idx mod 15 (ac_irl.py:203-218)."""
+        return [traj[idx % T_STEPS] for idx, traj in enumerate(list_trajectories)]
+
+    # ------------------------------------------------------------- reward net
+    def create_network(self):
+        """Reward net on demo and generated placeholders with SHARED variables (ac_irl.py:232-267)."""
+        print("Inside create_network")
+        self.demo_actions = Placeholder('demo_actions', [None, self.d, self.d])
+        self.demo_states = Placeholder('demo_states', [None, self.d])
+        self.gen_actions = Placeholder('gen_actions', [None, self.d, self.d])
+        self.gen_states = Placeholder('gen_states', [None, self.d])
+        fn = {'none': networks.r_net, 'dropout': networks.r_net_dropout, 'l1l2': networks.r_net_l1l2,
+              'dropout_l1l2': networks.r_net_dropout_l1l2}[self.reg]
+        networks._scopes.pop("reward", None)             # a fresh variable set per instance
+        with networks.variable_scope("reward", device=self.device, seed=self.net_seed):
+            self.reward_demo = fn(self.demo_states, self.demo_actions, f1=1, k1=5, f2=2, k2=3,
+                                  n_fc3=self.n_fc3, n_fc4=self.n_fc4, d=self.d)
+            self.reward_gen = fn(self.gen_states, self.gen_actions, f1=1, k1=5, f2=2, k2=3,
+                                 n_fc3=self.n_fc3, n_fc4=self.n_fc4, d=self.d)
+        self.reward_params = self.reward_demo.params
+        assert self.reward_gen.params is self.reward_params
+
+    def create_training_method(self):
+        """Loss = -1/N sum r_demo + ln(1/M sum_j [z_j] exp(sum_t r_gen[j,t])) [+ l1l2], Adam(lr_reward)
+        (ac_irl.py:382-426).  Nothing to build here beyond the optimiser state."""
+        print("Inside create_training_method")
+        self._dropout = self.reg in ('dropout', 'dropout_l1l2')
+        self._l1l2 = self.reg in ('l1l2', 'dropout_l1l2')
+        self.reward_params.m.zero_()
+        self.reward_params.v.zero_()
+        self.reward_params.step = 0
+
+    def _next_dropout_offset(self, n):
+        """Distinct Philox sample ids for every reward-net evaluation (TF draws fresh masks per run)."""
+        off = self._dropout_calls
+        self._dropout_calls += int(n)
+        return off
+
+    def _reward(self, states, actions):
+        """reward net on device tensors states [N,d], actions [N,d,d] -> [N]; dropout always active
+        for the dropout variants (quirk C.8)."""
+        p = self.reward_params
+        kw = {}
+        if self._dropout:
+            kw = dict(seed=self.seed ^ 0x5DEECE66D, sample_offset=self._next_dropout_offset(states.shape[0]))
+        return engine.rnet_forward(p.flat, states, actions, p.n_fc3, p.n_fc4, keep_prob=networks.KEEP_PROB, **kw)
+
+    def _fetch(self, fetch, feed):
+        if fetch is self.reward_gen:
+            s, a = feed[self.gen_states], feed[self.gen_actions]
+        elif fetch is self.reward_demo:
+            s, a = feed[self.demo_states], feed[self.demo_actions]
+        else:
+            raise KeyError("unknown fetch %r: this shim evaluates reward_demo / reward_gen only" % (fetch,))
+        s = self._dev(np.asarray(s, dtype=np.float32).reshape(-1, self.d), torch.float32)
+        a = self._dev(np.asarray(a, dtype=np.float32).reshape(-1, self.d, self.d), torch.float32)
+        return self._reward(s, a).cpu().numpy().reshape(-1, 1)
+
+    def save(self, path):
+        """Reward-net checkpoint (stands in for tf.train.Saver.save, ac_irl.py:948): an .npz of the
+        named tensors reward/{conv1,conv2,fc3,fc4,out}/{weights,biases} plus the Adam state."""
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        p = self.reward_params
+        tensors = {"reward/" + k: v for k, v in p.named().items()}
+        np.savez(path, adam_m=p.m.cpu().numpy(), adam_v=p.v.cpu().numpy(), adam_step=p.step, **tensors)
+
+    def restore(self, path):
+        if not path.endswith(".npz"):
+            path = path + ".npz"
+        z = np.load(path)
+        p = self.reward_params
+        p.load_named({k[len("reward/"):]: z[k] for k in z.files if k.startswith("reward/")})
+        if "adam_m" in z.files:
+            p.m.copy_(torch.as_tensor(z["adam_m"], device=p.device))
+            p.v.copy_(torch.as_tensor(z["adam_v"], device=p.device))
+            p.step = int(z["adam_step"])
+
+    # ------------------------------------------------------------- policy pieces
+    def calc_alpha_deriv(self, pi):
+        """mat_alpha_deriv = x / (1 + exp(-theta x)), x = pi_j - pi_i - shift (ac_irl.py:573-588)."""
+        pi = np.asarray(pi, dtype=np.float64).reshape(1, self.d)
+        dummy = self._dev(np.full((1, 1, self.d, self.d), 1.0 / self.d))
+        out = engine.rollout(self._dev(pi), self.theta, self.shift, self.alpha_scale, 1, reward="none",
+                             actions_in=dummy, outputs=("alpha", "alpha_deriv"))
+        self.mat_alpha_deriv = out["alpha_deriv"][0, 0].double().cpu().numpy()
+
+    # ------------------------------------------------------------- a8: forward solve with the learned reward
+    def train(self, max_episodes=4000, stop_criteria=0.01, gamma=1, constant=False, lr_critic=0.1, lr_actor=0.001,
+              consecutive=100, file_theta='results/theta.csv', file_pi='results/pi.csv',
+              file_reward='results/reward.csv', write_file=0, write_all=0, start_rows=None, noise_y=None,
+              verbose=True):
+        """Actor-critic with r = r_net(pi, P), per-step online updates of w then theta (ac_irl.py:634-732).
+
+        One serial learner: every transition is a dmfg_rollout (sample P, pi', gradient) -> dmfg_rnet_forward
+        -> dmfg_td_accumulate -> dmfg_ac_apply_update chain on the device; theta is read back once per
+        episode only when stop_criteria != -1.  ``start_rows`` [E] / ``noise_y`` [E,15,d,d] replay draws."""
+        if write_all:
+            raise NotImplementedError("write_all (dump of every P to temp.csv) is not supported")
+        if verbose:
+            print("----- Starting train -----")
+        d, T = self.d, T_STEPS
+        theta = torch.tensor([float(self.theta)], dtype=torch.float64, device=self.device)
+        w = self._w_dev().clone()
+        mat = self._dev(self.mat_pi0)
+        list_reward = []
+        prev_theta = float(self.theta)
+        episode = 0
+        for episode in range(1, max_episodes + 1):
+            if start_rows is not None:
+                row = int(start_rows[episode - 1])
+            else:
+                row = self._philox_randint(self._episodes + episode, self.num_start_samples)
+            pi = mat[row:row + 1].contiguous()
+            lr_c = lr_critic if constant else lr_critic / (episode + 1.0)
+            lr_a = lr_actor if constant else lr_actor / ((episode + 1.0) * math.log(math.log(episode + 20.0)))
+            disc = 1.0
+            total = torch.zeros((), dtype=torch.float64, device=self.device)
+            for t in range(T):
+                noise = None if noise_y is None else self._dev(np.asarray(noise_y[episode - 1][t]).reshape(1, 1, d, d))
+                out = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, 1, theta_dev=theta, reward="none",
+                                     noise_y=noise, seed=self.seed, step_offset=(self._episodes + episode) * T + t,
+                                     outputs=("states", "actions", "grads"))
+                r = self._reward(out["states"][0], out["actions"][0])
+                td = engine.td_accumulate(out["states"], r.reshape(1, 1), out["grads"], w, gamma=disc,
+                                          discount="step", want_deltas=False)
+                engine.apply_update(d, theta, w, td["acc"], lr_c, lr_a, 1.0)
+                total = total + td["acc"][-1]
+                disc *= gamma
+                pi = out["states"][1]
+            list_reward.append(total)
+            if episode % consecutive == 0:
+                self.theta = float(theta[0])
+                pi_host = pi[0].double().cpu().numpy()
+                reward_avg = float(torch.stack(list_reward).sum()) / consecutive
+                if verbose:
+                    print("Theta\n", self.theta)
+                    print("pi\n", pi_host)
+                    print("Average reward during previous %d episodes: " % consecutive, str(reward_avg))
+                list_reward = []
+                if write_file:
+                    self.train_log(np.array([self.theta]), file_theta, "%.5e")
+                    self.train_log(pi_host, file_pi, "%.3e")
+                    self.train_log(np.array([reward_avg]), file_reward, "%.3e")
+            if stop_criteria != -1:
+                cur = float(theta[0])
+                if abs(cur - prev_theta) < stop_criteria:
+                    break
+                prev_theta = cur
+        self.theta = float(theta[0])
+        self.w = w.cpu().numpy().reshape(-1, 1)
+        self._episodes += max_episodes
+        self.list_policies = (self.list_policies + [self.theta])[1:]                    # ac_irl.py:731
+        if verbose:
+            print("----- Exiting train at episode %d with theta %f -----" % (episode, self.theta))
+
+    def _philox_randint(self, counter, n):
+        w0 = engine.philox((0, 0, counter & 0xFFFFFFFF, 0xC0000000), (self.seed & 0xFFFFFFFF, self.seed >> 32))[0]
+        return (w0 * n) >> 32
+
+    # ------------------------------------------------------------- a9: sampling from the current policy
+    def generate_batch(self, n, from_test=False, theta=None):
+        """n trajectories from the current policy in ONE launch; returns device tensors
+        states [16,n,d], actions [15,n,d,d] (time-major record)."""
+        mat = self.mat_pi0_test if from_test else self.mat_pi0
+        rows = [self._philox_randint((1 << 20) + self._draws + i, mat.shape[0]) for i in range(n)]
+        pi0 = self._dev(mat[rows])
+        out = engine.rollout(pi0, self.theta if theta is None else theta, self.shift, self.alpha_scale, T_STEPS,
+                             reward="none", seed=self.seed, pop_offset=(1 << 32) + self._draws,
+                             outputs=("states", "actions"))
+        self._draws += n
+        return out["states"], out["actions"]
+
+    def generate_trajectories(self, n, from_test=False):
+        """List of n trajectories, each a list of 15 (state, action) tuples (ac_irl.py:735-767)."""
+        print("Inside generate_trajectories")
+        states, actions = self.generate_batch(n, from_test)
+        S = states.double().cpu().numpy()
+        A = actions.double().cpu().numpy()
+        return [[(S[t, j], A[t, j]) for t in range(T_STEPS)] for j in range(n)]
+
+    # ------------------------------------------------------------- a11/a12: reward update
+    def _pack(self, trajectories):
+        """list of trajectories -> trajectory-major device tensors states [n*15,d], actions [n*15,d,d]."""
+        s = np.asarray([pair[0] for traj in trajectories for pair in traj], dtype=np.float32).reshape(-1, self.d)
+        a = np.asarray([pair[1] for traj in trajectories for pair in traj], dtype=np.float32).reshape(-1, self.d, self.d)
+        return self._dev(s, torch.float32), self._dev(a, torch.float32)
+
+    def update_reward_batch(self, demo_states, demo_actions, gen_states, gen_actions, num_demo_traj, layout,
+                            group=None, masks=None):
+        """One gradient step on the reward net from device tensors (the kernel chain of update_reward):
+        forward demo + gen -> loss and dL/dr -> backward demo + gen -> (all-reduce) -> Adam.
+        gen_* hold M*15 transitions, `layout` 'time_major' | 'trajectory_major'.  Returns loss [4] (device)."""
+        import torch.distributed as dist
+        p = self.reward_params
+        kd, kg = {}, {}
+        if masks is not None:
+            kd = dict(mask3=masks["demo3"], mask4=masks["demo4"])
+            kg = dict(mask3=masks["gen3"], mask4=masks["gen4"])
+        elif self._dropout:
+            key = self.seed ^ 0x5DEECE66D
+            kd = dict(seed=key, sample_offset=self._next_dropout_offset(demo_states.shape[0]))
+            kg = dict(seed=key, sample_offset=self._next_dropout_offset(gen_states.shape[0]))
+        r_demo = engine.rnet_forward(p.flat, demo_states, demo_actions, p.n_fc3, p.n_fc4, keep_prob=networks.KEEP_PROB, **kd)
+        r_gen = engine.rnet_forward(p.flat, gen_states, gen_actions, p.n_fc3, p.n_fc4, keep_prob=networks.KEEP_PROB, **kg)
+        log_z = None
+        if self.use_z:
+            thetas = torch.as_tensor(np.asarray(self.list_policies, dtype=np.float64), device=self.device)
+            lq = engine.dirichlet_logq(gen_states, gen_actions, thetas, self.shift)
+            log_z = engine.irl_log_z(lq, T_STEPS, self.num_start_samples, layout=layout)
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized() and group is not False) else 1
+        res = engine.irl_loss_grad(r_demo, r_gen, T_STEPS, num_demo_traj, layout=layout, log_z=log_z)
+        grad = engine.rnet_backward(p.flat, demo_states, demo_actions, res["d_demo"], p.n_fc3, p.n_fc4,
+                                    keep_prob=networks.KEEP_PROB, **kd)
+        engine.rnet_backward(p.flat, gen_states, gen_actions, res["d_gen"], p.n_fc3, p.n_fc4, grad=grad,
+                             accumulate=True, keep_prob=networks.KEEP_PROB, **kg)
+        if world > 1:
+            dist.all_reduce(grad, group=group)
+        p.step += 1
+        reg = engine.adam_tf(p.flat, p.m, p.v, grad, p.step, self.lr_reward, grad_scale=1.0 / world,
+                             l1l2=self._l1l2, net=(p.d, p.n_fc3, p.n_fc4), want_reg_loss=self._l1l2)
+        loss = res["loss"]
+        if reg is not None:
+            loss = loss.clone()
+            loss[0] += reg[0]
+        self._last_grad = grad
+        return loss
+
+    def update_reward(self, summary=False, iteration=0):
+        """Sample 5 demo + 5 generated trajectories, one Adam step on the reward net (ac_irl.py:804-846)."""
+        if len(self.list_demonstrations) >= self.num_demo_samples:
+            demo_sampled = random.sample(self.list_demonstrations, self.num_demo_samples)
+        else:
+            demo_sampled = self.list_demonstrations[:]
+        if len(self.list_generated) >= self.num_gen_samples:
+            gen_sampled = random.sample(self.list_generated, self.num_gen_samples)
+        else:
+            gen_sampled = self.list_generated[:]
+        ds, da = self._pack(demo_sampled)
+        gs, ga = self._pack(gen_sampled)
+        loss = self.update_reward_batch(ds, da, gs, ga, self.num_demo_samples, "trajectory_major").cpu().numpy()
+        self.loss_val, self.first_term_val, self.second_term_val = float(loss[0]), float(loss[1]), float(loss[2])
+
+    def reward_iteration(self, max_iterations=500, stop_criteria=0.01, iter_check=10, verbose=True):
+        """Reward updates with an evaluation / early-stop check every iter_check (ac_irl.py:849-897)."""
+        prev_reward_demo_avg = -100
+        if verbose:
+            print("----- Starting reward_iteration -----")
+        it = 0
+        for it in range(1, max_iterations + 1):
+            self.reward_update_count += 1
+            if it % iter_check != 0:
+                self.update_reward(summary=False)
+                continue
+            if verbose:
+                print("Reward iteration %d" % it)
+            self.update_reward(summary=False, iteration=self.reward_update_count)
+            ds = self._dev(np.asarray([p[0] for p in self.list_eval_demo_transitions], dtype=np.float32), torch.float32)
+            da = self._dev(np.asarray([p[1] for p in self.list_eval_demo_transitions], dtype=np.float32), torch.float32)
+            gs = self._dev(np.asarray([p[0] for p in self.list_eval_gen_transitions], dtype=np.float32), torch.float32)
+            ga = self._dev(np.asarray([p[1] for p in self.list_eval_gen_transitions], dtype=np.float32), torch.float32)
+            reward_demo_avg = float(self._reward(ds, da).double().sum()) / len(self.list_eval_demo_transitions)
+            reward_gen_avg = float(self._reward(gs, ga).double().sum()) / len(self.list_eval_gen_transitions)
+            if verbose:
+                print("Reward demo avg %f | Reward gen avg %f" % (reward_demo_avg, reward_gen_avg))
+                print("First %f | Second %f | Loss %f" % (self.first_term_val, self.second_term_val, self.loss_val))
+            if np.isnan(reward_demo_avg) or np.isnan(reward_gen_avg):
+                break
+            os.makedirs("results", exist_ok=True)
+            with open("results/reward_training.csv", 'a') as f:
+                f.write("%f,%f\n" % (reward_demo_avg, reward_gen_avg))
+            if stop_criteria != -1 and abs(reward_demo_avg - prev_reward_demo_avg) < stop_criteria:
+                break
+            prev_reward_demo_avg = reward_demo_avg
+        if verbose:
+            print("----- Exiting reward_iteration at iter %d -----" % it)
+
+    # ------------------------------------------------------------- a14
+    def outerloop(self, num_iterations=20, num_gen_from_policy=5, max_reward_iterations=100,
+                  max_forward_episodes=200, gamma=1, constant=False, lr_critic=0.1, lr_actor=0.001,
+                  final_episodes=2000, verbose=True):
+        """Alternate reward learning and the forward solve (ac_irl.py:900-954); returns theta."""
+        self.list_generated = self.generate_trajectories(num_gen_from_policy * self.num_policies)
+        self.reward_update_count = 0
+        os.makedirs("results", exist_ok=True)
+        with open("results/reward_training.csv", 'w') as f:
+            f.write("reward_demo_avg,reward_gen_avg\n")
+        for it in range(num_iterations):
+            if verbose:
+                print("########## Outerloop iteration %d ##########" % it)
+            list_generated = self.generate_trajectories(num_gen_from_policy)
+            self.list_generated = (self.list_generated + list_generated)[num_gen_from_policy:]
+            self.list_eval_gen_transitions = [pair for traj in self.list_generated for pair in traj]
+            self.reward_iteration(max_iterations=max_reward_iterations, stop_criteria=0.0001, iter_check=10,
+                                  verbose=verbose)
+            self.theta = self.theta_initial                                        # quirk C.7
+            self.train(max_forward_episodes, -1, gamma, constant, lr_critic, lr_actor, consecutive=100,
+                       file_theta='results/theta.csv', file_pi='results/pi.csv', file_reward='results/reward.csv',
+                       write_file=1, write_all=0, verbose=verbose)
+        if verbose:
+            print("Saving network")
+        self.save("log/model_%s_%d_%d.ckpt" % (self.reg, self.n_fc3, self.n_fc4))
+        if verbose:
+            print("********** Final forward training **********")
+        self.theta = self.theta_initial
+        self.train(final_episodes, -1, gamma, constant, lr_critic, lr_actor, consecutive=100,
+                   file_theta='results/theta.csv', file_pi='results/pi.csv', file_reward='results/reward.csv',
+                   write_file=1, write_all=0, verbose=verbose)
+        return self.theta
+
+    # ------------------------------------------------------------- a13: importance weights
+    def calc_z(self, gen_states, gen_actions, layout="trajectory_major"):
+        """z_j = K / (N_start sum_k q_k(tau_j)) for generated trajectories (ac_irl.py:324-379), returned as
+        ln z_j (float32 device tensor [M]); log space replaces the reference's float64 + `c` normaliser."""
+        thetas = torch.as_tensor(np.asarray(self.list_policies, dtype=np.float64), device=self.device)
+        lq = engine.dirichlet_logq(gen_states, gen_actions, thetas, self.shift)
+        return engine.irl_log_z(lq, T_STEPS, self.num_start_samples, layout=layout)

@@ -582,8 +582,8 @@ __global__ void rnet_reduce_partials_kernel(const float* __restrict__ partials, 
 // rollout records use (M, 1), the reference's trajectory-major feed uses (1, T).
 //   first  = -(1/num_demo_traj) sum r_demo;  second = ln((1/M) sum_j z_j exp(sum_t r_gen[j,t]))
 //   d_demo[n] = -1/num_demo_traj;  d_gen[j,t] = softmax_j(R_j + ln z_j)
-// Stage 1: per-trajectory E_j = exp(R_j + lnz_j) and per-block partial sums (double);
-// stage 2 (one block): totals -> out[0..3] = {loss, first, second, sum E}; stage 3: d_gen.
+// Stage 1: per-trajectory R_j + lnz_j, per-block max and demo sums (double); stage 2 (one block):
+// log-sum-exp -> out[0..3] = {loss, first, second, ln sum_j z_j e^{R_j}}; stage 3: d_gen.
 // ---------------------------------------------------------------------------------------------------
 struct IrlLossParams {
     long long n_demo, M;
@@ -612,37 +612,51 @@ __device__ __forceinline__ double block_sum_double(double v, double* sh) {
 
 __global__ void __launch_bounds__(256) irl_loss_stage1_kernel(const IrlLossParams p) {
     __shared__ double sh[8];
-    double se = 0.0, sd = 0.0;
+    double mx = -1e300, sd = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < p.M; j += stride) {
         double R = 0.0;
         for (int t = 0; t < p.T; ++t) R += (double)p.r_gen[t * p.gen_t_stride + j * p.gen_j_stride];
         if (p.log_z) R += (double)p.log_z[j];
-        const double e = exp(R);
-        p.traj_e[j] = e;
-        se += e;
+        p.traj_e[j] = R;                       // R_j + ln z_j; exponentiated against the global max in stage 2
+        mx = fmax(mx, R);
     }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_demo; i += stride) {
         sd += (double)p.r_demo[i];
         if (p.d_demo) p.d_demo[i] = (float)(-1.0 / p.num_demo_traj);
     }
-    se = block_sum_double(se, sh);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmax(mx, sh[i]);
+        p.partials[2 * blockIdx.x] = mx;
+    }
+    __syncthreads();
     sd = block_sum_double(sd, sh);
-    if (threadIdx.x == 0) { p.partials[2 * blockIdx.x] = se; p.partials[2 * blockIdx.x + 1] = sd; }
+    if (threadIdx.x == 0) p.partials[2 * blockIdx.x + 1] = sd;
 }
-__global__ void irl_loss_stage2_kernel(const IrlLossParams p, int nblocks) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double se = 0.0, sd = 0.0;
-    for (int b = 0; b < nblocks; ++b) { se += p.partials[2 * b]; sd += p.partials[2 * b + 1]; }
-    const double first = -sd / p.num_demo_traj;
-    const double second = log(se / (double)p.M);
-    p.out[0] = first + second;
-    p.out[1] = first;
-    p.out[2] = second;
-    p.out[3] = se;
+// one block: global max, log-sum-exp over the trajectories, loss terms
+__global__ void __launch_bounds__(256) irl_loss_stage2_kernel(const IrlLossParams p, int nblocks) {
+    __shared__ double sh[8];
+    double mx = -1e300, sd = 0.0;
+    for (int b = 0; b < nblocks; ++b) { mx = fmax(mx, p.partials[2 * b]); sd += p.partials[2 * b + 1]; }
+    double se = 0.0;
+    for (long long j = threadIdx.x; j < p.M; j += blockDim.x) se += exp(p.traj_e[j] - mx);
+    se = block_sum_double(se, sh);
+    if (threadIdx.x == 0) {
+        const double first = -sd / p.num_demo_traj;
+        const double lse = mx + log(se);
+        const double second = lse - log((double)p.M);
+        p.out[0] = first + second;
+        p.out[1] = first;
+        p.out[2] = second;
+        p.out[3] = lse;
+    }
 }
 __global__ void __launch_bounds__(256) irl_loss_stage3_kernel(const IrlLossParams p) {
-    const double inv = 1.0 / p.out[3];
+    const double lse = p.out[3];
     const long long total = p.M * p.T;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -650,7 +664,7 @@ __global__ void __launch_bounds__(256) irl_loss_stage3_kernel(const IrlLossParam
         long long j; int t;
         if (p.gen_j_stride == 1) { t = (int)(i / p.M); j = i - (long long)t * p.M; }
         else { j = i / p.T; t = (int)(i - j * p.T); }
-        p.d_gen[t * p.gen_t_stride + j * p.gen_j_stride] = (float)(p.traj_e[j] * inv);
+        p.d_gen[t * p.gen_t_stride + j * p.gen_j_stride] = (float)exp(p.traj_e[j] - lse);
     }
 }
 

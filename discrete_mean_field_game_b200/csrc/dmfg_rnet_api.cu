@@ -169,7 +169,7 @@ int dmfg_irl_loss_grad(const dmfg_irl_loss_args* a, void* stream) {
     if (blocks < 1) blocks = 1;
     irl_loss_stage1_kernel<<<blocks, 256, 0, st>>>(p);
     DMFG_CUDA(cudaGetLastError());
-    irl_loss_stage2_kernel<<<1, 32, 0, st>>>(p, blocks);
+    irl_loss_stage2_kernel<<<1, 256, 0, st>>>(p, blocks);
     DMFG_CUDA(cudaGetLastError());
     if (a->d_gen) {
         long long b3 = (a->M * a->T + 255) / 256;

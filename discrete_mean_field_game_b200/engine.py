@@ -363,7 +363,7 @@ def rnet_backward(params, states, actions, drewards, n_fc3, n_fc4, *, grad=None,
 def irl_loss_grad(r_demo, r_gen, T, num_demo_traj, *, layout="time_major", log_z=None, want_grads=True):
     """IRL loss terms and dL/dr (ac_irl.py:390-406).  r_gen holds M*T rewards, time-major [T,M] (rollout
     record) or trajectory-major [M,T] (the reference's feed).  Returns dict(loss [4] float64 device =
-    {first+second, first, second, sum_j z_j e^{R_j}}, d_demo, d_gen)."""
+    {first+second, first, second, ln sum_j z_j e^{R_j}}, d_demo, d_gen)."""
     from ._lib import IrlLossArgs
     lib = _lib.load()
     device = r_gen.device

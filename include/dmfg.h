@@ -274,7 +274,8 @@ int dmfg_rnet_backward(const dmfg_rnet_args* args, void* stream);
  *   second = ln((1/M) * sum_j z_j * exp(sum_t r_gen[j,t]))     (z_j = 1 when log_z == NULL, as upstream :406)
  * r_gen[j,t] lives at r_gen[t*gen_t_stride + j*gen_j_stride] (time-major record: (M,1); the reference's
  * trajectory-major feed: (1,T)); d_gen uses the same indexing.
- * loss_out[4] (double, device) = {first+second, first, second, sum_j z_j exp(R_j)}.   */
+ * loss_out[4] (double, device) = {first+second, first, second, ln sum_j z_j exp(R_j)},
+ * evaluated as a log-sum-exp (ln z_j can be ~ -6000, which is why upstream needs its `c` normaliser).  */
 typedef struct dmfg_irl_loss_args {
     uint32_t struct_size;
     int32_t  T;

@@ -213,9 +213,9 @@ def irl_loss(r_demo, r_gen, num_demo_traj, log_z=None):
     R = r_gen.sum(axis=1)
     if log_z is not None:
         R = R + np.asarray(log_z, dtype=np.float64)
-    e = np.exp(R)
-    second = math.log(e.sum() / M)
-    sm = e / e.sum()
+    lse = special.logsumexp(R)             # the reference exponentiates directly (:401); same value, no overflow
+    second = lse - math.log(M)
+    sm = np.exp(R - lse)
     return first, second, np.full(r_demo.shape, -1.0 / num_demo_traj), np.repeat(sm[:, None], r_gen.shape[1], axis=1)
 
 

@@ -1,0 +1,231 @@
+"""AC_IRL drop-in (ac_irl.py:31-954) on the GPU against the oracle: constructor surface, sess.run shim,
+train() with the reward net in the loop, update_reward (loss, gradient, Adam), reward_iteration, outerloop.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mfg_oracle as O
+from oracle import rnet_oracle as R
+
+D, N3, N4, T = 15, 8, 4, 15
+
+
+@pytest.fixture(scope="module")
+def data():
+    rng = np.random.RandomState(0)
+    mat = O.synthetic_start_states(n_rows=21, n_cols=20, d=D, seed=0)
+    demos = []
+    for j in range(8):                                   # synthetic "measured" trajectories at theta* = 8.06
+        pi = mat[rng.randint(21)].copy()
+        traj = []
+        for t in range(T):
+            alpha, _ = O.policy_alpha(pi, 8.06, 0.0)
+            P = O.normalise_gamma(rng.gamma(alpha * 1e4))
+            traj.append((pi, P))
+            pi = O.mean_field_step(P, pi)
+        demos.append(traj)
+    return mat, demos
+
+
+def make(data, reg="none", **kw):
+    from discrete_mean_field_game_b200.ac_irl import AC_IRL
+    mat, demos = data
+    np.random.seed(1)
+    return AC_IRL(theta=6.5, d=D, reg=reg, n_fc3=N3, n_fc4=N4, mat_pi0=mat, demonstrations=demos,
+                  seed=5, net_seed=2, **kw)
+
+
+def test_constructor_surface_and_session_shim(data):
+    ac = make(data)
+    assert (ac.theta, ac.theta_initial, ac.shift, ac.alpha_scale, ac.d) == (6.5, 6.5, 0, 1e4, D)
+    assert ac.lr_reward == 1e-4 and ac.num_policies == 10 and ac.c == 2e11
+    assert ac.w.shape == (136, 1) and ac.num_start_samples == 21
+    assert ac.num_demo_samples == 5 and ac.num_gen_samples == 5 and ac.num_sampled_trajectories == 5
+    assert ac.list_policies == [6.5] * 10 and ac.list_generated == []
+    assert len(ac.list_eval_demo_transitions) == 8 * T
+    assert ac.reward_params.count == 3755
+    # test_acirl.py:60-70: sess.run(reward_gen, {gen_states: [...], gen_actions: [...]})
+    s = [p[0] for p in data[1][0]]
+    a = [p[1] for p in data[1][0]]
+    r = ac.sess.run(ac.reward_gen, feed_dict={ac.gen_states: s, ac.gen_actions: a})
+    assert r.shape == (T, 1)
+    ref = R.forward(ac.reward_params.flat.cpu().numpy(), np.float32(s), np.float32(a), N3, N4)
+    np.testing.assert_allclose(r[:, 0], ref, rtol=2e-5, atol=2e-6)
+    rd, rg = ac.sess.run([ac.reward_demo, ac.reward_gen], feed_dict={ac.demo_states: s, ac.demo_actions: a,
+                                                                    ac.gen_states: s[:3], ac.gen_actions: a[:3]})
+    np.testing.assert_allclose(rd, r, rtol=1e-6)
+    assert rg.shape == (3, 1)
+
+
+def test_generate_trajectories_structure(data):
+    ac = make(data)
+    trajs = ac.generate_trajectories(6)
+    assert len(trajs) == 6 and all(len(t) == T for t in trajs)
+    s0, a0 = trajs[2][0]
+    s1, _ = trajs[2][1]
+    assert s0.shape == (D,) and a0.shape == (D, D)
+    np.testing.assert_allclose(a0.sum(1), 1.0, atol=1e-6)
+    np.testing.assert_allclose(a0.T.dot(s0), s1, atol=3e-7)             # test_acirl.py:43-47
+    assert any(np.allclose(s0, row, atol=1e-7) for row in data[0])     # started from a training row
+
+
+def test_train_matches_serial_oracle_with_reward_net(data):
+    """3 episodes of AC_IRL.train with injected draws vs. the oracle's serial learner whose reward is
+    the oracle reward net on the same float32 parameters (ac_irl.py:634-732)."""
+    ac = make(data)
+    rng = np.random.RandomState(3)
+    E = 3
+    rows = rng.randint(21, size=E)
+    params = ac.reward_params.flat.cpu().numpy().astype(np.float64) + 0.2 * rng.randn(3755)   # non-trivial rewards
+    ac.reward_params.load_flat(params)
+    params = ac.reward_params.flat.cpu().numpy()
+    w0 = ac.w.copy()
+    # draw the Gamma variates along the ORACLE trajectory (float32-rounded so both sides see the same y)
+    ys = np.zeros((E, T, D, D), np.float32)
+
+    class Noise:
+        e, t = -1, 0
+
+        def start_index(self, n):
+            Noise.e += 1
+            Noise.t = 0
+            return int(rows[Noise.e])
+
+        def gamma_rows(self, shape):
+            y = np.float32(rng.gamma(shape))
+            ys[Noise.e, Noise.t] = y
+            Noise.t += 1
+            return y.astype(np.float64)
+
+    def reward_fn(pi, P):
+        return R.forward(params, np.float32(pi)[None], np.float32(P)[None], N3, N4)[0]
+
+    th, w, info = O.train_serial(data[0], 6.5, w0, 0.0, 1e4, E, lr_critic=0.1, lr_actor=0.001, flavour="ac_irl",
+                                 reward_fn=reward_fn, noise=Noise(), num_steps=T)
+    ac.train(max_episodes=E, stop_criteria=-1, lr_critic=0.1, lr_actor=0.001, start_rows=rows, noise_y=ys,
+             verbose=False)
+    np.testing.assert_allclose(ac.theta, th, rtol=2e-5)
+    np.testing.assert_allclose(ac.w.ravel(), w, rtol=2e-5, atol=1e-6)
+    assert ac.list_policies[-1] == ac.theta and len(ac.list_policies) == 10
+
+
+@pytest.mark.parametrize("reg", ["none", "l1l2"])
+def test_update_reward_matches_oracle(data, reg):
+    ac = make(data, reg=reg)
+    ac.list_generated = ac.generate_trajectories(10)
+    p0 = ac.reward_params.flat.cpu().numpy().astype(np.float64)
+    m = np.zeros_like(p0)
+    v = np.zeros_like(p0)
+    for step in range(1, 4):
+        random.seed(100 + step)
+        ac.update_reward()
+        random.seed(100 + step)
+        demo = random.sample(ac.list_demonstrations, 5)
+        gen = random.sample(ac.list_generated, 5)
+        ds = np.float32([p[0] for tr in demo for p in tr]); da = np.float32([p[1] for tr in demo for p in tr])
+        gs = np.float32([p[0] for tr in gen for p in tr]); ga = np.float32([p[1] for tr in gen for p in tr])
+        loss, (first, second), grad = R.loss_and_grad(p0, ds, da, gs, ga, N3, N4, 5, T, reg=reg)
+        np.testing.assert_allclose([ac.loss_val, ac.first_term_val, ac.second_term_val], [loss, first, second],
+                                   rtol=2e-5, atol=2e-6)
+        g_dev = ac._last_grad.cpu().numpy()
+        g_data = grad - (R.reg_grad(p0, D, N3, N4) if reg == "l1l2" else 0)
+        assert np.abs(g_dev - g_data).max() <= 3e-5 * np.abs(g_data).max() + 1e-6
+        p0, m, v = R.adam_tf(p0, m, v, grad, step, 1e-4)
+        # Adam normalises the step to ~lr, so a tiny gradient error can flip a coordinate early on:
+        # compare the parameters at the scale of one step
+        assert np.abs(ac.reward_params.flat.cpu().numpy() - p0).max() <= 2e-5
+        p0 = ac.reward_params.flat.cpu().numpy().astype(np.float64)       # re-sync (float32 storage)
+        m = ac.reward_params.m.cpu().numpy().astype(np.float64)
+        v = ac.reward_params.v.cpu().numpy().astype(np.float64)
+
+
+def test_update_reward_with_importance_weights(data):
+    ac = make(data, use_z=True)
+    ac.list_policies = list(np.linspace(6.0, 7.0, 10))
+    ac.list_generated = ac.generate_trajectories(10)
+    p0 = ac.reward_params.flat.cpu().numpy().astype(np.float64)
+    random.seed(7)
+    ac.update_reward()
+    random.seed(7)
+    demo = random.sample(ac.list_demonstrations, 5)
+    gen = random.sample(ac.list_generated, 5)
+    ds = np.float32([p[0] for tr in demo for p in tr]); da = np.float32([p[1] for tr in demo for p in tr])
+    gs = np.float32([p[0] for tr in gen for p in tr]); ga = np.float32([p[1] for tr in gen for p in tr])
+    lz = R.log_z(gs.reshape(5, T, D), ga.reshape(5, T, D, D), ac.list_policies, 0.0, 21)
+    loss, (first, second), grad = R.loss_and_grad(p0, ds, da, gs, ga, N3, N4, 5, T, log_z=lz)
+    np.testing.assert_allclose(ac.second_term_val, second, rtol=1e-5)
+    g_dev = ac._last_grad.cpu().numpy()
+    assert np.abs(g_dev - grad).max() <= 1e-4 * np.abs(grad).max() + 1e-6
+
+
+def test_dropout_variant_runs_and_is_stochastic(data):
+    ac = make(data, reg="dropout_l1l2")
+    s = [p[0] for p in data[1][0]]
+    a = [p[1] for p in data[1][0]]
+    ac.reward_params.load_flat(ac.reward_params.flat.cpu().numpy() + 0.3)
+    r1 = ac.sess.run(ac.reward_gen, feed_dict={ac.gen_states: s, ac.gen_actions: a})
+    r2 = ac.sess.run(ac.reward_gen, feed_dict={ac.gen_states: s, ac.gen_actions: a})
+    assert not np.array_equal(r1, r2)                   # fresh masks per run, active at inference (quirk C.8)
+    ac.list_generated = ac.generate_trajectories(10)
+    ac.update_reward()
+    assert np.isfinite(ac.loss_val) and ac.loss_val > ac.first_term_val + ac.second_term_val   # + regulariser
+
+
+def test_outerloop_smoke_and_checkpoint(data, tmp_path):
+    ac = make(data)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        theta = ac.outerloop(num_iterations=2, num_gen_from_policy=5, max_reward_iterations=20,
+                             max_forward_episodes=4, final_episodes=6, verbose=False)
+        assert np.isfinite(theta) and theta == ac.theta
+        assert len(ac.list_generated) == 50 and len(ac.list_policies) == 10
+        assert ac.list_policies[-1] == ac.theta
+        assert os.path.exists("results/reward_training.csv")       # theta.csv only at multiples of 100 episodes
+        ck = "log/model_none_8_4.ckpt.npz"
+        assert os.path.exists(ck)
+        before = ac.reward_params.flat.clone()
+        ac.reward_params.initialize(seed=99)
+        assert not torch.equal(before, ac.reward_params.flat)
+        ac.restore("log/model_none_8_4.ckpt")
+        assert torch.equal(before, ac.reward_params.flat)
+        lines = open("results/reward_training.csv").read().strip().splitlines()
+        assert lines[0] == "reward_demo_avg,reward_gen_avg" and len(lines) >= 3
+    finally:
+        os.chdir(cwd)
+
+
+def test_reads_reference_file_formats(data, tmp_path):
+    """trend_distribution_day<k>.csv (16 rows) and action_day<k>.txt (15 blocks of 20x20) as
+    read_demonstrations / init_pi0 parse them (ac_irl.py:164-200, 443-506)."""
+    from discrete_mean_field_game_b200.ac_irl import AC_IRL
+    rng = np.random.RandomState(4)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        for sd, adir, start, n in (("train_normalized_round2", "actions_2", 1, 3),
+                                   ("test_normalized_round2", "actions_test_2", 22, 2)):
+            os.makedirs(sd)
+            os.makedirs(adir)
+            for k in range(start, start + n):
+                st = rng.dirichlet(np.ones(20), size=16)
+                np.savetxt(os.path.join(sd, "trend_distribution_day%d.csv" % k), st, fmt="%.3e", delimiter=" ")
+                with open(os.path.join(adir, "action_day%d.txt" % k), "w") as f:
+                    for h in range(15):
+                        np.savetxt(f, rng.dirichlet(np.ones(20), size=20), fmt="%.3e", delimiter=" ")
+                        f.write("\n")
+        ac = AC_IRL(d=15, reg="none", seed=1)
+        assert ac.mat_pi0.shape == (3, 15) and ac.mat_pi0_test.shape == (2, 15)
+        assert len(ac.list_demonstrations) == 3 and len(ac.list_demonstrations_test) == 2
+        s, a = ac.list_demonstrations[1][4]
+        assert s.shape == (15,) and a.shape == (15, 15)
+        first = np.loadtxt("train_normalized_round2/trend_distribution_day2.csv")[4, :15]
+        np.testing.assert_array_equal(s, first)
+    finally:
+        os.chdir(cwd)

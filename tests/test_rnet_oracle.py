@@ -90,7 +90,7 @@ def test_loss_and_grad_match_torch_and_finite_differences():
             m = torch.tensor(R.reg_mask(D, N3, N4))
             lt = lt + (pt.abs() * m).sum() + 0.5 * (pt * pt * m).sum()
         lt.backward()
-        np.testing.assert_allclose(loss, float(lt), rtol=1e-12)
+        np.testing.assert_allclose(loss, float(lt.detach()), rtol=1e-12)
         np.testing.assert_allclose(grad, pt.grad.numpy(), rtol=1e-9, atol=1e-12)
     # finite differences on a few coordinates of every layer
     loss0, _, grad = R.loss_and_grad(p, ds, da, gs, ga, N3, N4, 5, T)
