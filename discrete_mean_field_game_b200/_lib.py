@@ -18,12 +18,12 @@ F32, F64 = 0, 1
 REWARD_NONE, REWARD_AC2, REWARD_SYNTHETIC = 0, 1, 2
 DISCOUNT_STEP, DISCOUNT_CUMULATIVE = 0, 1
 NOISE_INJECTED, NOISE_PHILOX, NOISE_ACTIONS = 0, 1, 2
-VARIANT_AUTO, VARIANT_GENERIC, VARIANT_FAST = 0, 1, 2
+VARIANT_AUTO, VARIANT_GENERIC, VARIANT_FAST, VARIANT_V2 = 0, 1, 2, 3
 DROPOUT_NONE, DROPOUT_MASKS, DROPOUT_PHILOX = 0, 1, 2
 MAX_D = 256
 
 REWARD_KINDS = {"none": REWARD_NONE, "ac2": REWARD_AC2, "synthetic": REWARD_SYNTHETIC}
-VARIANTS = {"auto": VARIANT_AUTO, "generic": VARIANT_GENERIC, "fast": VARIANT_FAST}
+VARIANTS = {"auto": VARIANT_AUTO, "generic": VARIANT_GENERIC, "fast": VARIANT_FAST, "v2": VARIANT_V2}
 
 
 class DmfgError(RuntimeError):

@@ -5,9 +5,10 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 
 #include "dmfg_error.h"
-#include "dmfg_rollout.cuh"
+#include "dmfg_rollout2.cuh"
 
 using namespace dmfg;
 
@@ -46,6 +47,11 @@ inline bool fast_d(int d) { return d == 4 || d == 15 || d == 16; }
 bool use_fast(const dmfg_rollout_args* a) {
     if (a->variant == DMFG_VARIANT_GENERIC) return false;
     return fast_d(a->d);
+}
+// the throughput kernel: float streams, d = 15 / 16, sampled or injected Gamma variates
+bool use_v2(const dmfg_rollout_args* a) {
+    if (a->variant != DMFG_VARIANT_AUTO && a->variant != DMFG_VARIANT_V2) return false;
+    return a->dtype == DMFG_F32 && (a->d == 15 || a->d == 16) && a->noise_kind != DMFG_NOISE_ACTIONS;
 }
 
 // workspace map of one dmfg_rollout call
@@ -88,8 +94,10 @@ int check_rollout(const dmfg_rollout_args* a) {
         return fail(DMFG_ERR_INVALID, "noise_kind %d", a->noise_kind);
     if (a->noise_kind == DMFG_NOISE_ACTIONS && a->T > 1)
         return fail(DMFG_ERR_INVALID, "noise_kind=ACTIONS evaluates single transitions (T must be <= 1)");
-    if (a->variant < DMFG_VARIANT_AUTO || a->variant > DMFG_VARIANT_FAST)
+    if (a->variant < DMFG_VARIANT_AUTO || a->variant > DMFG_VARIANT_V2)
         return fail(DMFG_ERR_INVALID, "variant %d", a->variant);
+    if (a->variant == DMFG_VARIANT_V2 && !use_v2(a))
+        return fail(DMFG_ERR_UNSUPPORTED, "the v2 kernel is built for float streams, d in {15,16}, sampled or injected noise");
     if (a->variant == DMFG_VARIANT_FAST && !fast_d(a->d))
         return fail(DMFG_ERR_UNSUPPORTED, "fast variant is built for d in {4,15,16}, not d=%d", a->d);
     if (a->B > 0 && !a->pi0) return fail(DMFG_ERR_INVALID, "pi0 is NULL");
@@ -135,6 +143,31 @@ int launch_fast(RolloutParams<R> p, bool td, int* grid_out, cudaStream_t st) {
     kern<<<(unsigned)grid, kFastThreads, smem, st>>>(p);
     DMFG_CUDA(cudaGetLastError());
     return DMFG_OK;
+}
+
+template <int D, int NOISE>
+int launch_v2(RolloutParams<float> p, bool td, int* grid_out, cudaStream_t st) {
+    auto kern = rollout_v2_kernel<D, NOISE>;
+    const size_t smem = (size_t)(td && p.partials ? V2Smem<D>::total_td : V2Smem<D>::total_notd) * sizeof(double);
+    DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(V2Smem<D>::total_td * sizeof(double))));
+    int occ = 0, sms = 0;
+    DMFG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kV2Threads, smem));
+    if (int rc = sm_count(&sms)) return rc;
+    if (occ < 1) return fail(DMFG_ERR_CUDA, "rollout_v2_kernel<%d> does not fit an SM", D);
+    const long long gpb = kV2Threads / kV2G;
+    const long long ntiles = (p.B + gpb - 1) / gpb;
+    long long grid = (long long)sms * occ;
+    if (grid > kMaxPartialCtas) grid = kMaxPartialCtas;
+    if (grid > ntiles) grid = ntiles;
+    *grid_out = (int)grid;
+    kern<<<(unsigned)grid, kV2Threads, smem, st>>>(p);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+int dispatch_v2(const RolloutParams<float>& p, int noise_kind, bool td, int* grid, cudaStream_t st) {
+    if (noise_kind == DMFG_NOISE_PHILOX)
+        return p.d == 15 ? launch_v2<15, DMFG_NOISE_PHILOX>(p, td, grid, st) : launch_v2<16, DMFG_NOISE_PHILOX>(p, td, grid, st);
+    return p.d == 15 ? launch_v2<15, DMFG_NOISE_INJECTED>(p, td, grid, st) : launch_v2<16, DMFG_NOISE_INJECTED>(p, td, grid, st);
 }
 
 template <typename R, int NOISE>
@@ -211,6 +244,17 @@ int rollout_typed(const dmfg_rollout_args* a, cudaStream_t st) {
     if (use_fast(a)) {
         if (accum) p.partials = (double*)(wsp + ws.partials);
         int grid = 0, rc;
+        if constexpr (std::is_same<R, float>::value) {
+            if (use_v2(a)) {
+                rc = dispatch_v2(p, a->noise_kind, td, &grid, st);
+                if (rc) return rc;
+                if (accum) {
+                    reduce_partials_kernel<<<(F + 2 + 127) / 128, 128, 0, st>>>(p.partials, grid, F + 2, a->acc);
+                    DMFG_CUDA(cudaGetLastError());
+                }
+                return DMFG_OK;
+            }
+        }
         if (a->noise_kind == DMFG_NOISE_PHILOX) rc = dispatch_fast<R, DMFG_NOISE_PHILOX>(p, td, &grid, st);
         else if (a->noise_kind == DMFG_NOISE_ACTIONS) rc = dispatch_fast<R, DMFG_NOISE_ACTIONS>(p, td, &grid, st);
         else rc = dispatch_fast<R, DMFG_NOISE_INJECTED>(p, td, &grid, st);

@@ -71,35 +71,48 @@ __host__ __device__ __forceinline__ uint32_t gamma_slot(uint32_t t, int d, int i
 #define DMFG_CTR_BOOST 0x80000000u   // counter word 3 of the boost uniforms (attempts count from 0)
 #define DMFG_CTR_START 0xC0000000u   // counter word 3 of the start-row draw of the learners
 
+// ---- MUFU-level primitives (approx, flush-to-zero): 1 instruction each on the XU pipe ----------------
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sin_approx(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cos_approx(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#define DMFG_LN2 0.69314718055994531f
+#define DMFG_LOG2E 1.4426950408889634f
+
 // uniform in (0,1), never 0 or 1
 __device__ __forceinline__ float u01(uint32_t w) {
     return fmaf(__uint2float_rz(w), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }
 
+// two standard normals from two 32-bit words (Box-Muller).  The angle is taken in (-pi, pi), where
+// sin/cos.approx are accurate to ~5e-7 absolute; the radius resolves 32 bits (tails to 6.6 sigma).
 __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& n0, float& n1) {
-    const float r = sqrtf(-2.0f * __logf(u01(w0)));
-    float s, c;
-    sincospif(2.0f * u01(w1), &s, &c);
-    n0 = r * c;
-    n1 = r * s;
+    const float r = sqrt_approx(-2.0f * DMFG_LN2 * lg2_approx(u01(w0)));
+    const float ang = fmaf(__uint2float_rz(w1), 1.4629180792671596e-9f, -3.1415925f);   // 2 pi 2^-32 w - pi
+    n0 = r * cos_approx(ang);
+    n1 = r * sin_approx(ang);
 }
 
-// One Marsaglia-Tsang proposal for Gamma(dd + 1/3, 1).  cc = 1/sqrt(9 dd).
-// The log test is evaluated in a cancellation-free form: with e = cc*x,
-//   x^2/2 + dd(1 - v + ln v),  v = (1+e)^3
-// equals  dd * 3 * sum_{k>=4} (-1)^(k+1) e^k / k  because dd*cc^2 = 1/9 cancels the
-// x^2/2 term exactly; the series is used for |e| < 1/4, the direct form otherwise.
+// One Marsaglia-Tsang proposal for Gamma(dd + 1/3, 1), cc = 1/sqrt(9 dd): y = dd (1 + cc x)^3, accepted
+// iff ln u < x^2/2 + dd (1 - v + ln v), v = (1 + cc x)^3.
+// With e = cc x the right-hand side is  -dd (0.75 e^4 - 0.6 e^5 + 0.5 e^6 - ...)  (dd cc^2 = 1/9 cancels the
+// x^2/2 term exactly), bounded below by -1.5 dd e^4 for |e| <= 1/2.  Since exp(-z) >= 1 - z,
+//     |e| <= 1/2  and  u < 1 - 1.5 dd e^4      ==> accept
+// is a squeeze that fails with probability ~0.055/dd only (Marsaglia & Tsang's generic 0.0331 x^4 squeeze
+// fails 10 % of the time for every shape); the exact test below it is evaluated cancellation-free.
 __device__ __forceinline__ bool mt_propose(float dd, float cc, float x, float u, float& y) {
     const float e = cc * x;
     const float v1 = 1.0f + e;
+    const float e2 = e * e;
+    y = dd * (v1 * v1 * v1);
+    if (fabsf(e) <= 0.5f && u < fmaf(-1.5f * dd, e2 * e2, 1.0f)) return true;
     if (v1 <= 0.0f) return false;
-    const float v = v1 * v1 * v1;
-    const float x2 = x * x;
-    y = dd * v;
-    if (u < 1.0f - 0.0331f * x2 * x2) return true;
     float rhs;
     if (fabsf(e) < 0.25f) {
-        // sum_{k>=4} (-1)^(k+1) e^k/k = -e^4 * h,  h = sum_{m=0..9} (-e)^m/(m+4)  (|e|<1/4: rel. err < 2e-7)
+        // sum_{k>=4} (-1)^(k+1) e^k/k = -e^4 h,  h = sum_{m=0..9} (-e)^m/(m+4)  (|e|<1/4: rel. err < 2e-7)
         float h = 1.0f / 13.0f;
         h = fmaf(h, -e, 1.0f / 12.0f);
         h = fmaf(h, -e, 1.0f / 11.0f);
@@ -110,10 +123,10 @@ __device__ __forceinline__ bool mt_propose(float dd, float cc, float x, float u,
         h = fmaf(h, -e, 1.0f / 6.0f);
         h = fmaf(h, -e, 1.0f / 5.0f);
         h = fmaf(h, -e, 1.0f / 4.0f);
-        const float e2 = e * e;
         rhs = -3.0f * dd * e2 * e2 * h;
     } else {
-        rhs = 0.5f * x2 + dd * (1.0f - v + __logf(v));
+        const float v = v1 * v1 * v1;
+        rhs = 0.5f * x * x + dd * (1.0f - v + __logf(v));
     }
     return __logf(u) < rhs;
 }
@@ -125,35 +138,44 @@ struct GammaSetup {
 __device__ __forceinline__ GammaSetup gamma_setup(float a) {
     GammaSetup g;
     g.boost = a < 1.0f;
-    g.inv_a = 1.0f / a;                   // inf for a == 0 -> boost factor 0 -> y = 0 (np.random.gamma(0) == 0)
+    g.inv_a = 0.0f;                        // filled in by the (rare) boost path
     const float a1 = g.boost ? a + 1.0f : a;
     g.dd = a1 - (1.0f / 3.0f);
-    g.cc = rsqrtf(9.0f * g.dd);
+    g.cc = rsqrt_approx(9.0f * g.dd);
     return g;
 }
 
-// Gamma(a0,1), Gamma(a1,1) for the pair in `slot`.  One Philox call feeds both
-// elements (two Box-Muller normals + two acceptance uniforms); rejected elements
-// move on to attempt+1.  Shapes < 1 take one more call for the boost uniforms.
-__device__ __forceinline__ void gamma_pair(const NoiseKey& nk, uint32_t slot, float a0, float a1,
-                                           float& y0, float& y1) {
+// Gamma(a0,1), Gamma(a1,1) for the pair in `slot`.  One Philox call feeds both elements (two Box-Muller
+// normals + two acceptance uniforms); rejected elements move on to attempt+1.  Shapes < 1 take one more
+// call for the boost uniforms: Gamma(a) = Gamma(a+1) U^(1/a); a == 0 gives 0 like np.random.gamma.
+static __device__ __noinline__ void gamma_pair_slow(const NoiseKey& nk, uint32_t slot, float a0, float a1, bool done0,
+                                             bool done1, float& y0, float& y1) {
     const GammaSetup g0 = gamma_setup(a0), g1 = gamma_setup(a1);
-    bool done0 = false, done1 = false;
-    uint32_t attempt = 0;
-    y0 = 0.0f; y1 = 0.0f;
-    do {
+    uint32_t attempt = 1;
+    while (!(done0 && done1) && attempt < 64u) {
         const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, attempt, nk.k0, nk.k1);
         float n0, n1;
         box_muller(w.x, w.y, n0, n1);
         if (!done0) done0 = mt_propose(g0.dd, g0.cc, n0, u01(w.z), y0);
         if (!done1) done1 = mt_propose(g1.dd, g1.cc, n1, u01(w.w), y1);
         ++attempt;
-    } while (!(done0 && done1) && attempt < 64u);
+    }
     if (g0.boost || g1.boost) {
         const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, DMFG_CTR_BOOST, nk.k0, nk.k1);
-        if (g0.boost) y0 *= exp2f(__log2f(u01(w.x)) * g0.inv_a);
-        if (g1.boost) y1 *= exp2f(__log2f(u01(w.y)) * g1.inv_a);
+        if (g0.boost) y0 = a0 > 0.0f ? y0 * ex2_approx(lg2_approx(u01(w.x)) / a0) : 0.0f;
+        if (g1.boost) y1 = a1 > 0.0f ? y1 * ex2_approx(lg2_approx(u01(w.y)) / a1) : 0.0f;
     }
+}
+__device__ __forceinline__ void gamma_pair(const NoiseKey& nk, uint32_t slot, float a0, float a1,
+                                           float& y0, float& y1) {
+    const GammaSetup g0 = gamma_setup(a0), g1 = gamma_setup(a1);
+    const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, 0u, nk.k0, nk.k1);
+    float n0, n1;
+    box_muller(w.x, w.y, n0, n1);
+    const bool done0 = mt_propose(g0.dd, g0.cc, n0, u01(w.z), y0);
+    const bool done1 = mt_propose(g1.dd, g1.cc, n1, u01(w.w), y1);
+    // rare: a rejection (~0.06/shape) or a shape below 1 -- kept out of line so the hot loop stays small
+    if (!(done0 && done1) || g0.boost || g1.boost) gamma_pair_slow(nk, slot, a0, a1, done0, done1, y0, y1);
 }
 
 // ------------------------------------------------------------ policy alpha
@@ -227,6 +249,45 @@ __device__ __forceinline__ double digamma(double x) {
 // ln(P) with the reference's P == 0 -> 1e-100 substitution (mfg_ac2.py:369).
 __device__ __forceinline__ float log_prob(float p) { return p > 0.0f ? logf(p) : -230.25850929940458f; }
 __device__ __forceinline__ double log_prob(double p) { return p > 0.0 ? log(p) : -230.25850929940458; }
+
+// ------------------------------------------------- fast float variants (throughput kernels)
+// Same functions as policy_alpha<float> / digamma(float) built from single MUFU operations; relative
+// error <= ~3e-6 on alpha, alpha', psi over the operating range (tests/test_device_math_gpu.py).
+__device__ __forceinline__ void policy_alpha_fast(float theta, float x, float& alpha, float& alpha_deriv) {
+    const float t = theta * x;
+    const float e = ex2_approx(-fabsf(t) * DMFG_LOG2E);             // exp(-|t|) in (0,1]
+    const float u = 1.0f + e;
+    // log1p(e): 5-term series below 1/16 (lg2.approx has 2^-22 ABSOLUTE error near 1), lg2 above
+    float pl = fmaf(-1.0f / 6.0f, e, 0.2f);
+    pl = fmaf(pl, e, -0.25f);
+    pl = fmaf(pl, e, 1.0f / 3.0f);
+    pl = fmaf(pl, e, -0.5f);
+    pl = fmaf(pl, e, 1.0f);
+    const float l = e < 0.0625f ? pl * e : lg2_approx(u) * DMFG_LN2;
+    const float ru = rcp_approx(u);
+    const bool pos = t >= 0.0f;
+    alpha = fmaxf(t, 0.0f) + l;
+    alpha_deriv = x * ((pos ? 1.0f : e) * ru);
+}
+
+// psi(x), x > 0: 4-step recurrence folded into one division, x(x+3) = q, (x+1)(x+2) = q+2:
+//   sum_{k<4} 1/(x+k) = (2x+3)(2q+2) / (q (q+2)),   then the asymptotic series at z = x + 4 (error < 7e-8).
+// One reciprocal serves both the recurrence and 1/z.
+__device__ __forceinline__ float digamma_fast(float x) {
+    const float q = fmaxf(fmaf(x, x, 3.0f * x), 1e-30f);
+    const float num = fmaf(2.0f, x, 3.0f) * fmaf(2.0f, q, 2.0f);
+    const float den = q * (q + 2.0f);
+    const float z = x + 4.0f;
+    const float R = rcp_approx(den * z);
+    const float s = num * (z * R);
+    const float rz = den * R;
+    const float r2 = rz * rz;
+    float p = fmaf(r2, -1.0f / 252.0f, 1.0f / 120.0f);
+    p = fmaf(r2, p, -1.0f / 12.0f);
+    float res = fmaf(lg2_approx(z), DMFG_LN2, -s);
+    res = fmaf(-0.5f, rz, res);
+    return fmaf(r2, p, res);
+}
 
 // ------------------------------------------------------- sub-warp reductions
 template <int G>

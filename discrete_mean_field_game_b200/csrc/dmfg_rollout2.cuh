@@ -1,0 +1,248 @@
+// rollout_v2_kernel -- the throughput version of the fused population step for d = 15 / 16, float
+// streams (sm_100a).  Same arithmetic contract as rollout_fast_kernel (dmfg_rollout.cuh), restructured
+// around what ncu showed on the first version (profiles/r1_rollout_fast_train_ncu_summary.md: 2.8 k warp
+// instructions per population-step, a fully unrolled 120 KB body thrashing the instruction cache, 21 % of
+// the XU pipe spent on float<->double conversions and precise libm calls):
+//
+//   * a group of 16 lanes owns one population, lane r owns ROW r of P (as before), but the row is walked
+//     by two ROLLED loops, so the hot body is a few KB:
+//       pass 1 (per column pair): alpha, alpha' (one ex2, one lg2, one rcp), psi(alpha) (one rcp, one lg2),
+//               the Gamma pair (one Philox call, Box-Muller on MUFU, squeeze-accepted Marsaglia-Tsang);
+//               {y, alpha'} parked in an 8-byte shared slot, row sum of y in double;
+//       pass 2 (per column, after the row sum is known): P = y / s, ln P, the reward term P^2 (pi_j - pi_i)
+//               and the flux pi_i P_ij in double, written back INTO the same slot;
+//   * pi' = P^T pi is a transposed read of those slots (15 LDS.64 + 15 DADD per lane) instead of 60
+//     shuffles; the state vector lives in a double-buffered shared array (double + float copies) that
+//     all lanes of the group read as broadcasts;
+//   * float everywhere except where the TD error needs it: row sums, P, reward, flux, state, critic
+//     value and all reductions stay double, every float -> double conversion that
+//     remains is per element of pass 2 or per row;
+//   * critic weights are staged once per CTA in a [slot][lane] table shared by all groups (2 KB instead
+//     of 35 KB), so three CTAs fit an SM.
+#pragma once
+#include "dmfg_rollout.cuh"
+
+namespace dmfg {
+
+constexpr int kV2Threads = 256;
+constexpr int kV2G = 16;
+constexpr int kV2Slots = 17;          // 8-byte slots per lane row (16 columns + 1 pad => odd stride)
+
+template <int D>
+struct V2Smem {
+    static constexpr int GPB = kV2Threads / kV2G;
+    static constexpr int NSLOT = D + 2;
+    // offsets in doubles
+    static constexpr int tile = 0;                                  // [GPB][16][17] slots
+    static constexpr int pid = tile + GPB * kV2G * kV2Slots;        // [2][GPB][16] state, double
+    static constexpr int wl = pid + 2 * GPB * kV2G;                 // [NSLOT][16] critic slots
+    static constexpr int pif = wl + NSLOT * kV2G;                   // [2][GPB][16] state, float (GPB*16 doubles)
+    static constexpr int acc = pif + GPB * kV2G;                    // [NSLOT][NT] accumulators (train only)
+    static constexpr int total_notd = acc;
+    static constexpr int total_td = acc + NSLOT * kV2Threads;
+};
+
+// critic value from the shared state buffer: lane r sums w[r,k] pi_r pi_k over k >= r (zeros below)
+template <int D>
+__device__ __forceinline__ double critic_value_v2(const double* __restrict__ wl, const double* __restrict__ pi,
+                                                  double pi_self, int r) {
+    double v = 0.0;
+#pragma unroll 5
+    for (int k = 0; k < D; ++k) v = fma(wl[k * kV2G + r], pi[k], v);
+    v = fma(v, pi_self, wl[D * kV2G + r] * pi_self) + wl[(D + 1) * kV2G + r];
+    return group_sum<kV2G>(v);
+}
+
+template <int D, int NOISE>
+__global__ void __launch_bounds__(kV2Threads, 3)
+rollout_v2_kernel(const RolloutParams<float> p) {
+    using S = V2Smem<D>;
+    constexpr int G = kV2G, NT = kV2Threads, GPB = S::GPB, NSLOT = S::NSLOT, PD = (D + 1) / 2;
+    constexpr int F = num_features_c(D);
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, r = tid & (G - 1), grp = tid / G;
+    double* slots = smem + S::tile + (grp * G + r) * kV2Slots;            // this lane's row of slots
+    const double* col = smem + S::tile + grp * G * kV2Slots + r;          // column r of the group's tile
+    double* pid = smem + S::pid + grp * G;                                 // [2] buffers, stride GPB*G
+    float* pif = reinterpret_cast<float*>(smem + S::pif) + grp * G;        // [2] buffers, stride GPB*G
+    const double* wl = smem + S::wl;
+    double* acc = smem + S::acc + tid;
+    const bool td = p.w != nullptr;
+    const bool want_acc = td && p.partials != nullptr;
+    const bool row_ok = r < D;
+    if (td) {
+        if (tid < G) stage_critic_slots<D>(smem + S::wl + tid, G, p.w, tid);
+        if (want_acc) {
+#pragma unroll
+            for (int k = 0; k < NSLOT; ++k) acc[k * NT] = 0.0;
+        }
+    }
+    __syncthreads();
+    const float theta = (float)(p.theta_dev ? *p.theta_dev : p.theta);
+    const float shift = (float)p.shift, scale = (float)p.alpha_scale;
+    double sum_dg = 0.0, sum_r = 0.0;
+    const long long ntiles = (p.B + GPB - 1) / GPB;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        long long b = tile * GPB + grp;
+        const bool live = b < p.B;                 // dead groups shadow the last population, writes masked
+        if (!live) b = p.B - 1;
+        const bool wr = live && row_ok;
+        const NoiseKey nk = make_noise_key(p.seed, (unsigned long long)(p.pop_offset + b));
+        double pi_self = row_ok ? (double)p.pi0[b * D + r] : 0.0;
+        int cur = 0;
+        pid[r] = pi_self;
+        pif[r] = (float)pi_self;
+        __syncwarp();
+        double v_cur = td ? critic_value_v2<D>(wl, pid, pi_self, r) : 0.0;
+        double disc = 1.0;
+        if (p.states != nullptr && wr) p.states[b * D + r] = (float)pi_self;
+        for (int t = 0; t < p.T; ++t) {
+            const long long tb = (long long)t * p.B + b;
+            const long long row = (tb * D + r) * D;
+            const double* pic = pid + cur * (GPB * G);
+            const float* pfc = pif + cur * (GPB * G);
+            // ------------------------------------------------------------------ pass 1
+            const float xi = (float)pi_self + shift;
+            float asum = 0.f, dsum = 0.f, g1 = 0.f;
+            double ysum = 0.0;
+#pragma unroll 2
+            for (int pp = 0; pp < PD; ++pp) {
+                const float2 pj = *reinterpret_cast<const float2*>(pfc + 2 * pp);
+                const bool ok1 = (2 * pp + 1) < D;                     // only the last pair of an odd D
+                float a0, a1, d0, d1;
+                policy_alpha_fast(theta, pj.x - xi, a0, d0);
+                policy_alpha_fast(theta, pj.y - xi, a1, d1);
+                if (!ok1) { a1 = 1.0f; d1 = 0.0f; }
+                g1 = fmaf(-digamma_fast(a0), d0, g1);
+                g1 = fmaf(-digamma_fast(a1), d1, g1);
+                asum += a0 + (ok1 ? a1 : 0.0f);
+                dsum += d0 + d1;
+                float y0, y1;
+                if (NOISE == DMFG_NOISE_PHILOX) {
+                    gamma_pair(nk, gamma_slot((uint32_t)(p.step_offset + t), D, r, pp), a0 * scale, a1 * scale, y0, y1);
+                } else {
+                    y0 = row_ok ? p.noise_y[row + 2 * pp] : 1.0f;
+                    y1 = (row_ok && ok1) ? p.noise_y[row + 2 * pp + 1] : 1.0f;
+                }
+                if (y0 == 0.0f) y0 = 1e-20f;                             // mfg_ac2.py:244
+                if (y1 == 0.0f) y1 = 1e-20f;
+                if (!ok1) y1 = 0.0f;
+                ysum += (double)y0 + (double)y1;
+                *reinterpret_cast<float2*>(slots + 2 * pp) = make_float2(y0, d0);
+                *reinterpret_cast<float2*>(slots + 2 * pp + 1) = make_float2(y1, d1);
+                if (p.alpha != nullptr && wr) {
+                    p.alpha[row + 2 * pp] = a0;
+                    p.alpha_deriv[row + 2 * pp] = d0;
+                    if (ok1) { p.alpha[row + 2 * pp + 1] = a1; p.alpha_deriv[row + 2 * pp + 1] = d1; }
+                }
+            }
+            // ------------------------------------------------------------------ row level
+            double inv = (double)rcp_approx((float)ysum);              // 1/s: float seed + 2 Newton steps
+            inv = inv * (2.0 - ysum * inv);
+            inv = inv * (2.0 - ysum * inv);
+            const float inv_f = (float)inv;
+            const double q = pi_self * inv;
+            const float psi_row = digamma_fast(asum);
+            // ------------------------------------------------------------------ pass 2
+            double racc = 0.0;
+            float g2 = 0.f;
+            float* act_row = (p.actions != nullptr && wr) ? p.actions + row : nullptr;
+#pragma unroll 5
+            for (int j = 0; j < D; ++j) {
+                const float2 yd = *reinterpret_cast<const float2*>(slots + j);
+                const double yv = (double)yd.x;
+                const double P = yv * inv;
+                const float Pf = yd.x * inv_f;
+                g2 = fmaf(lg2_approx(Pf), yd.y, g2);
+                if (p.reward_kind == DMFG_REWARD_AC2) racc = fma(P * P, pic[j] - pi_self, racc);
+                else racc = fma(P, P, racc);
+                slots[j] = yv * q;                                       // flux pi_i P_ij
+                if (act_row != nullptr) act_row[j] = Pf;
+            }
+            __syncwarp();
+            // ------------------------------------------------------------------ pi' = P^T pi (transposed read)
+            double next_self = 0.0;
+#pragma unroll 5
+            for (int i = 0; i < D; ++i) next_self += col[i * kV2Slots];
+            if (!row_ok) next_self = 0.0;
+            double rew = 0.0;
+            if (p.reward_kind == DMFG_REWARD_AC2) rew = pi_self * racc;
+            else if (p.reward_kind == DMFG_REWARD_SYNTHETIC) rew = -0.5 * pi_self * racc;
+            const double glane = row_ok ? (double)(g1 + DMFG_LN2 * g2 + psi_row * dsum) : 0.0;
+            rew = group_sum<G>(rew);
+            const double grad = group_sum<G>(glane);
+            const int nxt = cur ^ 1;
+            pid[nxt * (GPB * G) + r] = next_self;
+            pif[nxt * (GPB * G) + r] = (float)next_self;
+            __syncwarp();
+            if (p.rewards_in != nullptr) rew = (double)p.rewards_in[tb];
+            if (td) {
+                const double v_next = critic_value_v2<D>(wl, pid + nxt * (GPB * G), next_self, r);
+                const double gfac = p.discount_kind == DMFG_DISCOUNT_STEP ? p.gamma : disc;
+                const double delta = rew + gfac * v_next - v_cur;
+                if (want_acc && live) {
+                    const double dp = delta * pi_self;
+#pragma unroll 5
+                    for (int k = 0; k < D; ++k) acc[k * NT] = fma(dp, pic[k], acc[k * NT]);
+                    acc[D * NT] += dp;
+                    acc[(D + 1) * NT] += delta;
+                    if (r == 0) sum_dg = fma(delta, grad, sum_dg);
+                }
+                if (p.deltas != nullptr && live && r == 0) p.deltas[tb] = (float)delta;
+                v_cur = v_next;
+            }
+            if (live && r == 0) {
+                sum_r += rew;
+                if (p.rewards != nullptr) p.rewards[tb] = (float)rew;
+                if (p.grads != nullptr) p.grads[tb] = (float)grad;
+            }
+            disc *= p.gamma;
+            pi_self = next_self;
+            cur = nxt;
+            if (p.states != nullptr && wr) p.states[(tb + p.B) * D + r] = (float)pi_self;
+        }
+        if (p.pi_final != nullptr && wr) p.pi_final[b * D + r] = (float)pi_self;
+        // make the next population start from buffer 0 again
+        __syncwarp();
+    }
+    if (!want_acc) return;
+    // ---- per-CTA partial sums, fixed order (deterministic) -- same layout as rollout_fast_kernel -------
+    __shared__ double red[2][NT / 32];
+    {
+        double a = sum_dg, c = sum_r;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        if ((tid & 31) == 0) { red[0][tid >> 5] = a; red[1][tid >> 5] = c; }
+    }
+    __syncthreads();
+    double* out = p.partials + (long long)blockIdx.x * (2 + F);
+    const double* accbase = smem + S::acc;
+    for (int f = tid; f < F; f += NT) {
+        int rw, k;
+        constexpr int Q = D * (D + 1) / 2;
+        if (f < Q) {
+            rw = 0;
+            int rem = f;
+            while (rem >= D - rw) { rem -= D - rw; ++rw; }
+            k = rw + rem;
+        } else if (f < Q + D) {
+            rw = f - Q; k = D;
+        } else {
+            rw = 0; k = D + 1;
+        }
+        double s = 0.0;
+        for (int g = 0; g < GPB; ++g) s += accbase[k * NT + g * G + rw];
+        out[1 + f] = s;
+    }
+    if (tid == 0) {
+        double a = 0.0, c = 0.0;
+        for (int wv = 0; wv < NT / 32; ++wv) { a += red[0][wv]; c += red[1][wv]; }
+        out[0] = a;
+        out[1 + F] = c;
+    }
+}
+
+}  // namespace dmfg

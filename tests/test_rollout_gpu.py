@@ -319,3 +319,89 @@ def test_per_episode_update_on_device(dev, trace):
     eng.apply_update(15, theta, w, out["acc"], 0.1, 0.01, 1.0 / 3)
     np.testing.assert_allclose(N_(theta)[0], 8.86349 + 0.01 / 3 * acc[0], rtol=1e-14)
     np.testing.assert_allclose(N_(w), trace["w0"] + 0.1 / 3 * acc[1:137], rtol=1e-14)
+
+
+# ----------------------------------------------------------------------------- throughput kernel (v2)
+@pytest.mark.parametrize("discount", ["step", "cumulative"])
+@pytest.mark.parametrize("reward", ["ac2", "synthetic"])
+def test_v2_frozen_rollout_d15_vs_oracle(dev, trace, discount, reward):
+    """The kernel bench.py times (rollout_v2_kernel, float streams) on the reference's own Gamma draws:
+    same checks and the same tolerances as the float32 rows of test_frozen_rollout_d15_vs_oracle."""
+    pi0, y = _trace_frozen_inputs(trace)
+    th, sh, sc = float(trace["theta0"]), float(trace["shift"]), float(trace["alpha_scale"])
+    gamma = 0.9 if discount == "cumulative" else 1.0
+    dtype = torch.float32
+    w = torch.as_tensor(trace["w0"], dtype=torch.float64, device=dev)
+    out = eng.rollout(T_(pi0, dev, dtype), th, sh, sc, y.shape[0], w=w, gamma=gamma, discount=discount,
+                      reward=reward, noise_y=T_(y, dev, dtype), outputs=ALL_OUT, want_acc=True, variant="v2")
+    ref = O.rollout_frozen(N_(T_(pi0, dev, dtype)), th, sh, sc, N_(T_(y, dev, dtype)), w=trace["w0"],
+                           gamma=gamma, discount=discount, reward=reward)
+    rt = RT[dtype]
+    for k in ("states", "actions", "alpha", "alpha_deriv", "grads"):
+        np.testing.assert_allclose(N_(out[k]), ref[k], rtol=rt, err_msg=k)
+    np.testing.assert_allclose(N_(out["pi_final"]), ref["states"][-1], rtol=rt)
+    v = np.abs(O.features(ref["states"]) @ trace["w0"])
+    scale = np.abs(ref["rewards"]) + v[1:] + v[:-1]
+    tol = 1e-6
+    assert np.all(np.abs(N_(out["rewards"]) - ref["rewards"]) <= tol * np.maximum(scale, 1e-3))
+    assert np.all(np.abs(N_(out["deltas"]) - ref["deltas"]) <= tol * scale)
+    acc = N_(out["acc"])
+    F = O.num_features(15)
+    assert abs(acc[0] - ref["G_theta"]) <= 10 * tol * np.sum(np.abs(ref["deltas"] * ref["grads"]))
+    wscale = np.sum(np.abs(ref["deltas"])[..., None] * np.abs(O.features(ref["states"][:-1])), axis=(0, 1))
+    assert np.all(np.abs(acc[1:1 + F] - ref["G_w"]) <= 10 * tol * wscale)
+    assert abs(acc[1 + F] - ref["R"]) <= 10 * tol * np.sum(np.abs(ref["rewards"]))
+
+
+@pytest.mark.parametrize("d", [15, 16])
+def test_v2_random_batch_vs_oracle(dev, d):
+    """d = 15 and 16, 200 populations x 6 steps (not a multiple of the 16-population tile), random
+    Gamma variates including shapes below 1 and an exact zero."""
+    rng = np.random.RandomState(d)
+    B, T = 200, 6
+    pi0 = np.float32(rng.dirichlet(np.ones(d) * 0.7, size=B))
+    F = O.num_features(d)
+    w = rng.rand(F)
+    # draw the variates along the oracle's own trajectory, rounded to float32
+    y = np.zeros((T, B, d, d), np.float32)
+    pi = pi0.astype(np.float64)
+    for t in range(T):
+        alpha, _ = O.policy_alpha(pi, 8.64, 0.05)
+        y[t] = np.float32(rng.gamma(alpha * 1e4))
+        if t == 2:
+            y[t, 5, 3, 7] = 0.0
+        pi = O.mean_field_step(O.normalise_gamma(y[t].astype(np.float64)), pi)
+    ref = O.rollout_frozen(pi0.astype(np.float64), 8.64, 0.05, 1e4, y.astype(np.float64), w=w)
+    out = eng.rollout(T_(pi0, dev, torch.float32), 8.64, 0.05, 1e4, T, w=T_(w, dev, torch.float64),
+                      noise_y=T_(y, dev, torch.float32), outputs=ALL_OUT, want_acc=True, variant="v2")
+    for k in ("states", "alpha"):
+        np.testing.assert_allclose(N_(out[k]), ref[k], rtol=2e-5, err_msg=k)
+    # alpha' = x sigma(theta x) crosses zero with x = pi_j - pi_i - shift: float32 inputs bound |err(x)| by ~1e-8
+    np.testing.assert_allclose(N_(out["alpha_deriv"]), ref["alpha_deriv"], rtol=2e-5, atol=3e-8)
+    np.testing.assert_allclose(N_(out["actions"]), ref["actions"], rtol=2e-5, atol=1e-30)
+    np.testing.assert_allclose(N_(out["grads"]), ref["grads"], rtol=2e-5, atol=2e-5)
+    v = np.abs(O.features(ref["states"]) @ w)
+    scale = np.abs(ref["rewards"]) + v[1:] + v[:-1]
+    assert np.all(np.abs(N_(out["deltas"]) - ref["deltas"]) <= 1e-6 * scale)
+    assert np.all(np.abs(N_(out["rewards"]) - ref["rewards"]) <= 1e-6 * np.maximum(scale, 1e-3))
+    acc = N_(out["acc"])
+    np.testing.assert_allclose(acc[0], ref["G_theta"], rtol=1e-4)
+    np.testing.assert_allclose(acc[1:1 + F], ref["G_w"], rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("d", [15, 16])
+def test_v2_philox_draws_match_other_variants(dev, d):
+    """Same (seed, population, step, row, pair) -> same Gamma variates in every kernel variant."""
+    B, T = 53, 4
+    rng = np.random.RandomState(d + 1)
+    pi0 = T_(rng.dirichlet(np.ones(d), size=B), dev, torch.float32)
+    kw = dict(seed=4321, outputs=("states", "actions", "rewards", "grads"))
+    a = eng.rollout(pi0, 8.64, 0.0, 1e4, T, variant="v2", **kw)
+    b = eng.rollout(pi0, 8.64, 0.0, 1e4, T, variant="fast", **kw)
+    for k in ("states", "actions"):
+        np.testing.assert_allclose(N_(a[k]), N_(b[k]), rtol=3e-5, atol=1e-9, err_msg=k)
+    np.testing.assert_allclose(N_(a["grads"]), N_(b["grads"]), rtol=1e-4, atol=1e-4)
+    h = eng.rollout(pi0[16:].contiguous(), 8.64, 0.0, 1e4, T, variant="v2", pop_offset=16, **kw)
+    assert torch.equal(h["actions"], a["actions"][:, 16:])
+    auto = eng.rollout(pi0, 8.64, 0.0, 1e4, T, **kw)                       # AUTO picks v2 here
+    assert torch.equal(auto["actions"], a["actions"])
