@@ -122,6 +122,8 @@ RolloutParams<R> make_params(const dmfg_rollout_args* a) {
     p.states = (R*)a->states; p.actions = (R*)a->actions; p.alpha = (R*)a->alpha;
     p.alpha_deriv = (R*)a->alpha_deriv; p.rewards = (R*)a->rewards; p.deltas = (R*)a->deltas;
     p.grads = (R*)a->grads; p.pi_final = (R*)a->pi_final; p.partials = nullptr;
+    p.rk = make_philox_keys(a->seed);
+    p.shift_f = (float)a->shift; p.scale_f = (float)a->alpha_scale;
     return p;
 }
 
@@ -145,9 +147,9 @@ int launch_fast(RolloutParams<R> p, bool td, int* grid_out, cudaStream_t st) {
     return DMFG_OK;
 }
 
-template <int D, int NOISE>
+template <int D, int NOISE, bool REC>
 int launch_v2(RolloutParams<float> p, bool td, int* grid_out, cudaStream_t st) {
-    auto kern = rollout_v2_kernel<D, NOISE>;
+    auto kern = rollout_v2_kernel<D, NOISE, REC>;
     const size_t smem = (size_t)(td && p.partials ? V2Smem<D>::total_td : V2Smem<D>::total_notd) * sizeof(double);
     DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(V2Smem<D>::total_td * sizeof(double))));
     int occ = 0, sms = 0;
@@ -164,10 +166,17 @@ int launch_v2(RolloutParams<float> p, bool td, int* grid_out, cudaStream_t st) {
     DMFG_CUDA(cudaGetLastError());
     return DMFG_OK;
 }
-int dispatch_v2(const RolloutParams<float>& p, int noise_kind, bool td, int* grid, cudaStream_t st) {
+template <int D>
+int dispatch_v2_d(const RolloutParams<float>& p, int noise_kind, bool td, int* grid, cudaStream_t st) {
+    // REC = any per-element stream (actions / alpha / alpha') is written; the train step compiles them out
+    const bool rec = p.actions != nullptr || p.alpha != nullptr;
     if (noise_kind == DMFG_NOISE_PHILOX)
-        return p.d == 15 ? launch_v2<15, DMFG_NOISE_PHILOX>(p, td, grid, st) : launch_v2<16, DMFG_NOISE_PHILOX>(p, td, grid, st);
-    return p.d == 15 ? launch_v2<15, DMFG_NOISE_INJECTED>(p, td, grid, st) : launch_v2<16, DMFG_NOISE_INJECTED>(p, td, grid, st);
+        return rec ? launch_v2<D, DMFG_NOISE_PHILOX, true>(p, td, grid, st)
+                   : launch_v2<D, DMFG_NOISE_PHILOX, false>(p, td, grid, st);
+    return launch_v2<D, DMFG_NOISE_INJECTED, true>(p, td, grid, st);
+}
+int dispatch_v2(const RolloutParams<float>& p, int noise_kind, bool td, int* grid, cudaStream_t st) {
+    return p.d == 15 ? dispatch_v2_d<15>(p, noise_kind, td, grid, st) : dispatch_v2_d<16>(p, noise_kind, td, grid, st);
 }
 
 template <typename R, int NOISE>

@@ -51,6 +51,29 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1
     return make_uint4(c0, c1, c2, c3);
 }
 
+// The same generator with the ten round keys (k + r*W) precomputed: the kernels take them as launch
+// parameters so the key schedule costs nothing per call; 64-bit products map to one IMAD.WIDE each.
+struct PhiloxKeys { uint32_t k[20]; };
+__host__ __device__ __forceinline__ PhiloxKeys make_philox_keys(uint64_t seed) {
+    PhiloxKeys K;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { K.k[2 * r] = k0; K.k[2 * r + 1] = k1; k0 += DMFG_PHILOX_W0; k1 += DMFG_PHILOX_W1; }
+    return K;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               const PhiloxKeys& K) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)DMFG_PHILOX_M0 * c0;
+        const uint64_t p1 = (uint64_t)DMFG_PHILOX_M1 * c2;
+        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k[2 * r];
+        c1 = (uint32_t)p1;
+        c2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k[2 * r + 1];
+        c3 = (uint32_t)p0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 // Identifies one stream of draws: key = seed, counter words 0/1 = global population id.
 struct NoiseKey {
     uint32_t k0, k1;     // seed
@@ -176,6 +199,38 @@ __device__ __forceinline__ void gamma_pair(const NoiseKey& nk, uint32_t slot, fl
     const bool done1 = mt_propose(g1.dd, g1.cc, n1, u01(w.w), y1);
     // rare: a rejection (~0.06/shape) or a shape below 1 -- kept out of line so the hot loop stays small
     if (!(done0 && done1) || g0.boost || g1.boost) gamma_pair_slow(nk, slot, a0, a1, done0, done1, y0, y1);
+}
+
+// ---- branch-light variant for the throughput kernel --------------------------------------------------
+// Same draws as gamma_pair (same counters, same accept/reject decisions): the straight-line part evaluates
+// attempt 0 with the squeeze only; anything else (squeeze miss ~0.06/shape, shape < 1) re-runs the pair
+// out of line through the exact path.  One predictable branch per pair.
+static __device__ __noinline__ float2 gamma_pair_redo(uint32_t p0, uint32_t p1, uint32_t k0, uint32_t k1,
+                                                      uint32_t slot, float a0, float a1) {
+    NoiseKey nk;
+    nk.k0 = k0; nk.k1 = k1; nk.p0 = p0; nk.p1 = p1;
+    float y0, y1;
+    gamma_pair(nk, slot, a0, a1, y0, y1);
+    return make_float2(y0, y1);
+}
+__device__ __forceinline__ void gamma_pair_fast(const NoiseKey& nk, const PhiloxKeys& K, uint32_t slot, float a0,
+                                                float a1, float& y0, float& y1) {
+    const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, 0u, K);
+    float n0, n1;
+    box_muller(w.x, w.y, n0, n1);
+    const float dd0 = a0 - (1.0f / 3.0f), dd1 = a1 - (1.0f / 3.0f);
+    const float e0 = rsqrt_approx(9.0f * dd0) * n0, e1 = rsqrt_approx(9.0f * dd1) * n1;
+    const float v0 = 1.0f + e0, v1 = 1.0f + e1;
+    const float q0 = e0 * e0, q1 = e1 * e1;
+    y0 = dd0 * (v0 * v0 * v0);
+    y1 = dd1 * (v1 * v1 * v1);
+    const bool ok0 = (fabsf(e0) <= 0.5f) & (u01(w.z) < fmaf(-1.5f * dd0, q0 * q0, 1.0f)) & (a0 >= 1.0f);
+    const bool ok1 = (fabsf(e1) <= 0.5f) & (u01(w.w) < fmaf(-1.5f * dd1, q1 * q1, 1.0f)) & (a1 >= 1.0f);
+    if (!(ok0 & ok1)) {
+        const float2 yy = gamma_pair_redo(nk.p0, nk.p1, nk.k0, nk.k1, slot, a0, a1);
+        y0 = yy.x;
+        y1 = yy.y;
+    }
 }
 
 // ------------------------------------------------------------ policy alpha

@@ -49,6 +49,8 @@ struct RolloutParams {
     const R* rewards_in;
     R *states, *actions, *alpha, *alpha_deriv, *rewards, *deltas, *grads, *pi_final;
     double* partials;      // [gridDim.x][2+F] per-CTA sums (fast variant with w)
+    PhiloxKeys rk;         // round keys of `seed` (v2 kernel)
+    float shift_f, scale_f;
 };
 
 // ---------------------------------------------------------------------------

@@ -53,7 +53,7 @@ __device__ __forceinline__ double critic_value_v2(const double* __restrict__ wl,
     return group_sum<kV2G>(v);
 }
 
-template <int D, int NOISE>
+template <int D, int NOISE, bool REC>
 __global__ void __launch_bounds__(kV2Threads, 3)
 rollout_v2_kernel(const RolloutParams<float> p) {
     using S = V2Smem<D>;
@@ -79,7 +79,8 @@ rollout_v2_kernel(const RolloutParams<float> p) {
     }
     __syncthreads();
     const float theta = (float)(p.theta_dev ? *p.theta_dev : p.theta);
-    const float shift = (float)p.shift, scale = (float)p.alpha_scale;
+    const float shift = p.shift_f, scale = p.scale_f;
+    const bool ac2 = p.reward_kind == DMFG_REWARD_AC2;
     double sum_dg = 0.0, sum_r = 0.0;
     const long long ntiles = (p.B + GPB - 1) / GPB;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -119,7 +120,8 @@ rollout_v2_kernel(const RolloutParams<float> p) {
                 dsum += d0 + d1;
                 float y0, y1;
                 if (NOISE == DMFG_NOISE_PHILOX) {
-                    gamma_pair(nk, gamma_slot((uint32_t)(p.step_offset + t), D, r, pp), a0 * scale, a1 * scale, y0, y1);
+                    gamma_pair_fast(nk, p.rk, gamma_slot((uint32_t)(p.step_offset + t), D, r, pp), a0 * scale,
+                                    a1 * scale, y0, y1);
                 } else {
                     y0 = row_ok ? p.noise_y[row + 2 * pp] : 1.0f;
                     y1 = (row_ok && ok1) ? p.noise_y[row + 2 * pp + 1] : 1.0f;
@@ -130,7 +132,7 @@ rollout_v2_kernel(const RolloutParams<float> p) {
                 ysum += (double)y0 + (double)y1;
                 *reinterpret_cast<float2*>(slots + 2 * pp) = make_float2(y0, d0);
                 *reinterpret_cast<float2*>(slots + 2 * pp + 1) = make_float2(y1, d1);
-                if (p.alpha != nullptr && wr) {
+                if (REC && p.alpha != nullptr && wr) {
                     p.alpha[row + 2 * pp] = a0;
                     p.alpha_deriv[row + 2 * pp] = d0;
                     if (ok1) { p.alpha[row + 2 * pp + 1] = a1; p.alpha_deriv[row + 2 * pp + 1] = d1; }
@@ -146,7 +148,7 @@ rollout_v2_kernel(const RolloutParams<float> p) {
             // ------------------------------------------------------------------ pass 2
             double racc = 0.0;
             float g2 = 0.f;
-            float* act_row = (p.actions != nullptr && wr) ? p.actions + row : nullptr;
+            float* act_row = (REC && p.actions != nullptr && wr) ? p.actions + row : nullptr;
 #pragma unroll 5
             for (int j = 0; j < D; ++j) {
                 const float2 yd = *reinterpret_cast<const float2*>(slots + j);
@@ -154,10 +156,11 @@ rollout_v2_kernel(const RolloutParams<float> p) {
                 const double P = yv * inv;
                 const float Pf = yd.x * inv_f;
                 g2 = fmaf(lg2_approx(Pf), yd.y, g2);
-                if (p.reward_kind == DMFG_REWARD_AC2) racc = fma(P * P, pic[j] - pi_self, racc);
-                else racc = fma(P, P, racc);
+                // AC2: P^2 (pi_j - pi_i); synthetic: P^2 (the factor is hoisted out of the element loop)
+                const double dlt = ac2 ? pic[j] - pi_self : 1.0;
+                racc = fma(P * P, dlt, racc);
                 slots[j] = yv * q;                                       // flux pi_i P_ij
-                if (act_row != nullptr) act_row[j] = Pf;
+                if (REC && act_row != nullptr) act_row[j] = Pf;
             }
             __syncwarp();
             // ------------------------------------------------------------------ pi' = P^T pi (transposed read)
@@ -166,7 +169,7 @@ rollout_v2_kernel(const RolloutParams<float> p) {
             for (int i = 0; i < D; ++i) next_self += col[i * kV2Slots];
             if (!row_ok) next_self = 0.0;
             double rew = 0.0;
-            if (p.reward_kind == DMFG_REWARD_AC2) rew = pi_self * racc;
+            if (ac2) rew = pi_self * racc;
             else if (p.reward_kind == DMFG_REWARD_SYNTHETIC) rew = -0.5 * pi_self * racc;
             const double glane = row_ok ? (double)(g1 + DMFG_LN2 * g2 + psi_row * dsum) : 0.0;
             rew = group_sum<G>(rew);
