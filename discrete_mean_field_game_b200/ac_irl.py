@@ -358,7 +358,7 @@ class AC_IRL(_actor_critic):
         """One gradient step on the reward net from device tensors (the kernel chain of update_reward):
         forward demo + gen -> loss and dL/dr -> backward demo + gen -> (all-reduce) -> Adam.
         gen_* hold M*15 transitions, `layout` 'time_major' | 'trajectory_major'.  Returns loss [4] (device)."""
-        import torch.distributed as dist
+        from . import parallel
         p = self.reward_params
         kd, kg = {}, {}
         if masks is not None:
@@ -375,14 +375,13 @@ class AC_IRL(_actor_critic):
             thetas = torch.as_tensor(np.asarray(self.list_policies, dtype=np.float64), device=self.device)
             lq = engine.dirichlet_logq(gen_states, gen_actions, thetas, self.shift)
             log_z = engine.irl_log_z(lq, T_STEPS, self.num_start_samples, layout=layout)
-        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized() and group is not False) else 1
+        _, world = parallel.world_info(group)
         res = engine.irl_loss_grad(r_demo, r_gen, T_STEPS, num_demo_traj, layout=layout, log_z=log_z)
         grad = engine.rnet_backward(p.flat, demo_states, demo_actions, res["d_demo"], p.n_fc3, p.n_fc4,
                                     keep_prob=networks.KEEP_PROB, **kd)
         engine.rnet_backward(p.flat, gen_states, gen_actions, res["d_gen"], p.n_fc3, p.n_fc4, grad=grad,
                              accumulate=True, keep_prob=networks.KEEP_PROB, **kg)
-        if world > 1:
-            dist.all_reduce(grad, group=group)
+        parallel.allreduce_sum_(grad, group)
         p.step += 1
         reg = engine.adam_tf(p.flat, p.m, p.v, grad, p.step, self.lr_reward, grad_scale=1.0 / world,
                              l1l2=self._l1l2, net=(p.d, p.n_fc3, p.n_fc4), want_reg_loss=self._l1l2)

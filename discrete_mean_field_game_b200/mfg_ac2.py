@@ -301,13 +301,12 @@ class actor_critic:
         pi0 [B,d]: host array / pinned tensor (copied in every episode) or a CUDA tensor.
         Returns dict(theta, mean_reward [num_episodes]).
         """
-        import torch.distributed as dist
+        from . import parallel
         d = self.d
         seed = self.seed if seed is None else seed
         theta = torch.tensor([float(self.theta)], dtype=torch.float64, device=self.device)
         w = self._w_dev().clone()
-        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()
-                                               and group is not False) else 1
+        _, world = parallel.world_info(group)
         first = self.first_episode if first_episode is None else first_episode
         mean_rewards = []
         for e in range(num_episodes):
@@ -320,9 +319,7 @@ class actor_critic:
                 out = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, T, w=w, theta_dev=theta, gamma=gamma,
                                      reward=self.reward_kind, discount=self.discount_kind, seed=seed,
                                      pop_offset=pop_offset, step_offset=episode * T, outputs=(), want_acc=True)
-                acc = out["acc"]
-                if world > 1:
-                    dist.all_reduce(acc, group=group)
+                acc = parallel.allreduce_sum_(out["acc"], group)
                 engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / (B * world))
                 mean_rewards.append(acc[-1] / (B * world))
             elif update == "per_step":
@@ -332,9 +329,7 @@ class actor_critic:
                     out = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, 1, w=w, theta_dev=theta,
                                          gamma=g_next, reward=self.reward_kind, seed=seed, pop_offset=pop_offset,
                                          step_offset=episode * T + t, outputs=("pi_final",), want_acc=True)
-                    acc = out["acc"]
-                    if world > 1:
-                        dist.all_reduce(acc, group=group)
+                    acc = parallel.allreduce_sum_(out["acc"], group)
                     engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / (B * world))
                     tot = tot + acc[-1] / (B * world)
                     disc *= gamma
