@@ -284,6 +284,23 @@ def run_ours(args):
                  "rollout_record": {"value": Br * T / (ms_rec * 1e-3), "unit": UNIT, "populations": Br,
                                     "hbm_gbs": Br * T * ALGO_BYTES_RECORD / (ms_rec * 1e-3) / 1e9}}
         del rec_out
+        # IRL iterations/s (BASELINE config 2): 4096 demonstration + 4096 generated trajectories x 15 steps,
+        # one update_reward-equivalent = r_net forward (demo, gen) + loss + backward (demo, gen) + Adam
+        import contextlib
+        from discrete_mean_field_game_b200.ac_irl import AC_IRL
+        M = 4096
+        with contextlib.redirect_stdout(sys.stderr):          # the class prints like the reference does
+            irl = AC_IRL(theta=8.64, shift=0, alpha_scale=1e4, d=D, reg="none", n_fc3=8, n_fc4=4,
+                         mat_pi0=synthetic_pi0(64, seed=5), demonstrations=[], device=dev, seed=1, net_seed=2)
+        ds, da = irl.generate_batch(M, theta=8.06)
+        gs, ga = irl.generate_batch(M)
+        ds, da = ds[:15].reshape(-1, D), da.reshape(-1, D, D)
+        gs, ga = gs[:15].reshape(-1, D), ga.reshape(-1, D, D)
+        ms_irl = timed(lambda: irl.update_reward_batch(ds, da, gs, ga, M, "time_major", group=False), n=5)
+        modes["irl_update"] = {"value": 1e3 / ms_irl, "unit": "IRL iters/s", "demo_trajectories": M,
+                               "generated_trajectories": M, "transitions_per_iter": 2 * M * 15,
+                               "transitions_per_s": 2 * M * 15 / (ms_irl * 1e-3), "gpu_launches_per_iter": 10}
+        del irl, ds, da, gs, ga
 
     if world > 1:
         dist.barrier()
@@ -295,7 +312,7 @@ def run_ours(args):
     peak, peak_src = load_peaks()
     achieved = B * T * ALGO_BYTES_TRAIN / (ms_kern * 1e-3) / 1e9
     consts = load_profile_constants()
-    roofline = {"bound": "hbm", "kernel": "rollout_fast_kernel<15,16,float,PHILOX>", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "rollout_v2_kernel<15,PHILOX,train>", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": consts.get("train_dram_bytes_per_launch"),
                 "peak_source": peak_src, "kernel_ms": ms_kern,
                 "algorithmic_bytes_per_population_step": ALGO_BYTES_TRAIN,

@@ -7,7 +7,7 @@ import torch
 from discrete_mean_field_game_b200 import engine
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--log2-pops", type=int, default=18)
+ap.add_argument("--log2-pops", type=int, default=20)
 ap.add_argument("--mode", default="train", choices=["train", "record", "rollout"])
 ap.add_argument("--iters", type=int, default=3)
 a = ap.parse_args()
