@@ -147,9 +147,9 @@ int launch_fast(RolloutParams<R> p, bool td, int* grid_out, cudaStream_t st) {
     return DMFG_OK;
 }
 
-template <int D, int NOISE, bool REC>
+template <int D, int NOISE, bool REC, bool TRAIN>
 int launch_v2(RolloutParams<float> p, bool td, int* grid_out, cudaStream_t st) {
-    auto kern = rollout_v2_kernel<D, NOISE, REC>;
+    auto kern = rollout_v2_kernel<D, NOISE, REC, TRAIN>;
     const size_t smem = (size_t)(td && p.partials ? V2Smem<D>::total_td : V2Smem<D>::total_notd) * sizeof(double);
     DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(V2Smem<D>::total_td * sizeof(double))));
     int occ = 0, sms = 0;
@@ -170,10 +170,14 @@ template <int D>
 int dispatch_v2_d(const RolloutParams<float>& p, int noise_kind, bool td, int* grid, cudaStream_t st) {
     // REC = any per-element stream (actions / alpha / alpha') is written; the train step compiles them out
     const bool rec = p.actions != nullptr || p.alpha != nullptr;
-    if (noise_kind == DMFG_NOISE_PHILOX)
-        return rec ? launch_v2<D, DMFG_NOISE_PHILOX, true>(p, td, grid, st)
-                   : launch_v2<D, DMFG_NOISE_PHILOX, false>(p, td, grid, st);
-    return launch_v2<D, DMFG_NOISE_INJECTED, true>(p, td, grid, st);
+    const bool train = !rec && td && p.partials != nullptr && !p.states && !p.rewards && !p.deltas && !p.grads &&
+                       !p.pi_final && !p.rewards_in;
+    if (noise_kind == DMFG_NOISE_PHILOX) {
+        if (train) return launch_v2<D, DMFG_NOISE_PHILOX, false, true>(p, td, grid, st);
+        return rec ? launch_v2<D, DMFG_NOISE_PHILOX, true, false>(p, td, grid, st)
+                   : launch_v2<D, DMFG_NOISE_PHILOX, false, false>(p, td, grid, st);
+    }
+    return launch_v2<D, DMFG_NOISE_INJECTED, true, false>(p, td, grid, st);
 }
 int dispatch_v2(const RolloutParams<float>& p, int noise_kind, bool td, int* grid, cudaStream_t st) {
     return p.d == 15 ? dispatch_v2_d<15>(p, noise_kind, td, grid, st) : dispatch_v2_d<16>(p, noise_kind, td, grid, st);

@@ -110,11 +110,16 @@ __device__ __forceinline__ float u01(uint32_t w) {
     return fmaf(__uint2float_rz(w), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }
 
+// 23-bit uniform in [0,1) without an int->float conversion (those run on the quarter-rate XU pipe):
+// the top 23 bits become the mantissa of a float in [1,2).
+__device__ __forceinline__ float u01_23(uint32_t w) { return __uint_as_float((w >> 9) | 0x3f800000u) - 1.0f; }
+
 // two standard normals from two 32-bit words (Box-Muller).  The angle is taken in (-pi, pi), where
 // sin/cos.approx are accurate to ~5e-7 absolute; the radius resolves 32 bits (tails to 6.6 sigma).
 __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& n0, float& n1) {
     const float r = sqrt_approx(-2.0f * DMFG_LN2 * lg2_approx(u01(w0)));
-    const float ang = fmaf(__uint2float_rz(w1), 1.4629180792671596e-9f, -3.1415925f);   // 2 pi 2^-32 w - pi
+    // angle in (-pi, pi) from the top 23 bits of w1: [1,2) * 2pi - 3pi (+ half a step so that neither end is hit)
+    const float ang = fmaf(__uint_as_float((w1 >> 9) | 0x3f800000u), 6.2831845f, -9.4247770f);
     n0 = r * cos_approx(ang);
     n1 = r * sin_approx(ang);
 }

@@ -37,9 +37,14 @@ struct V2Smem {
     static constexpr int pid = tile + GPB * kV2G * kV2Slots;        // [2][GPB][16] state, double
     static constexpr int wl = pid + 2 * GPB * kV2G;                 // [NSLOT][16] critic slots
     static constexpr int pif = wl + NSLOT * kV2G;                   // [2][GPB][16] state, float (GPB*16 doubles)
-    static constexpr int acc = pif + GPB * kV2G;                    // [NSLOT][NT] accumulators (train only)
+    // per-group gradient accumulators (train only), TRIANGULAR: lane r of a group only ever touches the
+    // quadratic features (r,k) with k >= r -> [k(k+1)/2 + r] for k < D, then the D linear slots (padded to
+    // 16) and the bias: 137 / 153 doubles per group instead of 17 x 16 (3 CTAs per SM instead of 2)
+    static constexpr int Q = D * (D + 1) / 2;
+    static constexpr int acc_group = (Q + kV2G + 1 + 1) & ~1;
+    static constexpr int acc = pif + GPB * kV2G;
     static constexpr int total_notd = acc;
-    static constexpr int total_td = acc + NSLOT * kV2Threads;
+    static constexpr int total_td = acc + GPB * acc_group;
 };
 
 // critic value from the shared state buffer: lane r sums w[r,k] pi_r pi_k over k >= r (zeros below)
@@ -53,7 +58,9 @@ __device__ __forceinline__ double critic_value_v2(const double* __restrict__ wl,
     return group_sum<kV2G>(v);
 }
 
-template <int D, int NOISE, bool REC>
+// TRAIN = the batched train step: accumulators wanted and NO per-step output stream requested -- every
+// output test is compiled out of the step loop.  REC = some per-element stream (actions / alpha) is written.
+template <int D, int NOISE, bool REC, bool TRAIN>
 __global__ void __launch_bounds__(kV2Threads, 3)
 rollout_v2_kernel(const RolloutParams<float> p) {
     using S = V2Smem<D>;
@@ -66,16 +73,14 @@ rollout_v2_kernel(const RolloutParams<float> p) {
     double* pid = smem + S::pid + grp * G;                                 // [2] buffers, stride GPB*G
     float* pif = reinterpret_cast<float*>(smem + S::pif) + grp * G;        // [2] buffers, stride GPB*G
     const double* wl = smem + S::wl;
-    double* acc = smem + S::acc + tid;
-    const bool td = p.w != nullptr;
-    const bool want_acc = td && p.partials != nullptr;
+    double* acc = smem + S::acc + grp * S::acc_group;                      // this group's triangular block
+    const bool td = TRAIN || p.w != nullptr;
+    const bool want_acc = TRAIN || (td && p.partials != nullptr);
     const bool row_ok = r < D;
     if (td) {
         if (tid < G) stage_critic_slots<D>(smem + S::wl + tid, G, p.w, tid);
-        if (want_acc) {
-#pragma unroll
-            for (int k = 0; k < NSLOT; ++k) acc[k * NT] = 0.0;
-        }
+        if (want_acc)
+            for (int k = r; k < S::acc_group; k += G) acc[k] = 0.0;
     }
     __syncthreads();
     const float theta = (float)(p.theta_dev ? *p.theta_dev : p.theta);
@@ -96,7 +101,7 @@ rollout_v2_kernel(const RolloutParams<float> p) {
         __syncwarp();
         double v_cur = td ? critic_value_v2<D>(wl, pid, pi_self, r) : 0.0;
         double disc = 1.0;
-        if (p.states != nullptr && wr) p.states[b * D + r] = (float)pi_self;
+        if (!TRAIN && p.states != nullptr && wr) p.states[b * D + r] = (float)pi_self;
         for (int t = 0; t < p.T; ++t) {
             const long long tb = (long long)t * p.B + b;
             const long long row = (tb * D + r) * D;
@@ -129,7 +134,7 @@ rollout_v2_kernel(const RolloutParams<float> p) {
                 if (y0 == 0.0f) y0 = 1e-20f;                             // mfg_ac2.py:244
                 if (y1 == 0.0f) y1 = 1e-20f;
                 if (!ok1) y1 = 0.0f;
-                ysum += (double)y0 + (double)y1;
+                ysum += (double)(y0 + y1);       // pair sum in float: <= 6e-8 relative on the pair, one conversion
                 *reinterpret_cast<float2*>(slots + 2 * pp) = make_float2(y0, d0);
                 *reinterpret_cast<float2*>(slots + 2 * pp + 1) = make_float2(y1, d1);
                 if (REC && p.alpha != nullptr && wr) {
@@ -178,33 +183,39 @@ rollout_v2_kernel(const RolloutParams<float> p) {
             pid[nxt * (GPB * G) + r] = next_self;
             pif[nxt * (GPB * G) + r] = (float)next_self;
             __syncwarp();
-            if (p.rewards_in != nullptr) rew = (double)p.rewards_in[tb];
+            if (!TRAIN && p.rewards_in != nullptr) rew = (double)p.rewards_in[tb];
             if (td) {
                 const double v_next = critic_value_v2<D>(wl, pid + nxt * (GPB * G), next_self, r);
                 const double gfac = p.discount_kind == DMFG_DISCOUNT_STEP ? p.gamma : disc;
                 const double delta = rew + gfac * v_next - v_cur;
                 if (want_acc && live) {
                     const double dp = delta * pi_self;
-#pragma unroll 5
-                    for (int k = 0; k < D; ++k) acc[k * NT] = fma(dp, pic[k], acc[k * NT]);
-                    acc[D * NT] += dp;
-                    acc[(D + 1) * NT] += delta;
-                    if (r == 0) sum_dg = fma(delta, grad, sum_dg);
+                    // quadratic features (r,k), k >= r, at [k(k+1)/2 + r]; linear at [Q + r]; bias at [Q + 16]
+#pragma unroll
+                    for (int k = 0; k < D; ++k)
+                        if (k >= r) acc[k * (k + 1) / 2 + r] = fma(dp, pic[k], acc[k * (k + 1) / 2 + r]);
+                    if (row_ok) acc[S::Q + r] += dp;
+                    if (r == 0) {
+                        acc[S::Q + G] += delta;
+                        sum_dg = fma(delta, grad, sum_dg);
+                    }
                 }
-                if (p.deltas != nullptr && live && r == 0) p.deltas[tb] = (float)delta;
+                if (!TRAIN && p.deltas != nullptr && live && r == 0) p.deltas[tb] = (float)delta;
                 v_cur = v_next;
             }
             if (live && r == 0) {
                 sum_r += rew;
-                if (p.rewards != nullptr) p.rewards[tb] = (float)rew;
-                if (p.grads != nullptr) p.grads[tb] = (float)grad;
+                if (!TRAIN) {
+                    if (p.rewards != nullptr) p.rewards[tb] = (float)rew;
+                    if (p.grads != nullptr) p.grads[tb] = (float)grad;
+                }
             }
             disc *= p.gamma;
             pi_self = next_self;
             cur = nxt;
-            if (p.states != nullptr && wr) p.states[(tb + p.B) * D + r] = (float)pi_self;
+            if (!TRAIN && p.states != nullptr && wr) p.states[(tb + p.B) * D + r] = (float)pi_self;
         }
-        if (p.pi_final != nullptr && wr) p.pi_final[b * D + r] = (float)pi_self;
+        if (!TRAIN && p.pi_final != nullptr && wr) p.pi_final[b * D + r] = (float)pi_self;
         // make the next population start from buffer 0 again
         __syncwarp();
     }
@@ -224,20 +235,21 @@ rollout_v2_kernel(const RolloutParams<float> p) {
     double* out = p.partials + (long long)blockIdx.x * (2 + F);
     const double* accbase = smem + S::acc;
     for (int f = tid; f < F; f += NT) {
-        int rw, k;
-        constexpr int Q = D * (D + 1) / 2;
+        // feature f of the reference order -> slot of the triangular per-group block
+        int slot;
+        constexpr int Q = S::Q;
         if (f < Q) {
-            rw = 0;
-            int rem = f;
+            int rw = 0, rem = f;
             while (rem >= D - rw) { rem -= D - rw; ++rw; }
-            k = rw + rem;
+            const int k = rw + rem;
+            slot = k * (k + 1) / 2 + rw;
         } else if (f < Q + D) {
-            rw = f - Q; k = D;
+            slot = Q + (f - Q);
         } else {
-            rw = 0; k = D + 1;
+            slot = Q + G;
         }
         double s = 0.0;
-        for (int g = 0; g < GPB; ++g) s += accbase[k * NT + g * G + rw];
+        for (int g = 0; g < GPB; ++g) s += accbase[g * S::acc_group + slot];
         out[1 + f] = s;
     }
     if (tid == 0) {
