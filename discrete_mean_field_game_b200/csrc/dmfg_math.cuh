@@ -124,20 +124,28 @@ __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& n0, 
     n1 = r * sin_approx(ang);
 }
 
-// One Marsaglia-Tsang proposal for Gamma(dd + 1/3, 1), cc = 1/sqrt(9 dd): y = dd (1 + cc x)^3, accepted
-// iff ln u < x^2/2 + dd (1 - v + ln v), v = (1 + cc x)^3.
+// Marsaglia-Tsang proposal for Gamma(dd + 1/3, 1), cc = 1/sqrt(9 dd): y = dd (1 + cc x)^3, accepted iff
+// ln u < x^2/2 + dd (1 - v + ln v), v = (1 + cc x)^3.
 // With e = cc x the right-hand side is  -dd (0.75 e^4 - 0.6 e^5 + 0.5 e^6 - ...)  (dd cc^2 = 1/9 cancels the
 // x^2/2 term exactly), bounded below by -1.5 dd e^4 for |e| <= 1/2.  Since exp(-z) >= 1 - z,
-//     |e| <= 1/2  and  u < 1 - 1.5 dd e^4      ==> accept
+//     |e| <= 1/2  and  u < thr = 1 - 1.5 dd e^4      ==> accept
 // is a squeeze that fails with probability ~0.055/dd only (Marsaglia & Tsang's generic 0.0331 x^4 squeeze
-// fails 10 % of the time for every shape); the exact test below it is evaluated cancellation-free.
-__device__ __forceinline__ bool mt_propose(float dd, float cc, float x, float u, float& y) {
-    const float e = cc * x;
-    const float v1 = 1.0f + e;
-    const float e2 = e * e;
-    y = dd * (v1 * v1 * v1);
-    if (fabsf(e) <= 0.5f && u < fmaf(-1.5f * dd, e2 * e2, 1.0f)) return true;
+// fails 10 % of the time for every shape).  __fmul_rn / __fadd_rn pin the roundings, so every kernel
+// variant computes bit-identical proposals.
+__device__ __forceinline__ bool mt_squeeze(float dd, float cc, float x, float u, float& y, float& thr) {
+    const float e = __fmul_rn(cc, x);
+    const float v1 = __fadd_rn(1.0f, e);
+    const float e2 = __fmul_rn(e, e);
+    y = __fmul_rn(dd, __fmul_rn(v1, __fmul_rn(v1, v1)));
+    thr = __fmaf_rn(__fmul_rn(-1.5f, dd), __fmul_rn(e2, e2), 1.0f);
+    return (fabsf(e) <= 0.5f) & (u < thr);
+}
+// the exact acceptance test (only reached when the squeeze failed), cancellation-free
+__device__ __forceinline__ bool mt_exact(float dd, float cc, float x, float u) {
+    const float e = __fmul_rn(cc, x);
+    const float v1 = __fadd_rn(1.0f, e);
     if (v1 <= 0.0f) return false;
+    const float e2 = e * e;
     float rhs;
     if (fabsf(e) < 0.25f) {
         // sum_{k>=4} (-1)^(k+1) e^k/k = -e^4 h,  h = sum_{m=0..9} (-e)^m/(m+4)  (|e|<1/4: rel. err < 2e-7)
@@ -159,57 +167,66 @@ __device__ __forceinline__ bool mt_propose(float dd, float cc, float x, float u,
     return __logf(u) < rhs;
 }
 
+// Shapes below 1: Gamma(a) = Gamma(a+1) U^(1/a) with U uniform and independent of the Gamma(a+1) draw
+// (a == 0 gives 0 like np.random.gamma).  When the proposal was accepted by the squeeze, u | accept is
+// uniform on (0, thr) whatever x was, so U = u / thr costs nothing; otherwise a fresh word is drawn.
+__device__ __forceinline__ float boost_apply(float y, float a, float U) {
+    return a > 0.0f ? __fmul_rn(y, ex2_approx(__fmul_rn(lg2_approx(U), rcp_approx(a)))) : 0.0f;
+}
+__device__ __forceinline__ float squeeze_uniform(float u, float thr) { return __fmul_rn(u, rcp_approx(thr)); }
+
 struct GammaSetup {
-    float dd, cc, inv_a;
+    float dd, cc;
     bool boost;
 };
 __device__ __forceinline__ GammaSetup gamma_setup(float a) {
     GammaSetup g;
     g.boost = a < 1.0f;
-    g.inv_a = 0.0f;                        // filled in by the (rare) boost path
-    const float a1 = g.boost ? a + 1.0f : a;
-    g.dd = a1 - (1.0f / 3.0f);
-    g.cc = rsqrt_approx(9.0f * g.dd);
+    const float a1 = g.boost ? __fadd_rn(a, 1.0f) : a;
+    g.dd = __fadd_rn(a1, -(1.0f / 3.0f));
+    g.cc = rsqrt_approx(__fmul_rn(9.0f, g.dd));
     return g;
 }
 
-// Gamma(a0,1), Gamma(a1,1) for the pair in `slot`.  One Philox call feeds both elements (two Box-Muller
-// normals + two acceptance uniforms); rejected elements move on to attempt+1.  Shapes < 1 take one more
-// call for the boost uniforms: Gamma(a) = Gamma(a+1) U^(1/a); a == 0 gives 0 like np.random.gamma.
-static __device__ __noinline__ void gamma_pair_slow(const NoiseKey& nk, uint32_t slot, float a0, float a1, bool done0,
-                                             bool done1, float& y0, float& y1) {
-    const GammaSetup g0 = gamma_setup(a0), g1 = gamma_setup(a1);
-    uint32_t attempt = 1;
-    while (!(done0 && done1) && attempt < 64u) {
-        const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, attempt, nk.k0, nk.k1);
-        float n0, n1;
-        box_muller(w.x, w.y, n0, n1);
-        if (!done0) done0 = mt_propose(g0.dd, g0.cc, n0, u01(w.z), y0);
-        if (!done1) done1 = mt_propose(g1.dd, g1.cc, n1, u01(w.w), y1);
-        ++attempt;
-    }
-    if (g0.boost || g1.boost) {
-        const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, DMFG_CTR_BOOST, nk.k0, nk.k1);
-        if (g0.boost) y0 = a0 > 0.0f ? y0 * ex2_approx(lg2_approx(u01(w.x)) / a0) : 0.0f;
-        if (g1.boost) y1 = a1 > 0.0f ? y1 * ex2_approx(lg2_approx(u01(w.y)) / a1) : 0.0f;
-    }
-}
+// Gamma(a0,1), Gamma(a1,1) for the pair in `slot` -- the reference form of the sampler (generic / parity
+// kernels, and the out-of-line path of the throughput kernel).  One Philox call per attempt feeds both
+// elements (two Box-Muller normals + two acceptance uniforms); rejected elements move on to attempt+1.
 __device__ __forceinline__ void gamma_pair(const NoiseKey& nk, uint32_t slot, float a0, float a1,
                                            float& y0, float& y1) {
     const GammaSetup g0 = gamma_setup(a0), g1 = gamma_setup(a1);
-    const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, 0u, nk.k0, nk.k1);
-    float n0, n1;
-    box_muller(w.x, w.y, n0, n1);
-    const bool done0 = mt_propose(g0.dd, g0.cc, n0, u01(w.z), y0);
-    const bool done1 = mt_propose(g1.dd, g1.cc, n1, u01(w.w), y1);
-    // rare: a rejection (~0.06/shape) or a shape below 1 -- kept out of line so the hot loop stays small
-    if (!(done0 && done1) || g0.boost || g1.boost) gamma_pair_slow(nk, slot, a0, a1, done0, done1, y0, y1);
+    bool done0 = false, done1 = false, sq0 = false, sq1 = false;
+    float ub0 = 0.5f, ub1 = 0.5f;
+    y0 = 0.0f; y1 = 0.0f;
+    uint32_t attempt = 0;
+    do {
+        const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, attempt, nk.k0, nk.k1);
+        float n0, n1, thr;
+        box_muller(w.x, w.y, n0, n1);
+        if (!done0) {
+            const float u = u01(w.z);
+            if (mt_squeeze(g0.dd, g0.cc, n0, u, y0, thr)) { done0 = sq0 = true; ub0 = squeeze_uniform(u, thr); }
+            else done0 = mt_exact(g0.dd, g0.cc, n0, u);
+        }
+        if (!done1) {
+            const float u = u01(w.w);
+            if (mt_squeeze(g1.dd, g1.cc, n1, u, y1, thr)) { done1 = sq1 = true; ub1 = squeeze_uniform(u, thr); }
+            else done1 = mt_exact(g1.dd, g1.cc, n1, u);
+        }
+        ++attempt;
+    } while (!(done0 && done1) && attempt < 64u);
+    if ((g0.boost && !sq0) || (g1.boost && !sq1)) {
+        const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, DMFG_CTR_BOOST, nk.k0, nk.k1);
+        if (!sq0) ub0 = u01(w.x);
+        if (!sq1) ub1 = u01(w.y);
+    }
+    if (g0.boost) y0 = boost_apply(y0, a0, ub0);
+    if (g1.boost) y1 = boost_apply(y1, a1, ub1);
 }
 
 // ---- branch-light variant for the throughput kernel --------------------------------------------------
-// Same draws as gamma_pair (same counters, same accept/reject decisions): the straight-line part evaluates
-// attempt 0 with the squeeze only; anything else (squeeze miss ~0.06/shape, shape < 1) re-runs the pair
-// out of line through the exact path.  One predictable branch per pair.
+// Same draws as gamma_pair (same counters, roundings and accept decisions): the straight-line part covers
+// attempt 0 accepted by the squeeze, including shapes below 1; a squeeze miss (~0.06/shape) re-runs the pair
+// out of line.  One rarely taken branch per pair.
 static __device__ __noinline__ float2 gamma_pair_redo(uint32_t p0, uint32_t p1, uint32_t k0, uint32_t k1,
                                                       uint32_t slot, float a0, float a1) {
     NoiseKey nk;
@@ -221,20 +238,19 @@ static __device__ __noinline__ float2 gamma_pair_redo(uint32_t p0, uint32_t p1, 
 __device__ __forceinline__ void gamma_pair_fast(const NoiseKey& nk, const PhiloxKeys& K, uint32_t slot, float a0,
                                                 float a1, float& y0, float& y1) {
     const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, 0u, K);
-    float n0, n1;
+    float n0, n1, thr0, thr1;
     box_muller(w.x, w.y, n0, n1);
-    const float dd0 = a0 - (1.0f / 3.0f), dd1 = a1 - (1.0f / 3.0f);
-    const float e0 = rsqrt_approx(9.0f * dd0) * n0, e1 = rsqrt_approx(9.0f * dd1) * n1;
-    const float v0 = 1.0f + e0, v1 = 1.0f + e1;
-    const float q0 = e0 * e0, q1 = e1 * e1;
-    y0 = dd0 * (v0 * v0 * v0);
-    y1 = dd1 * (v1 * v1 * v1);
-    const bool ok0 = (fabsf(e0) <= 0.5f) & (u01(w.z) < fmaf(-1.5f * dd0, q0 * q0, 1.0f)) & (a0 >= 1.0f);
-    const bool ok1 = (fabsf(e1) <= 0.5f) & (u01(w.w) < fmaf(-1.5f * dd1, q1 * q1, 1.0f)) & (a1 >= 1.0f);
+    const GammaSetup g0 = gamma_setup(a0), g1 = gamma_setup(a1);
+    const float u0 = u01(w.z), u1 = u01(w.w);
+    const bool ok0 = mt_squeeze(g0.dd, g0.cc, n0, u0, y0, thr0);
+    const bool ok1 = mt_squeeze(g1.dd, g1.cc, n1, u1, y1, thr1);
     if (!(ok0 & ok1)) {
         const float2 yy = gamma_pair_redo(nk.p0, nk.p1, nk.k0, nk.k1, slot, a0, a1);
         y0 = yy.x;
         y1 = yy.y;
+    } else if (g0.boost | g1.boost) {
+        if (g0.boost) y0 = boost_apply(y0, a0, squeeze_uniform(u0, thr0));
+        if (g1.boost) y1 = boost_apply(y1, a1, squeeze_uniform(u1, thr1));
     }
 }
 
