@@ -1,0 +1,24 @@
+"""Tiny driver for ncu: a few IRL reward updates at BASELINE config 2 (4096 + 4096 trajectories x 15 steps)."""
+import contextlib
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from discrete_mean_field_game_b200.ac_irl import AC_IRL
+
+M, D = 4096, 15
+dev = torch.device("cuda:0")
+rng = np.random.RandomState(5)
+g = rng.standard_gamma(1.0, size=(64, D))
+with contextlib.redirect_stdout(sys.stderr):
+    irl = AC_IRL(theta=8.64, shift=0, alpha_scale=1e4, d=D, reg="none", n_fc3=8, n_fc4=4,
+                 mat_pi0=g / g.sum(1, keepdims=True), demonstrations=[], device=dev, seed=1, net_seed=2)
+ds, da = irl.generate_batch(M, theta=8.06)
+gs, ga = irl.generate_batch(M)
+ds, da = ds[:15].reshape(-1, D), da.reshape(-1, D, D)
+gs, ga = gs[:15].reshape(-1, D), ga.reshape(-1, D, D)
+for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
+    irl.update_reward_batch(ds, da, gs, ga, M, "time_major", group=False)
+torch.cuda.synchronize()
+print("done")
