@@ -345,7 +345,7 @@ __global__ void gamma_sample_kernel(const float* __restrict__ shape, long long n
     if (i >= n) return;
     const float a0 = shape[i], a1 = (i + 1 < n) ? shape[i + 1] : 1.0f;
     float y0, y1;
-    gamma_pair(nk, (uint32_t)pair, a0, a1, y0, y1);
+    gamma_pair(nk, (uint32_t)pair, a0, a1, 1.0f, y0, y1);
     out[i] = y0;
     if (i + 1 < n) out[i + 1] = y1;
 }

@@ -134,7 +134,8 @@ __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& n0, 
 // variant computes bit-identical proposals.
 __device__ __forceinline__ bool mt_squeeze(float dd, float cc, float x, float u, float& y, float& thr) {
     const float e = __fmul_rn(cc, x);
-    const float v1 = __fadd_rn(1.0f, e);
+    const float v1 = __fmaf_rn(cc, x, 1.0f);       // every mul-add site of the proposal is an EXPLICIT fma, so
+                                                   // scalar and packed (f32x2) code cannot round differently
     const float e2 = __fmul_rn(e, e);
     y = __fmul_rn(dd, __fmul_rn(v1, __fmul_rn(v1, v1)));
     thr = __fmaf_rn(__fmul_rn(-1.5f, dd), __fmul_rn(e2, e2), 1.0f);
@@ -143,7 +144,7 @@ __device__ __forceinline__ bool mt_squeeze(float dd, float cc, float x, float u,
 // the exact acceptance test (only reached when the squeeze failed), cancellation-free
 __device__ __forceinline__ bool mt_exact(float dd, float cc, float x, float u) {
     const float e = __fmul_rn(cc, x);
-    const float v1 = __fadd_rn(1.0f, e);
+    const float v1 = __fmaf_rn(cc, x, 1.0f);
     if (v1 <= 0.0f) return false;
     const float e2 = e * e;
     float rhs;
@@ -179,11 +180,12 @@ struct GammaSetup {
     float dd, cc;
     bool boost;
 };
-__device__ __forceinline__ GammaSetup gamma_setup(float a) {
+// shape = alpha * scale; shapes below 1 are sampled as Gamma(shape + 1) and boosted afterwards.
+// dd = shape (+1) - 1/3 as ONE fma of (alpha, scale)
+__device__ __forceinline__ GammaSetup gamma_setup(float alpha, float scale) {
     GammaSetup g;
-    g.boost = a < 1.0f;
-    const float a1 = g.boost ? __fadd_rn(a, 1.0f) : a;
-    g.dd = __fadd_rn(a1, -(1.0f / 3.0f));
+    g.boost = __fmul_rn(alpha, scale) < 1.0f;
+    g.dd = __fmaf_rn(alpha, scale, g.boost ? (2.0f / 3.0f) : -(1.0f / 3.0f));
     g.cc = rsqrt_approx(__fmul_rn(9.0f, g.dd));
     return g;
 }
@@ -191,9 +193,10 @@ __device__ __forceinline__ GammaSetup gamma_setup(float a) {
 // Gamma(a0,1), Gamma(a1,1) for the pair in `slot` -- the reference form of the sampler (generic / parity
 // kernels, and the out-of-line path of the throughput kernel).  One Philox call per attempt feeds both
 // elements (two Box-Muller normals + two acceptance uniforms); rejected elements move on to attempt+1.
-__device__ __forceinline__ void gamma_pair(const NoiseKey& nk, uint32_t slot, float a0, float a1,
+__device__ __forceinline__ void gamma_pair(const NoiseKey& nk, uint32_t slot, float al0, float al1, float scale,
                                            float& y0, float& y1) {
-    const GammaSetup g0 = gamma_setup(a0), g1 = gamma_setup(a1);
+    const GammaSetup g0 = gamma_setup(al0, scale), g1 = gamma_setup(al1, scale);
+    const float a0 = __fmul_rn(al0, scale), a1 = __fmul_rn(al1, scale);
     bool done0 = false, done1 = false, sq0 = false, sq1 = false;
     float ub0 = 0.5f, ub1 = 0.5f;
     y0 = 0.0f; y1 = 0.0f;
@@ -203,12 +206,12 @@ __device__ __forceinline__ void gamma_pair(const NoiseKey& nk, uint32_t slot, fl
         float n0, n1, thr;
         box_muller(w.x, w.y, n0, n1);
         if (!done0) {
-            const float u = u01(w.z);
+            const float u = u01_23(w.z);
             if (mt_squeeze(g0.dd, g0.cc, n0, u, y0, thr)) { done0 = sq0 = true; ub0 = squeeze_uniform(u, thr); }
             else done0 = mt_exact(g0.dd, g0.cc, n0, u);
         }
         if (!done1) {
-            const float u = u01(w.w);
+            const float u = u01_23(w.w);
             if (mt_squeeze(g1.dd, g1.cc, n1, u, y1, thr)) { done1 = sq1 = true; ub1 = squeeze_uniform(u, thr); }
             else done1 = mt_exact(g1.dd, g1.cc, n1, u);
         }
@@ -228,29 +231,51 @@ __device__ __forceinline__ void gamma_pair(const NoiseKey& nk, uint32_t slot, fl
 // attempt 0 accepted by the squeeze, including shapes below 1; a squeeze miss (~0.06/shape) re-runs the pair
 // out of line.  One rarely taken branch per pair.
 static __device__ __noinline__ float2 gamma_pair_redo(uint32_t p0, uint32_t p1, uint32_t k0, uint32_t k1,
-                                                      uint32_t slot, float a0, float a1) {
+                                                      uint32_t slot, float al0, float al1, float scale) {
     NoiseKey nk;
     nk.k0 = k0; nk.k1 = k1; nk.p0 = p0; nk.p1 = p1;
     float y0, y1;
-    gamma_pair(nk, slot, a0, a1, y0, y1);
+    gamma_pair(nk, slot, al0, al1, scale, y0, y1);
     return make_float2(y0, y1);
 }
-__device__ __forceinline__ void gamma_pair_fast(const NoiseKey& nk, const PhiloxKeys& K, uint32_t slot, float a0,
-                                                float a1, float& y0, float& y1) {
+// packed single precision (Blackwell FFMA2 / FMUL2 / FADD2: two lanes of math per issue slot)
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+
+__device__ __forceinline__ void gamma_pair_fast(const NoiseKey& nk, const PhiloxKeys& K, uint32_t slot, float2 al,
+                                                float scale, float& y0, float& y1) {
     const uint4 w = philox4x32_10(nk.p0, nk.p1, slot, 0u, K);
-    float n0, n1, thr0, thr1;
-    box_muller(w.x, w.y, n0, n1);
-    const GammaSetup g0 = gamma_setup(a0), g1 = gamma_setup(a1);
-    const float u0 = u01(w.z), u1 = u01(w.w);
-    const bool ok0 = mt_squeeze(g0.dd, g0.cc, n0, u0, y0, thr0);
-    const bool ok1 = mt_squeeze(g1.dd, g1.cc, n1, u1, y1, thr1);
+    // Box-Muller: (n0, n1) = r (cos, sin)
+    const float r = sqrt_approx(-2.0f * DMFG_LN2 * lg2_approx(u01(w.x)));
+    const float ang = fmaf(__uint_as_float((w.y >> 9) | 0x3f800000u), 6.2831845f, -9.4247770f);
+    const float2 n = __fmul2_rn(splat2(r), make_float2(cos_approx(ang), sin_approx(ang)));
+    // gamma_setup for both elements
+    const float2 a = __fmul2_rn(al, splat2(scale));
+    const bool b0 = a.x < 1.0f, b1 = a.y < 1.0f;
+    const float2 dd = __ffma2_rn(al, splat2(scale), make_float2(b0 ? (2.0f / 3.0f) : -(1.0f / 3.0f),
+                                                                b1 ? (2.0f / 3.0f) : -(1.0f / 3.0f)));
+    const float2 dd9 = __fmul2_rn(splat2(9.0f), dd);
+    const float2 cc = make_float2(rsqrt_approx(dd9.x), rsqrt_approx(dd9.y));
+    // mt_squeeze for both elements
+    const float2 e = __fmul2_rn(cc, n);
+    const float2 v1 = __ffma2_rn(cc, n, splat2(1.0f));
+    const float2 e2 = __fmul2_rn(e, e);
+    const float2 y = __fmul2_rn(dd, __fmul2_rn(v1, __fmul2_rn(v1, v1)));
+    const float2 thr = __ffma2_rn(__fmul2_rn(splat2(-1.5f), dd), __fmul2_rn(e2, e2), splat2(1.0f));
+    // acceptance uniforms: top 23 bits as the mantissa of [1,2), minus 1 -- no int->float conversion (XU pipe)
+    const float2 u = __fadd2_rn(make_float2(__uint_as_float((w.z >> 9) | 0x3f800000u),
+                                            __uint_as_float((w.w >> 9) | 0x3f800000u)), splat2(-1.0f));
+    const bool ok0 = (fabsf(e.x) <= 0.5f) & (u.x < thr.x);
+    const bool ok1 = (fabsf(e.y) <= 0.5f) & (u.y < thr.y);
+    y0 = y.x;
+    y1 = y.y;
     if (!(ok0 & ok1)) {
-        const float2 yy = gamma_pair_redo(nk.p0, nk.p1, nk.k0, nk.k1, slot, a0, a1);
+        const float2 yy = gamma_pair_redo(nk.p0, nk.p1, nk.k0, nk.k1, slot, al.x, al.y, scale);
         y0 = yy.x;
         y1 = yy.y;
-    } else if (g0.boost | g1.boost) {
-        if (g0.boost) y0 = boost_apply(y0, a0, squeeze_uniform(u0, thr0));
-        if (g1.boost) y1 = boost_apply(y1, a1, squeeze_uniform(u1, thr1));
+    } else if (b0 | b1) {
+        if (b0) y0 = boost_apply(y0, a.x, squeeze_uniform(u.x, thr.x));
+        if (b1) y1 = boost_apply(y1, a.y, squeeze_uniform(u.y, thr.y));
     }
 }
 
@@ -363,6 +388,83 @@ __device__ __forceinline__ float digamma_fast(float x) {
     float res = fmaf(lg2_approx(z), DMFG_LN2, -s);
     res = fmaf(-0.5f, rz, res);
     return fmaf(r2, p, res);
+}
+
+// packed (two elements per instruction) forms of the two functions above
+__device__ __forceinline__ void policy_alpha_fast2(float theta, float2 x, float2& alpha, float2& alpha_deriv) {
+    const float2 t = __fmul2_rn(splat2(theta), x);
+    const float2 arg = __fmul2_rn(make_float2(fabsf(t.x), fabsf(t.y)), splat2(-DMFG_LOG2E));
+    const float2 e = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
+    const float2 u = __fadd2_rn(e, splat2(1.0f));
+    float2 pl = __ffma2_rn(splat2(-1.0f / 6.0f), e, splat2(0.2f));
+    pl = __ffma2_rn(pl, e, splat2(-0.25f));
+    pl = __ffma2_rn(pl, e, splat2(1.0f / 3.0f));
+    pl = __ffma2_rn(pl, e, splat2(-0.5f));
+    pl = __ffma2_rn(pl, e, splat2(1.0f));
+    pl = __fmul2_rn(pl, e);
+    const float2 lg = __fmul2_rn(make_float2(lg2_approx(u.x), lg2_approx(u.y)), splat2(DMFG_LN2));
+    const float2 l = make_float2(e.x < 0.0625f ? pl.x : lg.x, e.y < 0.0625f ? pl.y : lg.y);
+    const float2 ru = make_float2(rcp_approx(u.x), rcp_approx(u.y));
+    const float2 sg = __fmul2_rn(make_float2(t.x >= 0.0f ? 1.0f : e.x, t.y >= 0.0f ? 1.0f : e.y), ru);
+    alpha = __fadd2_rn(make_float2(fmaxf(t.x, 0.0f), fmaxf(t.y, 0.0f)), l);
+    alpha_deriv = __fmul2_rn(x, sg);
+}
+__device__ __forceinline__ float2 digamma_fast2(float2 x) {
+    float2 q = __ffma2_rn(x, x, __fmul2_rn(splat2(3.0f), x));
+    q = make_float2(fmaxf(q.x, 1e-30f), fmaxf(q.y, 1e-30f));
+    const float2 num = __fmul2_rn(__ffma2_rn(splat2(2.0f), x, splat2(3.0f)), __ffma2_rn(splat2(2.0f), q, splat2(2.0f)));
+    const float2 den = __fmul2_rn(q, __fadd2_rn(q, splat2(2.0f)));
+    const float2 z = __fadd2_rn(x, splat2(4.0f));
+    const float2 dz = __fmul2_rn(den, z);
+    const float2 R = make_float2(rcp_approx(dz.x), rcp_approx(dz.y));
+    const float2 s = __fmul2_rn(num, __fmul2_rn(z, R));
+    const float2 rz = __fmul2_rn(den, R);
+    const float2 r2 = __fmul2_rn(rz, rz);
+    float2 p = __ffma2_rn(r2, splat2(-1.0f / 252.0f), splat2(1.0f / 120.0f));
+    p = __ffma2_rn(r2, p, splat2(-1.0f / 12.0f));
+    float2 res = __ffma2_rn(make_float2(lg2_approx(z.x), lg2_approx(z.y)), splat2(DMFG_LN2), neg2(s));
+    res = __ffma2_rn(splat2(-0.5f), rz, res);
+    return __ffma2_rn(r2, p, res);
+}
+
+// alpha, alpha' and psi(alpha) of a pair in one go: the sigmoid's 1/(1+e) and the digamma's 1/(den z) share
+// ONE reciprocal (R0 = 1/((1+e) den z)), so a pair costs 12 MUFU operations instead of 14
+__device__ __forceinline__ void alpha_psi_fast2(float theta, float2 x, float2& alpha, float2& alpha_deriv, float2& psi) {
+    const float2 t = __fmul2_rn(splat2(theta), x);
+    const float2 arg = __fmul2_rn(make_float2(fabsf(t.x), fabsf(t.y)), splat2(-DMFG_LOG2E));
+    const float2 e = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
+    const float2 u = __fadd2_rn(e, splat2(1.0f));
+    float2 pl = __ffma2_rn(splat2(-1.0f / 6.0f), e, splat2(0.2f));
+    pl = __ffma2_rn(pl, e, splat2(-0.25f));
+    pl = __ffma2_rn(pl, e, splat2(1.0f / 3.0f));
+    pl = __ffma2_rn(pl, e, splat2(-0.5f));
+    pl = __ffma2_rn(pl, e, splat2(1.0f));
+    pl = __fmul2_rn(pl, e);
+    const float2 lg = __fmul2_rn(make_float2(lg2_approx(u.x), lg2_approx(u.y)), splat2(DMFG_LN2));
+    const float2 l = make_float2(e.x < 0.0625f ? pl.x : lg.x, e.y < 0.0625f ? pl.y : lg.y);
+    const float2 a = __fadd2_rn(make_float2(fmaxf(t.x, 0.0f), fmaxf(t.y, 0.0f)), l);
+    alpha = a;
+    // digamma(a): 4-step recurrence folded into one quotient + asymptotic series at z = a + 4
+    float2 q = __ffma2_rn(a, a, __fmul2_rn(splat2(3.0f), a));
+    q = make_float2(fmaxf(q.x, 1e-30f), fmaxf(q.y, 1e-30f));
+    const float2 num = __fmul2_rn(__ffma2_rn(splat2(2.0f), a, splat2(3.0f)), __ffma2_rn(splat2(2.0f), q, splat2(2.0f)));
+    const float2 den = __fmul2_rn(q, __fadd2_rn(q, splat2(2.0f)));
+    const float2 z = __fadd2_rn(a, splat2(4.0f));
+    const float2 dz = __fmul2_rn(den, z);
+    const float2 m = __fmul2_rn(u, dz);
+    const float2 R0 = make_float2(rcp_approx(m.x), rcp_approx(m.y));
+    const float2 ru = __fmul2_rn(dz, R0);                       // 1 / (1 + e)
+    const float2 R = __fmul2_rn(u, R0);                         // 1 / (den z)
+    const float2 sg = __fmul2_rn(make_float2(t.x >= 0.0f ? 1.0f : e.x, t.y >= 0.0f ? 1.0f : e.y), ru);
+    alpha_deriv = __fmul2_rn(x, sg);
+    const float2 srec = __fmul2_rn(num, __fmul2_rn(z, R));
+    const float2 rz = __fmul2_rn(den, R);
+    const float2 r2 = __fmul2_rn(rz, rz);
+    float2 p = __ffma2_rn(r2, splat2(-1.0f / 252.0f), splat2(1.0f / 120.0f));
+    p = __ffma2_rn(r2, p, splat2(-1.0f / 12.0f));
+    float2 res = __ffma2_rn(make_float2(lg2_approx(z.x), lg2_approx(z.y)), splat2(DMFG_LN2), neg2(srec));
+    res = __ffma2_rn(splat2(-0.5f), rz, res);
+    psi = __ffma2_rn(r2, p, res);
 }
 
 // ------------------------------------------------------- sub-warp reductions

@@ -131,8 +131,7 @@ struct StepCore {
             }
             if (NOISE == DMFG_NOISE_PHILOX) {
                 float y0, y1;
-                gamma_pair(nk, gamma_slot(step, D, r, p), (float)(a[0] * alpha_scale),
-                           (float)(a[1] * alpha_scale), y0, y1);
+                gamma_pair(nk, gamma_slot(step, D, r, p), (float)a[0], (float)a[1], (float)alpha_scale, y0, y1);
                 yv[2 * p] = (R)y0;
                 yv[2 * p + 1] = (R)y1;
             } else {
@@ -385,7 +384,7 @@ rollout_generic_kernel(const RolloutParams<R> p) {
                     if (NOISE == DMFG_NOISE_PHILOX) {
                         float y0, y1;
                         gamma_pair_fast(nk, p.rk, gamma_slot((uint32_t)(p.step_offset + t), d, i, pp),
-                                        (float)(a[0] * scale), (float)(a[1] * scale), y0, y1);
+                                        make_float2((float)a[0], (float)a[1]), (float)scale, y0, y1);
                         yv[0] = (R)y0; yv[1] = (R)y1;
                     } else {
 #pragma unroll

@@ -61,7 +61,7 @@ __device__ __forceinline__ double critic_value_v2(const double* __restrict__ wl,
 // TRAIN = the batched train step: accumulators wanted and NO per-step output stream requested -- every
 // output test is compiled out of the step loop.  REC = some per-element stream (actions / alpha) is written.
 template <int D, int NOISE, bool REC, bool TRAIN>
-__global__ void __launch_bounds__(kV2Threads, 3)
+__global__ void __launch_bounds__(kV2Threads, 2)
 rollout_v2_kernel(const RolloutParams<float> p) {
     using S = V2Smem<D>;
     constexpr int G = kV2G, NT = kV2Threads, GPB = S::GPB, NSLOT = S::NSLOT, PD = (D + 1) / 2;
@@ -109,24 +109,22 @@ rollout_v2_kernel(const RolloutParams<float> p) {
             const float* pfc = pif + cur * (GPB * G);
             // ------------------------------------------------------------------ pass 1
             const float xi = (float)pi_self + shift;
-            float asum = 0.f, dsum = 0.f, g1 = 0.f;
+            float2 asum2 = make_float2(0.f, 0.f), dsum2 = asum2, g12 = asum2;
             double ysum = 0.0;
-#pragma unroll 2
+#pragma unroll 4
             for (int pp = 0; pp < PD; ++pp) {
                 const float2 pj = *reinterpret_cast<const float2*>(pfc + 2 * pp);
                 const bool ok1 = (2 * pp + 1) < D;                     // only the last pair of an odd D
-                float a0, a1, d0, d1;
-                policy_alpha_fast(theta, pj.x - xi, a0, d0);
-                policy_alpha_fast(theta, pj.y - xi, a1, d1);
-                if (!ok1) { a1 = 1.0f; d1 = 0.0f; }
-                g1 = fmaf(-digamma_fast(a0), d0, g1);
-                g1 = fmaf(-digamma_fast(a1), d1, g1);
-                asum += a0 + (ok1 ? a1 : 0.0f);
-                dsum += d0 + d1;
+                // the pair (columns 2pp, 2pp+1) runs as packed f32x2 math: one issue slot per two elements
+                float2 a, dv, psi;
+                alpha_psi_fast2(theta, __fadd2_rn(pj, splat2(-xi)), a, dv, psi);
+                if (!ok1) { a.y = 1.0f; dv.y = 0.0f; }
+                g12 = __ffma2_rn(psi, neg2(dv), g12);
+                asum2 = __fadd2_rn(asum2, make_float2(a.x, ok1 ? a.y : 0.0f));
+                dsum2 = __fadd2_rn(dsum2, dv);
                 float y0, y1;
                 if (NOISE == DMFG_NOISE_PHILOX) {
-                    gamma_pair_fast(nk, p.rk, gamma_slot((uint32_t)(p.step_offset + t), D, r, pp), a0 * scale,
-                                    a1 * scale, y0, y1);
+                    gamma_pair_fast(nk, p.rk, gamma_slot((uint32_t)(p.step_offset + t), D, r, pp), a, scale, y0, y1);
                 } else {
                     y0 = row_ok ? p.noise_y[row + 2 * pp] : 1.0f;
                     y1 = (row_ok && ok1) ? p.noise_y[row + 2 * pp + 1] : 1.0f;
@@ -135,14 +133,15 @@ rollout_v2_kernel(const RolloutParams<float> p) {
                 if (y1 == 0.0f) y1 = 1e-20f;
                 if (!ok1) y1 = 0.0f;
                 ysum += (double)(y0 + y1);       // pair sum in float: <= 6e-8 relative on the pair, one conversion
-                *reinterpret_cast<float2*>(slots + 2 * pp) = make_float2(y0, d0);
-                *reinterpret_cast<float2*>(slots + 2 * pp + 1) = make_float2(y1, d1);
+                *reinterpret_cast<float2*>(slots + 2 * pp) = make_float2(y0, dv.x);
+                *reinterpret_cast<float2*>(slots + 2 * pp + 1) = make_float2(y1, dv.y);
                 if (REC && p.alpha != nullptr && wr) {
-                    p.alpha[row + 2 * pp] = a0;
-                    p.alpha_deriv[row + 2 * pp] = d0;
-                    if (ok1) { p.alpha[row + 2 * pp + 1] = a1; p.alpha_deriv[row + 2 * pp + 1] = d1; }
+                    p.alpha[row + 2 * pp] = a.x;
+                    p.alpha_deriv[row + 2 * pp] = dv.x;
+                    if (ok1) { p.alpha[row + 2 * pp + 1] = a.y; p.alpha_deriv[row + 2 * pp + 1] = dv.y; }
                 }
             }
+            const float asum = asum2.x + asum2.y, dsum = dsum2.x + dsum2.y, g1 = g12.x + g12.y;
             // ------------------------------------------------------------------ row level
             double inv = (double)rcp_approx((float)ysum);              // 1/s: float seed + 2 Newton steps
             inv = inv * (2.0 - ysum * inv);
