@@ -119,10 +119,10 @@ struct StepCore {
                 const int j = 2 * p + e;
                 if (j < D) {
                     const R x = (R)(pi[j] - pi_self) - shift;
-                    policy_alpha<R>(theta, x, a[e], dv[j]);
+                    StreamMath<R>::alpha(theta, x, a[e], dv[j]);
                     asum += (double)a[e];
                     dsum += (double)dv[j];
-                    g1 -= (double)(digamma(a[e]) * dv[j]);
+                    g1 -= (double)(StreamMath<R>::psi(a[e]) * dv[j]);
                     if (alpha_row != nullptr && row_ok) { alpha_row[j] = a[e]; deriv_row[j] = dv[j]; }
                 } else {
                     a[e] = R(1);
@@ -151,7 +151,7 @@ struct StepCore {
             }
         }
         const double inv = NOISE == DMFG_NOISE_ACTIONS ? 1.0 : 1.0 / ysum;
-        const R psi_row = digamma((R)asum);
+        const R psi_row = StreamMath<R>::psi((R)asum);
         double c[G];
         double racc = 0.0, g2 = 0.0;
 #pragma unroll
@@ -159,7 +159,7 @@ struct StepCore {
             if (j < D) {
                 const double P = (double)yv[j] * inv;
                 const R Pr = (R)P;
-                g2 += (double)(log_prob(Pr) * dv[j]);
+                g2 += (double)(StreamMath<R>::lnp(Pr) * dv[j]);
                 c[j] = pi_self * P;
                 if (reward_kind == DMFG_REWARD_AC2) racc += P * P * (pi[j] - pi_self);
                 else racc += P * P;
