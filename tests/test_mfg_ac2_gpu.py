@@ -216,3 +216,32 @@ def test_train_batch_per_episode_matches_oracle(start_states):
     np.testing.assert_allclose(res["theta"], th, rtol=1e-11)
     np.testing.assert_allclose(ac.w.ravel(), w, rtol=1e-10)
     np.testing.assert_allclose(res["mean_reward"][0], r.sum() / B, rtol=1e-9)
+
+
+def test_mfg_synthetic_dropin(start_states):
+    """mfg_synthetic.actor_critic: synthetic reward (mfg_synthetic.py:249-265) and the (shift, theta0) sweep of
+    its __main__ (:902-925) as independent learners -- each learner equals a separate train() run."""
+    from discrete_mean_field_game_b200 import mfg_synthetic
+    np.random.seed(0)
+    ac = mfg_synthetic.actor_critic(theta=2.6, shift=0.02, alpha_scale=10000, d=15, mat_pi0=start_states,
+                                    dtype="float64", seed=3)
+    rng = np.random.RandomState(1)
+    P = rng.dirichlet(np.ones(15), size=15)
+    pi = rng.dirichlet(np.ones(15))
+    np.testing.assert_allclose(ac.calc_reward(P, pi, 15)[0], -0.5 * pi.dot((P * P).sum(1)), rtol=1e-12)
+    np.random.seed(5)
+    res = ac.sweep(shifts=[0.0, 0.02], thetas=[1.0, 2.5, 4.0], num_episodes=6)
+    assert res.shape == (6, 3) and np.all(np.isfinite(res))
+    np.testing.assert_array_equal(res[:, 0], [0, 0, 0, 0.02, 0.02, 0.02])
+    assert np.all(res[:, 2] != res[:, 1])                    # every learner moved
+    # learner 4 (shift 0.02, theta0 2.5) == an independent train() with the same w0 / seed / learner id
+    np.random.seed(5)
+    w0 = np.random.rand(6, 136)
+    import torch
+    from discrete_mean_field_game_b200 import engine
+    th = torch.tensor([2.5], dtype=torch.float64, device=ac.device)
+    w = torch.as_tensor(w0[4:5].copy(), device=ac.device)
+    engine.learners(th, w, ac._dev(ac.mat_pi0), 6, 15, shift=0.02, alpha_scale=10000.0, lr_critic=0.1,
+                    lr_actor=0.001, constant=True, reward="synthetic", seed=3, learner_offset=4,
+                    want_total_reward=False)
+    np.testing.assert_allclose(res[4, 2], float(th[0]), rtol=1e-12)
