@@ -110,6 +110,8 @@ SYMBOLS = [
     ("dmfg_td_accumulate", C.c_int, [C.POINTER(TdArgs), C.c_void_p]),
     ("dmfg_critic_eval", C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    ("dmfg_traj_metrics", C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dmfg_ac_apply_update", C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_double, C.c_double, C.c_void_p]),
     ("dmfg_ac_learners", C.c_int, [C.POINTER(LearnersArgs), C.c_void_p]),

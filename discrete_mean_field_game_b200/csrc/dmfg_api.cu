@@ -438,6 +438,25 @@ int dmfg_critic_eval(int32_t dtype, int32_t d, int64_t N, const void* states, co
     return DMFG_OK;
 }
 
+int dmfg_traj_metrics(int32_t dtype, int32_t d, int64_t B, int32_t H, const void* generated, int64_t gen_stride_b,
+                      int64_t gen_stride_h, const void* empirical, int64_t emp_stride_b, int64_t emp_stride_h,
+                      double* l1, double* jsd, void* stream) {
+    if (dtype != DMFG_F32 && dtype != DMFG_F64) return fail(DMFG_ERR_INVALID, "dtype %d", dtype);
+    if (d < 1 || B < 0 || H < 1) return fail(DMFG_ERR_INVALID, "dmfg_traj_metrics: bad d/B/H");
+    if (B > 0 && (!generated || !empirical)) return fail(DMFG_ERR_INVALID, "dmfg_traj_metrics: NULL input");
+    if (B == 0) return DMFG_OK;
+    const unsigned grid = (unsigned)((B * H + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DMFG_F64)
+        traj_metrics_kernel<double><<<grid, 128, 0, st>>>(d, B, H, (const double*)generated, gen_stride_b, gen_stride_h,
+                                                        (const double*)empirical, emp_stride_b, emp_stride_h, l1, jsd);
+    else
+        traj_metrics_kernel<float><<<grid, 128, 0, st>>>(d, B, H, (const float*)generated, gen_stride_b, gen_stride_h,
+                                                       (const float*)empirical, emp_stride_b, emp_stride_h, l1, jsd);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
 int dmfg_ac_apply_update(int32_t d, double* theta_dev, double* w, const double* acc, double lr_critic_eff,
                          double lr_actor_eff, double scale, void* stream) {
     if (d < 1 || d > DMFG_MAX_D || !w || !acc) return fail(DMFG_ERR_INVALID, "dmfg_ac_apply_update: bad argument");

@@ -583,6 +583,47 @@ __global__ void critic_value_kernel(int d, long long N, const R* __restrict__ st
     if (lane == 0) values[warp] = (R)v;
 }
 
+// L1 distance and Jensen-Shannon divergence between generated and empirical distributions, one warp per
+// (trajectory, hour): mfg_ac2.py:546-563 (JSD: zeros -> 1e-100, M from the unnormalised inputs, entropy()
+// normalises each argument) and :627-650.  Element (b,h,j) of X sits at X[b*sb + h*sh + j].
+template <typename R>
+__global__ void __launch_bounds__(128) traj_metrics_kernel(int d, long long B, int H, const R* __restrict__ gen,
+                                                           long long gsb, long long gsh,
+                                                           const R* __restrict__ emp, long long esb, long long esh,
+                                                           double* __restrict__ l1, double* __restrict__ jsd) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= B * H) return;
+    const long long b = warp / H;
+    const int h = (int)(warp - b * H);
+    const R* g = gen + b * gsb + h * gsh;
+    const R* e = emp + b * esb + h * esh;
+    double sl1 = 0.0, sp = 0.0, sq = 0.0;
+    for (int j = lane; j < d; j += 32) {
+        const double p = (double)g[j], q = (double)e[j];
+        sl1 += fabs(q - p);
+        sp += p == 0.0 ? 1e-100 : p;
+        sq += q == 0.0 ? 1e-100 : q;
+    }
+    sl1 = group_sum<32>(sl1); sp = group_sum<32>(sp); sq = group_sum<32>(sq);
+    const double sm = 0.5 * (sp + sq);
+    double kp = 0.0, kq = 0.0;
+    for (int j = lane; j < d; j += 32) {
+        double p = (double)g[j], q = (double)e[j];
+        p = p == 0.0 ? 1e-100 : p;
+        q = q == 0.0 ? 1e-100 : q;
+        const double m = 0.5 * (p + q) / sm;
+        p /= sp; q /= sq;
+        kp += p * log(p / m);
+        kq += q * log(q / m);
+    }
+    kp = group_sum<32>(kp); kq = group_sum<32>(kq);
+    if (lane == 0) {
+        if (l1) l1[warp] = sl1;
+        if (jsd) jsd[warp] = 0.5 * (kp + kq);
+    }
+}
+
 // theta += lr_a*scale*acc[0];  w[f] += lr_c*scale*acc[1+f]   (mfg_ac2.py:511-522)
 __global__ void ac_apply_update_kernel(int F, double* theta, double* w, const double* __restrict__ acc,
                                        double lr_c, double lr_a, double scale) {

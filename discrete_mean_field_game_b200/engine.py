@@ -187,6 +187,27 @@ def critic_eval(states, w=None, want_features=True, want_values=False):
     return res
 
 
+def traj_metrics(generated, empirical, time_major=True):
+    """L1 and Jensen-Shannon divergence per (trajectory, hour) (mfg_ac2.py:546-563, 627-650).
+    generated: rollout states [H,B,d] (time_major) or [B,H,d]; empirical [B,H,d].  Returns (l1, jsd) [B,H] float64."""
+    lib = _lib.load()
+    device, dtype = generated.device, generated.dtype
+    if time_major:
+        H, B, d = generated.shape
+        gsb, gsh = d, B * d
+    else:
+        B, H, d = generated.shape
+        gsb, gsh = H * d, d
+    _require(generated, "generated", device, dtype, tuple(generated.shape))
+    _require(empirical, "empirical", device, dtype, (B, H, d))
+    with torch.cuda.device(device):
+        l1 = torch.empty((B, H), dtype=torch.float64, device=device)
+        js = torch.empty((B, H), dtype=torch.float64, device=device)
+        check(lib.dmfg_traj_metrics(_dtype_code(dtype), d, B, H, _ptr(generated), gsb, gsh, _ptr(empirical), H * d, d,
+                                    _ptr(l1), _ptr(js), _stream_ptr(device)))
+    return l1, js
+
+
 def apply_update(d, theta_dev, w, acc, lr_critic_eff, lr_actor_eff, scale):
     """theta += lr_a*scale*acc[0]; w += lr_c*scale*acc[1:1+F]  (mfg_ac2.py:511-522), on device."""
     lib = _lib.load()

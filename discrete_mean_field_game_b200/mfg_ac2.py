@@ -265,6 +265,68 @@ class actor_critic:
             self._draws += T
         return out["states"][:, 0].double().cpu().numpy()
 
+    # ------------------------------------------------ consumer of a9: evaluation against measured days
+    def JSD(self, P, Q):
+        """Jensen-Shannon divergence (mfg_ac2.py:546-563); inputs are not mutated."""
+        P = np.asarray(P, dtype=np.float64).reshape(1, 1, -1)
+        Q = np.asarray(Q, dtype=np.float64).reshape(1, 1, -1)
+        _, js = engine.traj_metrics(self._dev(P, torch.float64), self._dev(Q, torch.float64), time_major=False)
+        return float(js[0, 0])
+
+    def evaluate(self, theta=8.86349, shift=0.5, alpha_scale=1e4, d=21, episode_length=16,
+                 indir='test_normalized_round2', outfile='eval_mfg_round2/test_eval_fixed_reward.csv',
+                 write_header=0, empirical=None, y=None):
+        """Roll the fixed policy forward from the first row of every test day and compare with the measured
+        trajectory: mean L1 / Jensen-Shannon of the final distribution and over the day (mfg_ac2.py:595-670).
+        All test days run as ONE batched rollout + one metrics launch.  Files are visited in SORTED order
+        (the reference uses directory order).  ``empirical`` [n,episode_length,>=d] replaces reading ``indir``;
+        ``y`` [n,episode_length-1,d,d] injects the Gamma variates (parity)."""
+        self.theta, self.shift, self.alpha_scale, self.d = theta, shift, alpha_scale, d
+        if empirical is None:
+            path = os.path.join(os.getcwd(), indir)
+            empirical = np.stack([np.loadtxt(os.path.join(path, f), delimiter=' ', ndmin=2) for f in sorted(os.listdir(path))])
+        emp = np.ascontiguousarray(np.asarray(empirical, dtype=np.float64)[:, :episode_length, :d])
+        n, T = emp.shape[0], episode_length - 1
+        noise = None if y is None else self._dev(np.ascontiguousarray(np.transpose(np.asarray(y), (1, 0, 2, 3))))
+        out = engine.rollout(self._dev(emp[:, 0]), theta, shift, alpha_scale, T, reward="none", noise_y=noise,
+                             seed=self.seed, step_offset=self._draws, outputs=("states",))
+        if y is None:
+            self._draws += T
+        l1, js = engine.traj_metrics(out["states"], self._dev(emp))
+        l1, js = l1.cpu().numpy(), js.cpu().numpy()
+        arrays = (l1[:, -1], l1.mean(1), js[:, -1], js.mean(1))
+        stats = [(float(np.mean(a)), float(np.std(a))) for a in arrays]
+        if outfile:
+            os.makedirs(os.path.dirname(outfile) or ".", exist_ok=True)
+            with open(outfile, 'a') as f:
+                if write_header:
+                    f.write('theta,shift,alpha_scale,mean_l1_final,std_l1_final,mean_l1_mean,std_l1_mean,'
+                            'mean_JSD_final,std_JSD_final,mean_JSD_mean,std_JSD_mean\n')
+                f.write("%f,%f,%f,%.3e,%.3e,%.3e,%.3e,%.3e,%.3e,%.3e,%.3e\n" % (
+                    (theta, shift, alpha_scale) + tuple(v for ms in stats for v in ms)))
+        return tuple(m for m, _ in stats)
+
+    def gridsearch(self, theta_range, shift_range, alpha_range, indir, outfile, empirical=None, verbose=True):
+        """Best (theta, shift, alpha_scale) per metric over the grid (mfg_ac2.py:673-689); returns the list of
+        [value, theta, shift, alpha_scale] the reference prints."""
+        best = [[100, 0, 0, 0] for _ in range(4)]
+        if empirical is None:
+            path = os.path.join(os.getcwd(), indir)
+            empirical = np.stack([np.loadtxt(os.path.join(path, f), delimiter=' ', ndmin=2) for f in sorted(os.listdir(path))])
+        for theta in theta_range:
+            for shift in shift_range:
+                for alpha_scale in alpha_range:
+                    if verbose:
+                        print("Theta %f, shift %f, alpha %d" % (theta, shift, alpha_scale))
+                    result = self.evaluate(theta, shift, alpha_scale, d=self.d, indir=indir, outfile=outfile,
+                                           write_header=0, empirical=empirical)
+                    for idx in range(4):
+                        if result[idx] <= best[idx][0]:
+                            best[idx] = [result[idx], theta, shift, alpha_scale]
+        if verbose:
+            print(best)
+        return best
+
     # ------------------------------------------------ batched path (extension)
     def rollout_batch(self, pi0, T=15, record=False, seed=None, pop_offset=0, noise_y=None, with_td=True):
         """B independent populations, frozen (theta, w): host arrays in, host arrays out.

@@ -164,6 +164,16 @@ int dmfg_td_accumulate(const dmfg_td_args* args, void* stream);
 int dmfg_critic_eval(int32_t dtype, int32_t d, int64_t N, const void* states, const double* w,
                      void* features, void* values, void* stream);
 
+/* ---- consumer of a9: evaluation metrics of generated trajectories ---------- *
+ * actor_critic.evaluate / JSD (mfg_ac2.py:546-563, 595-670; ac_irl.py:1495-1570): per (trajectory b, hour h)
+ * the L1 distance and the Jensen-Shannon divergence between the generated and the empirical distribution
+ * (zeros -> 1e-100, M = (P+Q)/2 from the unnormalised inputs, each entropy() argument normalised).
+ * Element (b,h,j) of X is X[b*stride_b + h*stride_h + j]: a time-major rollout record [H][B][d] has
+ * (stride_b, stride_h) = (d, B*d).  l1 / jsd: [B][H] doubles, either may be NULL.                     */
+int dmfg_traj_metrics(int32_t dtype, int32_t d, int64_t B, int32_t H, const void* generated, int64_t gen_stride_b,
+                      int64_t gen_stride_h, const void* empirical, int64_t emp_stride_b, int64_t emp_stride_h,
+                      double* l1, double* jsd, void* stream);
+
 /* ---- a5, a7: apply one actor-critic update on device --------------------- *
  * theta += lr_actor_eff * scale * acc[0];  w += lr_critic_eff * scale * acc[1..F]
  * (mfg_ac2.py:511-522).  lr_*_eff are the already-decayed step sizes; scale is

@@ -20,6 +20,7 @@ train_trace.npz   config 1: mfg_ac2.actor_critic.train, d=15, 3 episodes, every
                   draw (start row, Gamma variates) and every per-step result
 traj_d15.npz      generate_trajectory (rollout only) with its recorded draws
 forward_d47.npz   test2.test_forward's d=47 start state, 3 transitions
+eval_metrics.npz  actor_critic.evaluate (L1 / Jensen-Shannon against empirical days) with its draws
 """
 import importlib
 import os
@@ -226,6 +227,38 @@ def forward_d47(mfg_ac2):
     print("forward_d47: rewards", rewards)
 
 
+def eval_metrics(mfg_ac2, tmp, d=15, n_files=4):
+    """mfg_ac2.actor_critic.evaluate (mfg_ac2.py:595-670) on synthetic test days: the empirical
+    trajectories, the recorded Gamma draws, the four returned means and the reference's own JSD values."""
+    rng = np.random.RandomState(21)
+    indir = "test_golden"
+    os.makedirs(os.path.join(tmp, indir))
+    emp = rng.dirichlet(np.ones(20), size=(n_files, 16))
+    emp[1, 5, 3] = 0.0                                        # exercises the zero -> 1e-100 replacement
+    for k in range(n_files):
+        np.savetxt(os.path.join(tmp, indir, "trend_distribution_day%d.csv" % (22 + k)), emp[k], fmt="%.6e",
+                   delimiter=" ")
+    emp = np.stack([np.loadtxt(os.path.join(tmp, indir, "trend_distribution_day%d.csv" % (22 + k)))
+                    for k in range(n_files)])[:, :, :d]
+    ac = mfg_ac2.actor_critic(theta=8.0, shift=0.16, alpha_scale=12000, d=d)
+    real_listdir = os.listdir
+    os.listdir = lambda path: sorted(real_listdir(path))      # the reference iterates in directory order
+    np.random.seed(13)
+    try:
+        with Recorder() as rec:
+            res = ac.evaluate(theta=8.0, shift=0.16, alpha_scale=12000, d=d, episode_length=16, indir=indir,
+                              outfile=os.path.join(tmp, "eval.csv"), write_header=1)
+    finally:
+        os.listdir = real_listdir
+    y = np.stack(rec.gamma_calls).reshape(n_files, 15, d, d)
+    P = np.array([0.2, 0.0, 0.5, 0.3])
+    Q = np.array([0.1, 0.4, 0.0, 0.5])
+    np.savez(os.path.join(OUT, "eval_metrics.npz"), d=d, theta=8.0, shift=0.16, alpha_scale=12000.0,
+             empirical=emp, y=y, result=np.array(res), csv=np.array(open(os.path.join(tmp, "eval.csv")).read()),
+             jsd_P=P, jsd_Q=Q, jsd_value=mfg_ac2.actor_critic.JSD(None, P.copy(), Q.copy()))
+    print("eval_metrics:", res)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     with tempfile.TemporaryDirectory() as tmp:
@@ -243,6 +276,7 @@ def main():
             train_trace(mfg_ac2)
             traj_d15(mfg_ac2)
             forward_d47(mfg_ac2)
+            eval_metrics(mfg_ac2, tmp)
         finally:
             os.chdir(cwd)
 

@@ -340,6 +340,33 @@ def generate_trajectory(pi0, total_hours, theta, shift, alpha_scale, noise=None)
     return out
 
 
+# --------------------------------------------------------------------------
+# evaluation metrics of generate_trajectory's consumer (mfg_ac2.py:546-563, 595-670)
+# --------------------------------------------------------------------------
+def jsd(P, Q):
+    """Jensen-Shannon divergence as mfg_ac2.py:546-563 computes it: zeros -> 1e-100, M = (P+Q)/2 from the
+    UNNORMALISED inputs, then scipy.stats.entropy semantics (each argument normalised to sum 1)."""
+    P = np.where(np.asarray(P, dtype=np.float64) == 0, 1e-100, P)
+    Q = np.where(np.asarray(Q, dtype=np.float64) == 0, 1e-100, Q)
+    M = 0.5 * (P + Q)
+
+    def kl(a, b):
+        a = a / a.sum(-1, keepdims=True)
+        b = b / b.sum(-1, keepdims=True)
+        return (a * np.log(a / b)).sum(-1)
+    return 0.5 * (kl(P, M) + kl(Q, M))
+
+
+def trajectory_metrics(generated, empirical):
+    """Per-trajectory (l1_final, l1_mean, JSD_final, JSD_mean) of mfg_ac2.py:627-650.
+    generated / empirical: [B, H, d]."""
+    g = np.asarray(generated, dtype=np.float64)
+    e = np.asarray(empirical, dtype=np.float64)
+    l1 = np.abs(e - g).sum(-1)                      # [B, H]
+    js = jsd(g, e)                                  # [B, H]
+    return l1[:, -1], l1.mean(1), js[:, -1], js.mean(1)
+
+
 def synthetic_start_states(n_rows=21, n_cols=20, d=15, seed=0):
     """Dirichlet(1_20) rows rounded to %.3e, first d columns,
     not renormalised (mirrors the parse at mfg_ac2.py:191-198)."""

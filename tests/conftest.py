@@ -37,3 +37,8 @@ def traj15():
 @pytest.fixture(scope="session")
 def fwd47():
     return load_golden("forward_d47.npz")
+
+
+@pytest.fixture(scope="session")
+def evalm():
+    return load_golden("eval_metrics.npz")

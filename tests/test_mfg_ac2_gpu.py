@@ -245,3 +245,33 @@ def test_mfg_synthetic_dropin(start_states):
                     lr_actor=0.001, constant=True, reward="synthetic", seed=3, learner_offset=4,
                     want_total_reward=False)
     np.testing.assert_allclose(res[4, 2], float(th[0]), rtol=1e-12)
+
+
+def test_evaluate_and_jsd_match_reference(start_states, evalm, tmp_path):
+    """actor_critic.evaluate / JSD / gridsearch (mfg_ac2.py:546-689) with the reference's own draws."""
+    d = int(evalm["d"])
+    ac = mfg_ac2.actor_critic(d=d, mat_pi0=start_states, dtype="float64", seed=1)
+    np.testing.assert_allclose(ac.JSD(evalm["jsd_P"], evalm["jsd_Q"]), float(evalm["jsd_value"]), rtol=1e-12)
+    out = tmp_path / "eval" / "res.csv"
+    res = ac.evaluate(theta=float(evalm["theta"]), shift=float(evalm["shift"]), alpha_scale=float(evalm["alpha_scale"]),
+                      d=d, episode_length=16, outfile=str(out), write_header=1, empirical=evalm["empirical"],
+                      y=evalm["y"])
+    np.testing.assert_allclose(res, evalm["result"], rtol=1e-10)
+    assert out.read_text() == str(evalm["csv"])                       # same header and formatted line
+    # reading the test days from files (sorted order), float32 streams, Philox noise
+    indir = tmp_path / "days"
+    indir.mkdir()
+    for k, m in enumerate(evalm["empirical"]):
+        np.savetxt(indir / ("trend_distribution_day%d.csv" % (22 + k)), m, fmt="%.6e", delimiter=" ")
+    import os
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        ac32 = mfg_ac2.actor_critic(d=d, mat_pi0=start_states, dtype="float32", seed=2)
+        r1 = ac32.evaluate(theta=8.0, shift=0.16, alpha_scale=12000, d=d, indir="days", outfile=None)
+        assert all(np.isfinite(r1)) and abs(r1[0] - float(evalm["result"][0])) < 0.1
+        best = ac32.gridsearch([7.0, 8.0], [0.1, 0.16], [12000], "days", str(tmp_path / "grid.csv"), verbose=False)
+        assert len(best) == 4 and all(b[1] in (7.0, 8.0) and b[2] in (0.1, 0.16) for b in best)
+        assert len(open(tmp_path / "grid.csv").read().strip().splitlines()) == 4
+    finally:
+        os.chdir(cwd)

@@ -133,3 +133,17 @@ def test_float32_cancellation_is_where_the_survey_says(trace):
     assert rel(a32["grads"], a64["grads"]) < 2e-5
     # deltas lose several digits in float32 -- the CUDA path accumulates these in float64
     assert rel(a32["deltas"], a64["deltas"]) > 1e-6
+
+
+def test_metrics_oracle_against_reference_evaluate(evalm):
+    """jsd / trajectory_metrics against the reference's own JSD and evaluate() (mfg_ac2.py:546-563, 595-670)."""
+    assert np.isclose(O.jsd(evalm["jsd_P"], evalm["jsd_Q"]), float(evalm["jsd_value"]), rtol=1e-13)
+    emp, y = evalm["empirical"], evalm["y"]
+    gen = []
+    for k in range(emp.shape[0]):
+        noise = O.InjectedNoise(start_rows=np.zeros(1, int), y=y[k][None])
+        noise.start_index(1)
+        gen.append(O.generate_trajectory(emp[k, 0], 16, float(evalm["theta"]), float(evalm["shift"]),
+                                         float(evalm["alpha_scale"]), noise))
+    res = [np.mean(a) for a in O.trajectory_metrics(np.stack(gen), emp)]
+    np.testing.assert_allclose(res, evalm["result"], rtol=1e-12)
