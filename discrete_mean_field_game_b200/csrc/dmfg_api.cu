@@ -150,8 +150,8 @@ int launch_fast(RolloutParams<R> p, bool td, int* grid_out, cudaStream_t st) {
 template <int D, int NOISE, bool REC, bool TRAIN>
 int launch_v2(RolloutParams<float> p, bool td, int* grid_out, cudaStream_t st) {
     auto kern = rollout_v2_kernel<D, NOISE, REC, TRAIN>;
-    const size_t smem = (size_t)(td && p.partials ? V2Smem<D>::total_td : V2Smem<D>::total_notd) * sizeof(double);
-    DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(V2Smem<D>::total_td * sizeof(double))));
+    const size_t smem = (size_t)V2Smem<D>::total * sizeof(double);
+    DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0, sms = 0;
     DMFG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kV2Threads, smem));
     if (int rc = sm_count(&sms)) return rc;

@@ -269,13 +269,15 @@ __device__ __forceinline__ void gamma_pair_fast(const NoiseKey& nk, const Philox
     const bool ok1 = (fabsf(e.y) <= 0.5f) & (u.y < thr.y);
     y0 = y.x;
     y1 = y.y;
+    // A squeeze-accepted variate without boost is dd v^3 with v >= 1/2: never 0.  Only the two rare paths can
+    // underflow to 0, so the reference's y == 0 -> 1e-20 substitution (mfg_ac2.py:244) lives there.
     if (!(ok0 & ok1)) {
         const float2 yy = gamma_pair_redo(nk.p0, nk.p1, nk.k0, nk.k1, slot, al.x, al.y, scale);
-        y0 = yy.x;
-        y1 = yy.y;
+        y0 = yy.x == 0.0f ? 1e-20f : yy.x;
+        y1 = yy.y == 0.0f ? 1e-20f : yy.y;
     } else if (b0 | b1) {
-        if (b0) y0 = boost_apply(y0, a.x, squeeze_uniform(u.x, thr.x));
-        if (b1) y1 = boost_apply(y1, a.y, squeeze_uniform(u.y, thr.y));
+        if (b0) { y0 = boost_apply(y0, a.x, squeeze_uniform(u.x, thr.x)); if (y0 == 0.0f) y0 = 1e-20f; }
+        if (b1) { y1 = boost_apply(y1, a.y, squeeze_uniform(u.y, thr.y)); if (y1 == 0.0f) y1 = 1e-20f; }
     }
 }
 

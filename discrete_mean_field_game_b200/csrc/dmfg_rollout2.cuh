@@ -1,24 +1,30 @@
 // rollout_v2_kernel -- the throughput version of the fused population step for d = 15 / 16, float
 // streams (sm_100a).  Same arithmetic contract as rollout_fast_kernel (dmfg_rollout.cuh), restructured
-// around what ncu showed on the first version (profiles/r1_rollout_fast_train_ncu_summary.md: 2.8 k warp
-// instructions per population-step, a fully unrolled 120 KB body thrashing the instruction cache, 21 % of
-// the XU pipe spent on float<->double conversions and precise libm calls):
+// around what ncu showed (profiles/r1_rollout_fast_train_ncu_summary.md for the first kernel,
+// profiles/r1_rollout_v2_ncu_summary.md for the two-pass form of this one):
 //
-//   * a group of 16 lanes owns one population, lane r owns ROW r of P (as before), but the row is walked
-//     by two ROLLED loops, so the hot body is a few KB:
-//       pass 1 (per column pair): alpha, alpha' (one ex2, one lg2, one rcp), psi(alpha) (one rcp, one lg2),
-//               the Gamma pair (one Philox call, Box-Muller on MUFU, squeeze-accepted Marsaglia-Tsang);
-//               {y, alpha'} parked in an 8-byte shared slot, row sum of y in double;
-//       pass 2 (per column, after the row sum is known): P = y / s, ln P, the reward term P^2 (pi_j - pi_i)
-//               and the flux pi_i P_ij in double, written back INTO the same slot;
-//   * pi' = P^T pi is a transposed read of those slots (15 LDS.64 + 15 DADD per lane) instead of 60
-//     shuffles; the state vector lives in a double-buffered shared array (double + float copies) that
-//     all lanes of the group read as broadcasts;
-//   * float everywhere except where the TD error needs it: row sums, P, reward, flux, state, critic
-//     value and all reductions stay double, every float -> double conversion that
-//     remains is per element of pass 2 or per row;
-//   * critic weights are staged once per CTA in a [slot][lane] table shared by all groups (2 KB instead
-//     of 35 KB), so three CTAs fit an SM.
+//   * a group of 16 lanes owns one population, lane r owns ROW r of P, walked by ONE rolled loop over
+//     column pairs (packed f32x2 math):  alpha, alpha', psi(alpha) (alpha_psi_fast2), the Gamma pair (one
+//     Philox call, Box-Muller on MUFU, squeeze-accepted Marsaglia-Tsang), and -- because every row-wise
+//     sum is linear in the UNNORMALISED variates --
+//         sum_j y_ij,   sum_j y_ij^2 (pi_j - pi_i)   [reward],   sum_j alpha'_ij lg2 y_ij   [ln P term]
+//     in the same pass; y goes to a [row][column] shared tile as a double.  There is no second pass
+//     over the row: 1/s_i enters as a per-row factor afterwards
+//         r_i = pi_i s_i^-2 sum_j y_ij^2 (pi_j - pi_i),   sum_j alpha'_ij ln P_ij = ln2 (sum_j alpha'_ij lg2 y_ij - lg2 s_i sum_j alpha'_ij);
+//   * pi'_j = sum_i (pi_i / s_i) y_ij is a transposed read of the tile against the 16 published
+//     q_i = pi_i / s_i (three independent partial sums: the chain was latency-bound);
+//   * the TD error needs ONE 16-lane reduction per step: lanes carry their partial of V(pi) and
+//     delta = sum_lanes (r_lane + gamma V'_lane - V_lane); sum delta*g is accumulated per lane (linear);
+//   * the critic gradient  sum_n delta_n pi_n pi_n^T  is a real contraction over samples: it runs on the
+//     FP64 tensor-core path (DMMA.8x8x4): every two steps the warp's 4 samples (2 populations x 2 steps)
+//     are staged as A = delta*pi (16x4), B = pi (4x16) and three m8n8k4 MMAs update the upper-triangular
+//     8x8 tiles of the 16x16 Gram matrix held in 6 double registers per thread for the whole kernel
+//     (the previous form spent 10 % of the step on 15 LDS+DFMA+STS triples per lane);
+//   * shared memory is addressed through explicit 32-bit shared-window addresses (ld/st.shared): the
+//     generic-pointer form made the compiler rebuild the window base (S2UR SR_CgaCtaId + 3 uniform
+//     ops) in front of every access of the rolled loop;
+//   * float everywhere except where the TD error needs it: row sums, reward, flux, state, critic
+//     value and all reductions stay double.
 #pragma once
 #include "dmfg_rollout.cuh"
 
@@ -26,36 +32,63 @@ namespace dmfg {
 
 constexpr int kV2Threads = 256;
 constexpr int kV2G = 16;
-constexpr int kV2Slots = 17;          // 8-byte slots per lane row (16 columns + 1 pad => odd stride)
+constexpr int kV2Slots = 17;          // doubles per tile row (16 columns + 1 pad => conflict-free both ways)
+constexpr int kV2StageRow = 20;       // doubles per staged sample (16 + 4 pad => conflict-free fragment loads)
 
 template <int D>
 struct V2Smem {
     static constexpr int GPB = kV2Threads / kV2G;
+    static constexpr int NW = kV2Threads / 32;
     static constexpr int NSLOT = D + 2;
     // offsets in doubles
-    static constexpr int tile = 0;                                  // [GPB][16][17] slots
+    static constexpr int tile = 0;                                  // [GPB][16][17] y_ij, double
     static constexpr int pid = tile + GPB * kV2G * kV2Slots;        // [2][GPB][16] state, double
-    static constexpr int wl = pid + 2 * GPB * kV2G;                 // [NSLOT][16] critic slots
+    static constexpr int qv = pid + 2 * GPB * kV2G;                 // [GPB][16] q_i = pi_i / s_i
+    static constexpr int wl = qv + GPB * kV2G;                      // [NSLOT][16] critic slots
     static constexpr int pif = wl + NSLOT * kV2G;                   // [2][GPB][16] state, float (GPB*16 doubles)
-    // per-group gradient accumulators (train only), TRIANGULAR: lane r of a group only ever touches the
-    // quadratic features (r,k) with k >= r -> [k(k+1)/2 + r] for k < D, then the D linear slots (padded to
-    // 16) and the bias: 137 / 153 doubles per group instead of 17 x 16 (3 CTAs per SM instead of 2)
-    static constexpr int Q = D * (D + 1) / 2;
-    static constexpr int acc_group = (Q + kV2G + 1 + 1) & ~1;
-    static constexpr int acc = pif + GPB * kV2G;
-    static constexpr int total_notd = acc;
-    static constexpr int total_td = acc + GPB * acc_group;
+    static constexpr int stage = pif + GPB * kV2G;                  // [NW][2][4][20] staged samples (A, B)
+    static constexpr int total = stage + NW * 2 * 4 * kV2StageRow;
+    // the end-of-kernel reduction reuses the tile: [NW][16][17] Gram tiles, [GPB][16] linear, [GPB] bias
+    static constexpr int gram = tile;
+    static constexpr int lin = gram + NW * kV2G * kV2Slots;
+    static constexpr int bias = lin + GPB * kV2G;
+    static_assert(bias + GPB <= pid, "reduction scratch must fit the tile");
 };
 
-// critic value from the shared state buffer: lane r sums w[r,k] pi_r pi_k over k >= r (zeros below)
+// ---- explicit shared-window accesses (32-bit addresses from __cvta_generic_to_shared) -----------------
+__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
+    double2 v; asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+    float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void warp_fence() { asm volatile("bar.warp.sync 0xffffffff;" ::: "memory"); }
+
+// D += A(8x4, row) * B(4x8, col) on the FP64 tensor-core path: thread (g = lane/4, t = lane%4) holds
+// A[g][t], B[t][g] and C[g][2t], C[g][2t+1]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// this lane's partial of V(pi): lane r sums w[r,k] pi_r pi_k over k >= r (zero slots below), + linear + bias
 template <int D>
-__device__ __forceinline__ double critic_value_v2(const double* __restrict__ wl, const double* __restrict__ pi,
-                                                  double pi_self, int r) {
-    double v = 0.0;
-#pragma unroll 5
-    for (int k = 0; k < D; ++k) v = fma(wl[k * kV2G + r], pi[k], v);
-    v = fma(v, pi_self, wl[D * kV2G + r] * pi_self) + wl[(D + 1) * kV2G + r];
-    return group_sum<kV2G>(v);
+__device__ __forceinline__ double critic_partial_v2(uint32_t a_wl_r, uint32_t a_pid, double pi_self) {
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 1 < D; k += 2) {
+        const double2 pk = lds_f64x2(a_pid + 8 * k);
+        const double w0 = lds_f64(a_wl_r + 8 * kV2G * k), w1 = lds_f64(a_wl_r + 8 * kV2G * (k + 1));
+        if ((k / 2) % 3 == 0) { v0 = fma(w0, pk.x, v0); v1 = fma(w1, pk.y, v1); }
+        else if ((k / 2) % 3 == 1) { v2 = fma(w0, pk.x, v2); v0 = fma(w1, pk.y, v0); }
+        else { v1 = fma(w0, pk.x, v1); v2 = fma(w1, pk.y, v2); }
+    }
+    if (D & 1) v2 = fma(lds_f64(a_wl_r + 8 * kV2G * (D - 1)), lds_f64(a_pid + 8 * (D - 1)), v2);
+    const double v = (v0 + v1) + v2;
+    return fma(v, pi_self, lds_f64(a_wl_r + 8 * kV2G * D) * pi_self) + lds_f64(a_wl_r + 8 * kV2G * (D + 1));
 }
 
 // TRAIN = the batched train step: accumulators wanted and NO per-step output stream requested -- every
@@ -64,58 +97,69 @@ template <int D, int NOISE, bool REC, bool TRAIN>
 __global__ void __launch_bounds__(kV2Threads, 2)
 rollout_v2_kernel(const RolloutParams<float> p) {
     using S = V2Smem<D>;
-    constexpr int G = kV2G, NT = kV2Threads, GPB = S::GPB, NSLOT = S::NSLOT, PD = (D + 1) / 2;
+    constexpr int G = kV2G, NT = kV2Threads, GPB = S::GPB, PD = (D + 1) / 2;
     constexpr int F = num_features_c(D);
-    extern __shared__ double smem[];
-    const int tid = threadIdx.x, r = tid & (G - 1), grp = tid / G;
-    double* slots = smem + S::tile + (grp * G + r) * kV2Slots;            // this lane's row of slots
-    const double* col = smem + S::tile + grp * G * kV2Slots + r;          // column r of the group's tile
-    double* pid = smem + S::pid + grp * G;                                 // [2] buffers, stride GPB*G
-    float* pif = reinterpret_cast<float*>(smem + S::pif) + grp * G;        // [2] buffers, stride GPB*G
-    const double* wl = smem + S::wl;
-    double* acc = smem + S::acc + grp * S::acc_group;                      // this group's triangular block
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, r = tid & (G - 1), grp = tid / G, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t a_row = sb + 8u * (S::tile + (grp * G + r) * kV2Slots);      // this lane's row of the tile
+    const uint32_t a_col = sb + 8u * (S::tile + grp * G * kV2Slots + r);        // column r of the group's tile
+    const uint32_t a_pid = sb + 8u * (S::pid + grp * G);                         // [2] buffers, stride GPB*G doubles
+    const uint32_t a_pif = sb + 8u * S::pif + 4u * (grp * G);                    // [2] buffers, stride GPB*G floats
+    const uint32_t a_q = sb + 8u * (S::qv + grp * G);
+    const uint32_t a_wl_r = sb + 8u * (S::wl + r);
+    const uint32_t a_stage = sb + 8u * (S::stage + warp * (2 * 4 * kV2StageRow));
+    constexpr uint32_t kBufD = 8u * GPB * G, kBufF = 4u * GPB * G, kStageB = 8u * 4 * kV2StageRow;
     const bool td = TRAIN || p.w != nullptr;
     const bool want_acc = TRAIN || (td && p.partials != nullptr);
     const bool row_ok = r < D;
     if (td) {
         if (tid < G) stage_critic_slots<D>(smem + S::wl + tid, G, p.w, tid);
-        if (want_acc)
-            for (int k = r; k < S::acc_group; k += G) acc[k] = 0.0;
     }
+    for (int k = tid; k < S::NW * 2 * 4 * kV2StageRow; k += NT) smem[S::stage + k] = 0.0;
     __syncthreads();
     const float theta = (float)(p.theta_dev ? *p.theta_dev : p.theta);
     const float shift = p.shift_f, scale = p.scale_f;
     const bool ac2 = p.reward_kind == DMFG_REWARD_AC2;
-    double sum_dg = 0.0, sum_r = 0.0;
+    const bool has_reward = p.reward_kind != DMFG_REWARD_NONE;
+    const double rew_scale = ac2 ? 1.0 : -0.5;
+    double sum_dg = 0.0, sum_r = 0.0;            // per-LANE partial sums (reduced once, at the end)
+    double c00a = 0.0, c00b = 0.0, c01a = 0.0, c01b = 0.0, c11a = 0.0, c11b = 0.0;   // Gram tiles (warp-wide)
+    double lin_acc = 0.0, bias_acc = 0.0;
+    const int half = (tid >> 4) & 1, gid = lane >> 2, tig = lane & 3;
+    const uint32_t a_frag = a_stage + 8u * (tig * kV2StageRow + gid);             // A[gid][tig] of the low tile
     const long long ntiles = (p.B + GPB - 1) / GPB;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         long long b = tile * GPB + grp;
         const bool live = b < p.B;                 // dead groups shadow the last population, writes masked
         if (!live) b = p.B - 1;
         const bool wr = live && row_ok;
+        const double livef = live ? 1.0 : 0.0;
         const NoiseKey nk = make_noise_key(p.seed, (unsigned long long)(p.pop_offset + b));
         double pi_self = row_ok ? (double)p.pi0[b * D + r] : 0.0;
-        int cur = 0;
-        pid[r] = pi_self;
-        pif[r] = (float)pi_self;
-        __syncwarp();
-        double v_cur = td ? critic_value_v2<D>(wl, pid, pi_self, r) : 0.0;
+        uint32_t cur = 0;
+        sts_f64(a_pid + 8 * r, pi_self);
+        sts_f32(a_pif + 4 * r, (float)pi_self);
+        warp_fence();
+        double vc_lane = td ? critic_partial_v2<D>(a_wl_r, a_pid, pi_self) : 0.0;
+        double v_cur = (td && !TRAIN) ? group_sum<G>(vc_lane) : 0.0;
         double disc = 1.0;
         if (!TRAIN && p.states != nullptr && wr) p.states[b * D + r] = (float)pi_self;
         for (int t = 0; t < p.T; ++t) {
             const long long tb = (long long)t * p.B + b;
             const long long row = (tb * D + r) * D;
-            const double* pic = pid + cur * (GPB * G);
-            const float* pfc = pif + cur * (GPB * G);
-            // ------------------------------------------------------------------ pass 1
+            const uint32_t a_pic = a_pid + cur * kBufD, a_pfc = a_pif + cur * kBufF;
+            // ------------------------------------------------------------------ the row
             const float xi = (float)pi_self + shift;
-            float2 asum2 = make_float2(0.f, 0.f), dsum2 = asum2, g12 = asum2;
-            double ysum = 0.0;
+            // reward weights: AC2 sum_j y^2 (pi_j - pi_i);  synthetic sum_j y^2
+            const double c1 = ac2 ? 1.0 : 0.0, c0 = ac2 ? -pi_self : 1.0;
+            float2 asum2 = make_float2(0.f, 0.f), dsum2 = asum2, g12 = asum2, g22 = asum2;
+            double ysum0 = 0.0, ysum1 = 0.0, racc0 = 0.0, racc1 = 0.0;
+            const uint32_t slot0 = gamma_slot((uint32_t)(p.step_offset + t), D, r, 0);
 #pragma unroll 4
             for (int pp = 0; pp < PD; ++pp) {
-                const float2 pj = *reinterpret_cast<const float2*>(pfc + 2 * pp);
+                const float2 pj = lds_f32x2(a_pfc + 8 * pp);
                 const bool ok1 = (2 * pp + 1) < D;                     // only the last pair of an odd D
-                // the pair (columns 2pp, 2pp+1) runs as packed f32x2 math: one issue slot per two elements
                 float2 a, dv, psi;
                 alpha_psi_fast2(theta, __fadd2_rn(pj, splat2(-xi)), a, dv, psi);
                 if (!ok1) { a.y = 1.0f; dv.y = 0.0f; }
@@ -124,90 +168,118 @@ rollout_v2_kernel(const RolloutParams<float> p) {
                 dsum2 = __fadd2_rn(dsum2, dv);
                 float y0, y1;
                 if (NOISE == DMFG_NOISE_PHILOX) {
-                    gamma_pair_fast(nk, p.rk, gamma_slot((uint32_t)(p.step_offset + t), D, r, pp), a, scale, y0, y1);
+                    gamma_pair_fast(nk, p.rk, slot0 + (uint32_t)pp, a, scale, y0, y1);   // never returns 0
                 } else {
                     y0 = row_ok ? p.noise_y[row + 2 * pp] : 1.0f;
                     y1 = (row_ok && ok1) ? p.noise_y[row + 2 * pp + 1] : 1.0f;
+                    if (y0 == 0.0f) y0 = 1e-20f;                         // mfg_ac2.py:244
+                    if (y1 == 0.0f) y1 = 1e-20f;
                 }
-                if (y0 == 0.0f) y0 = 1e-20f;                             // mfg_ac2.py:244
-                if (y1 == 0.0f) y1 = 1e-20f;
-                if (!ok1) y1 = 0.0f;
-                ysum += (double)(y0 + y1);       // pair sum in float: <= 6e-8 relative on the pair, one conversion
-                *reinterpret_cast<float2*>(slots + 2 * pp) = make_float2(y0, dv.x);
-                *reinterpret_cast<float2*>(slots + 2 * pp + 1) = make_float2(y1, dv.y);
+                if (!ok1) y1 = 1.0f;
+                g22 = __ffma2_rn(make_float2(lg2_approx(y0), lg2_approx(y1)), dv, g22);
+                const double yd0 = (double)y0, yd1 = ok1 ? (double)y1 : 0.0;
+                ysum0 += yd0;
+                ysum1 += yd1;
+                if (has_reward) {
+                    const double2 pjd = lds_f64x2(a_pic + 16 * pp);
+                    racc0 = fma(yd0 * yd0, fma(c1, pjd.x, c0), racc0);
+                    racc1 = fma(yd1 * yd1, fma(c1, pjd.y, c0), racc1);
+                }
+                sts_f64(a_row + 16 * pp, yd0);
+                sts_f64(a_row + 16 * pp + 8, yd1);
                 if (REC && p.alpha != nullptr && wr) {
                     p.alpha[row + 2 * pp] = a.x;
                     p.alpha_deriv[row + 2 * pp] = dv.x;
                     if (ok1) { p.alpha[row + 2 * pp + 1] = a.y; p.alpha_deriv[row + 2 * pp + 1] = dv.y; }
                 }
             }
-            const float asum = asum2.x + asum2.y, dsum = dsum2.x + dsum2.y, g1 = g12.x + g12.y;
+            const float asum = asum2.x + asum2.y, dsum = dsum2.x + dsum2.y, g1 = g12.x + g12.y, g2 = g22.x + g22.y;
             // ------------------------------------------------------------------ row level
-            double inv = (double)rcp_approx((float)ysum);              // 1/s: float seed + 2 Newton steps
+            const double ysum = ysum0 + ysum1;
+            const float ysum_f = (float)ysum;
+            double inv = (double)rcp_approx(ysum_f);                   // 1/s: float seed + 2 Newton steps
             inv = inv * (2.0 - ysum * inv);
             inv = inv * (2.0 - ysum * inv);
-            const float inv_f = (float)inv;
             const double q = pi_self * inv;
+            sts_f64(a_q + 8 * r, q);
             const float psi_row = digamma_fast(asum);
-            // ------------------------------------------------------------------ pass 2
-            double racc = 0.0;
-            float g2 = 0.f;
-            float* act_row = (REC && p.actions != nullptr && wr) ? p.actions + row : nullptr;
+            // sum_j alpha'_ij ln P_ij = ln2 (sum_j alpha'_ij lg2 y_ij - lg2 s_i sum_j alpha'_ij)
+            const float lnp_term = DMFG_LN2 * fmaf(-lg2_approx(ysum_f), dsum, g2);
+            const double glane = row_ok ? (double)(g1 + lnp_term + psi_row * dsum) : 0.0;
+            double rew_lane = has_reward ? rew_scale * (q * inv) * (racc0 + racc1) : 0.0;
+            if (REC && p.actions != nullptr) {
+                const float inv_f = (float)inv;
+                if (wr) {
+                    float* act_row = p.actions + row;
 #pragma unroll 5
-            for (int j = 0; j < D; ++j) {
-                const float2 yd = *reinterpret_cast<const float2*>(slots + j);
-                const double yv = (double)yd.x;
-                const double P = yv * inv;
-                const float Pf = yd.x * inv_f;
-                g2 = fmaf(lg2_approx(Pf), yd.y, g2);
-                // AC2: P^2 (pi_j - pi_i); synthetic: P^2 (the factor is hoisted out of the element loop)
-                const double dlt = ac2 ? pic[j] - pi_self : 1.0;
-                racc = fma(P * P, dlt, racc);
-                slots[j] = yv * q;                                       // flux pi_i P_ij
-                if (REC && act_row != nullptr) act_row[j] = Pf;
+                    for (int j = 0; j < D; ++j) act_row[j] = (float)lds_f64(a_row + 8 * j) * inv_f;
+                }
             }
-            __syncwarp();
-            // ------------------------------------------------------------------ pi' = P^T pi (transposed read)
-            double next_self = 0.0;
-#pragma unroll 5
-            for (int i = 0; i < D; ++i) next_self += col[i * kV2Slots];
-            if (!row_ok) next_self = 0.0;
-            double rew = 0.0;
-            if (ac2) rew = pi_self * racc;
-            else if (p.reward_kind == DMFG_REWARD_SYNTHETIC) rew = -0.5 * pi_self * racc;
-            const double glane = row_ok ? (double)(g1 + DMFG_LN2 * g2 + psi_row * dsum) : 0.0;
-            rew = group_sum<G>(rew);
-            const double grad = group_sum<G>(glane);
-            const int nxt = cur ^ 1;
-            pid[nxt * (GPB * G) + r] = next_self;
-            pif[nxt * (GPB * G) + r] = (float)next_self;
-            __syncwarp();
-            if (!TRAIN && p.rewards_in != nullptr) rew = (double)p.rewards_in[tb];
-            if (td) {
-                const double v_next = critic_value_v2<D>(wl, pid + nxt * (GPB * G), next_self, r);
-                const double gfac = p.discount_kind == DMFG_DISCOUNT_STEP ? p.gamma : disc;
-                const double delta = rew + gfac * v_next - v_cur;
-                if (want_acc && live) {
-                    const double dp = delta * pi_self;
-                    // quadratic features (r,k), k >= r, at [k(k+1)/2 + r]; linear at [Q + r]; bias at [Q + 16]
+            warp_fence();
+            // ------------------------------------------------------------------ pi' = sum_i q_i y_ij
+            double n0 = 0.0, n1 = 0.0, n2 = 0.0;
 #pragma unroll
-                    for (int k = 0; k < D; ++k)
-                        if (k >= r) acc[k * (k + 1) / 2 + r] = fma(dp, pic[k], acc[k * (k + 1) / 2 + r]);
-                    if (row_ok) acc[S::Q + r] += dp;
-                    if (r == 0) {
-                        acc[S::Q + G] += delta;
-                        sum_dg = fma(delta, grad, sum_dg);
+            for (int i = 0; i + 1 < D; i += 2) {
+                const double2 qq = lds_f64x2(a_q + 8 * i);
+                const double ya = lds_f64(a_col + 8 * kV2Slots * i), yb = lds_f64(a_col + 8 * kV2Slots * (i + 1));
+                if ((i / 2) % 3 == 0) { n0 = fma(qq.x, ya, n0); n1 = fma(qq.y, yb, n1); }
+                else if ((i / 2) % 3 == 1) { n2 = fma(qq.x, ya, n2); n0 = fma(qq.y, yb, n0); }
+                else { n1 = fma(qq.x, ya, n1); n2 = fma(qq.y, yb, n2); }
+            }
+            if (D & 1) n2 = fma(lds_f64(a_q + 8 * (D - 1)), lds_f64(a_col + 8 * kV2Slots * (D - 1)), n2);
+            double next_self = (n0 + n1) + n2;
+            if (!row_ok) next_self = 0.0;
+            const uint32_t nxt = cur ^ 1u;
+            sts_f64(a_pid + nxt * kBufD + 8 * r, next_self);
+            sts_f32(a_pif + nxt * kBufF + 4 * r, (float)next_self);
+            warp_fence();
+            // ------------------------------------------------------------------ TD error, accumulators
+            double rew = 0.0, grad = 0.0;
+            if (!TRAIN) {
+                rew = group_sum<G>(rew_lane);
+                grad = group_sum<G>(glane);
+                if (p.rewards_in != nullptr) rew = (double)p.rewards_in[tb];
+            }
+            if (td) {
+                const double vn_lane = critic_partial_v2<D>(a_wl_r, a_pid + nxt * kBufD, next_self);
+                const double gfac = p.discount_kind == DMFG_DISCOUNT_STEP ? p.gamma : disc;
+                double delta;
+                if (TRAIN) {
+                    delta = group_sum<G>(rew_lane + fma(gfac, vn_lane, -vc_lane));
+                } else {
+                    const double v_next = group_sum<G>(vn_lane);
+                    delta = rew + gfac * v_next - v_cur;
+                    v_cur = v_next;
+                    if (p.deltas != nullptr && live && r == 0) p.deltas[tb] = (float)delta;
+                }
+                vc_lane = vn_lane;
+                if (want_acc) {
+                    const double dl = delta * livef;
+                    const double dp = dl * pi_self;
+                    sum_dg = fma(dl, glane, sum_dg);
+                    lin_acc += dp;
+                    bias_acc += dl;
+                    // stage sample k = 2 (t & 1) + half:  A[k][r] = delta pi_r,  B[k][r] = pi_r
+                    const uint32_t a_smp = a_stage + 8u * ((2 * (t & 1) + half) * kV2StageRow + r);
+                    sts_f64(a_smp, dp);
+                    sts_f64(a_smp + kStageB, pi_self);
+                    const bool last = t == p.T - 1;
+                    if ((t & 1) || last) {
+                        if (!(t & 1)) sts_f64(a_smp + 8u * 2 * kV2StageRow, 0.0);     // odd T: samples 2, 3 are empty
+                        warp_fence();
+                        const double a_lo = lds_f64(a_frag), a_hi = lds_f64(a_frag + 64);
+                        const double b_lo = lds_f64(a_frag + kStageB), b_hi = lds_f64(a_frag + kStageB + 64);
+                        dmma884(c00a, c00b, a_lo, b_lo);       // rows 0-7  x cols 0-7
+                        dmma884(c01a, c01b, a_lo, b_hi);       // rows 0-7  x cols 8-15
+                        dmma884(c11a, c11b, a_hi, b_hi);       // rows 8-15 x cols 8-15   (rows 8-15 x cols 0-7 is below the diagonal)
+                        warp_fence();
                     }
                 }
-                if (!TRAIN && p.deltas != nullptr && live && r == 0) p.deltas[tb] = (float)delta;
-                v_cur = v_next;
             }
-            if (live && r == 0) {
-                sum_r += rew;
-                if (!TRAIN) {
-                    if (p.rewards != nullptr) p.rewards[tb] = (float)rew;
-                    if (p.grads != nullptr) p.grads[tb] = (float)grad;
-                }
+            sum_r = fma(livef, TRAIN ? rew_lane : (r == 0 ? rew : 0.0), sum_r);
+            if (!TRAIN && live && r == 0) {
+                if (p.rewards != nullptr) p.rewards[tb] = (float)rew;
+                if (p.grads != nullptr) p.grads[tb] = (float)grad;
             }
             disc *= p.gamma;
             pi_self = next_self;
@@ -215,8 +287,8 @@ rollout_v2_kernel(const RolloutParams<float> p) {
             if (!TRAIN && p.states != nullptr && wr) p.states[(tb + p.B) * D + r] = (float)pi_self;
         }
         if (!TRAIN && p.pi_final != nullptr && wr) p.pi_final[b * D + r] = (float)pi_self;
-        // make the next population start from buffer 0 again
-        __syncwarp();
+        // the next population starts from buffer 0 again: move on only when every lane is done reading
+        warp_fence();
     }
     if (!want_acc) return;
     // ---- per-CTA partial sums, fixed order (deterministic) -- same layout as rollout_fast_kernel -------
@@ -228,27 +300,36 @@ rollout_v2_kernel(const RolloutParams<float> p) {
             a += __shfl_xor_sync(0xffffffffu, a, o);
             c += __shfl_xor_sync(0xffffffffu, c, o);
         }
-        if ((tid & 31) == 0) { red[0][tid >> 5] = a; red[1][tid >> 5] = c; }
+        if (lane == 0) { red[0][warp] = a; red[1][warp] = c; }
+    }
+    __syncthreads();                                   // everyone is done with the tile: reuse it
+    {
+        double* gw = smem + S::gram + warp * (G * kV2Slots);
+        gw[gid * kV2Slots + 2 * tig] = c00a;
+        gw[gid * kV2Slots + 2 * tig + 1] = c00b;
+        gw[gid * kV2Slots + 8 + 2 * tig] = c01a;
+        gw[gid * kV2Slots + 8 + 2 * tig + 1] = c01b;
+        gw[(8 + gid) * kV2Slots + 8 + 2 * tig] = c11a;
+        gw[(8 + gid) * kV2Slots + 8 + 2 * tig + 1] = c11b;
+        smem[S::lin + grp * G + r] = lin_acc;
+        if (r == 0) smem[S::bias + grp] = bias_acc;
     }
     __syncthreads();
     double* out = p.partials + (long long)blockIdx.x * (2 + F);
-    const double* accbase = smem + S::acc;
     for (int f = tid; f < F; f += NT) {
-        // feature f of the reference order -> slot of the triangular per-group block
-        int slot;
-        constexpr int Q = S::Q;
-        if (f < Q) {
-            int rw = 0, rem = f;
-            while (rem >= D - rw) { rem -= D - rw; ++rw; }
-            const int k = rw + rem;
-            slot = k * (k + 1) / 2 + rw;
-        } else if (f < Q + D) {
-            slot = Q + (f - Q);
-        } else {
-            slot = Q + G;
-        }
+        constexpr int Q = D * (D + 1) / 2;
         double s = 0.0;
-        for (int g = 0; g < GPB; ++g) s += accbase[g * S::acc_group + slot];
+        if (f < Q) {
+            // feature f of the reference order (itertools.combinations_with_replacement) -> (i <= j)
+            int i = 0, rem = f;
+            while (rem >= D - i) { rem -= D - i; ++i; }
+            const int j = i + rem;
+            for (int wv = 0; wv < S::NW; ++wv) s += smem[S::gram + wv * (G * kV2Slots) + i * kV2Slots + j];
+        } else if (f < Q + D) {
+            for (int g = 0; g < GPB; ++g) s += smem[S::lin + g * G + (f - Q)];
+        } else {
+            for (int g = 0; g < GPB; ++g) s += smem[S::bias + g];
+        }
         out[1 + f] = s;
     }
     if (tid == 0) {
