@@ -345,7 +345,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32 (transcendentals) + f64 (state, reductions)", "data": "synthetic",
         "config": {"workload": "configs[2]: batched actor-critic train step (a1-a7), %d populations/GPU x d=15 x "
                                "16-step episodes, per-episode batch-mean update" % B,
-                   "populations_per_gpu": B, "d": D, "T": T, "update": "per_episode", "noise": "philox4x32-10",
+                   "populations_per_gpu": B, "d": D, "T": T, "update": "per_episode", "noise": "philox4x32-7 (in-kernel Gamma sampler)",
                    "l2": "flushed between timed iterations (256 MiB write)", "parallelism": "dp%d" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 4,
                 "d2h_bytes_per_step": (F + 1) * 8 + 8, "steps": e2e_steps},

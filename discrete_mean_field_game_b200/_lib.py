@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdmfg.so")
+LIB_PATH = os.environ.get("DMFG_LIB_PATH") or os.path.join(_HERE, "libdmfg.so")   # override: A/B builds of the kernels
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
 F32, F64 = 0, 1
@@ -130,6 +130,8 @@ SYMBOLS = [
     ("dmfg_irl_log_z", C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_double,
                                  C.c_void_p, C.c_void_p]),
     ("dmfg_philox4x32_10", None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("dmfg_gamma_philox_rounds", C.c_int32, []),
+    ("dmfg_philox4x32_gamma", None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("dmfg_gamma_sample", C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     ("dmfg_digamma", C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 ]

@@ -550,6 +550,13 @@ void dmfg_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out)
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
+int32_t dmfg_gamma_philox_rounds(void) { return DMFG_GAMMA_ROUNDS; }
+
+void dmfg_philox4x32_gamma(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    const uint4 r = philox_gamma(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
 int dmfg_gamma_sample(const float* shape, int64_t n, uint64_t seed, uint64_t pop, float* out, void* stream) {
     if (n < 0 || (n > 0 && (!shape || !out))) return fail(DMFG_ERR_INVALID, "dmfg_gamma_sample: bad argument");
     if (n == 0) return DMFG_OK;

@@ -30,7 +30,14 @@
 
 namespace dmfg {
 
+#ifndef DMFG_V2_UNROLL
+#define DMFG_V2_UNROLL 4
+#endif
+#ifndef DMFG_V2_MINB
+#define DMFG_V2_MINB 2
+#endif
 constexpr int kV2Threads = 256;
+constexpr int kV2Unroll = DMFG_V2_UNROLL;
 constexpr int kV2G = 16;
 constexpr int kV2Slots = 17;          // doubles per tile row (16 columns + 1 pad => conflict-free both ways)
 constexpr int kV2StageRow = 20;       // doubles per staged sample (16 + 4 pad => conflict-free fragment loads)
@@ -94,7 +101,7 @@ __device__ __forceinline__ double critic_partial_v2(uint32_t a_wl_r, uint32_t a_
 // TRAIN = the batched train step: accumulators wanted and NO per-step output stream requested -- every
 // output test is compiled out of the step loop.  REC = some per-element stream (actions / alpha) is written.
 template <int D, int NOISE, bool REC, bool TRAIN>
-__global__ void __launch_bounds__(kV2Threads, 2)
+__global__ void __launch_bounds__(kV2Threads, DMFG_V2_MINB)
 rollout_v2_kernel(const RolloutParams<float> p) {
     using S = V2Smem<D>;
     constexpr int G = kV2G, NT = kV2Threads, GPB = S::GPB, PD = (D + 1) / 2;
@@ -155,16 +162,20 @@ rollout_v2_kernel(const RolloutParams<float> p) {
             const double c1 = ac2 ? 1.0 : 0.0, c0 = ac2 ? -pi_self : 1.0;
             float2 asum2 = make_float2(0.f, 0.f), dsum2 = asum2, g12 = asum2, g22 = asum2;
             double ysum0 = 0.0, ysum1 = 0.0, racc0 = 0.0, racc1 = 0.0;
+            float a_last = 0.0f;
             const uint32_t slot0 = gamma_slot((uint32_t)(p.step_offset + t), D, r, 0);
-#pragma unroll 4
+#pragma unroll kV2Unroll
             for (int pp = 0; pp < PD; ++pp) {
                 const float2 pj = lds_f32x2(a_pfc + 8 * pp);
                 const bool ok1 = (2 * pp + 1) < D;                     // only the last pair of an odd D
                 float2 a, dv, psi;
                 alpha_psi_fast2(theta, __fadd2_rn(pj, splat2(-xi)), a, dv, psi);
-                if (!ok1) { a.y = 1.0f; dv.y = 0.0f; }
+                // the phantom column of an odd D (state slot D is 0): alpha' = 0 removes it from every weighted
+                // sum, its alpha is taken out of the row sum after the loop, its variate is masked below
+                if (!ok1) dv.y = 0.0f;
+                a_last = a.y;
                 g12 = __ffma2_rn(psi, neg2(dv), g12);
-                asum2 = __fadd2_rn(asum2, make_float2(a.x, ok1 ? a.y : 0.0f));
+                asum2 = __fadd2_rn(asum2, a);
                 dsum2 = __fadd2_rn(dsum2, dv);
                 float y0, y1;
                 if (NOISE == DMFG_NOISE_PHILOX) {
@@ -175,9 +186,8 @@ rollout_v2_kernel(const RolloutParams<float> p) {
                     if (y0 == 0.0f) y0 = 1e-20f;                         // mfg_ac2.py:244
                     if (y1 == 0.0f) y1 = 1e-20f;
                 }
-                if (!ok1) y1 = 1.0f;
                 g22 = __ffma2_rn(make_float2(lg2_approx(y0), lg2_approx(y1)), dv, g22);
-                const double yd0 = (double)y0, yd1 = ok1 ? (double)y1 : 0.0;
+                const double yd0 = (double)y0, yd1 = (double)(ok1 ? y1 : 0.0f);
                 ysum0 += yd0;
                 ysum1 += yd1;
                 if (has_reward) {
@@ -193,7 +203,7 @@ rollout_v2_kernel(const RolloutParams<float> p) {
                     if (ok1) { p.alpha[row + 2 * pp + 1] = a.y; p.alpha_deriv[row + 2 * pp + 1] = dv.y; }
                 }
             }
-            const float asum = asum2.x + asum2.y, dsum = dsum2.x + dsum2.y, g1 = g12.x + g12.y, g2 = g22.x + g22.y;
+            const float asum = asum2.x + ((D & 1) ? asum2.y - a_last : asum2.y), dsum = dsum2.x + dsum2.y, g1 = g12.x + g12.y, g2 = g22.x + g22.y;
             // ------------------------------------------------------------------ row level
             const double ysum = ysum0 + ysum1;
             const float ysum_f = (float)ysum;

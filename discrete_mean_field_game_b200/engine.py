@@ -296,14 +296,19 @@ def digamma(x):
     return out
 
 
-def philox(ctr, key):
-    """Host evaluation of the library's Philox4x32-10 (known-answer tests)."""
+def philox(ctr, key, gamma_stream=False):
+    """Host evaluation of the library's Philox4x32-10 (known-answer tests); gamma_stream=True evaluates the
+    block function of the Gamma sampler (dmfg_gamma_philox_rounds() rounds) instead."""
     lib = _lib.load()
     c = (C.c_uint32 * 4)(*ctr)
     k = (C.c_uint32 * 2)(*key)
     o = (C.c_uint32 * 4)()
-    lib.dmfg_philox4x32_10(c, k, o)
+    (lib.dmfg_philox4x32_gamma if gamma_stream else lib.dmfg_philox4x32_10)(c, k, o)
     return tuple(int(v) for v in o)
+
+
+def gamma_philox_rounds():
+    return int(_lib.load().dmfg_gamma_philox_rounds())
 
 
 # ----------------------------------------------------------------------------- IRL path (a10-a13)

@@ -329,6 +329,11 @@ int dmfg_irl_log_z(int64_t M, int32_t T, int32_t K, int64_t t_stride, int64_t j_
 /* ---- testing aids: direct access to the device math ---------------------- */
 /* Philox4x32-10 on the host (same code the kernels run): out[4] = philox(ctr[4], key[2]) */
 void dmfg_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out);
+/* The Gamma sampler of the rollout kernels (the replacement of np.random.gamma, mfg_ac2.py:242) runs the
+ * same generator with dmfg_gamma_philox_rounds() = 7 rounds (Philox4x32-7, the smallest Crush-resistant
+ * member of the family in Salmon et al. SC'11); this is that block function on the host. */
+int32_t dmfg_gamma_philox_rounds(void);
+void dmfg_philox4x32_gamma(const uint32_t* ctr, const uint32_t* key, uint32_t* out);
 /* n Gamma(shape[i],1) variates (float, device pointers) drawn exactly as the rollout kernels
  * draw them: element i uses pair slot i/2 of population `pop` */
 int dmfg_gamma_sample(const float* shape, int64_t n, uint64_t seed, uint64_t pop, float* out, void* stream);

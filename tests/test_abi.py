@@ -70,6 +70,33 @@ def test_philox_known_answers(lib):
         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
 
 
+def _philox_numpy(ctr, key, rounds):
+    """Independent restatement of Philox4x32-R (Salmon et al., SC'11) in Python integers."""
+    M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    c0, c1, c2, c3 = ctr
+    k0, k1 = key
+    for _ in range(rounds):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = (p1 >> 32) ^ c1 ^ k0, p1 & MASK, (p0 >> 32) ^ c3 ^ k1, p0 & MASK
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return (c0, c1, c2, c3)
+
+
+def test_gamma_stream_philox_rounds(lib):
+    """The Gamma sampler's block function is Philox4x32-7: checked against an independent restatement that
+    itself reproduces the published Random123 vectors at 10 rounds."""
+    cases = [((0, 0, 0, 0), (0, 0)), ((0xffffffff,) * 4, (0xffffffff,) * 2),
+             ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)),
+             ((12345, 0, 678, 3), (1234, 0))]
+    assert _philox_numpy(*cases[0], 10) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert _philox_numpy(*cases[2], 10) == (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+    rounds = engine.gamma_philox_rounds()
+    assert rounds == 7
+    for ctr, key in cases:
+        assert engine.philox(ctr, key) == _philox_numpy(ctr, key, 10)
+        assert engine.philox(ctr, key, gamma_stream=True) == _philox_numpy(ctr, key, rounds)
+
+
 def test_workspace_query(lib):
     a = _lib.RolloutArgs()
     a.struct_size = C.sizeof(_lib.RolloutArgs)
