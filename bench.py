@@ -299,7 +299,7 @@ def run_ours(args):
         ms_irl = timed(lambda: irl.update_reward_batch(ds, da, gs, ga, M, "time_major", group=False), n=5)
         modes["irl_update"] = {"value": 1e3 / ms_irl, "unit": "IRL iters/s", "demo_trajectories": M,
                                "generated_trajectories": M, "transitions_per_iter": 2 * M * 15,
-                               "transitions_per_s": 2 * M * 15 / (ms_irl * 1e-3), "gpu_launches_per_iter": 10}
+                               "transitions_per_s": 2 * M * 15 / (ms_irl * 1e-3), "gpu_launches_per_iter": 9}
         del irl, ds, da, gs, ga
 
     if world > 1:

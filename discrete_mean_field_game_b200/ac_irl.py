@@ -193,6 +193,7 @@ class AC_IRL(_actor_critic):
         (ac_irl.py:382-426).  Nothing to build here beyond the optimiser state."""
         print("Inside create_training_method")
         self._dropout = self.reg in ('dropout', 'dropout_l1l2')
+        self._d_demo_const = {}
         self._l1l2 = self.reg in ('l1l2', 'dropout_l1l2')
         self.reward_params.m.zero_()
         self.reward_params.v.zero_()
@@ -368,7 +369,16 @@ class AC_IRL(_actor_critic):
             key = self.seed ^ 0x5DEECE66D
             kd = dict(seed=key, sample_offset=self._next_dropout_offset(demo_states.shape[0]))
             kg = dict(seed=key, sample_offset=self._next_dropout_offset(gen_states.shape[0]))
-        r_demo = engine.rnet_forward(p.flat, demo_states, demo_actions, p.n_fc3, p.n_fc4, keep_prob=networks.KEEP_PROB, **kd)
+        # dL/dr of a demonstration transition is the constant -1/N (first term of ac_irl.py:390), so the
+        # demonstrations need no separate forward pass: their backward launch recomputes the forward anyway
+        # and hands back r_demo for the loss value.  4 -> 3 reward-net launches per update.
+        n_demo = demo_states.shape[0]
+        d_const = self._d_demo_const.get((n_demo, float(num_demo_traj)))
+        if d_const is None:
+            d_const = torch.full((n_demo,), -1.0 / float(num_demo_traj), dtype=torch.float32, device=self.device)
+            self._d_demo_const = {(n_demo, float(num_demo_traj)): d_const}
+        grad, r_demo = engine.rnet_backward(p.flat, demo_states, demo_actions, d_const, p.n_fc3, p.n_fc4,
+                                            keep_prob=networks.KEEP_PROB, want_rewards=True, **kd)
         r_gen = engine.rnet_forward(p.flat, gen_states, gen_actions, p.n_fc3, p.n_fc4, keep_prob=networks.KEEP_PROB, **kg)
         log_z = None
         if self.use_z:
@@ -377,8 +387,6 @@ class AC_IRL(_actor_critic):
             log_z = engine.irl_log_z(lq, T_STEPS, self.num_start_samples, layout=layout)
         _, world = parallel.world_info(group)
         res = engine.irl_loss_grad(r_demo, r_gen, T_STEPS, num_demo_traj, layout=layout, log_z=log_z)
-        grad = engine.rnet_backward(p.flat, demo_states, demo_actions, res["d_demo"], p.n_fc3, p.n_fc4,
-                                    keep_prob=networks.KEEP_PROB, **kd)
         engine.rnet_backward(p.flat, gen_states, gen_actions, res["d_gen"], p.n_fc3, p.n_fc4, grad=grad,
                              accumulate=True, keep_prob=networks.KEEP_PROB, **kg)
         parallel.allreduce_sum_(grad, group)

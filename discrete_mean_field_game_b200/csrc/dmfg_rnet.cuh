@@ -183,9 +183,15 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     const float inv_keep = p.dropout ? 1.0f / p.keep_prob : 1.0f;
     // persistent register accumulators (backward)
     float gw3[2][NP], gw4pi[NP], gw4h[NP];
+    float gk1[kK1 * kK1 + 1];            // d conv1/weights [dh][dw] + bias: thread-owned for the whole kernel
+    float gk2[kK2 * kK2 * 2 + 2];        // d conv2/weights [dh][dw][c] + 2 biases
     if (BWD) {
 #pragma unroll
         for (int n = 0; n < NP; ++n) { gw3[0][n] = gw3[1][n] = 0.f; gw4pi[n] = gw4h[n] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < kK1 * kK1 + 1; ++i) gk1[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < kK2 * kK2 * 2 + 2; ++i) gk2[i] = 0.f;
     }
     const long long ntiles = (p.N + GPB - 1) / GPB;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -397,12 +403,9 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                         Dt[c * RC * SC + (h + 1) * SC + w + 1] = dz2[c][w];
                     }
                 }
-                float* ga = smem + S.gacc + tid;
                 // d conv2/weights [dh][dw][c] and biases
                 {
-                    float gk[kK2 * kK2 * 2];
-#pragma unroll
-                    for (int i = 0; i < kK2 * kK2 * 2; ++i) gk[i] = 0.f;
+                    float* gk = gk2;
 #pragma unroll
                     for (int dh = 0; dh < kK2; ++dh) {
                         const float* row = Ct + (h + dh) * SC;
@@ -419,13 +422,8 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                             }
                         }
                     }
-                    float sb0 = 0.f, sb1 = 0.f;
 #pragma unroll
-                    for (int w = 0; w < G; ++w) { sb0 += dz2[0][w]; sb1 += dz2[1][w]; }
-#pragma unroll
-                    for (int i = 0; i < 18; ++i) ga[(26 + i) * kRnetThreads] += gk[i];
-                    ga[44 * kRnetThreads] += sb0;
-                    ga[45 * kRnetThreads] += sb1;
+                    for (int w = 0; w < G; ++w) { gk2[18] += dz2[0][w]; gk2[19] += dz2[1][w]; }
                 }
                 __syncwarp();
                 // d conv1 output row h: full correlation of dz2 with the flipped conv2 kernel
@@ -455,9 +453,6 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                 for (int w = 0; w < G; ++w) dz1[w] = c1[w] > 0.f ? dz1[w] : 0.f;
                 // d conv1/weights [dh][dw] and bias
                 {
-                    float gk[kK1 * kK1];
-#pragma unroll
-                    for (int i = 0; i < kK1 * kK1; ++i) gk[i] = 0.f;
 #pragma unroll
                     for (int dh = 0; dh < kK1; ++dh) {
                         const float* row = At + (h + dh) * SA;
@@ -467,16 +462,12 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 #pragma unroll
                             for (int dw = 0; dw < kK1; ++dw) {
                                 const int w = wp - dw;
-                                if (w >= 0 && w < G) gk[dh * kK1 + dw] = fmaf(v, dz1[w], gk[dh * kK1 + dw]);
+                                if (w >= 0 && w < G) gk1[dh * kK1 + dw] = fmaf(v, dz1[w], gk1[dh * kK1 + dw]);
                             }
                         }
                     }
-                    float sb = 0.f;
 #pragma unroll
-                    for (int w = 0; w < G; ++w) sb += dz1[w];
-#pragma unroll
-                    for (int i = 0; i < 25; ++i) ga[i * kRnetThreads] += gk[i];
-                    ga[25 * kRnetThreads] += sb;
+                    for (int w = 0; w < G; ++w) gk1[kK1 * kK1] += dz1[w];
                 }
             }
             __syncwarp();      // tiles are rewritten by the next transition of this group
@@ -497,10 +488,12 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                 const float f0 = k0 < K ? fl[k0] : 0.f;
                 const float f1 = k1 < K ? fl[k1] : 0.f;
 #pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    const float dzj = dzt[j];
-                    gw3[0][j] = fmaf(f0, dzj, gw3[0][j]);
-                    gw3[1][j] = fmaf(f1, dzj, gw3[1][j]);
+                for (int q = 0; q < NP / 4; ++q) {
+                    const float4 dz = reinterpret_cast<const float4*>(dzt)[q];      // broadcast LDS.128
+                    gw3[0][4 * q + 0] = fmaf(f0, dz.x, gw3[0][4 * q + 0]); gw3[1][4 * q + 0] = fmaf(f1, dz.x, gw3[1][4 * q + 0]);
+                    gw3[0][4 * q + 1] = fmaf(f0, dz.y, gw3[0][4 * q + 1]); gw3[1][4 * q + 1] = fmaf(f1, dz.y, gw3[1][4 * q + 1]);
+                    gw3[0][4 * q + 2] = fmaf(f0, dz.z, gw3[0][4 * q + 2]); gw3[1][4 * q + 2] = fmaf(f1, dz.z, gw3[1][4 * q + 2]);
+                    gw3[0][4 * q + 3] = fmaf(f0, dz.w, gw3[0][4 * q + 3]); gw3[1][4 * q + 3] = fmaf(f1, dz.w, gw3[1][4 * q + 3]);
                 }
             }
             __syncthreads();
@@ -522,6 +515,10 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
         }
     }
     float* ga = smem + S.gacc;
+#pragma unroll
+    for (int i = 0; i < kK1 * kK1 + 1; ++i) ga[i * kRnetThreads + tid] = gk1[i];
+#pragma unroll
+    for (int i = 0; i < kK2 * kK2 * 2 + 2; ++i) ga[(26 + i) * kRnetThreads + tid] = gk2[i];
 #pragma unroll
     for (int m = 0; m < NP; ++m) {
         ga[(46 + m) * kRnetThreads + tid] = gw4pi[m];
