@@ -457,6 +457,23 @@ int dmfg_traj_metrics(int32_t dtype, int32_t d, int64_t B, int32_t H, const void
     return DMFG_OK;
 }
 
+int dmfg_synthetic_check(int32_t dtype, int32_t d, int64_t B, int32_t T, const void* actions, double* l1, double* jsd,
+                         void* stream) {
+    if (dtype != DMFG_F32 && dtype != DMFG_F64) return fail(DMFG_ERR_INVALID, "dtype %d", dtype);
+    if (d < 1 || d > DMFG_MAX_D || B < 0 || T < 1) return fail(DMFG_ERR_INVALID, "dmfg_synthetic_check: bad d/B/T");
+    if (B > 0 && (!actions || (!l1 && !jsd))) return fail(DMFG_ERR_INVALID, "dmfg_synthetic_check: NULL argument");
+    if (B == 0) return DMFG_OK;
+    const unsigned grid = (unsigned)((B + 3) / 4);
+    const size_t smem = (size_t)4 * 2 * d * sizeof(double);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DMFG_F64)
+        synthetic_check_kernel<double><<<grid, 128, smem, st>>>(d, B, T, (const double*)actions, l1, jsd);
+    else
+        synthetic_check_kernel<float><<<grid, 128, smem, st>>>(d, B, T, (const float*)actions, l1, jsd);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
 int dmfg_ac_apply_update(int32_t d, double* theta_dev, double* w, const double* acc, double lr_critic_eff,
                          double lr_actor_eff, double scale, void* stream) {
     if (d < 1 || d > DMFG_MAX_D || !w || !acc) return fail(DMFG_ERR_INVALID, "dmfg_ac_apply_update: bad argument");

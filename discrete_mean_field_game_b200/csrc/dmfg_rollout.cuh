@@ -624,6 +624,76 @@ __global__ void __launch_bounds__(128) traj_metrics_kernel(int d, long long B, i
     }
 }
 
+// Analytic check of a policy against the MFG backward equation (mfg_synthetic.py:726-899), warp per
+// trajectory.  V^T = 0;  V^n = r(P^n) + P^n V^{n+1},  r_i = -1/2 ||P_i||^2;  then per step n the predicted
+// matrix A_ij = V_j - V_i (i != j), A_ii = 1 - (sum_j V_j - d V_i):  l1[b][n] = sum_ij |P_ij - A_ij|,
+// jsd[b][n] = sum_i JSD(P_i, A_i) with mfg_synthetic.py:529-546's JSD (entries <= 0 -> 1e-100).
+// actions: time-major record [T][B][d][d];  shared memory: 2 d doubles per warp.
+template <typename R>
+__global__ void __launch_bounds__(128) synthetic_check_kernel(int d, long long B, int T, const R* __restrict__ actions,
+                                                              double* __restrict__ l1, double* __restrict__ jsd) {
+    extern __shared__ double vsm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (b >= B) return;
+    double* Vn = vsm + (size_t)wib * 2 * d;
+    double* Vo = Vn + d;
+    for (int j = lane; j < d; j += 32) Vo[j] = 0.0;
+    __syncwarp();
+    for (int n = T - 1; n >= 0; --n) {
+        const R* P = actions + ((long long)n * B + b) * d * d;
+        for (int i = 0; i < d; ++i) {
+            double s2 = 0.0, sv = 0.0;
+            for (int j = lane; j < d; j += 32) {
+                const double p = (double)P[i * d + j];
+                s2 = fma(p, p, s2);
+                sv = fma(p, Vo[j], sv);
+            }
+            s2 = group_sum<32>(s2); sv = group_sum<32>(sv);
+            if (lane == 0) Vn[i] = -0.5 * s2 + sv;
+        }
+        __syncwarp();
+        double sV = 0.0;
+        for (int j = lane; j < d; j += 32) sV += Vn[j];
+        sV = group_sum<32>(sV);
+        double dl1 = 0.0, djs = 0.0;
+        for (int i = 0; i < d; ++i) {
+            const double vi = Vn[i];
+            double a = 0.0, sp = 0.0, sq = 0.0;
+            for (int j = lane; j < d; j += 32) {
+                const double p = (double)P[i * d + j];
+                const double q = (i == j) ? 1.0 - (sV - d * vi) : Vn[j] - vi;
+                a += fabs(p - q);
+                sp += p <= 0.0 ? 1e-100 : p;
+                sq += q <= 0.0 ? 1e-100 : q;
+            }
+            a = group_sum<32>(a); sp = group_sum<32>(sp); sq = group_sum<32>(sq);
+            dl1 += a;
+            if (jsd != nullptr) {
+                const double sm = 0.5 * (sp + sq);
+                double kp = 0.0, kq = 0.0;
+                for (int j = lane; j < d; j += 32) {
+                    double p = (double)P[i * d + j];
+                    double q = (i == j) ? 1.0 - (sV - d * vi) : Vn[j] - vi;
+                    p = p <= 0.0 ? 1e-100 : p;
+                    q = q <= 0.0 ? 1e-100 : q;
+                    const double m = 0.5 * (p + q) / sm;
+                    p /= sp; q /= sq;
+                    kp += p * log(p / m);
+                    kq += q * log(q / m);
+                }
+                djs += 0.5 * (group_sum<32>(kp) + group_sum<32>(kq));
+            }
+        }
+        if (lane == 0) {
+            if (l1 != nullptr) l1[b * T + n] = dl1;
+            if (jsd != nullptr) jsd[b * T + n] = djs;
+        }
+        __syncwarp();
+        double* tmp = Vn; Vn = Vo; Vo = tmp;
+    }
+}
+
 // theta += lr_a*scale*acc[0];  w[f] += lr_c*scale*acc[1+f]   (mfg_ac2.py:511-522)
 __global__ void ac_apply_update_kernel(int F, double* theta, double* w, const double* __restrict__ acc,
                                        double lr_c, double lr_a, double scale) {

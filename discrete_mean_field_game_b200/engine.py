@@ -208,6 +208,23 @@ def traj_metrics(generated, empirical, time_major=True):
     return l1, js
 
 
+def synthetic_check(actions, want_jsd=True):
+    """Analytic check of recorded trajectories against the MFG backward equation (mfg_synthetic.py:726-899).
+    actions: time-major rollout record [T,B,d,d].  Returns (l1, jsd) [B,T] float64 (jsd None if not wanted)."""
+    lib = _lib.load()
+    device, dtype = actions.device, actions.dtype
+    T, B, d, d2 = actions.shape
+    if d != d2:
+        raise ValueError("actions must be [T,B,d,d]")
+    _require(actions, "actions", device, dtype, (T, B, d, d))
+    with torch.cuda.device(device):
+        l1 = torch.empty((B, T), dtype=torch.float64, device=device)
+        js = torch.empty((B, T), dtype=torch.float64, device=device) if want_jsd else None
+        check(lib.dmfg_synthetic_check(_dtype_code(dtype), d, B, T, _ptr(actions), _ptr(l1),
+                                       _ptr(js) if want_jsd else None, _stream_ptr(device)))
+    return l1, js
+
+
 def apply_update(d, theta_dev, w, acc, lr_critic_eff, lr_actor_eff, scale):
     """theta += lr_a*scale*acc[0]; w += lr_c*scale*acc[1:1+F]  (mfg_ac2.py:511-522), on device."""
     lib = _lib.load()

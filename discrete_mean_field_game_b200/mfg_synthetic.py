@@ -5,7 +5,9 @@ Everything else is inherited from the mfg_ac2 drop-in (same policy, critic, upda
 reference's ``__main__`` experiment (:902-925) -- one independent learner per (shift, theta_initial) pair,
 1000 episodes each with constant step sizes -- run as ONE launch of independent serial learners instead of
 200 sequential runs.  The analytic check of the learned policy against the MFG backward equation
-(:726-899) is evaluation code and out of scope.
+(``calc_reward_vector``, ``evaluate_synthetic``, ``evaluate_synthetic_JSD``, :726-899) rolls
+all start rows out in ONE launch and evaluates the backward equation on the recorded actions on the device
+(``dmfg_synthetic_check``).
 """
 from __future__ import annotations
 
@@ -42,3 +44,58 @@ class actor_critic(_actor_critic):
                         lr_actor=lr_actor, constant=bool(constant), reward=self.reward_kind,
                         discount=self.discount_kind, seed=self.seed, want_total_reward=False)
         return np.column_stack([grid, theta.cpu().numpy()])
+
+    # ------------------------------------------------ consumer of a9: check against the MFG backward equation
+    def generate_trajectory(self, pi0, total_hours, y=None):
+        """(mat_trajectory [total_hours,d], array_actions [total_hours-1,d,d]) -- this variant also returns the
+        actions (mfg_synthetic.py:549-578)."""
+        pi0 = np.asarray(pi0, dtype=np.float64).reshape(1, self.d)
+        T = int(total_hours) - 1
+        noise = None if y is None else self._dev(np.asarray(y).reshape(T, 1, self.d, self.d))
+        out = engine.rollout(self._dev(pi0), self.theta, self.shift, self.alpha_scale, T, reward="none",
+                             noise_y=noise, seed=self.seed, step_offset=self._draws, outputs=("states", "actions"))
+        if y is None:
+            self._draws += T
+        return out["states"][:, 0].double().cpu().numpy(), out["actions"][:, 0].double().cpu().numpy()
+
+    def calc_reward_vector(self, P):
+        """v_i = -1/2 ||P_i||^2 (mfg_synthetic.py:726-738)."""
+        P = np.asarray(P, dtype=np.float64)
+        return -0.5 * np.sum(P * P, axis=1)
+
+    def _synthetic_check(self, day_first, day_last, actions, want_jsd):
+        """l1 / jsd [days, 15] of the rows day_first..day_last (1-based, inclusive).  ``actions`` [days,15,d,d]
+        replaces the rollout (parity against the reference's own sampled actions)."""
+        if actions is None:
+            pi0 = self._dev(self.mat_pi0[day_first - 1:day_last])
+            out = engine.rollout(pi0, self.theta, self.shift, self.alpha_scale, 15, reward="none", seed=self.seed,
+                                 step_offset=self._draws, outputs=("actions",))
+            self._draws += 15
+            acts = out["actions"]
+        else:
+            a = np.asarray(actions, dtype=np.float64)
+            acts = self._dev(np.ascontiguousarray(a.transpose(1, 0, 2, 3)), torch.float64)
+        return engine.synthetic_check(acts, want_jsd=want_jsd)
+
+    def evaluate_synthetic(self, day_first=1, day_last=26, verbose=0, actions=None):
+        """Mean and standard deviation over all (day, hour) of sum_ij |P_ij - A_ij|, A built from the value
+        function of the backward equation (mfg_synthetic.py:741-812)."""
+        l1, _ = self._synthetic_check(day_first, day_last, actions, False)
+        diff_mean, diff_std = float(l1.mean()), float(l1.std(unbiased=False))
+        if verbose:
+            print("Mean over all hours", diff_mean)
+            print("Standard deviation", diff_std)
+        return diff_mean, diff_std
+
+    def evaluate_synthetic_JSD(self, day_first=1, day_last=26, write_file=0, filename='synthetic_log.csv', verbose=0,
+                               actions=None):
+        """Same with sum_i JSD(P_i, A_i) (mfg_synthetic.py:815-899).  write_file is not supported: the log it
+        writes is a debugging dump of every row pair."""
+        if write_file:
+            raise NotImplementedError("write_file: the row-by-row dump of mfg_synthetic.py:879-882 is not provided")
+        _, js = self._synthetic_check(day_first, day_last, actions, True)
+        diff_mean, diff_std = float(js.mean()), float(js.std(unbiased=False))
+        if verbose:
+            print("Mean over all hours", diff_mean)
+            print("Standard deviation", diff_std)
+        return diff_mean, diff_std

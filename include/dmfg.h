@@ -174,6 +174,15 @@ int dmfg_traj_metrics(int32_t dtype, int32_t d, int64_t B, int32_t H, const void
                       int64_t gen_stride_h, const void* empirical, int64_t emp_stride_b, int64_t emp_stride_h,
                       double* l1, double* jsd, void* stream);
 
+/* ---- consumer of a9 (next row f4): analytic check against the MFG backward equation ---------- *
+ * mfg_synthetic.actor_critic.evaluate_synthetic / evaluate_synthetic_JSD (mfg_synthetic.py:726-899) for B
+ * recorded trajectories at once.  actions: the time-major record [T][B][d][d] dmfg_rollout writes.  Per
+ * trajectory: V^T = 0, V^n = r(P^n) + P^n V^{n+1} with r_i = -1/2 ||P_i||^2; A^n_ij = V^n_j - V^n_i (i != j),
+ * A^n_ii = 1 - (sum_j V^n_j - d V^n_i);  l1[b][n] = sum_ij |P^n_ij - A^n_ij|,  jsd[b][n] = sum_i JSD(P^n_i, A^n_i)
+ * (entries <= 0 -> 1e-100, mfg_synthetic.py:529-546).  l1 / jsd: [B][T] doubles, either may be NULL.            */
+int dmfg_synthetic_check(int32_t dtype, int32_t d, int64_t B, int32_t T, const void* actions, double* l1, double* jsd,
+                         void* stream);
+
 /* ---- a5, a7: apply one actor-critic update on device --------------------- *
  * theta += lr_actor_eff * scale * acc[0];  w += lr_critic_eff * scale * acc[1..F]
  * (mfg_ac2.py:511-522).  lr_*_eff are the already-decayed step sizes; scale is

@@ -21,6 +21,8 @@ train_trace.npz   config 1: mfg_ac2.actor_critic.train, d=15, 3 episodes, every
 traj_d15.npz      generate_trajectory (rollout only) with its recorded draws
 forward_d47.npz   test2.test_forward's d=47 start state, 3 transitions
 eval_metrics.npz  actor_critic.evaluate (L1 / Jensen-Shannon against empirical days) with its draws
+synthetic_check.npz  mfg_synthetic.evaluate_synthetic / evaluate_synthetic_JSD on 3 start rows: the sampled
+                  actions and the (mean, std) both functions return
 """
 import importlib
 import os
@@ -259,6 +261,32 @@ def eval_metrics(mfg_ac2, tmp, d=15, n_files=4):
     print("eval_metrics:", res)
 
 
+def synthetic_check(mfg_synthetic, d=15, days=3):
+    """mfg_synthetic.actor_critic.evaluate_synthetic / evaluate_synthetic_JSD (mfg_synthetic.py:741-899): the
+    actions both calls sample (captured from generate_trajectory) and the (mean, std) they return."""
+    ac = mfg_synthetic.actor_critic(theta=2.6, shift=0.5, alpha_scale=1e4, d=d)
+    # this variant's constructor does not read the start rows (init_pi0 wants *_reordered.csv files, :181)
+    ac.mat_pi0 = synthetic_start_states(n_rows=21, n_cols=20, d=d, seed=0)
+    captured = []
+    real = ac.generate_trajectory
+
+    def capture(pi0, total_hours):
+        traj, acts = real(pi0, total_hours)
+        captured.append(np.array(acts, copy=True))
+        return traj, acts
+    ac.generate_trajectory = capture
+    np.random.seed(17)
+    l1 = ac.evaluate_synthetic(day_first=1, day_last=days)
+    a_l1 = np.stack(captured)
+    captured.clear()
+    js = ac.evaluate_synthetic_JSD(day_first=1, day_last=days)
+    a_js = np.stack(captured)
+    np.savez(os.path.join(OUT, "synthetic_check.npz"), d=d, theta=2.6, shift=0.5, alpha_scale=1e4,
+             mat_pi0=ac.mat_pi0[:days], actions_l1=a_l1, l1_mean_std=np.array(l1), actions_jsd=a_js,
+             jsd_mean_std=np.array(js))
+    print("synthetic_check: l1", l1, "jsd", js)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     with tempfile.TemporaryDirectory() as tmp:
@@ -277,6 +305,7 @@ def main():
             traj_d15(mfg_ac2)
             forward_d47(mfg_ac2)
             eval_metrics(mfg_ac2, tmp)
+            synthetic_check(mfg_synthetic)
         finally:
             os.chdir(cwd)
 

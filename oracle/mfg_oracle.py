@@ -367,6 +367,38 @@ def trajectory_metrics(generated, empirical):
     return l1[:, -1], l1.mean(1), js[:, -1], js.mean(1)
 
 
+def jsd_synthetic(P, Q):
+    """mfg_synthetic.py:529-546: like jsd() but every entry <= 0 (not only == 0) becomes 1e-100 -- the analytic
+    rows V_j - V_i do go negative."""
+    P = np.where(np.asarray(P, dtype=np.float64) <= 0, 1e-100, P)
+    Q = np.where(np.asarray(Q, dtype=np.float64) <= 0, 1e-100, Q)
+    M = 0.5 * (P + Q)
+
+    def kl(a, b):
+        a = a / a.sum(-1, keepdims=True)
+        b = b / b.sum(-1, keepdims=True)
+        return (a * np.log(a / b)).sum(-1)
+    return 0.5 * (kl(P, M) + kl(Q, M))
+
+
+def synthetic_check(actions):
+    """The analytic check of mfg_synthetic.py:741-899 for ONE trajectory.  actions [T, d, d].
+    Backward equation V^n = r(P^n) + P^n V^{n+1}, V^T = 0, r_i = -1/2 ||P_i||^2 (:726-738, :775-778); then per
+    step n the matrix the MFG theory predicts, A_ij = V_j - V_i (i != j), A_ii = 1 - (sum_j V_j - d V_i)
+    (:786-794), and  l1[n] = sum_ij |P_ij - A_ij|  (:795),  jsd[n] = sum_i JSD(P_i, A_i)  (:866-877)."""
+    A = np.asarray(actions, dtype=np.float64)
+    T, d, _ = A.shape
+    V = np.zeros(d)
+    l1, js = np.zeros(T), np.zeros(T)
+    for n in range(T - 1, -1, -1):
+        V = -0.5 * (A[n] ** 2).sum(1) + A[n] @ V
+        pred = V[None, :] - V[:, None]
+        pred[np.arange(d), np.arange(d)] = 1.0 - (V.sum() - d * V)
+        l1[n] = np.abs(A[n] - pred).sum()
+        js[n] = jsd_synthetic(A[n], pred).sum()
+    return l1, js
+
+
 def synthetic_start_states(n_rows=21, n_cols=20, d=15, seed=0):
     """Dirichlet(1_20) rows rounded to %.3e, first d columns,
     not renormalised (mirrors the parse at mfg_ac2.py:191-198)."""

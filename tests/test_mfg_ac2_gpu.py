@@ -275,3 +275,33 @@ def test_evaluate_and_jsd_match_reference(start_states, evalm, tmp_path):
         assert len(open(tmp_path / "grid.csv").read().strip().splitlines()) == 4
     finally:
         os.chdir(cwd)
+
+
+def test_synthetic_analytic_check_matches_reference():
+    """evaluate_synthetic / evaluate_synthetic_JSD (mfg_synthetic.py:741-899): the GPU backward-equation check on
+    the reference's own sampled actions returns the reference's (mean, std); on its own rollout it matches the
+    oracle applied to the recorded actions; generate_trajectory returns (states, actions) like the reference."""
+    from conftest import load_golden
+    from discrete_mean_field_game_b200 import engine, mfg_synthetic
+    g = load_golden("synthetic_check.npz")
+    d = int(g["d"])
+    ac = mfg_synthetic.actor_critic(theta=float(g["theta"]), shift=float(g["shift"]), alpha_scale=float(g["alpha_scale"]),
+                                    d=d, mat_pi0=g["mat_pi0"], seed=3)
+    np.testing.assert_allclose(ac.evaluate_synthetic(1, 3, actions=g["actions_l1"]), g["l1_mean_std"], rtol=1e-10)
+    np.testing.assert_allclose(ac.evaluate_synthetic_JSD(1, 3, actions=g["actions_jsd"]), g["jsd_mean_std"], rtol=1e-10)
+    np.testing.assert_allclose(ac.calc_reward_vector(g["actions_l1"][0, 0]),
+                               -0.5 * (g["actions_l1"][0, 0] ** 2).sum(1), rtol=1e-14)
+    # own rollout (float streams): kernel vs oracle on the recorded actions
+    pi0 = torch.as_tensor(g["mat_pi0"], dtype=torch.float32, device=ac.device)
+    acts = engine.rollout(pi0, ac.theta, ac.shift, ac.alpha_scale, 15, reward="none", seed=5, outputs=("actions",))["actions"]
+    l1, js = engine.synthetic_check(acts)
+    A = acts.double().cpu().numpy()
+    for b in range(A.shape[1]):
+        rl1, rjs = O.synthetic_check(A[:, b])
+        np.testing.assert_allclose(l1[b].cpu().numpy(), rl1, rtol=1e-10)
+        np.testing.assert_allclose(js[b].cpu().numpy(), rjs, rtol=1e-9)
+    m, s_ = ac.evaluate_synthetic(1, 3)
+    assert np.isfinite(m) and np.isfinite(s_)
+    traj, actions = ac.generate_trajectory(g["mat_pi0"][0], 16)
+    assert traj.shape == (16, d) and actions.shape == (15, d, d)
+    np.testing.assert_allclose(np.einsum("ti,tij->tj", traj[:-1], actions), traj[1:], atol=3e-7)

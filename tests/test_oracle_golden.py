@@ -147,3 +147,14 @@ def test_metrics_oracle_against_reference_evaluate(evalm):
                                          float(evalm["alpha_scale"]), noise))
     res = [np.mean(a) for a in O.trajectory_metrics(np.stack(gen), emp)]
     np.testing.assert_allclose(res, evalm["result"], rtol=1e-12)
+
+
+def test_synthetic_check_oracle_against_reference():
+    """mfg_synthetic.evaluate_synthetic / evaluate_synthetic_JSD (mfg_synthetic.py:741-899) on the actions the
+    reference itself sampled: the oracle reproduces the (mean, std) both calls returned."""
+    from conftest import load_golden
+    g = load_golden("synthetic_check.npz")
+    l1 = np.concatenate([O.synthetic_check(a)[0] for a in g["actions_l1"]])
+    js = np.concatenate([O.synthetic_check(a)[1] for a in g["actions_jsd"]])
+    np.testing.assert_allclose([l1.mean(), l1.std()], g["l1_mean_std"], rtol=1e-12)
+    np.testing.assert_allclose([js.mean(), js.std()], g["jsd_mean_std"], rtol=1e-12)
