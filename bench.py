@@ -357,6 +357,12 @@ def run_ours(args):
 
 
 def main():
+    # ONE JSON line on stdout: libraries that write to fd 1 (NCCL prints its version there when NCCL_DEBUG is
+    # set on the box) are sent to stderr for the whole run; the line goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

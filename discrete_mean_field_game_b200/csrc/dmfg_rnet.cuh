@@ -81,6 +81,10 @@ struct RnetSmem {
         if (((w3stride / 4) & 1) == 0) w3stride += 4;
         w3s = o; o += G * w3stride;
         tile_stride = RA * SA + RC * SC + (BWD ? 2 * RC * SC : 0);
+        // a warp holds two groups (transitions): with odd row strides the 16 lanes of a group hit 16 distinct
+        // banks, and a tile offset of 16 (mod 32) words puts the other group on exactly the other 16
+        // (ncu: 34 % of the shared wavefronts were 2-way conflicts between the two groups before this)
+        tile_stride += (16 - (tile_stride & 31) + 32) & 31;
         tiles = o; o += GPB * tile_stride;
         flat = dz3 = gacc = gsmall = 0; flat_stride = 0;
         if (BWD) {

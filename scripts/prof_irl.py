@@ -18,7 +18,14 @@ ds, da = irl.generate_batch(M, theta=8.06)
 gs, ga = irl.generate_batch(M)
 ds, da = ds[:15].reshape(-1, D), da.reshape(-1, D, D)
 gs, ga = gs[:15].reshape(-1, D), ga.reshape(-1, D, D)
-for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+for i in range(n):
     irl.update_reward_batch(ds, da, gs, ga, M, "time_major", group=False)
 torch.cuda.synchronize()
-print("done")
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(n):
+    irl.update_reward_batch(ds, da, gs, ga, M, "time_major", group=False)
+e1.record()
+torch.cuda.synchronize()
+print("done: %.1f us per reward update (%d + %d trajectories)" % (1e3 * e0.elapsed_time(e1) / n, M, M))
