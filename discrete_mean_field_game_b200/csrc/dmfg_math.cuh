@@ -267,9 +267,12 @@ __device__ __forceinline__ void gamma_pair_fast(const NoiseKey& nk, const Philox
     const float2 n = __fmul2_rn(splat2(r), make_float2(cos_approx(ang), sin_approx(ang)));
     // gamma_setup for both elements
     const float2 a = __fmul2_rn(al, splat2(scale));
-    const bool b0 = a.x < 1.0f, b1 = a.y < 1.0f;
-    const float2 dd = __ffma2_rn(al, splat2(scale), make_float2(b0 ? (2.0f / 3.0f) : -(1.0f / 3.0f),
-                                                                b1 ? (2.0f / 3.0f) : -(1.0f / 3.0f)));
+    // shapes below 1 (sampled as shape + 1, boosted afterwards) are rare: one min + one test per pair decides
+    // whether the offset of dd needs its per-element select
+    const bool small = fminf(a.x, a.y) < 1.0f;
+    float2 off = splat2(-(1.0f / 3.0f));
+    if (small) off = make_float2(a.x < 1.0f ? (2.0f / 3.0f) : -(1.0f / 3.0f), a.y < 1.0f ? (2.0f / 3.0f) : -(1.0f / 3.0f));
+    const float2 dd = __ffma2_rn(al, splat2(scale), off);
     const float2 dd9 = __fmul2_rn(splat2(9.0f), dd);
     const float2 cc = make_float2(rsqrt_approx(dd9.x), rsqrt_approx(dd9.y));
     // mt_squeeze for both elements
@@ -291,9 +294,9 @@ __device__ __forceinline__ void gamma_pair_fast(const NoiseKey& nk, const Philox
         const float2 yy = gamma_pair_redo(nk.p0, nk.p1, nk.k0, nk.k1, slot, al.x, al.y, scale);
         y0 = yy.x == 0.0f ? 1e-20f : yy.x;
         y1 = yy.y == 0.0f ? 1e-20f : yy.y;
-    } else if (b0 | b1) {
-        if (b0) { y0 = boost_apply(y0, a.x, squeeze_uniform(u.x, thr.x)); if (y0 == 0.0f) y0 = 1e-20f; }
-        if (b1) { y1 = boost_apply(y1, a.y, squeeze_uniform(u.y, thr.y)); if (y1 == 0.0f) y1 = 1e-20f; }
+    } else if (small) {
+        if (a.x < 1.0f) { y0 = boost_apply(y0, a.x, squeeze_uniform(u.x, thr.x)); if (y0 == 0.0f) y0 = 1e-20f; }
+        if (a.y < 1.0f) { y1 = boost_apply(y1, a.y, squeeze_uniform(u.y, thr.y)); if (y1 == 0.0f) y1 = 1e-20f; }
     }
 }
 
@@ -472,11 +475,12 @@ __device__ __forceinline__ void alpha_psi_fast2(float theta, float2 x, float2& a
     const float2 e = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
     const float2 u = __fadd2_rn(e, splat2(1.0f));
     const float2 l = log1p_poly2(e);
-    const float2 a = __fadd2_rn(make_float2(fmaxf(t.x, 0.0f), fmaxf(t.y, 0.0f)), l);
+    // max(t, 0) + l as 0.5 (t + |t|) + l: t + |t| and the halving are exact, so the bits equal the scalar form
+    const float2 a = __ffma2_rn(__fadd2_rn(t, make_float2(fabsf(t.x), fabsf(t.y))), splat2(0.5f), l);
     alpha = a;
     // digamma(a): 4-step recurrence folded into one quotient + asymptotic series at z = a + 4
-    float2 q = __ffma2_rn(a, a, __fmul2_rn(splat2(3.0f), a));
-    q = make_float2(fmaxf(q.x, 1e-30f), fmaxf(q.y, 1e-30f));
+    // (q = a^2 + 3a, kept away from 0 by a 1e-30 addend that vanishes in the rounding for any a > 1e-22)
+    const float2 q = __ffma2_rn(a, a, __ffma2_rn(splat2(3.0f), a, splat2(1e-30f)));
     const float2 num = __fmul2_rn(__ffma2_rn(splat2(2.0f), a, splat2(3.0f)), __ffma2_rn(splat2(2.0f), q, splat2(2.0f)));
     const float2 den = __fmul2_rn(q, __fadd2_rn(q, splat2(2.0f)));
     const float2 z = __fadd2_rn(a, splat2(4.0f));
