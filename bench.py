@@ -13,7 +13,8 @@ of (theta, w) on the device.  population-steps per step = B * T per GPU.
 
 Prints ONE JSON line (rank 0).  `value` is timed on the device with inputs resident in HBM;
 `e2e` goes through the public NumPy-in/NumPy-out API (`actor_critic.train_batch`) with the
-start states copied from pinned host memory every step and theta/w read back every step.
+start states copied from pinned host memory every step (double-buffered under the previous step's
+kernel) and theta/w/mean reward of every step read back into pinned host memory.
 `--impl reference` times the CPU restatement of the reference's train() loop (oracle port:
 the reference is Python and does not exist on the GPU box) on all host cores.
 """
@@ -249,13 +250,16 @@ def run_ours(args):
     ac = actor_critic(theta=THETA, shift=SHIFT, alpha_scale=ALPHA_SCALE, d=D,
                       mat_pi0=np.full((1, D), 1.0 / D), device=dev, dtype="float32", seed=1234)
     ac.w = rng.rand(F, 1)
+    # every step copies its start states from pinned host memory (double-buffered under the previous step's
+    # kernel) and reads (theta, w, mean reward) of THAT step back into pinned host memory (history=True)
     e2e_steps = max(3, min(args.steps, 10))
-    ac.train_batch(pi0_host, num_episodes=1, T=T, lr_critic=LR_CRITIC, lr_actor=LR_ACTOR, pop_offset=pop_offset)
+    ac.train_batch(pi0_host, num_episodes=2, T=T, lr_critic=LR_CRITIC, lr_actor=LR_ACTOR, pop_offset=pop_offset,
+                   history=True)
     barrier()
     t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        ac.train_batch(pi0_host, num_episodes=1, T=T, lr_critic=LR_CRITIC, lr_actor=LR_ACTOR,
-                       pop_offset=pop_offset, first_episode=k + 1)
+    res = ac.train_batch(pi0_host, num_episodes=e2e_steps, T=T, lr_critic=LR_CRITIC, lr_actor=LR_ACTOR,
+                         pop_offset=pop_offset, first_episode=2, history=True)
+    assert res["theta_history"].shape == (e2e_steps,) and np.isfinite(res["theta_history"]).all()
     barrier()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:

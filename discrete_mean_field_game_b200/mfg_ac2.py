@@ -352,7 +352,7 @@ class actor_critic:
         return self._dev(x)
 
     def train_batch(self, pi0, num_episodes=1, T=15, gamma=1, constant=0, lr_critic=0.1, lr_actor=0.001,
-                    update="per_episode", seed=None, pop_offset=0, group=None, first_episode=None):
+                    update="per_episode", seed=None, pop_offset=0, group=None, first_episode=None, history=False):
         """Batched actor-critic: B populations share (theta, w).
 
         update="per_episode": parameters frozen within an episode, one batch-mean update
@@ -360,7 +360,11 @@ class actor_critic:
             (one all-reduce per episode when ``group`` is a torch.distributed process group);
         update="per_step": a synchronous batch-mean update after EVERY transition -- reduces to the
             reference's train() exactly at B = 1.
-        pi0 [B,d]: host array / pinned tensor (copied in every episode) or a CUDA tensor.
+        pi0 [B,d]: host array / pinned tensor (copied in every episode) or a CUDA tensor; a list / tuple of
+        ``num_episodes`` such arrays, or a callable ``episode_index -> array``, gives every episode its own start
+        states.  Host inputs are double-buffered: the copy of episode e+1 runs on a side stream under the kernel
+        of episode e, and with ``history=True`` (theta, w, mean reward) of EVERY episode are read back into pinned
+        host memory asynchronously (returned as ``theta_history`` / ``w_history``).
         Returns dict(theta, mean_reward [num_episodes]).
         """
         from . import parallel
@@ -371,9 +375,55 @@ class actor_critic:
         _, world = parallel.world_info(group)
         first = self.first_episode if first_episode is None else first_episode
         mean_rewards = []
+        F = w.numel()
+
+        def source(e):
+            if callable(pi0):
+                return pi0(e)
+            if isinstance(pi0, (list, tuple)):
+                return pi0[e]
+            return pi0
+
+        # ---- input pipeline: pinned host -> device on a side stream, two device buffers ------------------
+        on_device = isinstance(source(0), torch.Tensor) and source(0).is_cuda if num_episodes > 0 else True
+        compute = torch.cuda.current_stream(self.device)
+        bufs, ev_ready, ev_free = [None, None], [None, None], [None, None]
+        copy_stream = None
+        if not on_device and num_episodes > 0:
+            copy_stream = getattr(self, "_copy_stream", None)
+            if copy_stream is None:
+                copy_stream = self._copy_stream = torch.cuda.Stream(self.device)
+
+        def stage(e):
+            """issue the host->device copy of episode e into buffer e % 2 (side stream)"""
+            src = source(e)
+            if not isinstance(src, torch.Tensor):
+                src = torch.as_tensor(np.ascontiguousarray(src, dtype=np.float32 if self.dtype == torch.float32 else np.float64))
+            k = e & 1
+            with torch.cuda.stream(copy_stream):
+                if ev_free[k] is not None:
+                    copy_stream.wait_event(ev_free[k])            # the kernel that read this buffer is done
+                if bufs[k] is None or bufs[k].shape != src.shape:
+                    bufs[k] = torch.empty(src.shape, dtype=self.dtype, device=self.device)
+                bufs[k].copy_(src, non_blocking=True)
+                ev_ready[k] = torch.cuda.Event()
+                ev_ready[k].record(copy_stream)
+
+        hist = None
+        if history and num_episodes > 0:
+            hist = torch.empty((num_episodes, F + 2), dtype=torch.float64).pin_memory()
+        if copy_stream is not None:
+            copy_stream.wait_stream(compute)
+            stage(0)
         for e in range(num_episodes):
             episode = first + e
-            pi = self._to_device(pi0)
+            if copy_stream is not None:
+                compute.wait_event(ev_ready[e & 1])
+                pi = bufs[e & 1]
+                if e + 1 < num_episodes:
+                    stage(e + 1)
+            else:
+                pi = self._to_device(source(e))
             B = pi.shape[0]
             lr_c = lr_critic if constant else lr_critic / (episode + 1.0)
             lr_a = lr_actor if constant else lr_actor / ((episode + 1.0) * math.log(math.log(episode + 20.0)))
@@ -381,6 +431,9 @@ class actor_critic:
                 out = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, T, w=w, theta_dev=theta, gamma=gamma,
                                      reward=self.reward_kind, discount=self.discount_kind, seed=seed,
                                      pop_offset=pop_offset, step_offset=episode * T, outputs=(), want_acc=True)
+                if copy_stream is not None:
+                    ev_free[e & 1] = torch.cuda.Event()
+                    ev_free[e & 1].record(compute)
                 acc = parallel.allreduce_sum_(out["acc"], group)
                 engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / (B * world))
                 mean_rewards.append(acc[-1] / (B * world))
@@ -391,6 +444,9 @@ class actor_critic:
                     out = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, 1, w=w, theta_dev=theta,
                                          gamma=g_next, reward=self.reward_kind, seed=seed, pop_offset=pop_offset,
                                          step_offset=episode * T + t, outputs=("pi_final",), want_acc=True)
+                    if t == 0 and copy_stream is not None:
+                        ev_free[e & 1] = torch.cuda.Event()
+                        ev_free[e & 1].record(compute)
                     acc = parallel.allreduce_sum_(out["acc"], group)
                     engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / (B * world))
                     tot = tot + acc[-1] / (B * world)
@@ -399,7 +455,14 @@ class actor_critic:
                 mean_rewards.append(tot)
             else:
                 raise ValueError("update must be 'per_episode' or 'per_step'")
+            if hist is not None:                               # the step's result, device -> pinned host, async
+                row = torch.cat([theta, w, mean_rewards[-1].reshape(1)])
+                hist[e].copy_(row, non_blocking=True)
+        extra = {}
+        if hist is not None:
+            torch.cuda.current_stream(self.device).synchronize()
+            extra = dict(theta_history=hist[:, 0].numpy().copy(), w_history=hist[:, 1:1 + F].numpy().copy())
         self.theta = float(theta[0])                       # the device->host read of the step's result
         self.w = w.cpu().numpy().reshape(-1, 1)
         return dict(theta=self.theta, mean_reward=torch.stack(mean_rewards).cpu().numpy()
-                    if mean_rewards else np.zeros(0))
+                    if mean_rewards else np.zeros(0), **extra)

@@ -305,3 +305,33 @@ def test_synthetic_analytic_check_matches_reference():
     traj, actions = ac.generate_trajectory(g["mat_pi0"][0], 16)
     assert traj.shape == (16, d) and actions.shape == (15, d, d)
     np.testing.assert_allclose(np.einsum("ti,tij->tj", traj[:-1], actions), traj[1:], atol=3e-7)
+
+
+
+def test_train_batch_pipelined_inputs_and_history(start_states):
+    """Per-episode host inputs (list / callable) through the double-buffered copy pipeline give the same
+    trajectory of (theta, w) as one call per episode, and history=True returns every episode's parameters."""
+    rng = np.random.RandomState(4)
+    d, B, E, T = 15, 300, 5, 6
+    batches = [np.float32(rng.dirichlet(np.ones(d), size=B)) for _ in range(E)]
+    kw = dict(T=T, lr_critic=0.1, lr_actor=0.01, seed=9)
+
+    def fresh(w0=None):
+        ac = mfg_ac2.actor_critic(theta=8.0, shift=0.16, alpha_scale=12000, d=d, mat_pi0=start_states, seed=9)
+        if w0 is not None:
+            ac.w = w0.copy()
+        return ac
+    a = fresh()
+    w0 = np.asarray(a.w, dtype=np.float64).copy()
+    thetas, ws = [], []
+    for e in range(E):
+        a.train_batch(batches[e], num_episodes=1, first_episode=e, **kw)
+        thetas.append(a.theta)
+        ws.append(np.asarray(a.w).reshape(-1).copy())
+    pinned = [torch.from_numpy(x).pin_memory() for x in batches]
+    res = fresh(w0).train_batch(pinned, num_episodes=E, first_episode=0, history=True, **kw)
+    np.testing.assert_allclose(res["theta_history"], thetas, rtol=1e-14)
+    np.testing.assert_allclose(res["w_history"], np.stack(ws), rtol=1e-14)
+    r2 = fresh(w0).train_batch(lambda e: batches[e], num_episodes=E, first_episode=0, history=True, **kw)
+    np.testing.assert_allclose(r2["theta_history"], thetas, rtol=1e-14)
+    np.testing.assert_allclose(r2["w_history"], np.stack(ws), rtol=1e-14)
