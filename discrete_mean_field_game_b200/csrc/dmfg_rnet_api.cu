@@ -51,9 +51,9 @@ RnetParams make_params(const dmfg_rnet_args* a) {
     return p;
 }
 
-template <bool BWD>
+template <bool BWD, int DS>
 int rnet_grid(const dmfg_rnet_args* a, int* grid, size_t* smem_bytes) {
-    auto kern = rnet_kernel<kG, kNP, BWD>;
+    auto kern = rnet_kernel<kG, kNP, BWD, DS>;
     const RnetLayout L = rnet_layout(a->d, a->n_fc3, a->n_fc4);
     const RnetSmem<kG, kNP, BWD> S(a->d, L.total);
     const size_t smem = (size_t)S.total * sizeof(float);
@@ -108,8 +108,13 @@ int dmfg_rnet_forward(const dmfg_rnet_args* a, void* stream) {
     if (a->N == 0) return DMFG_OK;
     int grid = 0;
     size_t smem = 0;
-    if (int rc = rnet_grid<false>(a, &grid, &smem)) return rc;
-    rnet_kernel<kG, kNP, false><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
+    if (a->d == 15) {
+        if (int rc = rnet_grid<false, 15>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, false, 15><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
+    } else {
+        if (int rc = rnet_grid<false, 0>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, false, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
+    }
     DMFG_CUDA(cudaGetLastError());
     return DMFG_OK;
 }
@@ -128,10 +133,15 @@ int dmfg_rnet_backward(const dmfg_rnet_args* a, void* stream) {
                     (unsigned long long)(a->workspace ? a->workspace_bytes : 0));
     int grid = 0;
     size_t smem = 0;
-    if (int rc = rnet_grid<true>(a, &grid, &smem)) return rc;
     RnetParams p = make_params(a);
     p.partials = (float*)a->workspace;
-    rnet_kernel<kG, kNP, true><<<grid, kRnetThreads, smem, st>>>(p);
+    if (a->d == 15) {
+        if (int rc = rnet_grid<true, 15>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, true, 15><<<grid, kRnetThreads, smem, st>>>(p);
+    } else {
+        if (int rc = rnet_grid<true, 0>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, true, 0><<<grid, kRnetThreads, smem, st>>>(p);
+    }
     DMFG_CUDA(cudaGetLastError());
     rnet_reduce_partials_kernel<<<(total + 127) / 128, 128, 0, st>>>(p.partials, grid, total, a->accumulate, a->grad);
     DMFG_CUDA(cudaGetLastError());
