@@ -148,13 +148,14 @@ __device__ __forceinline__ void dropout_masks_philox(unsigned long long seed, un
 // reference's d -- every `w < d` test of the unrolled row loops folds away and the padding column is never
 // computed (-10 % on the reward update).  Tried and rejected: 20-word row strides with LDS.128 row reads (4x fewer
 // load instructions, but 2-way conflicts on the row-strided stores and spills at 255 registers: +2 %).
-template <int G, int NP, bool BWD, int DS>
+// N3S / N4S: the same for the two fully connected widths (0: from the arguments; 8 / 4 are the reference defaults).
+template <int G, int NP, bool BWD, int DS, int N3S, int N4S>
 __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const RnetParams p) {
     using SM = RnetSmem<G, NP, BWD>;
     constexpr int GPB = SM::GPB, SA = SM::SA, SC = SM::SC, RA = SM::RA, RC = SM::RC;
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) unsigned long long mbar;
-    const int d = DS ? DS : p.d, n3 = p.n3, n4 = p.n4;
+    const int d = DS ? DS : p.d, n3 = N3S ? N3S : p.n3, n4 = N4S ? N4S : p.n4;
     const RnetLayout L = rnet_layout(d, n3, n4);
     const SM S(d, L.total);
     const int tid = threadIdx.x, h = tid % G, grp = tid / G;

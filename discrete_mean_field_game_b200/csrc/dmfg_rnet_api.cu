@@ -51,9 +51,9 @@ RnetParams make_params(const dmfg_rnet_args* a) {
     return p;
 }
 
-template <bool BWD, int DS>
+template <bool BWD, int DS, int N3S, int N4S>
 int rnet_grid(const dmfg_rnet_args* a, int* grid, size_t* smem_bytes) {
-    auto kern = rnet_kernel<kG, kNP, BWD, DS>;
+    auto kern = rnet_kernel<kG, kNP, BWD, DS, N3S, N4S>;
     const RnetLayout L = rnet_layout(a->d, a->n_fc3, a->n_fc4);
     const RnetSmem<kG, kNP, BWD> S(a->d, L.total);
     const size_t smem = (size_t)S.total * sizeof(float);
@@ -108,12 +108,17 @@ int dmfg_rnet_forward(const dmfg_rnet_args* a, void* stream) {
     if (a->N == 0) return DMFG_OK;
     int grid = 0;
     size_t smem = 0;
-    if (a->d == 15) {
-        if (int rc = rnet_grid<false, 15>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, false, 15><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
+    // the reference's default shape (d = 15, n_fc3 = 8, n_fc4 = 4) and d = 15 with other widths are compiled with
+    // those sizes as constants; everything else takes them from the arguments
+    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) {
+        if (int rc = rnet_grid<false, 15, 8, 4>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, false, 15, 8, 4><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
+    } else if (a->d == 15) {
+        if (int rc = rnet_grid<false, 15, 0, 0>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, false, 15, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
     } else {
-        if (int rc = rnet_grid<false, 0>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, false, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
+        if (int rc = rnet_grid<false, 0, 0, 0>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, false, 0, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
     }
     DMFG_CUDA(cudaGetLastError());
     return DMFG_OK;
@@ -135,12 +140,13 @@ int dmfg_rnet_backward(const dmfg_rnet_args* a, void* stream) {
     size_t smem = 0;
     RnetParams p = make_params(a);
     p.partials = (float*)a->workspace;
+    // (the backward kernel sits at the 255-register limit: compile-time widths make it spill, so only d is fixed)
     if (a->d == 15) {
-        if (int rc = rnet_grid<true, 15>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, true, 15><<<grid, kRnetThreads, smem, st>>>(p);
+        if (int rc = rnet_grid<true, 15, 0, 0>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, true, 15, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
     } else {
-        if (int rc = rnet_grid<true, 0>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, true, 0><<<grid, kRnetThreads, smem, st>>>(p);
+        if (int rc = rnet_grid<true, 0, 0, 0>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, true, 0, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
     }
     DMFG_CUDA(cudaGetLastError());
     rnet_reduce_partials_kernel<<<(total + 127) / 128, 128, 0, st>>>(p.partials, grid, total, a->accumulate, a->grad);
