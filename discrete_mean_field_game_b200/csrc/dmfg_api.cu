@@ -147,9 +147,9 @@ int launch_fast(RolloutParams<R> p, bool td, int* grid_out, cudaStream_t st) {
     return DMFG_OK;
 }
 
-template <int D, int NOISE, bool REC, bool TRAIN>
+template <int D, int NOISE, bool REC, bool TRAIN, bool GRAD>
 int launch_v2(RolloutParams<float> p, bool td, int* grid_out, cudaStream_t st) {
-    auto kern = rollout_v2_kernel<D, NOISE, REC, TRAIN>;
+    auto kern = rollout_v2_kernel<D, NOISE, REC, TRAIN, GRAD>;
     const size_t smem = (size_t)V2Smem<D>::total * sizeof(double);
     DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0, sms = 0;
@@ -172,12 +172,16 @@ int dispatch_v2_d(const RolloutParams<float>& p, int noise_kind, bool td, int* g
     const bool rec = p.actions != nullptr || p.alpha != nullptr;
     const bool train = !rec && td && p.partials != nullptr && !p.states && !p.rewards && !p.deltas && !p.grads &&
                        !p.pi_final && !p.rewards_in;
+    // the policy gradient is only evaluated when something consumes it (critic attached or a grads stream)
+    const bool grad = td || p.grads != nullptr;
     if (noise_kind == DMFG_NOISE_PHILOX) {
-        if (train) return launch_v2<D, DMFG_NOISE_PHILOX, false, true>(p, td, grid, st);
-        return rec ? launch_v2<D, DMFG_NOISE_PHILOX, true, false>(p, td, grid, st)
-                   : launch_v2<D, DMFG_NOISE_PHILOX, false, false>(p, td, grid, st);
+        if (train) return launch_v2<D, DMFG_NOISE_PHILOX, false, true, true>(p, td, grid, st);
+        if (grad) return rec ? launch_v2<D, DMFG_NOISE_PHILOX, true, false, true>(p, td, grid, st)
+                             : launch_v2<D, DMFG_NOISE_PHILOX, false, false, true>(p, td, grid, st);
+        return rec ? launch_v2<D, DMFG_NOISE_PHILOX, true, false, false>(p, td, grid, st)
+                   : launch_v2<D, DMFG_NOISE_PHILOX, false, false, false>(p, td, grid, st);
     }
-    return launch_v2<D, DMFG_NOISE_INJECTED, true, false>(p, td, grid, st);
+    return launch_v2<D, DMFG_NOISE_INJECTED, true, false, true>(p, td, grid, st);
 }
 int dispatch_v2(const RolloutParams<float>& p, int noise_kind, bool td, int* grid, cudaStream_t st) {
     return p.d == 15 ? dispatch_v2_d<15>(p, noise_kind, td, grid, st) : dispatch_v2_d<16>(p, noise_kind, td, grid, st);
