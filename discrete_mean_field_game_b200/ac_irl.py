@@ -322,6 +322,53 @@ class AC_IRL(_actor_critic):
         if verbose:
             print("----- Exiting train at episode %d with theta %f -----" % (episode, self.theta))
 
+    def train_batch(self, pi0, num_episodes=1, gamma=1, constant=False, lr_critic=0.1, lr_actor=0.001, seed=None,
+                    pop_offset=0, group=None, first_episode=1, noise_y=None, keep_record=False):
+        """Batched forward solve with the reward net in the loop: B populations share (theta, w), parameters
+        frozen within an episode, one batch-mean update per episode (the data-parallel form of train(); equal to
+        it in expectation, not step by step -- DESIGN.md section 5).  Per episode, on the device:
+        rollout + record (states, actions, d log F/d theta)  ->  r = r_net(pi_t, P_t) for all B*15 transitions
+        ->  TD errors with the cumulative discount of ac_irl.py:691 and the [2+F] sums  ->  (one all-reduce when
+        ``group`` is a process group)  ->  theta, w update with train()'s step sizes (episodes count from 1).
+        pi0 [B,d]: CUDA tensor or host array.  ``noise_y`` [E,15,B,d,d] injects the Gamma variates (parity).
+        ``keep_record=True`` returns the last episode's (states [16,B,d], actions [15,B,d,d]) -- the generated
+        batch a reward update consumes, so sampling costs nothing extra.  Returns dict(theta, mean_reward [E])."""
+        from . import parallel
+        d, T = self.d, T_STEPS
+        seed = self.seed if seed is None else seed
+        theta = torch.tensor([float(self.theta)], dtype=torch.float64, device=self.device)
+        w = self._w_dev().clone()
+        pi = pi0 if isinstance(pi0, torch.Tensor) and pi0.is_cuda else self._dev(np.asarray(pi0, dtype=np.float32), torch.float32)
+        B = pi.shape[0]
+        _, world = parallel.world_info(group)
+        p = self.reward_params
+        mean_rewards, rec = [], None
+        for e in range(num_episodes):
+            episode = first_episode + e
+            lr_c = lr_critic if constant else lr_critic / (episode + 1.0)
+            lr_a = lr_actor if constant else lr_actor / ((episode + 1.0) * math.log(math.log(episode + 20.0)))
+            noise = None if noise_y is None else self._dev(np.asarray(noise_y[e], dtype=np.float32), torch.float32)
+            rec = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, T, theta_dev=theta, reward="none",
+                                 noise_y=noise, seed=seed, pop_offset=pop_offset, step_offset=episode * T,
+                                 outputs=("states", "actions", "grads"))
+            kd = {}
+            if self._dropout:
+                kd = dict(seed=self.seed ^ 0x5DEECE66D, sample_offset=self._next_dropout_offset(T * B))
+            r = engine.rnet_forward(p.flat, rec["states"][:T].reshape(-1, d), rec["actions"].reshape(-1, d, d),
+                                    p.n_fc3, p.n_fc4, keep_prob=networks.KEEP_PROB, **kd)
+            td = engine.td_accumulate(rec["states"], r.view(T, B), rec["grads"], w, gamma=gamma,
+                                      discount="cumulative", want_deltas=False)
+            acc = parallel.allreduce_sum_(td["acc"], group)
+            engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / (B * world))
+            mean_rewards.append(acc[-1] / (B * world))
+        self.theta = float(theta[0])
+        self.w = w.cpu().numpy().reshape(-1, 1)
+        self.list_policies = (self.list_policies + [self.theta])[1:]
+        out = dict(theta=self.theta, mean_reward=torch.stack(mean_rewards).cpu().numpy() if mean_rewards else np.zeros(0))
+        if keep_record and rec is not None:
+            out["states"], out["actions"] = rec["states"], rec["actions"]
+        return out
+
     def _philox_randint(self, counter, n):
         w0 = engine.philox((0, 0, counter & 0xFFFFFFFF, 0xC0000000), (self.seed & 0xFFFFFFFF, self.seed >> 32))[0]
         return (w0 * n) >> 32

@@ -4,9 +4,10 @@
         scripts/bench_irl_dp.py [--log2-traj 16] [--iters 10]
 
 Every rank owns 2^k generated + 2^k demonstration trajectories (x 15 transitions).  One iteration =
-  (a) the batched actor-critic episode over the rank's populations (rollout_v2_kernel, T = 15) with ONE all-reduce
+  (a) the batched forward solve of ac_irl.py over the rank's populations with the reward net in the loop
+      (AC_IRL.train_batch: rollout + record -> r_net forward over all transitions -> TD sums) with ONE all-reduce
       of the [2+F] double gradient buffer and the (theta, w) update on the device;
-  (b) generate the rank's trajectories from the current policy (rollout + record);
+  (b) its record is the rank's generated batch (no second rollout);
   (c) one reward update (reward-net backward over demo, forward + backward over generated, log-sum-exp loss over
       the LOCAL generated trajectories) with ONE all-reduce of the [|r_net|] float gradient and TF-Adam.
 Timed on the device (CUDA events), max over ranks; rank 0 prints one JSON line.
@@ -42,22 +43,14 @@ with contextlib.redirect_stdout(sys.stderr):
 ds, da = irl.generate_batch(M, theta=8.06)                     # "demonstrations" of this rank
 ds, da = ds[:T].reshape(-1, D), da.reshape(-1, D, D)
 pi0 = ds[:M].contiguous()                                      # start states of the rank's populations
-w = torch.as_tensor(np.random.RandomState(0).rand(F), dtype=torch.float64, device=dev)
-theta = torch.tensor([8.64], dtype=torch.float64, device=dev)
-out = {"acc": torch.empty(2 + F, dtype=torch.float64, device=dev)}
-rec = {"states": torch.empty((T + 1, M, D), device=dev), "actions": torch.empty((T, M, D, D), device=dev)}
 
 
 def iteration(k):
-    lr_c = 0.1 / (k + 1.0)
-    lr_a = 0.1 / ((k + 1.0) * math.log(math.log(k + 20.0)))
-    r = engine.rollout(pi0, 0.0, 0.0, 1e4, T, w=w, theta_dev=theta, seed=77, pop_offset=rank * M, step_offset=k * T,
-                       outputs=(), want_acc=True, out=out)
-    parallel.allreduce_sum_(r["acc"])
-    engine.apply_update(D, theta, w, r["acc"], lr_c, lr_a, 1.0 / (M * world))
-    engine.rollout(pi0, 0.0, 0.0, 1e4, T, theta_dev=theta, reward="none", seed=78, pop_offset=rank * M,
-                   step_offset=k * T, outputs=("states", "actions"), out=rec)
-    gs, ga = rec["states"][:T].reshape(-1, D), rec["actions"].reshape(-1, D, D)
+    # (a)+(b): batched forward solve with r = r_net(pi, P); its record IS the generated batch of the reward update
+    res = irl.train_batch(pi0, num_episodes=1, first_episode=1 + k, pop_offset=rank * M, group=None if world == 1 else dist.group.WORLD,
+                          keep_record=True)
+    gs, ga = res["states"][:T].reshape(-1, D), res["actions"].reshape(-1, D, D)
+    # (c): reward update, one all-reduce of the reward-net gradient
     return irl.update_reward_batch(ds, da, gs, ga, M, "time_major")
 
 
@@ -77,13 +70,14 @@ parallel.allreduce_max_(t)
 ms = float(t[0]) / a.iters
 if rank == 0:
     print(json.dumps({
-        "config": "BASELINE configs[4]: data-parallel IRL training step (actor-critic episode + trajectory generation + "
-                  "reward update), %d GPUs x 2^%d trajectories x %d transitions" % (world, a.log2_traj, T),
+        "config": "BASELINE configs[4]: data-parallel IRL training step (forward solve with the reward net in the loop, its "
+                  "record = the generated batch, + reward update), %d GPUs x 2^%d trajectories x %d transitions"
+                  % (world, a.log2_traj, T),
         "n_gpus": world, "trajectories_per_gpu": M, "ms_per_iteration": ms, "irl_iters_per_s": 1e3 / ms,
-        "reward_transitions_per_s": 2.0 * M * T * world / (ms * 1e-3),
-        "population_steps_per_s_in_the_loop": 2.0 * M * T * world / (ms * 1e-3),
+        "population_steps_per_s": 1.0 * M * T * world / (ms * 1e-3),
+        "reward_update_transitions_per_s": 2.0 * M * T * world / (ms * 1e-3),
         "allreduces_per_iteration": 2 if world > 1 else 0, "loss": [float(x) for x in loss.cpu()],
-        "theta": float(theta[0]),
+        "theta": irl.theta,
     }))
 if world > 1:
     dist.destroy_process_group()

@@ -229,3 +229,47 @@ def test_reads_reference_file_formats(data, tmp_path):
         np.testing.assert_array_equal(s, first)
     finally:
         os.chdir(cwd)
+
+
+def test_train_batch_with_reward_net_matches_oracle(data):
+    """AC_IRL.train_batch: the batched forward solve with r = r_net(pi, P) (rollout + record -> reward net -> TD
+    sums -> batch-mean update, cumulative discount of ac_irl.py:691) against the oracle fed the same Gamma draws."""
+    import math
+    ac = make(data)
+    rng = np.random.RandomState(11)
+    params = ac.reward_params.flat.cpu().numpy().astype(np.float64) + 0.2 * rng.randn(3755)
+    ac.reward_params.load_flat(params)
+    params = ac.reward_params.flat.cpu().numpy()
+    E, B, gamma = 2, 40, 0.95
+    pi0 = np.float32(rng.dirichlet(np.ones(D), size=B))
+    theta, w = 6.5, ac.w.ravel().copy()
+    ys = np.zeros((E, T, B, D, D), np.float32)
+    th_ref, w_ref, mean_r = [], [], []
+    for e in range(E):
+        episode = 1 + e
+        pi = pi0.astype(np.float64)
+        for t in range(T):                                   # draws along the oracle's own trajectory
+            alpha, _ = O.policy_alpha(pi, theta, 0.0)
+            ys[e, t] = np.float32(rng.gamma(alpha * 1e4))
+            pi = O.mean_field_step(O.normalise_gamma(ys[e, t].astype(np.float64)), pi)
+        first = O.rollout_frozen(pi0.astype(np.float64), theta, 0.0, 1e4, ys[e].astype(np.float64), reward="none")
+        r = R.forward(params, np.float32(first["states"][:T].reshape(-1, D)), np.float32(first["actions"].reshape(-1, D, D)),
+                      N3, N4).reshape(T, B)
+        ref = O.rollout_frozen(pi0.astype(np.float64), theta, 0.0, 1e4, ys[e].astype(np.float64), w=w, gamma=gamma,
+                               discount="cumulative", reward=r)
+        lr_c = 0.1 / (episode + 1.0)
+        lr_a = 0.001 / ((episode + 1.0) * math.log(math.log(episode + 20.0)))
+        theta = theta + lr_a / B * ref["G_theta"]
+        w = w + lr_c / B * ref["G_w"]
+        th_ref.append(theta); w_ref.append(w.copy()); mean_r.append(ref["R"] / B)
+    res = ac.train_batch(pi0, num_episodes=E, gamma=gamma, lr_critic=0.1, lr_actor=0.001, noise_y=ys, keep_record=True)
+    np.testing.assert_allclose(res["theta"], th_ref[-1], rtol=1e-6)
+    np.testing.assert_allclose(ac.w.ravel(), w_ref[-1], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(res["mean_reward"], mean_r, rtol=2e-4, atol=2e-5)
+    assert res["states"].shape == (T + 1, B, D) and res["actions"].shape == (T, B, D, D)
+    assert ac.list_policies[-1] == ac.theta
+    # sampled noise: runs, finite, reproducible
+    a1, a2 = make(data), make(data)
+    r1 = a1.train_batch(pi0, num_episodes=2)
+    r2 = a2.train_batch(pi0, num_episodes=2)
+    assert np.isfinite(r1["theta"]) and r1["theta"] == r2["theta"]
