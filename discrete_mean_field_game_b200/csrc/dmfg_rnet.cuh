@@ -578,8 +578,19 @@ __global__ void rnet_reduce_partials_kernel(const float* __restrict__ partials, 
                                             float* __restrict__ grad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float s = 0.f;
-    for (int c = 0; c < ncta; ++c) s += partials[(long long)c * n + i];
+    // four independent chains (fixed assignment c mod 4, fixed combination order): the loads pipeline instead of
+    // waiting on one serial add chain; still deterministic
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int c = 0;
+#pragma unroll 2
+    for (; c + 3 < ncta; c += 4) {
+        s0 += partials[(long long)c * n + i];
+        s1 += partials[(long long)(c + 1) * n + i];
+        s2 += partials[(long long)(c + 2) * n + i];
+        s3 += partials[(long long)(c + 3) * n + i];
+    }
+    for (; c < ncta; ++c) s0 += partials[(long long)c * n + i];
+    const float s = (s0 + s1) + (s2 + s3);
     grad[i] = accumulate ? grad[i] + s : s;
 }
 
@@ -646,8 +657,21 @@ __global__ void __launch_bounds__(256) irl_loss_stage1_kernel(const IrlLossParam
 // one block: global max, log-sum-exp over the trajectories, loss terms
 __global__ void __launch_bounds__(256) irl_loss_stage2_kernel(const IrlLossParams p, int nblocks) {
     __shared__ double sh[8];
+    __shared__ double shmx;
+    // the per-block (max, demo sum) pairs are reduced cooperatively (every thread used to walk all of them)
     double mx = -1e300, sd = 0.0;
-    for (int b = 0; b < nblocks; ++b) { mx = fmax(mx, p.partials[2 * b]); sd += p.partials[2 * b + 1]; }
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) { mx = fmax(mx, p.partials[2 * b]); sd += p.partials[2 * b + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmax(mx, sh[i]);
+        shmx = mx;
+    }
+    __syncthreads();
+    mx = shmx;
+    sd = block_sum_double(sd, sh);                   // valid on thread 0
     double se = 0.0;
     for (long long j = threadIdx.x; j < p.M; j += blockDim.x) se += exp(p.traj_e[j] - mx);
     se = block_sum_double(se, sh);

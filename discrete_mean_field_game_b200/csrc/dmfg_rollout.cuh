@@ -324,9 +324,18 @@ rollout_fast_kernel(const RolloutParams<R> p) {
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int ncta, int n, double* __restrict__ acc) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;
-    double s = 0.0;
-    for (int c = 0; c < ncta; ++c) s += partials[(long long)c * n + f];
-    acc[f] = s;
+    // four independent chains with a fixed assignment and combination order: deterministic, loads pipelined
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = 0;
+#pragma unroll 2
+    for (; c + 3 < ncta; c += 4) {
+        s0 += partials[(long long)c * n + f];
+        s1 += partials[(long long)(c + 1) * n + f];
+        s2 += partials[(long long)(c + 2) * n + f];
+        s3 += partials[(long long)(c + 3) * n + f];
+    }
+    for (; c < ncta; ++c) s0 += partials[(long long)c * n + f];
+    acc[f] = (s0 + s1) + (s2 + s3);
 }
 
 // ---------------------------------------------------------------------------
