@@ -362,4 +362,194 @@ rollout_v2_kernel(const RolloutParams<float> p) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// Independent serial learners on the v2 math (float streams, d = 15 / 16): one 16-lane group = one learner with
+// private (theta, w) and per-step online updates -- mfg_ac2.py:448-539 semantics exactly, as in
+// learners_fast_kernel, but with the single-pass packed row walk of rollout_v2_kernel (the pair loop below is
+// the GRAD = 1, REC = 0 form of the one in that kernel: keep them in step).
+// Shared memory per CTA: the y tile, double-buffered state, q, and the learners' critic slots [GPB][D+2][16].
+// ---------------------------------------------------------------------------
+template <int D>
+struct LearnersV2Smem {
+    static constexpr int GPB = kV2Threads / kV2G;
+    static constexpr int NSLOT = D + 2;
+    static constexpr int tile = 0;
+    static constexpr int pid = tile + GPB * kV2G * kV2Slots;
+    static constexpr int qv = pid + 2 * GPB * kV2G;
+    static constexpr int pif = qv + GPB * kV2G;                      // [2][GPB][16] floats
+    static constexpr int wl = pif + GPB * kV2G;                      // [GPB][NSLOT][16] doubles
+    static constexpr int total = wl + GPB * NSLOT * kV2G;
+};
+
+template <int D, int NOISE>
+__global__ void __launch_bounds__(kV2Threads, 2)
+learners_v2_kernel(const LearnerParams<float> p, const PhiloxKeys rk) {
+    using S = LearnersV2Smem<D>;
+    constexpr int G = kV2G, GPB = S::GPB, PD = (D + 1) / 2, NSLOT = S::NSLOT;
+    constexpr int F = num_features_c(D);
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, r = tid & (G - 1), grp = tid / G;
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t a_row = sb + 8u * (S::tile + (grp * G + r) * kV2Slots);
+    const uint32_t a_col = sb + 8u * (S::tile + grp * G * kV2Slots + r);
+    const uint32_t a_pid = sb + 8u * (S::pid + grp * G);
+    const uint32_t a_pif = sb + 8u * S::pif + 4u * (grp * G);
+    const uint32_t a_q = sb + 8u * (S::qv + grp * G);
+    const uint32_t a_wl_r = sb + 8u * (S::wl + grp * NSLOT * G + r);
+    constexpr uint32_t kBufD = 8u * GPB * G, kBufF = 4u * GPB * G;
+    const bool row_ok = r < D;
+    long long l = (long long)blockIdx.x * GPB + grp;
+    const bool live = l < p.L;
+    if (!live) l = p.L - 1;
+    stage_critic_slots<D>(smem + S::wl + grp * NSLOT * G + r, G, p.w + l * F, r);      // lane r only ever reads its own column
+    double theta = p.theta[l];
+    const float shift = (float)(p.shift ? p.shift[l] : p.shift_scalar);
+    const float scale = (float)(p.alpha_scale ? p.alpha_scale[l] : p.alpha_scale_scalar);
+    const bool ac2 = p.reward_kind == DMFG_REWARD_AC2;
+    const bool has_reward = p.reward_kind != DMFG_REWARD_NONE;
+    const double rew_scale = ac2 ? 1.0 : -0.5;
+    const NoiseKey nk = make_noise_key(p.seed, (unsigned long long)(p.learner_offset + l));
+    double pi_self = 0.0;
+    for (int e = 0; e < p.E; ++e) {
+        const int episode = p.episode0 + e;
+        int start;
+        if (p.start_rows != nullptr) {
+            start = p.start_rows[l * p.E + e];
+        } else {
+            const uint4 wv = philox4x32_10(nk.p0, nk.p1, (uint32_t)(episode + p.noise_episode_offset),
+                                           DMFG_CTR_START, nk.k0, nk.k1);
+            start = (int)__umulhi(wv.x, (uint32_t)p.S);          // randint(S), mfg_ac2.py:466
+        }
+        pi_self = row_ok ? (double)p.mat_pi0[(long long)start * D + r] : 0.0;
+        uint32_t cur = 0;
+        warp_fence();                                            // everyone is done with the previous episode's buffers
+        sts_f64(a_pid + 8 * r, pi_self);
+        sts_f32(a_pif + 4 * r, (float)pi_self);
+        warp_fence();
+        const double lr_c = p.constant_lr ? p.lr_critic : p.lr_critic / (episode + 1.0);
+        const double lr_a = p.constant_lr ? p.lr_actor : p.lr_actor / ((episode + 1.0) * log(log(episode + 20.0)));
+        double disc = 1.0, total_lane = 0.0;
+        for (int t = 0; t < p.T; ++t) {
+            const long long et = ((long long)l * p.E + e) * p.T + t;
+            const long long row = (et * D + r) * D;
+            const uint32_t a_pic = a_pid + cur * kBufD, a_pfc = a_pif + cur * kBufF;
+            const float thf = (float)theta;
+            // ------------------------------------------------------------------ the row (see rollout_v2_kernel)
+            const float xi = (float)pi_self + shift;
+            const double c1 = ac2 ? 1.0 : 0.0, c0 = ac2 ? -pi_self : 1.0;
+            float2 asum2 = make_float2(0.f, 0.f), dsum2 = asum2, g12 = asum2, g22 = asum2;
+            double ysum0 = 0.0, ysum1 = 0.0, racc0 = 0.0, racc1 = 0.0;
+            float a_last = 0.0f;
+            const uint32_t slot0 = gamma_slot((uint32_t)((episode + p.noise_episode_offset) * p.T + t), D, r, 0);
+#pragma unroll 4
+            for (int pp = 0; pp < PD; ++pp) {
+                const float2 pj = lds_f32x2(a_pfc + 8 * pp);
+                const bool ok1 = (2 * pp + 1) < D;
+                float2 a, dv, psi;
+                alpha_psi_fast2(thf, __fadd2_rn(pj, splat2(-xi)), a, dv, psi);
+                if (!ok1) dv.y = 0.0f;
+                a_last = a.y;
+                g12 = __ffma2_rn(psi, neg2(dv), g12);
+                asum2 = __fadd2_rn(asum2, a);
+                dsum2 = __fadd2_rn(dsum2, dv);
+                float y0, y1;
+                if (NOISE == DMFG_NOISE_PHILOX) {
+                    gamma_pair_fast(nk, rk, slot0 + (uint32_t)pp, a, scale, y0, y1);
+                } else {
+                    y0 = row_ok ? p.noise_y[row + 2 * pp] : 1.0f;
+                    y1 = (row_ok && ok1) ? p.noise_y[row + 2 * pp + 1] : 1.0f;
+                    if (y0 == 0.0f) y0 = 1e-20f;                         // mfg_ac2.py:244
+                    if (y1 == 0.0f) y1 = 1e-20f;
+                }
+                g22 = __ffma2_rn(make_float2(lg2_approx(y0), lg2_approx(y1)), dv, g22);
+                const double yd0 = (double)y0, yd1 = (double)(ok1 ? y1 : 0.0f);
+                ysum0 += yd0;
+                ysum1 += yd1;
+                if (has_reward) {
+                    const double2 pjd = lds_f64x2(a_pic + 16 * pp);
+                    racc0 = fma(yd0 * yd0, fma(c1, pjd.x, c0), racc0);
+                    racc1 = fma(yd1 * yd1, fma(c1, pjd.y, c0), racc1);
+                }
+                sts_f64(a_row + 16 * pp, yd0);
+                sts_f64(a_row + 16 * pp + 8, yd1);
+            }
+            const float asum = asum2.x + ((D & 1) ? asum2.y - a_last : asum2.y), dsum = dsum2.x + dsum2.y,
+                        g1 = g12.x + g12.y, g2 = g22.x + g22.y;
+            // ------------------------------------------------------------------ row level
+            const double ysum = ysum0 + ysum1;
+            const float ysum_f = (float)ysum;
+            double inv = (double)rcp_approx(ysum_f);
+            inv = inv * (2.0 - ysum * inv);
+            inv = inv * (2.0 - ysum * inv);
+            const double q = pi_self * inv;
+            sts_f64(a_q + 8 * r, q);
+            const float psi_row = digamma_fast(asum);
+            const float lnp_term = DMFG_LN2 * fmaf(-lg2_approx(ysum_f), dsum, g2);
+            const double glane = row_ok ? (double)(g1 + lnp_term + psi_row * dsum) : 0.0;
+            const double rew_lane = has_reward ? rew_scale * (q * inv) * (racc0 + racc1) : 0.0;
+            warp_fence();
+            // ------------------------------------------------------------------ pi' = sum_i q_i y_ij
+            double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+#pragma unroll
+            for (int i = 0; i + 1 < D; i += 2) {
+                const double2 qq = lds_f64x2(a_q + 8 * i);
+                const double ya = lds_f64(a_col + 8 * kV2Slots * i), yb = lds_f64(a_col + 8 * kV2Slots * (i + 1));
+                if ((i / 2) % 3 == 0) { n0 = fma(qq.x, ya, n0); n1 = fma(qq.y, yb, n1); }
+                else if ((i / 2) % 3 == 1) { n2 = fma(qq.x, ya, n2); n0 = fma(qq.y, yb, n0); }
+                else { n1 = fma(qq.x, ya, n1); n2 = fma(qq.y, yb, n2); }
+            }
+            if (D & 1) n2 = fma(lds_f64(a_q + 8 * (D - 1)), lds_f64(a_col + 8 * kV2Slots * (D - 1)), n2);
+            double next_self = (n0 + n1) + n2;
+            if (!row_ok) next_self = 0.0;
+            const uint32_t nxt = cur ^ 1u;
+            sts_f64(a_pid + nxt * kBufD + 8 * r, next_self);
+            sts_f32(a_pif + nxt * kBufF + 4 * r, (float)next_self);
+            warp_fence();
+            // ------------------------------------------------------------------ TD error with the CURRENT w, updates
+            const double vn_lane = critic_partial_v2<D>(a_wl_r, a_pid + nxt * kBufD, next_self);
+            const double vc_lane = critic_partial_v2<D>(a_wl_r, a_pic, pi_self);
+            const double gfac = p.discount_kind == DMFG_DISCOUNT_STEP ? p.gamma : disc;
+            const double delta = group_sum<G>(rew_lane + fma(gfac, vn_lane, -vc_lane));
+            const double grad = group_sum<G>(glane);
+            // critic first, then actor, both with the same delta (mfg_ac2.py:505-522)
+            const double step_w = lr_c * delta;
+            const double dp = step_w * pi_self;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                if (k >= r) {
+                    const uint32_t aw = a_wl_r + 8u * G * k;
+                    sts_f64(aw, fma(dp, lds_f64(a_pic + 8 * k), lds_f64(aw)));
+                }
+            }
+            if (row_ok) sts_f64(a_wl_r + 8u * G * D, lds_f64(a_wl_r + 8u * G * D) + dp);
+            if (r == 0) sts_f64(a_wl_r + 8u * G * (D + 1), lds_f64(a_wl_r + 8u * G * (D + 1)) + step_w);
+            theta = fma(lr_a * delta, grad, theta);
+            if (live && r == 0) {
+                if (p.theta_trace) p.theta_trace[et] = theta;
+                if (p.delta_trace) p.delta_trace[et] = delta;
+            }
+            total_lane += rew_lane;
+            disc *= p.gamma;
+            pi_self = next_self;
+            cur = nxt;
+        }
+        const double total = group_sum<G>(total_lane);
+        if (live && r == 0 && p.total_reward) p.total_reward[l * p.E + e] = total;
+    }
+    if (!live) return;
+    if (r == 0) p.theta[l] = theta;
+    if (p.pi_final && row_ok) p.pi_final[l * D + r] = (float)pi_self;
+    // write the private critic weights back in the reference's feature order
+    constexpr int Q = D * (D + 1) / 2;
+    double* wout = p.w + l * F;
+    const double* wl = smem + S::wl + grp * NSLOT * G + r;
+    if (row_ok) {
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            if (k >= r) wout[quad_index(D, r, k)] = wl[k * G];
+        wout[Q + r] = wl[D * G];
+    }
+    if (r == 0) wout[Q + D] = wl[(D + 1) * G];
+}
+
 }  // namespace dmfg
