@@ -21,6 +21,14 @@ for d, B, T in ((15, 37, 5), (16, 33, 4)):
     engine.rollout(pi0, 8.86349, 0.16, 12000.0, T, w=w, seed=1, want_acc=True,
                    outputs=("states", "actions", "alpha", "alpha_deriv", "rewards", "deltas", "grads", "pi_final"))  # record
     engine.rollout(pi0, 8.86349, 0.16, 12000.0, T, reward="none", seed=1, outputs=("pi_final",))                 # rollout only
+# independent serial learners (v2 math at d = 15 / 16, first-generation kernel at d = 4 and in float64)
+for d, dt in ((15, torch.float32), (16, torch.float32), (4, torch.float32), (15, torch.float64)):
+    F = d * (d + 1) // 2 + d + 1
+    L = 19
+    mat = torch.as_tensor(rng.dirichlet(np.ones(d), size=7), dtype=dt, device=dev)
+    th = torch.full((L,), 8.0, dtype=torch.float64, device=dev)
+    ww = torch.rand((L, F), dtype=torch.float64, device=dev)
+    engine.learners(th, ww, mat, 3, 5, shift=0.16, alpha_scale=12000.0, lr_critic=0.1, lr_actor=0.1, seed=1)
 pi0 = torch.as_tensor(rng.dirichlet(np.ones(64), size=5), dtype=torch.float32, device=dev)
 engine.rollout(pi0, 8.0, 0.1, 1e4, 3, seed=2, outputs=("states", "actions"))                                     # generic d
 acts = engine.rollout(pi0[:, :15].contiguous(), 8.0, 0.1, 1e4, 3, seed=2, reward="none", outputs=("actions",))["actions"]
