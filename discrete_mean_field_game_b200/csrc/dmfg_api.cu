@@ -197,8 +197,37 @@ int dispatch_fast(const RolloutParams<R>& p, bool td, int* grid, cudaStream_t st
     return fail(DMFG_ERR_UNSUPPORTED, "no fast kernel for d=%d", p.d);
 }
 
+// float streams, sampled or injected Gamma variates: the wide kernel (v2 math, warp per population)
+template <int NPL, int NOISE, bool GRAD>
+int launch_wide_n(const RolloutParams<float>& p, cudaStream_t st) {
+    auto kern = rollout_wide_kernel<NPL, NOISE, GRAD>;
+    constexpr int WPB = kWideThreads / 32;
+    const int pd = (p.d + 1) / 2;
+    const size_t smem = (size_t)WPB * ((3 * pd + 1) & ~1) * sizeof(double);
+    DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0, sms = 0;
+    DMFG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWideThreads, smem));
+    if (int rc = sm_count(&sms)) return rc;
+    if (occ < 1) return fail(DMFG_ERR_CUDA, "rollout_wide_kernel does not fit an SM at d=%d", p.d);
+    long long grid = (long long)sms * occ;
+    const long long need = (p.B + WPB - 1) / WPB;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, kWideThreads, smem, st>>>(p);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+template <int NOISE>
+int launch_wide(const RolloutParams<float>& p, cudaStream_t st) {
+    const int pd = (p.d + 1) / 2;
+    const bool grad = p.grads != nullptr;
+    if (pd <= 32) return grad ? launch_wide_n<1, NOISE, true>(p, st) : launch_wide_n<1, NOISE, false>(p, st);
+    if (pd <= 64) return grad ? launch_wide_n<2, NOISE, true>(p, st) : launch_wide_n<2, NOISE, false>(p, st);
+    return grad ? launch_wide_n<4, NOISE, true>(p, st) : launch_wide_n<4, NOISE, false>(p, st);
+}
+
 template <typename R, int NOISE>
 int launch_generic(const RolloutParams<R>& p, cudaStream_t st) {
+    if constexpr (std::is_same<R, float>::value && NOISE != DMFG_NOISE_ACTIONS) return launch_wide<NOISE>(p, st);
     auto kern = rollout_generic_kernel<R, NOISE>;
     constexpr int WPB = kGenericThreads / 32;
     const size_t smem = (size_t)WPB * 2 * p.d * (sizeof(double) + sizeof(R));

@@ -552,4 +552,162 @@ learners_v2_kernel(const LearnerParams<float> p, const PhiloxKeys rk) {
     if (r == 0) wout[Q + D] = wl[(D + 1) * G];
 }
 
+// ---------------------------------------------------------------------------
+// WIDE rollout kernel (float streams, any d <= DMFG_MAX_D): warp per population, rows in sequence, lane q*32+l
+// owns column pair l + 32 q of every row (NPL pairs per lane).  The v2 single-pass math per pair; per row only
+// three warp reductions (sum y in double, sum alpha, sum alpha'), everything else is kept as lane partials for the
+// whole step: the reward (pi_i / s_i^2 is row-uniform), the two linear gradient sums, and pi'_j = sum_i q_i y_ij
+// in registers (no shared-memory accumulation).  Actions are stored as coalesced runs of a row.
+// No critic here: TD errors for these d come from td_delta_kernel / td_gw_kernel on the record.
+// ---------------------------------------------------------------------------
+constexpr int kWideThreads = 128;
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NPL, int NOISE, bool GRAD>
+__global__ void __launch_bounds__(kWideThreads)
+rollout_wide_kernel(const RolloutParams<float> p) {
+    extern __shared__ __align__(16) double wsm[];
+    const int d = p.d, pd = (d + 1) >> 1, dpad = 2 * pd;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int WPB = kWideThreads / 32;
+    double* pid = wsm + (size_t)wib * ((dpad + pd + 1) & ~1);      // state, double [dpad] (16-byte aligned per warp)
+    float* pif = reinterpret_cast<float*>(pid + dpad);             // state, float [dpad]
+    const float theta = (float)(p.theta_dev ? *p.theta_dev : p.theta);
+    const float shift = p.shift_f, scale = p.scale_f;
+    const bool ac2 = p.reward_kind == DMFG_REWARD_AC2;
+    const bool has_reward = p.reward_kind != DMFG_REWARD_NONE;
+    const double rew_scale = ac2 ? 1.0 : -0.5;
+    for (long long b = (long long)blockIdx.x * WPB + wib; b < p.B; b += (long long)gridDim.x * WPB) {
+        const NoiseKey nk = make_noise_key(p.seed, (unsigned long long)(p.pop_offset + b));
+        for (int j = lane; j < dpad; j += 32) {
+            const float v = j < d ? p.pi0[b * d + j] : 0.0f;
+            pid[j] = (double)v;
+            pif[j] = v;
+            if (p.states != nullptr && j < d) p.states[b * d + j] = v;
+        }
+        __syncwarp();
+        for (int t = 0; t < p.T; ++t) {
+            const long long tb = (long long)t * p.B + b;
+            double nx0[NPL], nx1[NPL];
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) { nx0[q] = 0.0; nx1[q] = 0.0; }
+            double rew_acc = 0.0, grow = 0.0;
+            float2 g12 = make_float2(0.f, 0.f), g22 = g12;
+            for (int i = 0; i < d; ++i) {
+                const double pi_i = pid[i];
+                const long long row = (tb * d + i) * d;
+                const float xi = (float)pi_i + shift;
+                const double c1 = ac2 ? 1.0 : 0.0, c0 = ac2 ? -pi_i : 1.0;
+                float2 yv[NPL];
+                float2 as2 = make_float2(0.f, 0.f), ds2 = as2;
+                double ysum = 0.0, racc = 0.0;
+#pragma unroll
+                for (int q = 0; q < NPL; ++q) {
+                    const int pp = lane + 32 * q;
+                    yv[q] = make_float2(0.f, 0.f);
+                    if (pp < pd) {
+                        const bool ok1 = (2 * pp + 1) < d;
+                        const float2 pj = *reinterpret_cast<const float2*>(pif + 2 * pp);
+                        float2 a, dv, psi;
+                        if (GRAD) {
+                            alpha_psi_fast2(theta, __fadd2_rn(pj, splat2(-xi)), a, dv, psi);
+                        } else {
+                            policy_alpha_fast2(theta, __fadd2_rn(pj, splat2(-xi)), a, dv);
+                            psi = make_float2(0.f, 0.f);
+                        }
+                        if (!ok1) dv.y = 0.0f;
+                        if (GRAD) {
+                            g12 = __ffma2_rn(psi, neg2(dv), g12);
+                            as2 = __fadd2_rn(as2, make_float2(a.x, ok1 ? a.y : 0.0f));
+                            ds2 = __fadd2_rn(ds2, dv);
+                        }
+                        float y0, y1;
+                        if (NOISE == DMFG_NOISE_PHILOX) {
+                            gamma_pair_fast(nk, p.rk, gamma_slot((uint32_t)(p.step_offset + t), d, i, pp), a, scale, y0, y1);
+                        } else {
+                            y0 = p.noise_y[row + 2 * pp];
+                            y1 = ok1 ? p.noise_y[row + 2 * pp + 1] : 1.0f;
+                            if (y0 == 0.0f) y0 = 1e-20f;                     // mfg_ac2.py:244
+                            if (y1 == 0.0f) y1 = 1e-20f;
+                        }
+                        if (GRAD) g22 = __ffma2_rn(make_float2(lg2_approx(y0), lg2_approx(y1)), dv, g22);
+                        if (!ok1) y1 = 0.0f;
+                        yv[q] = make_float2(y0, y1);
+                        const double yd0 = (double)y0, yd1 = (double)y1;
+                        ysum += yd0 + yd1;
+                        if (has_reward) {
+                            const double2 pjd = *reinterpret_cast<const double2*>(pid + 2 * pp);
+                            racc = fma(yd0 * yd0, fma(c1, pjd.x, c0), racc);
+                            racc = fma(yd1 * yd1, fma(c1, pjd.y, c0), racc);
+                        }
+                        if (p.alpha != nullptr) {
+                            p.alpha[row + 2 * pp] = a.x;
+                            p.alpha_deriv[row + 2 * pp] = dv.x;
+                            if (ok1) { p.alpha[row + 2 * pp + 1] = a.y; p.alpha_deriv[row + 2 * pp + 1] = dv.y; }
+                        }
+                    }
+                }
+                ysum = group_sum<32>(ysum);
+                const float ysum_f = (float)ysum;
+                double inv = (double)rcp_approx(ysum_f);               // 1/s: float seed + 2 Newton steps
+                inv = inv * (2.0 - ysum * inv);
+                inv = inv * (2.0 - ysum * inv);
+                const double qi = pi_i * inv;
+                const float inv_f = (float)inv;
+                if (has_reward) rew_acc = fma(rew_scale * qi * inv, racc, rew_acc);
+                if (GRAD) {
+                    const float asum = warp_sum_f(as2.x + as2.y), dsum = warp_sum_f(ds2.x + ds2.y);
+                    // the two row-level terms of d log F / d theta: psi(sum_j alpha) sum_j alpha' - ln s sum_j alpha'
+                    grow += (double)(dsum * fmaf(-DMFG_LN2, lg2_approx(ysum_f), digamma_fast(asum)));
+                }
+#pragma unroll
+                for (int q = 0; q < NPL; ++q) {
+                    const int pp = lane + 32 * q;
+                    if (pp < pd) {
+                        nx0[q] = fma(qi, (double)yv[q].x, nx0[q]);
+                        nx1[q] = fma(qi, (double)yv[q].y, nx1[q]);
+                        if (p.actions != nullptr) {
+                            p.actions[row + 2 * pp] = yv[q].x * inv_f;
+                            if ((2 * pp + 1) < d) p.actions[row + 2 * pp + 1] = yv[q].y * inv_f;
+                        }
+                    }
+                }
+            }
+            __syncwarp();                                              // every lane is done reading this step's state
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+                const int pp = lane + 32 * q;
+                if (pp < pd) {
+                    const bool ok1 = (2 * pp + 1) < d;
+                    const double v0 = nx0[q], v1 = ok1 ? nx1[q] : 0.0;
+                    *reinterpret_cast<double2*>(pid + 2 * pp) = make_double2(v0, v1);
+                    *reinterpret_cast<float2*>(pif + 2 * pp) = make_float2((float)v0, (float)v1);
+                    if (p.states != nullptr) {
+                        p.states[(tb + p.B) * d + 2 * pp] = (float)v0;
+                        if (ok1) p.states[(tb + p.B) * d + 2 * pp + 1] = (float)v1;
+                    }
+                }
+            }
+            if (p.rewards != nullptr || p.grads != nullptr) {
+                const double rew = group_sum<32>(rew_acc);
+                double grad = 0.0;
+                if (GRAD) grad = group_sum<32>((double)((g12.x + g12.y) + DMFG_LN2 * (g22.x + g22.y))) + grow;
+                if (lane == 0) {
+                    if (p.rewards != nullptr) p.rewards[tb] = (float)rew;
+                    if (p.grads != nullptr) p.grads[tb] = (float)grad;
+                }
+            }
+            __syncwarp();
+        }
+        if (p.pi_final != nullptr)
+            for (int j = lane; j < d; j += 32) p.pi_final[b * d + j] = (float)pid[j];
+        __syncwarp();
+    }
+}
+
 }  // namespace dmfg

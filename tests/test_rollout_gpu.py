@@ -250,7 +250,10 @@ def test_philox_fast_equals_generic(dev, d):
     f = eng.rollout(pi0, 8.64, 0.0, 1e4, T, variant="fast", **kw)
     g = eng.rollout(pi0, 8.64, 0.0, 1e4, T, variant="generic", **kw)
     for k in kw["outputs"]:
-        np.testing.assert_allclose(N_(f[k]), N_(g[k]), rtol=2e-5, atol=1e-7, err_msg=k)
+        # g is a sum of d^2 terms of mixed sign (|terms| ~ 1): the two kernels sum it differently (per-element ln P
+        # vs. the unnormalised form sum alpha' lg2 y - lg2 s sum alpha'), so its bound is absolute, 2e-6 ~ 20 float ulps of a term
+        atol = 2e-6 if k == "grads" else 1e-7
+        np.testing.assert_allclose(N_(f[k]), N_(g[k]), rtol=2e-5, atol=atol, err_msg=k)
     # shard invariance: the second half alone, addressed by its global population ids
     h = eng.rollout(pi0[20:].contiguous(), 8.64, 0.0, 1e4, T, variant="fast", pop_offset=20, **kw)
     assert torch.equal(h["states"], f["states"][:, 20:])
