@@ -203,7 +203,7 @@ int launch_wide_n(const RolloutParams<float>& p, cudaStream_t st) {
     auto kern = rollout_wide_kernel<NPL, NOISE, GRAD>;
     constexpr int WPB = kWideThreads / 32;
     const int pd = (p.d + 1) / 2;
-    const size_t smem = (size_t)WPB * ((3 * pd + 1) & ~1) * sizeof(double);
+    const size_t smem = (size_t)WPB * (((3 * pd + 1) & ~1) + kWideBatch * 32) * sizeof(double);
     DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0, sms = 0;
     DMFG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWideThreads, smem));

@@ -561,6 +561,7 @@ learners_v2_kernel(const LearnerParams<float> p, const PhiloxKeys rk) {
 // No critic here: TD errors for these d come from td_delta_kernel / td_gw_kernel on the record.
 // ---------------------------------------------------------------------------
 constexpr int kWideThreads = 128;
+constexpr int kWideBatch = 8;
 
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
@@ -575,8 +576,13 @@ rollout_wide_kernel(const RolloutParams<float> p) {
     const int d = p.d, pd = (d + 1) >> 1, dpad = 2 * pd;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     constexpr int WPB = kWideThreads / 32;
-    double* pid = wsm + (size_t)wib * ((dpad + pd + 1) & ~1);      // state, double [dpad] (16-byte aligned per warp)
+    double* pid = wsm + (size_t)wib * (((dpad + pd + 1) & ~1) + kWideBatch * 32);   // state, double [dpad] (16-byte aligned per warp)
     float* pif = reinterpret_cast<float*>(pid + dpad);             // state, float [dpad]
+    // lane partials of (sum alpha, sum alpha') of the last kWideBatch rows: their warp totals are only needed for
+    // the row term psi(sum alpha) sum alpha', so they are reduced kWideBatch rows at a time (8 LDS + 2 SHFL per
+    // total instead of 10 SHFL per row) and digamma runs once per batch on 8 lane groups in parallel
+    float* asb = reinterpret_cast<float*>(pid + ((dpad + pd + 1) & ~1));   // [kWideBatch][32]
+    float* dsb = asb + kWideBatch * 32;                                    // [kWideBatch][32]
     const float theta = (float)(p.theta_dev ? *p.theta_dev : p.theta);
     const float shift = p.shift_f, scale = p.scale_f;
     const bool ac2 = p.reward_kind == DMFG_REWARD_AC2;
@@ -596,7 +602,8 @@ rollout_wide_kernel(const RolloutParams<float> p) {
             double nx0[NPL], nx1[NPL];
 #pragma unroll
             for (int q = 0; q < NPL; ++q) { nx0[q] = 0.0; nx1[q] = 0.0; }
-            double rew_acc = 0.0, grow = 0.0;
+            double rew_acc = 0.0, grow = 0.0;          // grow: lane partial of the psi(sum alpha) sum alpha' terms
+            float glin = 0.0f;                         // lane partial of -ln s_i sum_j alpha'_ij
             float2 g12 = make_float2(0.f, 0.f), g22 = g12;
             for (int i = 0; i < d; ++i) {
                 const double pi_i = pid[i];
@@ -661,9 +668,27 @@ rollout_wide_kernel(const RolloutParams<float> p) {
                 const float inv_f = (float)inv;
                 if (has_reward) rew_acc = fma(rew_scale * qi * inv, racc, rew_acc);
                 if (GRAD) {
-                    const float asum = warp_sum_f(as2.x + as2.y), dsum = warp_sum_f(ds2.x + ds2.y);
-                    // the two row-level terms of d log F / d theta: psi(sum_j alpha) sum_j alpha' - ln s sum_j alpha'
-                    grow += (double)(dsum * fmaf(-DMFG_LN2, lg2_approx(ysum_f), digamma_fast(asum)));
+                    // the two row-level terms of d log F / d theta: psi(sum_j alpha) sum_j alpha' - ln s sum_j alpha'.
+                    // The second is linear in the lane partials of sum alpha' (ln s is row-uniform): no reduction.
+                    const float dpart = ds2.x + ds2.y;
+                    glin = fmaf(-DMFG_LN2 * lg2_approx(ysum_f), dpart, glin);
+                    const int slot = i & (kWideBatch - 1);
+                    asb[slot * 32 + lane] = as2.x + as2.y;
+                    dsb[slot * 32 + lane] = dpart;
+                    if (slot == kWideBatch - 1 || i == d - 1) {
+                        __syncwarp();
+                        // lane group g = lane / 4 owns row g of the batch; its 4 lanes sum 8 partials each
+                        const int g = lane >> 2, sub = (lane & 3) * 8;
+                        float av = 0.f, dvv = 0.f;
+                        if (g <= slot) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) { av += asb[g * 32 + sub + k]; dvv += dsb[g * 32 + sub + k]; }
+                        }
+                        av += __shfl_xor_sync(0xffffffffu, av, 1); av += __shfl_xor_sync(0xffffffffu, av, 2);
+                        dvv += __shfl_xor_sync(0xffffffffu, dvv, 1); dvv += __shfl_xor_sync(0xffffffffu, dvv, 2);
+                        if (g <= slot && (lane & 3) == 0) grow += (double)(digamma_fast(av) * dvv);
+                        __syncwarp();
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < NPL; ++q) {
@@ -696,7 +721,7 @@ rollout_wide_kernel(const RolloutParams<float> p) {
             if (p.rewards != nullptr || p.grads != nullptr) {
                 const double rew = group_sum<32>(rew_acc);
                 double grad = 0.0;
-                if (GRAD) grad = group_sum<32>((double)((g12.x + g12.y) + DMFG_LN2 * (g22.x + g22.y))) + grow;
+                if (GRAD) grad = group_sum<32>((double)((g12.x + g12.y) + DMFG_LN2 * (g22.x + g22.y) + glin) + grow);
                 if (lane == 0) {
                     if (p.rewards != nullptr) p.rewards[tb] = (float)rew;
                     if (p.grads != nullptr) p.grads[tb] = (float)grad;
