@@ -347,12 +347,12 @@ int launch_learners(const LearnerParams<R>& p, cudaStream_t st) {
     return DMFG_OK;
 }
 // float streams, d = 15 / 16: the learners on the v2 math (single-pass packed row walk)
-template <int D, int NOISE>
+template <int D, int G, int NOISE>
 int launch_learners_v2(const LearnerParams<float>& p, cudaStream_t st) {
-    auto kern = learners_v2_kernel<D, NOISE>;
-    const size_t smem = (size_t)LearnersV2Smem<D>::total * sizeof(double);
+    auto kern = learners_v2_kernel<D, G, NOISE>;
+    const size_t smem = (size_t)LearnersV2Smem<D, G>::total * sizeof(double);
     DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long gpb = kV2Threads / kV2G;
+    const long long gpb = kV2Threads / G;
     const long long grid = (p.L + gpb - 1) / gpb;
     kern<<<(unsigned)grid, kV2Threads, smem, st>>>(p, make_philox_keys(p.seed));
     DMFG_CUDA(cudaGetLastError());
@@ -361,15 +361,16 @@ int launch_learners_v2(const LearnerParams<float>& p, cudaStream_t st) {
 template <typename R, int NOISE>
 int dispatch_learners(const LearnerParams<R>& p, cudaStream_t st) {
     if constexpr (std::is_same<R, float>::value) {
-        if (p.d == 15) return launch_learners_v2<15, NOISE>(p, st);
-        if (p.d == 16) return launch_learners_v2<16, NOISE>(p, st);
+        if (p.d == 15) return launch_learners_v2<15, 16, NOISE>(p, st);
+        if (p.d == 16) return launch_learners_v2<16, 16, NOISE>(p, st);
+        if (p.d == 21) return launch_learners_v2<21, 32, NOISE>(p, st);     // the reference's default d (mfg_ac2.py:25)
     }
     switch (p.d) {
         case 4: return launch_learners<4, 4, R, NOISE>(p, st);
         case 15: return launch_learners<15, 16, R, NOISE>(p, st);
         case 16: return launch_learners<16, 16, R, NOISE>(p, st);
     }
-    return fail(DMFG_ERR_UNSUPPORTED, "dmfg_ac_learners is built for d in {4,15,16}, not d=%d", p.d);
+    return fail(DMFG_ERR_UNSUPPORTED, "dmfg_ac_learners is built for d in {4,15,16} (and 21 for float streams), not d=%d", p.d);
 }
 template <typename R>
 int learners_typed(const dmfg_learners_args* a, cudaStream_t st) {

@@ -82,20 +82,20 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // this lane's partial of V(pi): lane r sums w[r,k] pi_r pi_k over k >= r (zero slots below), + linear + bias
-template <int D>
+template <int D, int GW = kV2G>
 __device__ __forceinline__ double critic_partial_v2(uint32_t a_wl_r, uint32_t a_pid, double pi_self) {
     double v0 = 0.0, v1 = 0.0, v2 = 0.0;
 #pragma unroll
     for (int k = 0; k + 1 < D; k += 2) {
         const double2 pk = lds_f64x2(a_pid + 8 * k);
-        const double w0 = lds_f64(a_wl_r + 8 * kV2G * k), w1 = lds_f64(a_wl_r + 8 * kV2G * (k + 1));
+        const double w0 = lds_f64(a_wl_r + 8 * GW * k), w1 = lds_f64(a_wl_r + 8 * GW * (k + 1));
         if ((k / 2) % 3 == 0) { v0 = fma(w0, pk.x, v0); v1 = fma(w1, pk.y, v1); }
         else if ((k / 2) % 3 == 1) { v2 = fma(w0, pk.x, v2); v0 = fma(w1, pk.y, v0); }
         else { v1 = fma(w0, pk.x, v1); v2 = fma(w1, pk.y, v2); }
     }
-    if (D & 1) v2 = fma(lds_f64(a_wl_r + 8 * kV2G * (D - 1)), lds_f64(a_pid + 8 * (D - 1)), v2);
+    if (D & 1) v2 = fma(lds_f64(a_wl_r + 8 * GW * (D - 1)), lds_f64(a_pid + 8 * (D - 1)), v2);
     const double v = (v0 + v1) + v2;
-    return fma(v, pi_self, lds_f64(a_wl_r + 8 * kV2G * D) * pi_self) + lds_f64(a_wl_r + 8 * kV2G * (D + 1));
+    return fma(v, pi_self, lds_f64(a_wl_r + 8 * GW * D) * pi_self) + lds_f64(a_wl_r + 8 * GW * (D + 1));
 }
 
 // TRAIN = the batched train step: accumulators wanted and NO per-step output stream requested -- every
@@ -363,35 +363,38 @@ rollout_v2_kernel(const RolloutParams<float> p) {
 }
 
 // ---------------------------------------------------------------------------
-// Independent serial learners on the v2 math (float streams, d = 15 / 16): one 16-lane group = one learner with
+// Independent serial learners on the v2 math (float streams; d = 15 / 16 with 16-lane groups, d = 21 -- the
+// reference's default, mfg_ac2.py:25 -- with 32-lane groups): one group = one learner with
 // private (theta, w) and per-step online updates -- mfg_ac2.py:448-539 semantics exactly, as in
 // learners_fast_kernel, but with the single-pass packed row walk of rollout_v2_kernel (the pair loop below is
 // the GRAD = 1, REC = 0 form of the one in that kernel: keep them in step).
 // Shared memory per CTA: the y tile, double-buffered state, q, and the learners' critic slots [GPB][D+2][16].
 // ---------------------------------------------------------------------------
-template <int D>
+template <int D, int G>
 struct LearnersV2Smem {
-    static constexpr int GPB = kV2Threads / kV2G;
+    static constexpr int GPB = kV2Threads / G;
     static constexpr int NSLOT = D + 2;
+    static constexpr int SL = G + 1;                                 // doubles per tile row (odd => conflict free)
     static constexpr int tile = 0;
-    static constexpr int pid = tile + GPB * kV2G * kV2Slots;
-    static constexpr int qv = pid + 2 * GPB * kV2G;
-    static constexpr int pif = qv + GPB * kV2G;                      // [2][GPB][16] floats
-    static constexpr int wl = pif + GPB * kV2G;                      // [GPB][NSLOT][16] doubles
-    static constexpr int total = wl + GPB * NSLOT * kV2G;
+    static constexpr int pid = tile + GPB * G * SL;
+    static constexpr int qv = pid + 2 * GPB * G;
+    static constexpr int pif = qv + GPB * G;                         // [2][GPB][G] floats
+    static constexpr int wl = pif + GPB * G;                         // [GPB][NSLOT][G] doubles
+    static constexpr int total = wl + GPB * NSLOT * G;
 };
 
-template <int D, int NOISE>
+template <int D, int G, int NOISE>
 __global__ void __launch_bounds__(kV2Threads, 2)
 learners_v2_kernel(const LearnerParams<float> p, const PhiloxKeys rk) {
-    using S = LearnersV2Smem<D>;
-    constexpr int G = kV2G, GPB = S::GPB, PD = (D + 1) / 2, NSLOT = S::NSLOT;
+    using S = LearnersV2Smem<D, G>;
+    constexpr int GPB = S::GPB, PD = (D + 1) / 2, NSLOT = S::NSLOT, SL = S::SL;
+    static_assert(D <= G && (G == 16 || G == 32), "one lane per row of P");
     constexpr int F = num_features_c(D);
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, r = tid & (G - 1), grp = tid / G;
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t a_row = sb + 8u * (S::tile + (grp * G + r) * kV2Slots);
-    const uint32_t a_col = sb + 8u * (S::tile + grp * G * kV2Slots + r);
+    const uint32_t a_row = sb + 8u * (S::tile + (grp * G + r) * SL);
+    const uint32_t a_col = sb + 8u * (S::tile + grp * G * SL + r);
     const uint32_t a_pid = sb + 8u * (S::pid + grp * G);
     const uint32_t a_pif = sb + 8u * S::pif + 4u * (grp * G);
     const uint32_t a_q = sb + 8u * (S::qv + grp * G);
@@ -493,12 +496,12 @@ learners_v2_kernel(const LearnerParams<float> p, const PhiloxKeys rk) {
 #pragma unroll
             for (int i = 0; i + 1 < D; i += 2) {
                 const double2 qq = lds_f64x2(a_q + 8 * i);
-                const double ya = lds_f64(a_col + 8 * kV2Slots * i), yb = lds_f64(a_col + 8 * kV2Slots * (i + 1));
+                const double ya = lds_f64(a_col + 8 * SL * i), yb = lds_f64(a_col + 8 * SL * (i + 1));
                 if ((i / 2) % 3 == 0) { n0 = fma(qq.x, ya, n0); n1 = fma(qq.y, yb, n1); }
                 else if ((i / 2) % 3 == 1) { n2 = fma(qq.x, ya, n2); n0 = fma(qq.y, yb, n0); }
                 else { n1 = fma(qq.x, ya, n1); n2 = fma(qq.y, yb, n2); }
             }
-            if (D & 1) n2 = fma(lds_f64(a_q + 8 * (D - 1)), lds_f64(a_col + 8 * kV2Slots * (D - 1)), n2);
+            if (D & 1) n2 = fma(lds_f64(a_q + 8 * (D - 1)), lds_f64(a_col + 8 * SL * (D - 1)), n2);
             double next_self = (n0 + n1) + n2;
             if (!row_ok) next_self = 0.0;
             const uint32_t nxt = cur ^ 1u;
@@ -506,8 +509,8 @@ learners_v2_kernel(const LearnerParams<float> p, const PhiloxKeys rk) {
             sts_f32(a_pif + nxt * kBufF + 4 * r, (float)next_self);
             warp_fence();
             // ------------------------------------------------------------------ TD error with the CURRENT w, updates
-            const double vn_lane = critic_partial_v2<D>(a_wl_r, a_pid + nxt * kBufD, next_self);
-            const double vc_lane = critic_partial_v2<D>(a_wl_r, a_pic, pi_self);
+            const double vn_lane = critic_partial_v2<D, G>(a_wl_r, a_pid + nxt * kBufD, next_self);
+            const double vc_lane = critic_partial_v2<D, G>(a_wl_r, a_pic, pi_self);
             const double gfac = p.discount_kind == DMFG_DISCOUNT_STEP ? p.gamma : disc;
             const double delta = group_sum<G>(rew_lane + fma(gfac, vn_lane, -vc_lane));
             const double grad = group_sum<G>(glane);

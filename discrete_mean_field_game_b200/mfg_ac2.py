@@ -213,7 +213,7 @@ class actor_critic:
     def _run_learner(self, theta, w, mat, n, T, episode0, noise_ep, gamma, constant, lr_critic, lr_actor, kw):
         """episode0 drives the step-size schedule (restarts at every train() call like the reference);
         noise_ep positions the Philox stream (never restarts)."""
-        if self.d in _FAST_D:
+        if self.d in _FAST_D or (self.d == 21 and self.dtype == torch.float32):    # d = 21: the reference's default
             return engine.learners(theta, w, mat, n, T, shift=self.shift, alpha_scale=self.alpha_scale,
                                    episode0=episode0, gamma=gamma, lr_critic=lr_critic, lr_actor=lr_actor,
                                    constant=bool(constant), reward=self.reward_kind, discount=self.discount_kind,

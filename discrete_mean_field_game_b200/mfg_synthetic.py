@@ -34,8 +34,8 @@ class actor_critic(_actor_critic):
         grid = np.array([(s, t) for s in shifts for t in thetas], dtype=np.float64)
         L = grid.shape[0]
         d = self.d
-        if d not in (4, 15, 16):
-            raise NotImplementedError("the learners kernel is built for d in {4, 15, 16}")
+        if d not in (4, 15, 16) and not (d == 21 and self.dtype == torch.float32):
+            raise NotImplementedError("the learners kernel is built for d in {4, 15, 16} (and 21 in float32)")
         theta = torch.as_tensor(grid[:, 1].copy(), device=self.device)
         shift = torch.as_tensor(grid[:, 0].copy(), device=self.device)
         w = torch.as_tensor(np.random.rand(L, num_features(d)), device=self.device)

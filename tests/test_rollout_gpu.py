@@ -184,6 +184,37 @@ def test_learners_are_independent_and_match_serial_oracle(dev, trace):
         np.testing.assert_allclose(N_(w)[l], ww, rtol=1e-10)
 
 
+@pytest.mark.parametrize("d", [15, 16, 21])
+def test_learners_v2_float_match_serial_oracle(dev, d):
+    """learners_v2_kernel (float streams; 16-lane groups at d = 15 / 16, 32-lane groups at the reference's default
+    d = 21): several learners with their own (theta0, shift), injected float32 Gamma variates and start rows, both
+    rewards / discount flavours, against the float64 serial oracle of mfg_ac2.train / AC_IRL.train."""
+    E, T, L = 2, 15, 19                                   # 19 learners: not a multiple of the learners per CTA
+    rng = np.random.RandomState(100 + d)
+    mat = np.float32(rng.dirichlet(np.ones(d), size=9))
+    theta0 = rng.uniform(6.0, 10.0, size=L)
+    shifts = rng.uniform(0.0, 0.4, size=L)
+    w0 = rng.rand(L, O.num_features(d))
+    start = rng.randint(0, mat.shape[0], size=(L, E)).astype(np.int32)
+    y = np.float32(rng.gamma(shape=50.0, size=(L, E, T, d, d)))
+    y[3, 1, 4, 2, 5] = 0.0                                # an exact zero variate (mfg_ac2.py:244)
+    for reward, discount, flavour, gamma in (("ac2", "step", "mfg_ac2", 1.0), ("synthetic", "cumulative", "ac_irl", 0.95)):
+        theta = torch.as_tensor(theta0, dtype=torch.float64, device=dev).clone()
+        w = torch.as_tensor(w0, dtype=torch.float64, device=dev).clone()
+        ep0 = 0 if flavour == "mfg_ac2" else 1
+        res = eng.learners(theta, w, T_(mat, dev, torch.float32), E, T,
+                           shift=torch.as_tensor(shifts, dtype=torch.float64, device=dev), alpha_scale=12000.0,
+                           episode0=ep0, gamma=gamma, lr_critic=0.1, lr_actor=0.01, constant=False, reward=reward,
+                           discount=discount, start_rows=torch.as_tensor(start, device=dev),
+                           noise_y=T_(y, dev, torch.float32))
+        for l in range(L):
+            th, ww, info = O.train_serial(mat.astype(np.float64), theta0[l], w0[l], shifts[l], 12000.0, E, gamma=gamma,
+                                          lr_critic=0.1, lr_actor=0.01, flavour=flavour, reward=reward,
+                                          noise=O.InjectedNoise(start[l], y[l].astype(np.float64)), num_steps=T)
+            np.testing.assert_allclose(N_(theta)[l], th, rtol=2e-6, err_msg="theta of learner %d" % l)
+            np.testing.assert_allclose(N_(w)[l], ww, rtol=2e-5, atol=2e-6, err_msg="w of learner %d" % l)
+
+
 def test_generate_trajectory_d15(dev, traj15):
     out = eng.rollout(T_(traj15["pi0"][None], dev, torch.float64), float(traj15["theta"]),
                       float(traj15["shift"]), float(traj15["alpha_scale"]), 15, reward="none",
