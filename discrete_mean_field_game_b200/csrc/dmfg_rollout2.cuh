@@ -98,6 +98,85 @@ __device__ __forceinline__ double critic_partial_v2(uint32_t a_wl_r, uint32_t a_
     return fma(v, pi_self, lds_f64(a_wl_r + 8 * GW * D) * pi_self) + lds_f64(a_wl_r + 8 * GW * (D + 1));
 }
 
+// ---------------------------------------------------------------------------
+// The single-pass walk over ONE row of P (lane = row), shared by rollout_v2_kernel and learners_v2_kernel:
+// per column pair alpha, alpha', psi(alpha) (GRAD), the Gamma pair, and the row sums that are linear in the
+// unnormalised variates; y goes to this lane's row of the shared tile as doubles.
+//   ysum = sum_j y_ij,  racc = sum_j y_ij^2 (c1 pi_j + c0)  [reward],  asum = sum_j alpha_ij,  dsum = sum_j alpha'_ij,
+//   g1 = -sum_j psi(alpha_ij) alpha'_ij,  g2 = sum_j alpha'_ij lg2 y_ij
+// a_pfc / a_pic: shared addresses of the current state (float / double copies); noise_row: injected variates of
+// this row (NOISE == INJECTED); alpha_row / deriv_row: optional record of alpha, alpha' (REC).
+// ---------------------------------------------------------------------------
+struct V2RowSums {
+    double ysum, racc;
+    float asum, dsum, g1, g2;
+};
+
+template <int D, int NOISE, bool GRAD, bool REC>
+__device__ __forceinline__ V2RowSums v2_row_walk(float theta, float xi, float scale, double c0, double c1, bool has_reward,
+                                                 uint32_t a_pfc, uint32_t a_pic, uint32_t a_row, const NoiseKey& nk,
+                                                 const PhiloxKeys& rk, uint32_t slot0, const float* __restrict__ noise_row,
+                                                 bool row_ok, float* __restrict__ alpha_row, float* __restrict__ deriv_row) {
+    constexpr int PD = (D + 1) / 2;
+    float2 asum2 = make_float2(0.f, 0.f), dsum2 = asum2, g12 = asum2, g22 = asum2;
+    double ysum0 = 0.0, ysum1 = 0.0, racc0 = 0.0, racc1 = 0.0;
+    float a_last = 0.0f;
+#pragma unroll kV2Unroll
+    for (int pp = 0; pp < PD; ++pp) {
+        const float2 pj = lds_f32x2(a_pfc + 8 * pp);
+        const bool ok1 = (2 * pp + 1) < D;                     // only the last pair of an odd D
+        float2 a, dv, psi;
+        if (GRAD) {
+            alpha_psi_fast2(theta, __fadd2_rn(pj, splat2(-xi)), a, dv, psi);
+        } else {
+            policy_alpha_fast2(theta, __fadd2_rn(pj, splat2(-xi)), a, dv);
+            psi = make_float2(0.f, 0.f);
+        }
+        // the phantom column of an odd D (state slot D is 0): alpha' = 0 removes it from every weighted
+        // sum, its alpha is taken out of the row sum after the loop, its variate is masked below
+        if (!ok1) dv.y = 0.0f;
+        a_last = a.y;
+        if (GRAD) {
+            g12 = __ffma2_rn(psi, neg2(dv), g12);
+            asum2 = __fadd2_rn(asum2, a);
+            dsum2 = __fadd2_rn(dsum2, dv);
+        }
+        float y0, y1;
+        if (NOISE == DMFG_NOISE_PHILOX) {
+            gamma_pair_fast(nk, rk, slot0 + (uint32_t)pp, a, scale, y0, y1);   // never returns 0
+        } else {
+            y0 = row_ok ? noise_row[2 * pp] : 1.0f;
+            y1 = (row_ok && ok1) ? noise_row[2 * pp + 1] : 1.0f;
+            if (y0 == 0.0f) y0 = 1e-20f;                         // mfg_ac2.py:244
+            if (y1 == 0.0f) y1 = 1e-20f;
+        }
+        if (GRAD) g22 = __ffma2_rn(make_float2(lg2_approx(y0), lg2_approx(y1)), dv, g22);
+        const double yd0 = (double)y0, yd1 = (double)(ok1 ? y1 : 0.0f);
+        ysum0 += yd0;
+        ysum1 += yd1;
+        if (has_reward) {
+            const double2 pjd = lds_f64x2(a_pic + 16 * pp);
+            racc0 = fma(yd0 * yd0, fma(c1, pjd.x, c0), racc0);
+            racc1 = fma(yd1 * yd1, fma(c1, pjd.y, c0), racc1);
+        }
+        sts_f64(a_row + 16 * pp, yd0);
+        sts_f64(a_row + 16 * pp + 8, yd1);
+        if (REC && alpha_row != nullptr) {
+            alpha_row[2 * pp] = a.x;
+            deriv_row[2 * pp] = dv.x;
+            if (ok1) { alpha_row[2 * pp + 1] = a.y; deriv_row[2 * pp + 1] = dv.y; }
+        }
+    }
+    V2RowSums o;
+    o.ysum = ysum0 + ysum1;
+    o.racc = racc0 + racc1;
+    o.asum = asum2.x + ((D & 1) ? asum2.y - a_last : asum2.y);
+    o.dsum = dsum2.x + dsum2.y;
+    o.g1 = g12.x + g12.y;
+    o.g2 = g22.x + g22.y;
+    return o;
+}
+
 // TRAIN = the batched train step: accumulators wanted and NO per-step output stream requested -- every
 // output test is compiled out of the step loop.  REC = some per-element stream (actions / alpha) is written.
 // GRAD = d log F / d theta is wanted (critic attached or a grads stream): without it -- the IRL sampler and
@@ -162,59 +241,15 @@ rollout_v2_kernel(const RolloutParams<float> p) {
             const float xi = (float)pi_self + shift;
             // reward weights: AC2 sum_j y^2 (pi_j - pi_i);  synthetic sum_j y^2
             const double c1 = ac2 ? 1.0 : 0.0, c0 = ac2 ? -pi_self : 1.0;
-            float2 asum2 = make_float2(0.f, 0.f), dsum2 = asum2, g12 = asum2, g22 = asum2;
-            double ysum0 = 0.0, ysum1 = 0.0, racc0 = 0.0, racc1 = 0.0;
-            float a_last = 0.0f;
             const uint32_t slot0 = gamma_slot((uint32_t)(p.step_offset + t), D, r, 0);
-#pragma unroll kV2Unroll
-            for (int pp = 0; pp < PD; ++pp) {
-                const float2 pj = lds_f32x2(a_pfc + 8 * pp);
-                const bool ok1 = (2 * pp + 1) < D;                     // only the last pair of an odd D
-                float2 a, dv, psi;
-                if (GRAD) {
-                    alpha_psi_fast2(theta, __fadd2_rn(pj, splat2(-xi)), a, dv, psi);
-                } else {
-                    policy_alpha_fast2(theta, __fadd2_rn(pj, splat2(-xi)), a, dv);
-                    psi = make_float2(0.f, 0.f);
-                }
-                // the phantom column of an odd D (state slot D is 0): alpha' = 0 removes it from every weighted
-                // sum, its alpha is taken out of the row sum after the loop, its variate is masked below
-                if (!ok1) dv.y = 0.0f;
-                a_last = a.y;
-                if (GRAD) {
-                    g12 = __ffma2_rn(psi, neg2(dv), g12);
-                    asum2 = __fadd2_rn(asum2, a);
-                    dsum2 = __fadd2_rn(dsum2, dv);
-                }
-                float y0, y1;
-                if (NOISE == DMFG_NOISE_PHILOX) {
-                    gamma_pair_fast(nk, p.rk, slot0 + (uint32_t)pp, a, scale, y0, y1);   // never returns 0
-                } else {
-                    y0 = row_ok ? p.noise_y[row + 2 * pp] : 1.0f;
-                    y1 = (row_ok && ok1) ? p.noise_y[row + 2 * pp + 1] : 1.0f;
-                    if (y0 == 0.0f) y0 = 1e-20f;                         // mfg_ac2.py:244
-                    if (y1 == 0.0f) y1 = 1e-20f;
-                }
-                if (GRAD) g22 = __ffma2_rn(make_float2(lg2_approx(y0), lg2_approx(y1)), dv, g22);
-                const double yd0 = (double)y0, yd1 = (double)(ok1 ? y1 : 0.0f);
-                ysum0 += yd0;
-                ysum1 += yd1;
-                if (has_reward) {
-                    const double2 pjd = lds_f64x2(a_pic + 16 * pp);
-                    racc0 = fma(yd0 * yd0, fma(c1, pjd.x, c0), racc0);
-                    racc1 = fma(yd1 * yd1, fma(c1, pjd.y, c0), racc1);
-                }
-                sts_f64(a_row + 16 * pp, yd0);
-                sts_f64(a_row + 16 * pp + 8, yd1);
-                if (REC && p.alpha != nullptr && wr) {
-                    p.alpha[row + 2 * pp] = a.x;
-                    p.alpha_deriv[row + 2 * pp] = dv.x;
-                    if (ok1) { p.alpha[row + 2 * pp + 1] = a.y; p.alpha_deriv[row + 2 * pp + 1] = dv.y; }
-                }
-            }
-            const float asum = asum2.x + ((D & 1) ? asum2.y - a_last : asum2.y), dsum = dsum2.x + dsum2.y, g1 = g12.x + g12.y, g2 = g22.x + g22.y;
+            const bool rec_alpha = REC && p.alpha != nullptr && wr;
+            const V2RowSums rs = v2_row_walk<D, NOISE, GRAD, REC>(
+                theta, xi, scale, c0, c1, has_reward, a_pfc, a_pic, a_row, nk, p.rk, slot0,
+                NOISE == DMFG_NOISE_PHILOX ? nullptr : p.noise_y + row, row_ok,
+                rec_alpha ? p.alpha + row : nullptr, rec_alpha ? p.alpha_deriv + row : nullptr);
+            const float asum = rs.asum, dsum = rs.dsum, g1 = rs.g1, g2 = rs.g2;
             // ------------------------------------------------------------------ row level
-            const double ysum = ysum0 + ysum1;
+            const double ysum = rs.ysum;
             const float ysum_f = (float)ysum;
             double inv = (double)rcp_approx(ysum_f);                   // 1/s: float seed + 2 Newton steps
             inv = inv * (2.0 - ysum * inv);
@@ -228,7 +263,7 @@ rollout_v2_kernel(const RolloutParams<float> p) {
                 const float lnp_term = DMFG_LN2 * fmaf(-lg2_approx(ysum_f), dsum, g2);
                 glane = row_ok ? (double)(g1 + lnp_term + psi_row * dsum) : 0.0;
             }
-            double rew_lane = has_reward ? rew_scale * (q * inv) * (racc0 + racc1) : 0.0;
+            double rew_lane = has_reward ? rew_scale * (q * inv) * rs.racc : 0.0;
             if (REC && p.actions != nullptr) {
                 const float inv_f = (float)inv;
                 if (wr) {
@@ -366,8 +401,7 @@ rollout_v2_kernel(const RolloutParams<float> p) {
 // Independent serial learners on the v2 math (float streams; d = 15 / 16 with 16-lane groups, d = 21 -- the
 // reference's default, mfg_ac2.py:25 -- with 32-lane groups): one group = one learner with
 // private (theta, w) and per-step online updates -- mfg_ac2.py:448-539 semantics exactly, as in
-// learners_fast_kernel, but with the single-pass packed row walk of rollout_v2_kernel (the pair loop below is
-// the GRAD = 1, REC = 0 form of the one in that kernel: keep them in step).
+// learners_fast_kernel, but with the single-pass packed row walk of rollout_v2_kernel (v2_row_walk).
 // Shared memory per CTA: the y tile, double-buffered state, q, and the learners' critic slots [GPB][D+2][16].
 // ---------------------------------------------------------------------------
 template <int D, int G>
@@ -440,46 +474,13 @@ learners_v2_kernel(const LearnerParams<float> p, const PhiloxKeys rk) {
             // ------------------------------------------------------------------ the row (see rollout_v2_kernel)
             const float xi = (float)pi_self + shift;
             const double c1 = ac2 ? 1.0 : 0.0, c0 = ac2 ? -pi_self : 1.0;
-            float2 asum2 = make_float2(0.f, 0.f), dsum2 = asum2, g12 = asum2, g22 = asum2;
-            double ysum0 = 0.0, ysum1 = 0.0, racc0 = 0.0, racc1 = 0.0;
-            float a_last = 0.0f;
             const uint32_t slot0 = gamma_slot((uint32_t)((episode + p.noise_episode_offset) * p.T + t), D, r, 0);
-#pragma unroll 4
-            for (int pp = 0; pp < PD; ++pp) {
-                const float2 pj = lds_f32x2(a_pfc + 8 * pp);
-                const bool ok1 = (2 * pp + 1) < D;
-                float2 a, dv, psi;
-                alpha_psi_fast2(thf, __fadd2_rn(pj, splat2(-xi)), a, dv, psi);
-                if (!ok1) dv.y = 0.0f;
-                a_last = a.y;
-                g12 = __ffma2_rn(psi, neg2(dv), g12);
-                asum2 = __fadd2_rn(asum2, a);
-                dsum2 = __fadd2_rn(dsum2, dv);
-                float y0, y1;
-                if (NOISE == DMFG_NOISE_PHILOX) {
-                    gamma_pair_fast(nk, rk, slot0 + (uint32_t)pp, a, scale, y0, y1);
-                } else {
-                    y0 = row_ok ? p.noise_y[row + 2 * pp] : 1.0f;
-                    y1 = (row_ok && ok1) ? p.noise_y[row + 2 * pp + 1] : 1.0f;
-                    if (y0 == 0.0f) y0 = 1e-20f;                         // mfg_ac2.py:244
-                    if (y1 == 0.0f) y1 = 1e-20f;
-                }
-                g22 = __ffma2_rn(make_float2(lg2_approx(y0), lg2_approx(y1)), dv, g22);
-                const double yd0 = (double)y0, yd1 = (double)(ok1 ? y1 : 0.0f);
-                ysum0 += yd0;
-                ysum1 += yd1;
-                if (has_reward) {
-                    const double2 pjd = lds_f64x2(a_pic + 16 * pp);
-                    racc0 = fma(yd0 * yd0, fma(c1, pjd.x, c0), racc0);
-                    racc1 = fma(yd1 * yd1, fma(c1, pjd.y, c0), racc1);
-                }
-                sts_f64(a_row + 16 * pp, yd0);
-                sts_f64(a_row + 16 * pp + 8, yd1);
-            }
-            const float asum = asum2.x + ((D & 1) ? asum2.y - a_last : asum2.y), dsum = dsum2.x + dsum2.y,
-                        g1 = g12.x + g12.y, g2 = g22.x + g22.y;
+            const V2RowSums rs = v2_row_walk<D, NOISE, true, false>(
+                thf, xi, scale, c0, c1, has_reward, a_pfc, a_pic, a_row, nk, rk, slot0,
+                NOISE == DMFG_NOISE_PHILOX ? nullptr : p.noise_y + row, row_ok, nullptr, nullptr);
+            const float asum = rs.asum, dsum = rs.dsum, g1 = rs.g1, g2 = rs.g2;
             // ------------------------------------------------------------------ row level
-            const double ysum = ysum0 + ysum1;
+            const double ysum = rs.ysum;
             const float ysum_f = (float)ysum;
             double inv = (double)rcp_approx(ysum_f);
             inv = inv * (2.0 - ysum * inv);
@@ -489,7 +490,7 @@ learners_v2_kernel(const LearnerParams<float> p, const PhiloxKeys rk) {
             const float psi_row = digamma_fast(asum);
             const float lnp_term = DMFG_LN2 * fmaf(-lg2_approx(ysum_f), dsum, g2);
             const double glane = row_ok ? (double)(g1 + lnp_term + psi_row * dsum) : 0.0;
-            const double rew_lane = has_reward ? rew_scale * (q * inv) * (racc0 + racc1) : 0.0;
+            const double rew_lane = has_reward ? rew_scale * (q * inv) * rs.racc : 0.0;
             warp_fence();
             // ------------------------------------------------------------------ pi' = sum_i q_i y_ij
             double n0 = 0.0, n1 = 0.0, n2 = 0.0;
