@@ -9,6 +9,7 @@
 
 #include "dmfg_error.h"
 #include "dmfg_rollout2.cuh"
+#include "dmfg_td_dmma.cuh"
 
 using namespace dmfg;
 
@@ -43,6 +44,33 @@ inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a 
 inline size_t esize(int dtype) { return dtype == DMFG_F64 ? 8 : 4; }
 inline bool fast_d(int d) { return d == 4 || d == 15 || d == 16; }
 
+// TD pass on the FP64 tensor-core path (dmfg_td_dmma.cuh): float streams, d a multiple of 16, d >= 32
+struct TdDmmaPlan {
+    bool use = false;
+    int nblk = 0, ksplit = 0;
+    long long kchunk = 0;
+    uint64_t off_U = 0, off_v = 0, off_part = 0, total = 0;
+};
+inline TdDmmaPlan td_dmma_plan(int dtype, int d, int T, long long B) {
+    TdDmmaPlan pl;
+    if (dtype != DMFG_F32 || d < 32 || (d % 16) != 0 || T < 1 || B < 1) return pl;
+    pl.use = true;
+    const int nb = d / 16;
+    pl.nblk = nb * (nb + 1) / 2;
+    const long long Nt = (long long)T * B;
+    long long ks = (148LL * 32 + pl.nblk - 1) / pl.nblk;              // ~32 warps per SM over all blocks
+    if (ks > (Nt + 63) / 64) ks = (Nt + 63) / 64;                        // at least 64 samples per warp
+    if (ks < 1) ks = 1;
+    pl.kchunk = ((Nt + ks - 1) / ks + 3) / 4 * 4;
+    pl.ksplit = (int)((Nt + pl.kchunk - 1) / pl.kchunk);
+    uint64_t off = 0;
+    pl.off_U = off; off += align_up((uint64_t)d * d * 8);
+    pl.off_v = off; off += align_up((uint64_t)(T + 1) * (uint64_t)B * 8);
+    pl.off_part = off; off += align_up((uint64_t)pl.ksplit * pl.nblk * 256 * 8);
+    pl.total = off;
+    return pl;
+}
+
 
 bool use_fast(const dmfg_rollout_args* a) {
     if (a->variant == DMFG_VARIANT_GENERIC) return false;
@@ -56,7 +84,7 @@ bool use_v2(const dmfg_rollout_args* a) {
 
 // workspace map of one dmfg_rollout call
 struct RolloutWs {
-    uint64_t partials = 0, states = 0, rewards = 0, grads = 0, delta_buf = 0, total = 0;
+    uint64_t partials = 0, states = 0, rewards = 0, grads = 0, delta_buf = 0, dmma = 0, total = 0;
     bool need_states = false, need_rewards = false, need_grads = false;
 };
 RolloutWs rollout_ws(const dmfg_rollout_args* a) {
@@ -72,6 +100,7 @@ RolloutWs rollout_ws(const dmfg_rollout_args* a) {
         if (!a->rewards && !a->rewards_in) { w.need_rewards = true; w.rewards = off; off += align_up(TB * es); }
         if (!a->grads) { w.need_grads = true; w.grads = off; off += align_up(TB * es); }
         w.delta_buf = off; off += align_up(TB * 8);
+        w.dmma = off; off += td_dmma_plan(a->dtype, a->d, a->T, a->B).total;
     }
     w.total = off;
     return w;
@@ -245,12 +274,34 @@ int launch_generic(const RolloutParams<R>& p, cudaStream_t st) {
 }
 
 template <typename R>
-int run_td(const TdParams<R>& p0, double* acc, double* partials, cudaStream_t st) {
+int run_td(const TdParams<R>& p0, double* acc, double* partials, cudaStream_t st, char* dmma_ws = nullptr) {
     TdParams<R> p = p0;
     const int F = num_features_c(p.d);
     int sms = 0;
     if (int rc = sm_count(&sms)) return rc;
-    {
+    TdDmmaPlan plan;
+    if constexpr (std::is_same<R, float>::value) {
+        if (dmma_ws != nullptr) plan = td_dmma_plan(DMFG_F32, p.d, p.T, p.B);
+    }
+    if constexpr (std::is_same<R, float>::value) {
+        if (plan.use) {
+            double* U = (double*)(dmma_ws + plan.off_U);
+            double* vbuf = (double*)(dmma_ws + plan.off_v);
+            const long long N = (long long)(p.T + 1) * p.B, Nt = (long long)p.T * p.B;
+            td_unpack_w_kernel<<<(p.d * p.d + 255) / 256, 256, 0, st>>>(p.d, p.w, U);
+            DMFG_CUDA(cudaGetLastError());
+            const size_t smem = (size_t)(kTdDmmaThreads / 32) * 8 * (p.d + 4) * sizeof(double);
+            DMFG_CUDA(cudaFuncSetAttribute(td_values_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            long long grid = ((N + 7) / 8 + 3) / 4;
+            if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+            td_values_dmma_kernel<<<(unsigned)grid, kTdDmmaThreads, smem, st>>>(p.d, N, p.states, U, p.w, vbuf);
+            DMFG_CUDA(cudaGetLastError());
+            td_delta_from_values_kernel<<<(unsigned)((Nt + 255) / 256), 256, 0, st>>>(p.T, p.B, p.gamma, p.discount_kind,
+                                                                                     p.rewards, vbuf, p.deltas, p.delta_buf);
+            DMFG_CUDA(cudaGetLastError());
+        }
+    }
+    if (!plan.use) {
         const long long warps_needed = p.B;
         long long grid = (warps_needed + 3) / 4;
         if (grid > (long long)sms * 16) grid = (long long)sms * 16;
@@ -264,10 +315,23 @@ int run_td(const TdParams<R>& p0, double* acc, double* partials, cudaStream_t st
         p.partials = partials;
         const size_t smem = (size_t)kTdChunk * (p.d + 3) * sizeof(double);
         DMFG_CUDA(cudaFuncSetAttribute(td_gw_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        td_gw_kernel<R><<<(unsigned)grid, 256, smem, st>>>(p, kTdChunk);
+        td_gw_kernel<R><<<(unsigned)grid, 256, smem, st>>>(p, kTdChunk, plan.use ? 1 : 0);
         DMFG_CUDA(cudaGetLastError());
         reduce_partials_kernel<<<(F + 2 + 127) / 128, 128, 0, st>>>(partials, (int)grid, F + 2, acc);
         DMFG_CUDA(cudaGetLastError());
+        if constexpr (std::is_same<R, float>::value) {
+            if (plan.use) {
+                // the quadratic features: Gram blocks on the FP64 tensor cores, split-K partials summed in fixed order
+                double* gpart = (double*)(dmma_ws + plan.off_part);
+                const long long warps = (long long)plan.nblk * plan.ksplit;
+                td_gram_dmma_kernel<<<(unsigned)((warps + 3) / 4), kTdDmmaThreads, 0, st>>>(
+                    p.d, N, p.states, p.delta_buf, plan.nblk, plan.ksplit, plan.kchunk, gpart);
+                DMFG_CUDA(cudaGetLastError());
+                const int Q = p.d * (p.d + 1) / 2;
+                td_gram_reduce_kernel<<<(Q + 127) / 128, 128, 0, st>>>(p.d, plan.nblk, plan.ksplit, gpart, acc);
+                DMFG_CUDA(cudaGetLastError());
+            }
+        }
     }
     return DMFG_OK;
 }
@@ -329,7 +393,7 @@ int rollout_typed(const dmfg_rollout_args* a, cudaStream_t st) {
         t.states = p.states; t.rewards = a->rewards_in ? (const R*)a->rewards_in : p.rewards;
         t.grads = p.grads; t.w = a->w; t.deltas = (R*)a->deltas;
         t.delta_buf = (double*)(wsp + ws.delta_buf); t.partials = nullptr;
-        return run_td<R>(t, accum ? a->acc : nullptr, accum ? (double*)(wsp + ws.partials) : nullptr, st);
+        return run_td<R>(t, accum ? a->acc : nullptr, accum ? (double*)(wsp + ws.partials) : nullptr, st, wsp + ws.dmma);
     }
     return DMFG_OK;
 }
@@ -430,6 +494,7 @@ uint64_t dmfg_td_workspace_bytes(const dmfg_td_args* a) {
     const uint64_t F = (uint64_t)num_features_c(a->d);
     uint64_t off = align_up((uint64_t)a->T * (uint64_t)a->B * 8);
     if (a->acc) off += align_up((uint64_t)kMaxPartialCtas * (2 + F) * 8);
+    off += td_dmma_plan(a->dtype, a->d, a->T, a->B).total;
     return off;
 }
 
@@ -452,6 +517,8 @@ int dmfg_td_accumulate(const dmfg_td_args* a, void* stream) {
     char* wsp = (char*)a->workspace;
     double* delta_buf = (double*)wsp;
     double* partials = (double*)(wsp + align_up((uint64_t)a->T * (uint64_t)a->B * 8));
+    char* dmma_ws = wsp + align_up((uint64_t)a->T * (uint64_t)a->B * 8) +
+                    (a->acc ? align_up((uint64_t)kMaxPartialCtas * (2 + (uint64_t)F) * 8) : 0);
     if (a->dtype == DMFG_F64) {
         TdParams<double> t{a->d, a->T, a->B, a->gamma, a->discount_kind, (const double*)a->states,
                            (const double*)a->rewards, (const double*)a->grads, a->w, (double*)a->deltas,
@@ -461,7 +528,7 @@ int dmfg_td_accumulate(const dmfg_td_args* a, void* stream) {
     TdParams<float> t{a->d, a->T, a->B, a->gamma, a->discount_kind, (const float*)a->states,
                       (const float*)a->rewards, (const float*)a->grads, a->w, (float*)a->deltas,
                       delta_buf, nullptr};
-    return run_td<float>(t, a->acc, partials, st);
+    return run_td<float>(t, a->acc, partials, st, dmma_ws);
 }
 
 int dmfg_critic_eval(int32_t dtype, int32_t d, int64_t N, const void* states, const double* w, void* features,

@@ -504,8 +504,9 @@ __global__ void __launch_bounds__(128) td_delta_kernel(const TdParams<R> p) {
 }
 
 // CTA per chunk of transitions, thread per feature: partial sums of delta*phi, delta*g, r
+// skip_quad: the quadratic features are accumulated elsewhere (td_gram_dmma_kernel), leave their slots at 0
 template <typename R>
-__global__ void __launch_bounds__(256) td_gw_kernel(const TdParams<R> p, int chunk) {
+__global__ void __launch_bounds__(256) td_gw_kernel(const TdParams<R> p, int chunk, int skip_quad) {
     extern __shared__ double smem[];
     const int d = p.d;
     const int F = num_features_c(d), Q = d * (d + 1) / 2;
@@ -529,6 +530,7 @@ __global__ void __launch_bounds__(256) td_gw_kernel(const TdParams<R> p, int chu
         __syncthreads();
         for (int f = threadIdx.x; f < F + 2; f += blockDim.x) {
             double s = 0.0;
+            if (skip_quad && f >= 1 && f <= Q) continue;
             if (f == 0) {
                 for (int e = 0; e < cnt; ++e) s += dl[chunk + e];
             } else if (f == F + 1) {

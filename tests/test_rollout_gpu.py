@@ -439,3 +439,37 @@ def test_v2_philox_draws_match_other_variants(dev, d):
     assert torch.equal(h["actions"], a["actions"][:, 16:])
     auto = eng.rollout(pi0, 8.64, 0.0, 1e4, T, **kw)                       # AUTO picks v2 here
     assert torch.equal(auto["actions"], a["actions"])
+
+
+@pytest.mark.parametrize("d,B,T", [(32, 37, 5), (64, 203, 3), (48, 16, 16)])
+@pytest.mark.parametrize("discount", ["step", "cumulative"])
+def test_td_pass_on_fp64_tensor_cores_matches_numpy(dev, d, B, T, discount):
+    """Wide states (d a multiple of 16, float streams): V = phi(pi).w and sum delta*phi run as DMMA GEMMs
+    (dmfg_td_dmma.cuh).  Sizes with ragged tiles (states not a multiple of 8, transitions not a multiple of 4);
+    checked against the float64 formulas of mfg_ac2.py:290-344, 505-514 on the same recorded batch."""
+    rng = np.random.RandomState(d + B)
+    F = O.num_features(d)
+    w = rng.randn(F)
+    pi0 = T_(rng.dirichlet(np.ones(d), size=B), dev, torch.float32)
+    rec = eng.rollout(pi0, 8.0, 0.1, 1e4, T, reward="ac2", seed=3, outputs=("states", "rewards", "grads"))
+    gamma = 0.9
+    wd = torch.as_tensor(w, dtype=torch.float64, device=dev)
+    td = eng.td_accumulate(rec["states"], rec["rewards"], rec["grads"], wd, gamma=gamma, discount=discount)
+    S, r, g = N_(rec["states"]), N_(rec["rewards"]), N_(rec["grads"])
+    phi = O.features(S)                                           # [T+1, B, F]
+    V = phi @ w
+    gf = np.full(T, gamma) if discount == "step" else gamma ** np.arange(T)
+    delta = r + gf[:, None] * V[1:] - V[:-1]
+    vs = np.abs(V[1:]) + np.abs(V[:-1]) + np.abs(r)
+    assert np.all(np.abs(N_(td["deltas"]) - delta) <= 1e-6 * vs + 1e-12)       # deltas are stored in float
+    acc = N_(td["acc"])
+    G_w = np.einsum("tb,tbf->f", delta, phi[:-1])
+    scale = np.einsum("tb,tbf->f", np.abs(delta), np.abs(phi[:-1]))
+    assert np.all(np.abs(acc[1:1 + F] - G_w) <= 1e-10 * scale + 1e-15), np.max(np.abs(acc[1:1 + F] - G_w) / (scale + 1e-300))
+    np.testing.assert_allclose(acc[0], np.sum(delta * g), rtol=1e-10)
+    np.testing.assert_allclose(acc[1 + F], np.sum(r), rtol=1e-12)
+    # the fused call (rollout + TD) gives the same sums as the two-step call on its own record
+    full = eng.rollout(pi0, 8.0, 0.1, 1e4, T, w=wd, gamma=gamma, discount=discount, reward="ac2", seed=3,
+                       outputs=("deltas",), want_acc=True)
+    np.testing.assert_allclose(N_(full["acc"]), acc, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(N_(full["deltas"]), N_(td["deltas"]), rtol=0, atol=0)
