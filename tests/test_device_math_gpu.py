@@ -80,9 +80,12 @@ def test_gamma_zero_shape(dev):
     assert torch.count_nonzero(y) == 0          # np.random.gamma(0) == 0; the rollout maps it to 1e-20
 
 
-def test_dirichlet_rows_from_rollout(dev):
-    """P rows ~ Dirichlet(alpha * alpha_scale): E[P_ij] = alpha_ij / sum_j alpha_ij (mfg_ac2.py:238-249)."""
-    d, B = 15, 1 << 15
+@pytest.mark.parametrize("d", [15, 16, 21, 64])
+def test_dirichlet_rows_from_rollout(dev, d):
+    """P rows ~ Dirichlet(alpha * alpha_scale): E[P_ij] = alpha_ij / sum_j alpha_ij (mfg_ac2.py:238-249), through
+    the v2 kernel (d = 15 / 16) and the wide kernel (odd d = 21, d = 64); alpha_scale = 50 puts many shapes below 1
+    (boost path) and makes squeeze misses frequent (redo path)."""
+    B = 1 << 15
     pi = np.random.RandomState(1).dirichlet(np.ones(d))
     pi0 = torch.as_tensor(np.repeat(pi[None], B, 0), dtype=torch.float32, device=dev)
     out = eng.rollout(pi0, 8.86349, 0.16, 50.0, 1, seed=3, outputs=("actions", "alpha", "alpha_deriv"))
