@@ -134,7 +134,8 @@ def test_train_replays_reference(start_states, trace, dtype, capsys):
 
 
 def test_train_generic_d_matches_oracle(start_states):
-    """d = 21 (the reference's default) has no fused learner kernel: host-driven per-step path."""
+    """d = 21 (the reference's default) in float64 has no fused learner kernel: host-driven per-step path
+    (float32 streams run learners_v2_kernel<21, 32>, tested in test_rollout_gpu.py)."""
     rng = np.random.RandomState(2)
     d, E, T = 21, 2, 15
     mat = O.synthetic_start_states(n_rows=21, n_cols=30, d=21, seed=4)
@@ -335,3 +336,17 @@ def test_train_batch_pipelined_inputs_and_history(start_states):
     r2 = fresh(w0).train_batch(lambda e: batches[e], num_episodes=E, first_episode=0, history=True, **kw)
     np.testing.assert_allclose(r2["theta_history"], thetas, rtol=1e-14)
     np.testing.assert_allclose(r2["w_history"], np.stack(ws), rtol=1e-14)
+
+
+def test_train_batch_learns(start_states):
+    """The batched per-episode actor-critic climbs the reward it is given: with constant step sizes the mean reward of
+    8192 populations rises by two orders of magnitude and theta settles (a policy-gradient sign or TD-error error
+    would show up here, not in the step-by-step parity tests)."""
+    rng = np.random.RandomState(0)
+    ac = mfg_ac2.actor_critic(theta=6.0, shift=0.16, alpha_scale=12000, d=15, mat_pi0=start_states, dtype="float32", seed=1)
+    pi0 = np.float32(rng.dirichlet(np.ones(15), size=8192))
+    res = ac.train_batch(pi0, num_episodes=60, T=15, constant=1, lr_critic=0.1, lr_actor=1.0, history=True)
+    mr, th = res["mean_reward"], res["theta_history"]
+    assert np.isfinite(mr).all() and np.isfinite(th).all()
+    assert mr[-10:].mean() > 50 * abs(mr[0]) and mr[-10:].mean() > mr[:5].mean()
+    assert th[-1] > 6.5 and np.ptp(th[-20:]) < 0.1
