@@ -739,7 +739,6 @@ __global__ void __launch_bounds__(kFastThreads)
 learners_fast_kernel(const LearnerParams<R> p) {
     constexpr int NT = kFastThreads;
     constexpr int GPB = NT / G;
-    constexpr int NSLOT = D + 2;
     constexpr int F = num_features_c(D);
     extern __shared__ double smem[];
     double* wl = smem + threadIdx.x;      // [NSLOT][NT] private critic weights

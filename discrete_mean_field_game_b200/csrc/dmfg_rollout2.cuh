@@ -185,7 +185,7 @@ template <int D, int NOISE, bool REC, bool TRAIN, bool GRAD>
 __global__ void __launch_bounds__(kV2Threads, DMFG_V2_MINB)
 rollout_v2_kernel(const RolloutParams<float> p) {
     using S = V2Smem<D>;
-    constexpr int G = kV2G, NT = kV2Threads, GPB = S::GPB, PD = (D + 1) / 2;
+    constexpr int G = kV2G, NT = kV2Threads, GPB = S::GPB;
     constexpr int F = num_features_c(D);
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, r = tid & (G - 1), grp = tid / G, lane = tid & 31, warp = tid >> 5;
@@ -421,7 +421,7 @@ template <int D, int G, int NOISE>
 __global__ void __launch_bounds__(kV2Threads, 2)
 learners_v2_kernel(const LearnerParams<float> p, const PhiloxKeys rk) {
     using S = LearnersV2Smem<D, G>;
-    constexpr int GPB = S::GPB, PD = (D + 1) / 2, NSLOT = S::NSLOT, SL = S::SL;
+    constexpr int GPB = S::GPB, NSLOT = S::NSLOT, SL = S::SL;
     static_assert(D <= G && (G == 16 || G == 32), "one lane per row of P");
     constexpr int F = num_features_c(D);
     extern __shared__ __align__(16) double smem[];
