@@ -45,7 +45,7 @@ class RolloutArgs(C.Structure):
         ("states", C.c_void_p), ("actions", C.c_void_p), ("alpha", C.c_void_p),
         ("alpha_deriv", C.c_void_p), ("rewards", C.c_void_p), ("deltas", C.c_void_p),
         ("grads", C.c_void_p), ("pi_final", C.c_void_p), ("acc", C.c_void_p),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("step_offset_dev", C.c_void_p),
     ]
 
 
@@ -114,6 +114,8 @@ SYMBOLS = [
                                     C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dmfg_ac_apply_update", C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_double, C.c_double, C.c_void_p]),
+    ("dmfg_ac_apply_update_dev", C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                           C.c_void_p]),
     ("dmfg_ac_learners", C.c_int, [C.POINTER(LearnersArgs), C.c_void_p]),
     ("dmfg_rnet_param_count", C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     ("dmfg_rnet_param_offsets", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),

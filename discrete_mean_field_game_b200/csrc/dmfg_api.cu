@@ -147,6 +147,7 @@ RolloutParams<R> make_params(const dmfg_rollout_args* a) {
     p.shift = a->shift; p.alpha_scale = a->alpha_scale; p.gamma = a->gamma;
     p.reward_kind = a->reward_kind; p.discount_kind = a->discount_kind;
     p.noise_y = (const R*)a->noise_y; p.seed = a->seed; p.step_offset = a->step_offset;
+    p.step_offset_dev = (const unsigned long long*)a->step_offset_dev;
     p.pi0 = (const R*)a->pi0; p.w = a->w; p.rewards_in = (const R*)a->rewards_in;
     p.states = (R*)a->states; p.actions = (R*)a->actions; p.alpha = (R*)a->alpha;
     p.alpha_deriv = (R*)a->alpha_deriv; p.rewards = (R*)a->rewards; p.deltas = (R*)a->deltas;
@@ -597,6 +598,15 @@ int dmfg_ac_apply_update(int32_t d, double* theta_dev, double* w, const double* 
     const int F = num_features_c(d);
     ac_apply_update_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(F, theta_dev, w, acc, lr_critic_eff,
                                                                             lr_actor_eff, scale);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
+int dmfg_ac_apply_update_dev(int32_t d, double* theta_dev, double* w, const double* acc, const double* lr_dev,
+                             double scale, void* stream) {
+    if (d < 1 || d > DMFG_MAX_D || !w || !acc || !lr_dev) return fail(DMFG_ERR_INVALID, "dmfg_ac_apply_update_dev: bad argument");
+    const int F = num_features_c(d);
+    ac_apply_update_dev_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(F, theta_dev, w, acc, lr_dev, scale);
     DMFG_CUDA(cudaGetLastError());
     return DMFG_OK;
 }

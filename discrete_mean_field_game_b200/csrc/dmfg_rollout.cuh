@@ -58,6 +58,7 @@ struct RolloutParams {
     int reward_kind, discount_kind;
     const R* noise_y;
     unsigned long long seed, step_offset;
+    const unsigned long long* step_offset_dev;   // optional device scalar ADDED to step_offset (CUDA-graph replays)
     const R* pi0;
     const double* w;
     const R* rewards_in;
@@ -66,6 +67,12 @@ struct RolloutParams {
     PhiloxKeys rk;         // round keys of `seed` (v2 kernel)
     float shift_f, scale_f;
 };
+
+// first Philox step index of this launch: the by-value offset plus the optional device-side one
+template <typename R>
+__device__ __forceinline__ unsigned long long step_base(const RolloutParams<R>& p) {
+    return p.step_offset + (p.step_offset_dev != nullptr ? *p.step_offset_dev : 0ull);
+}
 
 // ---------------------------------------------------------------------------
 // group collectives over G lanes (G power of two <= 32)
@@ -246,7 +253,7 @@ rollout_fast_kernel(const RolloutParams<R> p) {
             StepCore<D, G, R, NOISE>::run(
                 pi, pi_self, r, theta, shift, scale, p.reward_kind,
                 NOISE != DMFG_NOISE_PHILOX ? p.noise_y + row : nullptr, nk,
-                (uint32_t)(p.step_offset + t),
+                (uint32_t)(step_base(p) + t),
                 (p.actions && live) ? p.actions + row : nullptr,
                 (p.alpha && live) ? p.alpha + row : nullptr,
                 (p.alpha_deriv && live) ? p.alpha_deriv + row : nullptr,
@@ -392,7 +399,7 @@ rollout_generic_kernel(const RolloutParams<R> p) {
                     }
                     if (NOISE == DMFG_NOISE_PHILOX) {
                         float y0, y1;
-                        gamma_pair_fast(nk, p.rk, gamma_slot((uint32_t)(p.step_offset + t), d, i, pp),
+                        gamma_pair_fast(nk, p.rk, gamma_slot((uint32_t)(step_base(p) + t), d, i, pp),
                                         make_float2((float)a[0], (float)a[1]), (float)scale, y0, y1);
                         yv[0] = (R)y0; yv[1] = (R)y1;
                     } else {
@@ -711,6 +718,15 @@ __global__ void ac_apply_update_kernel(int F, double* theta, double* w, const do
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f < F) w[f] = fma(lr_c * scale, acc[1 + f], w[f]);
     if (f == 0 && theta != nullptr) *theta = fma(lr_a * scale, acc[0], *theta);
+}
+
+// the same update with the two effective step sizes read from device memory (lr[0] critic, lr[1] actor): the
+// launch arguments do not change between replays of a captured CUDA graph
+__global__ void ac_apply_update_dev_kernel(int F, double* theta, double* w, const double* __restrict__ acc,
+                                           const double* __restrict__ lr, double scale) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < F) w[f] = fma(lr[0] * scale, acc[1 + f], w[f]);
+    if (f == 0 && theta != nullptr) *theta = fma(lr[1] * scale, acc[0], *theta);
 }
 
 // ---------------------------------------------------------------------------

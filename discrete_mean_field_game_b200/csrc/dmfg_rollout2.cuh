@@ -241,7 +241,7 @@ rollout_v2_kernel(const RolloutParams<float> p) {
             const float xi = (float)pi_self + shift;
             // reward weights: AC2 sum_j y^2 (pi_j - pi_i);  synthetic sum_j y^2
             const double c1 = ac2 ? 1.0 : 0.0, c0 = ac2 ? -pi_self : 1.0;
-            const uint32_t slot0 = gamma_slot((uint32_t)(p.step_offset + t), D, r, 0);
+            const uint32_t slot0 = gamma_slot((uint32_t)(step_base(p) + t), D, r, 0);
             const bool rec_alpha = REC && p.alpha != nullptr && wr;
             const V2RowSums rs = v2_row_walk<D, NOISE, GRAD, REC>(
                 theta, xi, scale, c0, c1, has_reward, a_pfc, a_pic, a_row, nk, p.rk, slot0,
@@ -639,7 +639,7 @@ rollout_wide_kernel(const RolloutParams<float> p) {
                         }
                         float y0, y1;
                         if (NOISE == DMFG_NOISE_PHILOX) {
-                            gamma_pair_fast(nk, p.rk, gamma_slot((uint32_t)(p.step_offset + t), d, i, pp), a, scale, y0, y1);
+                            gamma_pair_fast(nk, p.rk, gamma_slot((uint32_t)(step_base(p) + t), d, i, pp), a, scale, y0, y1);
                         } else {
                             y0 = p.noise_y[row + 2 * pp];
                             y1 = ok1 ? p.noise_y[row + 2 * pp + 1] : 1.0f;

@@ -69,7 +69,7 @@ def require_cuda():
 
 def rollout(pi0, theta, shift, alpha_scale, T, *, w=None, gamma=1.0, reward="ac2", discount="step",
             noise_y=None, seed=0, pop_offset=0, step_offset=0, outputs=("states",), want_acc=False,
-            rewards_in=None, theta_dev=None, variant="auto", out=None, actions_in=None):
+            rewards_in=None, theta_dev=None, variant="auto", out=None, actions_in=None, step_offset_dev=None):
     """dmfg_rollout on CUDA tensors.
 
     pi0 [B,d] (float32/float64 selects the stream dtype); noise_y [T,B,d,d] selects
@@ -95,6 +95,8 @@ def rollout(pi0, theta, shift, alpha_scale, T, *, w=None, gamma=1.0, reward="ac2
     a.discount_kind = DISCOUNT_STEP if discount == "step" else DISCOUNT_CUMULATIVE
     a.variant = VARIANTS[variant]
     a.seed, a.step_offset = int(seed) & (2 ** 64 - 1), int(step_offset)
+    if step_offset_dev is not None:          # device scalar added to step_offset (CUDA-graph replays)
+        a.step_offset_dev = _ptr(_require(step_offset_dev, "step_offset_dev", device, torch.int64, (1,)))
     if actions_in is not None:
         a.noise_kind = NOISE_ACTIONS
         a.noise_y = _ptr(_require(actions_in, "actions_in", device, dtype, (T, B, d, d)))
@@ -225,11 +227,17 @@ def synthetic_check(actions, want_jsd=True):
     return l1, js
 
 
-def apply_update(d, theta_dev, w, acc, lr_critic_eff, lr_actor_eff, scale):
-    """theta += lr_a*scale*acc[0]; w += lr_c*scale*acc[1:1+F]  (mfg_ac2.py:511-522), on device."""
+def apply_update(d, theta_dev, w, acc, lr_critic_eff, lr_actor_eff, scale, lr_dev=None):
+    """theta += lr_a*scale*acc[0]; w += lr_c*scale*acc[1:1+F]  (mfg_ac2.py:511-522), on device.
+    ``lr_dev`` [2] float64 device tensor (lr_critic_eff, lr_actor_eff) replaces the two by-value step sizes."""
     lib = _lib.load()
     device = w.device
     with torch.cuda.device(device):
+        if lr_dev is not None:
+            check(lib.dmfg_ac_apply_update_dev(int(d), _ptr(theta_dev), _ptr(w), _ptr(acc),
+                                               _ptr(_require(lr_dev, "lr_dev", device, torch.float64, (2,))),
+                                               float(scale), _stream_ptr(device)))
+            return
         check(lib.dmfg_ac_apply_update(int(d), _ptr(theta_dev), _ptr(w), _ptr(acc), float(lr_critic_eff),
                                        float(lr_actor_eff), float(scale), _stream_ptr(device)))
 

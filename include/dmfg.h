@@ -128,6 +128,8 @@ typedef struct dmfg_rollout_args {
     void*    workspace;         /* scratch: per-CTA partial sums (deterministic two-stage reduction) and,
                                    for the generic variant with w != NULL, unrequested intermediates */
     uint64_t workspace_bytes;   /* >= dmfg_rollout_workspace_bytes(args) */
+    const uint64_t* step_offset_dev;  /* optional device scalar ADDED to step_offset: lets a captured CUDA graph of
+                                         launches be replayed with a different Philox position every time */
 } dmfg_rollout_args;
 
 /* exact scratch need of this call (0 when none); looks at d, T, B, dtype, variant, w, acc and
@@ -189,6 +191,10 @@ int dmfg_synthetic_check(int32_t dtype, int32_t d, int64_t B, int32_t T, const v
  * 1/B for the batch-mean update.  theta_dev and w are updated in place.     */
 int dmfg_ac_apply_update(int32_t d, double* theta_dev, double* w, const double* acc,
                          double lr_critic_eff, double lr_actor_eff, double scale, void* stream);
+/* the same with the two step sizes in device memory, lr_dev[0] = lr_critic_eff, lr_dev[1] = lr_actor_eff (a launch whose
+ * arguments do not change between CUDA-graph replays) */
+int dmfg_ac_apply_update_dev(int32_t d, double* theta_dev, double* w, const double* acc, const double* lr_dev,
+                             double scale, void* stream);
 
 /* ---- a8: independent serial learners (exact reference semantics) -------- *
  * L learners, each with its OWN (theta, w) and per-step online updates, run E

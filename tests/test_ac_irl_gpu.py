@@ -273,3 +273,19 @@ def test_train_batch_with_reward_net_matches_oracle(data):
     r1 = a1.train_batch(pi0, num_episodes=2)
     r2 = a2.train_batch(pi0, num_episodes=2)
     assert np.isfinite(r1["theta"]) and r1["theta"] == r2["theta"]
+
+
+def test_train_cuda_graph_replay_equals_eager_launches(data):
+    """AC_IRL.train captures the 60-launch chain of an episode as a CUDA graph and replays it with the start state,
+    step sizes and Philox position refreshed in device buffers: bit-identical to launching the chain eagerly."""
+    a, b = make(data), make(data)
+    b.w = a.w.copy()
+    kw = dict(max_episodes=6, stop_criteria=-1, lr_critic=0.1, lr_actor=0.01, verbose=False)
+    a.train(use_graph=True, **kw)
+    b.train(use_graph=False, **kw)
+    assert a.theta == b.theta and a.theta != 6.5
+    np.testing.assert_array_equal(a.w, b.w)
+    a.train(use_graph=True, **kw)                     # a second call continues the noise stream in both modes
+    b.train(use_graph=False, **kw)
+    assert a.theta == b.theta
+    np.testing.assert_array_equal(a.w, b.w)
