@@ -50,6 +50,7 @@ td_values_dmma_kernel(int d, long long N, const float* __restrict__ states, cons
         for (int cb = 0; cb < d / 8; ++cb) {
             double c0 = 0.0, c1 = 0.0;
             const double* Ub = U + 8 * cb + gid;
+#pragma unroll 4
             for (int kb = 0; kb <= 2 * cb + 1; ++kb)             // k = 4 kb .. 4 kb + 3 <= 8 cb + 7: on or above the diagonal
                 dmma884(c0, c1, Sg[4 * kb + tig], Ub[(size_t)(4 * kb + tig) * d]);
             const int j0 = 8 * cb + 2 * tig;
@@ -96,6 +97,7 @@ td_gram_dmma_kernel(int d, long long Nt, const float* __restrict__ states, const
     if (k_end > Nt) k_end = Nt;
     double c00a = 0, c00b = 0, c01a = 0, c01b = 0, c10a = 0, c10b = 0, c11a = 0, c11b = 0;
     const bool offdiag = I != J;
+#pragma unroll 4
     for (long long k0 = k_begin; k0 < k_end; k0 += 4) {
         const long long n = k0 + tig;
         double dl = 0.0, a_lo = 0.0, a_hi = 0.0, b_lo = 0.0, b_hi = 0.0;
