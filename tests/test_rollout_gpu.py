@@ -294,7 +294,7 @@ def test_philox_fast_equals_generic(dev, d):
     assert not torch.equal(k2["actions"], f["actions"])
 
 
-@pytest.mark.parametrize("d", [15, 21, 64])
+@pytest.mark.parametrize("d", [15, 21, 64, 255, 256])
 def test_philox_rollout_invariants(dev, d):
     """test2.py:26,32 and test_acirl.py:43-47: rows of P sum to 1, mass is conserved,
     state_{t+1} = action_t^T state_t -- at a size the oracle never sees."""
@@ -473,3 +473,40 @@ def test_td_pass_on_fp64_tensor_cores_matches_numpy(dev, d, B, T, discount):
                        outputs=("deltas",), want_acc=True)
     np.testing.assert_allclose(N_(full["acc"]), acc, rtol=1e-12, atol=1e-14)
     np.testing.assert_allclose(N_(full["deltas"]), N_(td["deltas"]), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("d", [21, 100, 200, 256])
+def test_wide_kernel_vs_oracle(dev, d):
+    """rollout_wide_kernel (float streams, any d; 1 / 2 / 4 column pairs per lane, odd and maximum d) with injected
+    Gamma variates against the float64 oracle: every per-step stream and the reduced sums (the TD pass runs on the
+    scalar kernels at d = 21 / 100 / 200 and on the FP64 tensor cores at d = 256)."""
+    rng = np.random.RandomState(d)
+    B, T = 3, 2
+    pi0 = np.float32(rng.dirichlet(np.ones(d) * 0.7, size=B))
+    F = O.num_features(d)
+    w = rng.rand(F)
+    y = np.zeros((T, B, d, d), np.float32)
+    pi = pi0.astype(np.float64)
+    for t in range(T):
+        alpha, _ = O.policy_alpha(pi, 8.64, 0.05)
+        y[t] = np.float32(rng.gamma(alpha * 1e4))
+        pi = O.mean_field_step(O.normalise_gamma(y[t].astype(np.float64)), pi)
+    y[1, 2, 5, 7] = 0.0                                       # an exact zero (mfg_ac2.py:244)
+    ref = O.rollout_frozen(pi0.astype(np.float64), 8.64, 0.05, 1e4, y.astype(np.float64), w=w)
+    out = eng.rollout(T_(pi0, dev, torch.float32), 8.64, 0.05, 1e4, T, w=T_(w, dev, torch.float64),
+                      noise_y=T_(y, dev, torch.float32), outputs=ALL_OUT, want_acc=True)
+    for k in ("states", "alpha"):
+        np.testing.assert_allclose(N_(out[k]), ref[k], rtol=2e-5, err_msg=k)
+    np.testing.assert_allclose(N_(out["alpha_deriv"]), ref["alpha_deriv"], rtol=2e-5, atol=3e-8)
+    np.testing.assert_allclose(N_(out["actions"]), ref["actions"], rtol=2e-5, atol=1e-30)
+    np.testing.assert_allclose(N_(out["pi_final"]), ref["states"][-1], rtol=2e-5)
+    # g sums d^2 terms of mixed sign: bound relative to the sum of their magnitudes (~ d for these inputs)
+    np.testing.assert_allclose(N_(out["grads"]), ref["grads"], rtol=2e-5, atol=2e-6 * d)
+    v = np.abs(O.features(ref["states"]) @ w)
+    scale = np.abs(ref["rewards"]) + v[1:] + v[:-1]
+    assert np.all(np.abs(N_(out["deltas"]) - ref["deltas"]) <= 1e-6 * scale)
+    assert np.all(np.abs(N_(out["rewards"]) - ref["rewards"]) <= 1e-6 * np.maximum(scale, 1e-3))
+    acc = N_(out["acc"])
+    wscale = np.sum(np.abs(ref["deltas"])[..., None] * np.abs(O.features(ref["states"][:-1])), axis=(0, 1))
+    assert np.all(np.abs(acc[1:1 + F] - ref["G_w"]) <= 1e-5 * wscale + 1e-12)
+    np.testing.assert_allclose(acc[1 + F], ref["R"], rtol=1e-4, atol=1e-9)
