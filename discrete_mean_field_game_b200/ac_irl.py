@@ -569,6 +569,22 @@ class AC_IRL(_actor_critic):
                    write_file=1, write_all=0, verbose=verbose)
         return self.theta
 
+    def test_reward_network(self):
+        """Average reward of the fixed reward network over all transitions of the training demonstrations, of the
+        test demonstrations and of freshly generated trajectories (ac_irl.py:1008-1043; gridsearch.py:28)."""
+        def avg(trajectories):
+            if not trajectories:
+                return float("nan")
+            s, a = self._pack(trajectories)
+            return float(self._reward(s, a).double().sum()) / s.shape[0]
+        self.list_generated = self.generate_trajectories(len(self.list_demonstrations))
+        reward_demo_avg_train = avg(self.list_demonstrations)
+        reward_gen_avg = avg(self.list_generated)
+        reward_demo_avg_test = avg(self.list_demonstrations_test)
+        print("Avg reward demo train %f | Avg reward demo test %f | Avg reward gen %f"
+              % (reward_demo_avg_train, reward_demo_avg_test, reward_gen_avg))
+        return reward_demo_avg_train, reward_demo_avg_test, reward_gen_avg
+
     # ------------------------------------------------------------- a13: importance weights
     def calc_z(self, gen_states, gen_actions, layout="trajectory_major"):
         """z_j = K / (N_start sum_k q_k(tau_j)) for generated trajectories (ac_irl.py:324-379), returned as

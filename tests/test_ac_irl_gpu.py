@@ -289,3 +289,22 @@ def test_train_cuda_graph_replay_equals_eager_launches(data):
     b.train(use_graph=False, **kw)
     assert a.theta == b.theta
     np.testing.assert_array_equal(a.w, b.w)
+
+
+def test_gridsearch_dropin(data, tmp_path, monkeypatch):
+    """gridsearch.py:1-31 with in-memory data and shortened loops: one CSV line per (reg, n_fc3, n_fc4) point,
+    test_reward_network (ac_irl.py:1008-1043) returns the three averages."""
+    from discrete_mean_field_game_b200 import gridsearch
+    monkeypatch.chdir(tmp_path)
+    mat, demos = data
+    rows = gridsearch.run(outfile=str(tmp_path / "results" / "grid.csv"), list_reg=["none", "dropout_l1l2"],
+                          list_nfc3=[8], list_nfc4=[4, 6],
+                          ac_kwargs=dict(d=D, mat_pi0=mat, demonstrations=demos, demonstrations_test=demos[:3], seed=5,
+                                         net_seed=2),
+                          outerloop_kwargs=dict(num_iterations=1, max_reward_iterations=10, max_forward_episodes=4,
+                                                final_episodes=4, verbose=False))
+    assert len(rows) == 4
+    lines = (tmp_path / "results" / "grid.csv").read_text().strip().split("\n")
+    assert lines[0].startswith("reg,n_fc3,n_fc4,") and len(lines) == 5
+    for reg, n3, n4, tr, te, ge, th in rows:
+        assert np.isfinite([tr, te, ge, th]).all() and -1.0 <= tr <= 1.0 and -1.0 <= ge <= 1.0
