@@ -569,6 +569,15 @@ class AC_IRL(_actor_critic):
                    write_file=1, write_all=0, verbose=verbose)
         return self.theta
 
+    def evaluate(self, theta=8.86349, shift=0.5, alpha_scale=1e4, d=15, episode_length=16,
+                 indir='test_normalized_round2', outfile='eval_mfg_round2/validation.csv', write_header=0,
+                 empirical=None, y=None):
+        """ac_irl.py:1495-1570: the same evaluation as mfg_ac2's (inherited implementation: all test days as one
+        batched rollout + dmfg_traj_metrics) with this class's defaults (d = 15, validation.csv).  JSD,
+        generate_trajectory and gridsearch (ac_irl.py:1445-1589) are inherited unchanged."""
+        return super().evaluate(theta=theta, shift=shift, alpha_scale=alpha_scale, d=d, episode_length=episode_length,
+                                indir=indir, outfile=outfile, write_header=write_header, empirical=empirical, y=y)
+
     def test_reward_network(self):
         """Average reward of the fixed reward network over all transitions of the training demonstrations, of the
         test demonstrations and of freshly generated trajectories (ac_irl.py:1008-1043; gridsearch.py:28)."""

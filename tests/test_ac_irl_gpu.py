@@ -308,3 +308,17 @@ def test_gridsearch_dropin(data, tmp_path, monkeypatch):
     assert lines[0].startswith("reg,n_fc3,n_fc4,") and len(lines) == 5
     for reg, n3, n4, tr, te, ge, th in rows:
         assert np.isfinite([tr, te, ge, th]).all() and -1.0 <= tr <= 1.0 and -1.0 <= ge <= 1.0
+
+
+def test_evaluate_surface_of_ac_irl(data, tmp_path, evalm):
+    """ac_irl.py:1445-1589: JSD / generate_trajectory / evaluate exist on AC_IRL with its own defaults and give the
+    reference's numbers on the golden evaluation fixture (same code path as mfg_ac2's, pinned there)."""
+    ac = make(data)
+    out = tmp_path / "validation.csv"
+    res = ac.evaluate(theta=float(evalm["theta"]), shift=float(evalm["shift"]), alpha_scale=float(evalm["alpha_scale"]),
+                      outfile=str(out), write_header=1, empirical=evalm["empirical"], y=evalm["y"])
+    np.testing.assert_allclose(res, evalm["result"], rtol=2e-5)
+    assert out.read_text().startswith("theta,shift,alpha_scale,mean_l1_final")
+    np.testing.assert_allclose(ac.JSD(evalm["jsd_P"].copy(), evalm["jsd_Q"].copy()), float(evalm["jsd_value"]), rtol=1e-12)
+    traj = ac.generate_trajectory(data[0][0], 16)
+    assert traj.shape == (16, D)
