@@ -61,15 +61,49 @@ def load_profile_constants():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock, power and throttle reasons DURING the timed region (B200_PROFILING.md).  NVML is polled in-process
+    every 20 ms (a sample costs ~50 us and is available from the first step on); `nvidia-smi -lms 100` -- which needs
+    more than a short timed region to print its first line on an 8-GPU box -- is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.handle, self.samples, self.stop_flag = None, None, [], False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if visible:
+                ids = [x.strip() for x in visible.split(",") if x.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((float(sm), float(mx), pw, int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        if self.nvml is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -84,6 +118,18 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            sm = [x[0] for x in self.samples]
+            reasons = set()
+            for x in self.samples:
+                for bit, name in self.NVML_REASONS.items():
+                    if x[3] & bit:
+                        reasons.add(name)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(x[1] for x in self.samples) if sm else None,
+                    "power_w_max": max(x[2] for x in self.samples) if sm else None, "samples": len(sm),
+                    "reasons": sorted(reasons), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -105,7 +151,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi"}
 
 
 def synthetic_pi0(B, seed):
