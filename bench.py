@@ -81,7 +81,12 @@ class ClockSampler:
                 ids = [x.strip() for x in visible.split(",") if x.strip()]
                 if index < len(ids) and ids[index].isdigit():
                     phys = int(ids[index])
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            try:                                     # exact match whatever the visibility mask looks like
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.nvml = pynvml
         except Exception:
             self.nvml = None
