@@ -201,6 +201,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     budget = 150.0 / (args.steps + args.warmup)                    # whole run within a few minutes
     episodes = max(1, int(1400.0 * min(budget, 20.0) / T))         # ~1.4 k steps/s/core
+    episodes = int(os.environ.get("DMFG_BENCH_CPU_EPISODES", episodes))   # tests shrink the sample
     pool = make_pool(cores)
     for _ in range(args.warmup):
         cpu_throughput(max(1, episodes // 8), cores, pool)
