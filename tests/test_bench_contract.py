@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -30,3 +32,28 @@ def test_reference_arm_other_ranks_print_nothing():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_one_json_line_with_the_contract_keys():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--log2-pops", "13", "--steps", "3",
+                          "--warmup", "3", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 3 and d["data"] == "synthetic"
+    assert d["gpu_launches"] == 9 and "workload" in d["config"] and "l2" in d["config"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == (1 << 13) * 15 * 4 and e["d2h_bytes_per_step"] == (136 + 2) * 8
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert r["traffic"] is not None and "issue" in r
+    assert d["clocks"]["samples"] >= 0 and isinstance(d["clocks"]["reasons"], list)
+    assert d["modes"]["irl_update"]["value"] > 0
