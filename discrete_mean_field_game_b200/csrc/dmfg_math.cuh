@@ -258,6 +258,9 @@ static __device__ __noinline__ float2 gamma_pair_redo(uint32_t p0, uint32_t p1, 
 __device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
+// y == 0 -> 1e-20 (mfg_ac2.py:244); 0 < y < FLT_MIN (denormal) -> FLT_MIN
+__device__ __forceinline__ float gamma_floor(float y) { return y == 0.0f ? 1e-20f : fmaxf(y, 1.17549435e-38f); }
+
 __device__ __forceinline__ void gamma_pair_fast(const NoiseKey& nk, const PhiloxKeys& K, uint32_t slot, float2 al,
                                                 float scale, float& y0, float& y1) {
     const uint4 w = philox_gamma(nk.p0, nk.p1, slot, 0u, K);
@@ -290,13 +293,16 @@ __device__ __forceinline__ void gamma_pair_fast(const NoiseKey& nk, const Philox
     y1 = y.y;
     // A squeeze-accepted variate without boost is dd v^3 with v >= 1/2: never 0.  Only the two rare paths can
     // underflow to 0, so the reference's y == 0 -> 1e-20 substitution (mfg_ac2.py:244) lives there.
+    // A boosted variate can also land in the float denormal range (y U^(1/a) with a tiny shape): the MUFU units
+    // flush denormals to zero (lg2 -> -inf), so those are lifted to the smallest normal float -- they stand for
+    // transition probabilities below 1e-38 either way (found by the random-regime test at theta = 28).
     if (!(ok0 & ok1)) {
         const float2 yy = gamma_pair_redo(nk.p0, nk.p1, nk.k0, nk.k1, slot, al.x, al.y, scale);
-        y0 = yy.x == 0.0f ? 1e-20f : yy.x;
-        y1 = yy.y == 0.0f ? 1e-20f : yy.y;
+        y0 = gamma_floor(yy.x);
+        y1 = gamma_floor(yy.y);
     } else if (small) {
-        if (a.x < 1.0f) { y0 = boost_apply(y0, a.x, squeeze_uniform(u.x, thr.x)); if (y0 == 0.0f) y0 = 1e-20f; }
-        if (a.y < 1.0f) { y1 = boost_apply(y1, a.y, squeeze_uniform(u.y, thr.y)); if (y1 == 0.0f) y1 = 1e-20f; }
+        if (a.x < 1.0f) y0 = gamma_floor(boost_apply(y0, a.x, squeeze_uniform(u.x, thr.x)));
+        if (a.y < 1.0f) y1 = gamma_floor(boost_apply(y1, a.y, squeeze_uniform(u.y, thr.y)));
     }
 }
 

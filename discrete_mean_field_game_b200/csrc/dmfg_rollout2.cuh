@@ -145,10 +145,8 @@ __device__ __forceinline__ V2RowSums v2_row_walk(float theta, float xi, float sc
         if (NOISE == DMFG_NOISE_PHILOX) {
             gamma_pair_fast(nk, rk, slot0 + (uint32_t)pp, a, scale, y0, y1);   // never returns 0
         } else {
-            y0 = row_ok ? noise_row[2 * pp] : 1.0f;
-            y1 = (row_ok && ok1) ? noise_row[2 * pp + 1] : 1.0f;
-            if (y0 == 0.0f) y0 = 1e-20f;                         // mfg_ac2.py:244
-            if (y1 == 0.0f) y1 = 1e-20f;
+            y0 = gamma_floor(row_ok ? noise_row[2 * pp] : 1.0f);                  // mfg_ac2.py:244 (+ denormals)
+            y1 = gamma_floor((row_ok && ok1) ? noise_row[2 * pp + 1] : 1.0f);
         }
         if (GRAD) g22 = __ffma2_rn(make_float2(lg2_approx(y0), lg2_approx(y1)), dv, g22);
         const double yd0 = (double)y0, yd1 = (double)(ok1 ? y1 : 0.0f);
@@ -641,10 +639,8 @@ rollout_wide_kernel(const RolloutParams<float> p) {
                         if (NOISE == DMFG_NOISE_PHILOX) {
                             gamma_pair_fast(nk, p.rk, gamma_slot((uint32_t)(step_base(p) + t), d, i, pp), a, scale, y0, y1);
                         } else {
-                            y0 = p.noise_y[row + 2 * pp];
-                            y1 = ok1 ? p.noise_y[row + 2 * pp + 1] : 1.0f;
-                            if (y0 == 0.0f) y0 = 1e-20f;                     // mfg_ac2.py:244
-                            if (y1 == 0.0f) y1 = 1e-20f;
+                            y0 = gamma_floor(p.noise_y[row + 2 * pp]);                       // mfg_ac2.py:244 (+ denormals)
+                            y1 = gamma_floor(ok1 ? p.noise_y[row + 2 * pp + 1] : 1.0f);
                         }
                         if (GRAD) g22 = __ffma2_rn(make_float2(lg2_approx(y0), lg2_approx(y1)), dv, g22);
                         if (!ok1) y1 = 0.0f;

@@ -510,3 +510,33 @@ def test_wide_kernel_vs_oracle(dev, d):
     wscale = np.sum(np.abs(ref["deltas"])[..., None] * np.abs(O.features(ref["states"][:-1])), axis=(0, 1))
     assert np.all(np.abs(acc[1:1 + F] - ref["G_w"]) <= 1e-5 * wscale + 1e-12)
     np.testing.assert_allclose(acc[1 + F], ref["R"], rtol=1e-4, atol=1e-9)
+
+
+def test_random_regimes_invariants_and_variant_agreement(dev):
+    """30 random parameter regimes (theta 1..30, shift 0..0.6, alpha_scale 10..1e5: shapes from 1e-4 -- boost and redo
+    paths -- to 1e6, d in {15, 16, 21, 64}, ragged B, odd / even T): every output finite, rows of P on the simplex,
+    mass conserved, and -- the draws being keyed by (seed, population, step, row, pair) -- the v2 kernel and the wide
+    kernel produce the same trajectories wherever both exist."""
+    rng = np.random.RandomState(2024)
+    for trial in range(30):
+        d = int(rng.choice([15, 16, 21, 64]))
+        B, T = int(rng.randint(1, 70)), int(rng.randint(1, 9))
+        theta, shift = float(rng.uniform(1.0, 30.0)), float(rng.uniform(0.0, 0.6))
+        scale = float(rng.choice([10.0, 100.0, 1e4, 1e5]))
+        conc = float(rng.choice([0.05, 0.3, 1.0]))                       # sparse .. flat start states
+        pi0 = T_(rng.dirichlet(np.ones(d) * conc, size=B), dev, torch.float32)
+        w = T_(rng.rand(O.num_features(d)), dev, torch.float64)
+        kw = dict(w=w, seed=trial, outputs=("states", "actions", "rewards", "grads", "deltas"), want_acc=True)
+        a = eng.rollout(pi0, theta, shift, scale, T, **kw)
+        tag = "trial %d: d=%d B=%d T=%d theta=%.2f shift=%.2f scale=%g" % (trial, d, B, T, theta, shift, scale)
+        for k, v in a.items():
+            assert torch.isfinite(v).all(), tag + " " + k
+        P, S = a["actions"].double(), a["states"].double()
+        assert torch.all(P > 0), tag
+        assert float((P.sum(-1) - 1).abs().max()) <= 2e-6, tag
+        assert float((S.sum(-1) - S[0].sum(-1)).abs().max()) <= 2e-6, tag
+        assert float((torch.einsum("tbi,tbij->tbj", S[:-1], P) - S[1:]).abs().max()) <= 3e-7, tag
+        if d in (15, 16):
+            g = eng.rollout(pi0, theta, shift, scale, T, variant="generic", **kw)
+            np.testing.assert_allclose(N_(a["states"]), N_(g["states"]), rtol=3e-5, atol=1e-8, err_msg=tag)
+            np.testing.assert_allclose(N_(a["rewards"]), N_(g["rewards"]), rtol=1e-4, atol=1e-7, err_msg=tag)
