@@ -540,3 +540,31 @@ def test_random_regimes_invariants_and_variant_agreement(dev):
             g = eng.rollout(pi0, theta, shift, scale, T, variant="generic", **kw)
             np.testing.assert_allclose(N_(a["states"]), N_(g["states"]), rtol=3e-5, atol=1e-8, err_msg=tag)
             np.testing.assert_allclose(N_(a["rewards"]), N_(g["rewards"]), rtol=1e-4, atol=1e-7, err_msg=tag)
+
+
+def test_random_regimes_learners_float_vs_double(dev):
+    """The v2 learners (float streams) against the first-generation learners in float64 on the SAME Philox draws, in
+    12 random regimes (theta, shift, alpha_scale, step sizes, both reward / discount flavours): the per-step online
+    updates of (theta, w) agree to float accuracy after several episodes, and stay finite."""
+    rng = np.random.RandomState(77)
+    for trial in range(12):
+        d = int(rng.choice([15, 16]))
+        L, E, T = int(rng.randint(1, 40)), int(rng.randint(1, 4)), int(rng.randint(1, 16))
+        theta0 = rng.uniform(2.0, 20.0, size=L)
+        shifts = rng.uniform(0.0, 0.5, size=L)
+        scale = float(rng.choice([100.0, 1e4, 1e5]))
+        mat = rng.dirichlet(np.ones(d) * float(rng.choice([0.2, 1.0])), size=11)
+        w0 = rng.rand(L, O.num_features(d))
+        reward, discount = [("ac2", "step"), ("synthetic", "cumulative")][trial % 2]
+        res = {}
+        for dt in (torch.float32, torch.float64):
+            th = torch.as_tensor(theta0, dtype=torch.float64, device=dev).clone()
+            w = torch.as_tensor(w0, dtype=torch.float64, device=dev).clone()
+            eng.learners(th, w, T_(np.float32(mat), dev, dt), E, T,
+                         shift=torch.as_tensor(shifts, dtype=torch.float64, device=dev), alpha_scale=scale, episode0=1,
+                         gamma=0.97, lr_critic=0.1, lr_actor=0.01, reward=reward, discount=discount, seed=1000 + trial)
+            res[dt] = (N_(th), N_(w))
+        tag = "trial %d: d=%d L=%d E=%d T=%d scale=%g %s/%s" % (trial, d, L, E, T, scale, reward, discount)
+        assert np.isfinite(res[torch.float32][0]).all() and np.isfinite(res[torch.float32][1]).all(), tag
+        np.testing.assert_allclose(res[torch.float32][0], res[torch.float64][0], rtol=5e-6, err_msg=tag)
+        np.testing.assert_allclose(res[torch.float32][1], res[torch.float64][1], rtol=5e-5, atol=5e-6, err_msg=tag)
