@@ -181,3 +181,34 @@ def test_rnet_argument_errors(dev):
     assert r.numel() == 0
     g = engine.rnet_backward(T_(p, dev), T_(s[:0], dev), T_(a[:0], dev), torch.zeros(0, device=dev), 8, 4)
     assert float(g.abs().sum()) == 0.0
+
+
+def test_random_shapes_forward_backward_vs_oracle(dev):
+    """12 random (d, n_fc3, n_fc4, N, dropout) shapes -- every d up to 16, widths 1..8, ragged N down to a single
+    transition, sparse actions -- through the specialised (d = 15) and the generic instantiations of the kernels."""
+    from discrete_mean_field_game_b200 import engine
+    rng = np.random.RandomState(31)
+    for trial in range(12):
+        d = int(rng.choice([15, 15, 16, 3, 8, 11]))
+        n3, n4 = int(rng.randint(1, 9)), int(rng.randint(1, 9))
+        n = int(rng.choice([1, 15, 17, 100, 333]))
+        p = f32(R.xavier_init(d, n3, n4, rng) + 0.1 * rng.randn(R.param_count(d, n3, n4)))
+        s = f32(rng.dirichlet(np.ones(d) * 0.3, size=n))
+        a = f32(rng.dirichlet(np.ones(d) * float(rng.choice([0.05, 0.5])), size=(n, d)))
+        dropout = bool(trial % 2)
+        m3 = (rng.rand(n, n3) < 0.4) if dropout else None
+        m4 = (rng.rand(n, n4) < 0.4) if dropout else None
+        dr = f32(rng.randn(n))
+        r_ref, cache = R.forward(p, s, a, n3, n4, m3, m4, cache=True)
+        g_ref = R.backward(cache, dr)
+        kw = dict(mask3=T_(m3, dev, torch.uint8), mask4=T_(m4, dev, torch.uint8)) if dropout else {}
+        tag = "trial %d: d=%d n3=%d n4=%d N=%d dropout=%s" % (trial, d, n3, n4, n, dropout)
+        r_f = engine.rnet_forward(T_(p, dev), T_(s, dev), T_(a, dev), n3, n4, **kw).cpu().numpy()
+        g, r_b = engine.rnet_backward(T_(p, dev), T_(s, dev), T_(a, dev), T_(dr, dev), n3, n4, want_rewards=True, **kw)
+        np.testing.assert_allclose(r_f, r_ref, rtol=2e-5, atol=2e-6, err_msg=tag)
+        np.testing.assert_array_equal(r_b.cpu().numpy(), r_f, err_msg=tag)
+        g = g.cpu().numpy()
+        for name, shp, off in R.layout(d, n3, n4):
+            sl = slice(off, off + int(np.prod(shp)))
+            scale = np.abs(g_ref[sl]).max() + 1e-6
+            assert np.abs(g[sl] - g_ref[sl]).max() <= 2e-5 * scale + 1e-6, tag + " " + name
