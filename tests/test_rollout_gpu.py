@@ -537,6 +537,10 @@ def test_random_regimes_invariants_and_variant_agreement(dev):
         assert float((S.sum(-1) - S[0].sum(-1)).abs().max()) <= 2e-6, tag
         assert float((torch.einsum("tbi,tbij->tbj", S[:-1], P) - S[1:]).abs().max()) <= 3e-7, tag
         if d in (15, 16):
+            # the TRAIN specialisation (no per-step stream: one merged reduction per step) sums the same things
+            tr = eng.rollout(pi0, theta, shift, scale, T, w=w, seed=trial, outputs=(), want_acc=True)
+            sc = float(a["deltas"].double().abs().sum()) * max(1.0, float(a["grads"].double().abs().max()))
+            assert float((tr["acc"] - a["acc"]).abs().max()) <= 1e-9 * max(sc, 1e-30) + 1e-12, tag
             g = eng.rollout(pi0, theta, shift, scale, T, variant="generic", **kw)
             np.testing.assert_allclose(N_(a["states"]), N_(g["states"]), rtol=3e-5, atol=1e-8, err_msg=tag)
             np.testing.assert_allclose(N_(a["rewards"]), N_(g["rewards"]), rtol=1e-4, atol=1e-7, err_msg=tag)
