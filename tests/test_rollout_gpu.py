@@ -441,7 +441,7 @@ def test_v2_philox_draws_match_other_variants(dev, d):
     assert torch.equal(auto["actions"], a["actions"])
 
 
-@pytest.mark.parametrize("d,B,T", [(32, 37, 5), (64, 203, 3), (48, 16, 16)])
+@pytest.mark.parametrize("d,B,T", [(32, 37, 5), (64, 203, 3), (48, 16, 16), (80, 5, 17), (128, 3, 1), (32, 1, 1)])
 @pytest.mark.parametrize("discount", ["step", "cumulative"])
 def test_td_pass_on_fp64_tensor_cores_matches_numpy(dev, d, B, T, discount):
     """Wide states (d a multiple of 16, float streams): V = phi(pi).w and sum delta*phi run as DMMA GEMMs
