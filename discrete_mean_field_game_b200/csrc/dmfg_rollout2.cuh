@@ -36,7 +36,10 @@ namespace dmfg {
 #ifndef DMFG_V2_MINB
 #define DMFG_V2_MINB 2
 #endif
-constexpr int kV2Threads = 256;
+#ifndef DMFG_V2_THREADS
+#define DMFG_V2_THREADS 256
+#endif
+constexpr int kV2Threads = DMFG_V2_THREADS;
 constexpr int kV2Unroll = DMFG_V2_UNROLL;
 constexpr int kV2G = 16;
 constexpr int kV2Slots = 17;          // doubles per tile row (16 columns + 1 pad => conflict-free both ways)
