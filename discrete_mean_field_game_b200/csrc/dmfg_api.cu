@@ -72,14 +72,17 @@ inline TdDmmaPlan td_dmma_plan(int dtype, int d, int T, long long B) {
 }
 
 
-bool use_fast(const dmfg_rollout_args* a) {
-    if (a->variant == DMFG_VARIANT_GENERIC) return false;
-    return fast_d(a->d);
-}
-// the throughput kernel: float streams, d = 15 / 16, sampled or injected Gamma variates
+// the throughput kernel: float streams, d = 15 / 16 (16-lane groups) and d = 21 / 32 (32-lane groups; 21 is the
+// default of mfg_ac2.py:25), sampled or injected Gamma variates
+bool v2_d(int d) { return d == 15 || d == 16 || d == 21 || d == 32; }
 bool use_v2(const dmfg_rollout_args* a) {
     if (a->variant != DMFG_VARIANT_AUTO && a->variant != DMFG_VARIANT_V2) return false;
-    return a->dtype == DMFG_F32 && (a->d == 15 || a->d == 16) && a->noise_kind != DMFG_NOISE_ACTIONS;
+    return a->dtype == DMFG_F32 && v2_d(a->d) && a->noise_kind != DMFG_NOISE_ACTIONS;
+}
+// a fused kernel (TD in the rollout) exists for this call
+bool use_fast(const dmfg_rollout_args* a) {
+    if (a->variant == DMFG_VARIANT_GENERIC) return false;
+    return fast_d(a->d) || use_v2(a);
 }
 
 // workspace map of one dmfg_rollout call
@@ -126,7 +129,7 @@ int check_rollout(const dmfg_rollout_args* a) {
     if (a->variant < DMFG_VARIANT_AUTO || a->variant > DMFG_VARIANT_V2)
         return fail(DMFG_ERR_INVALID, "variant %d", a->variant);
     if (a->variant == DMFG_VARIANT_V2 && !use_v2(a))
-        return fail(DMFG_ERR_UNSUPPORTED, "the v2 kernel is built for float streams, d in {15,16}, sampled or injected noise");
+        return fail(DMFG_ERR_UNSUPPORTED, "the v2 kernel is built for float streams, d in {15,16,21,32}, sampled or injected noise");
     if (a->variant == DMFG_VARIANT_FAST && !fast_d(a->d))
         return fail(DMFG_ERR_UNSUPPORTED, "fast variant is built for d in {4,15,16}, not d=%d", a->d);
     if (a->B > 0 && !a->pi0) return fail(DMFG_ERR_INVALID, "pi0 is NULL");
@@ -186,7 +189,7 @@ int launch_v2(RolloutParams<float> p, bool td, int* grid_out, cudaStream_t st) {
     DMFG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kV2Threads, smem));
     if (int rc = sm_count(&sms)) return rc;
     if (occ < 1) return fail(DMFG_ERR_CUDA, "rollout_v2_kernel<%d> does not fit an SM", D);
-    const long long gpb = kV2Threads / kV2G;
+    const long long gpb = V2Smem<D>::GPB;
     const long long ntiles = (p.B + gpb - 1) / gpb;
     long long grid = (long long)sms * occ;
     if (grid > kMaxPartialCtas) grid = kMaxPartialCtas;
@@ -214,7 +217,13 @@ int dispatch_v2_d(const RolloutParams<float>& p, int noise_kind, bool td, int* g
     return launch_v2<D, DMFG_NOISE_INJECTED, true, false, true>(p, td, grid, st);
 }
 int dispatch_v2(const RolloutParams<float>& p, int noise_kind, bool td, int* grid, cudaStream_t st) {
-    return p.d == 15 ? dispatch_v2_d<15>(p, noise_kind, td, grid, st) : dispatch_v2_d<16>(p, noise_kind, td, grid, st);
+    switch (p.d) {
+        case 15: return dispatch_v2_d<15>(p, noise_kind, td, grid, st);
+        case 16: return dispatch_v2_d<16>(p, noise_kind, td, grid, st);
+        case 21: return dispatch_v2_d<21>(p, noise_kind, td, grid, st);
+        case 32: return dispatch_v2_d<32>(p, noise_kind, td, grid, st);
+    }
+    return fail(DMFG_ERR_UNSUPPORTED, "no v2 kernel for d=%d", p.d);
 }
 
 template <typename R, int NOISE>

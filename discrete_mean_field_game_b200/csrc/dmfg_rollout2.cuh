@@ -42,27 +42,35 @@ namespace dmfg {
 constexpr int kV2Threads = DMFG_V2_THREADS;
 constexpr int kV2Unroll = DMFG_V2_UNROLL;
 constexpr int kV2G = 16;
-constexpr int kV2Slots = 17;          // doubles per tile row (16 columns + 1 pad => conflict-free both ways)
-constexpr int kV2StageRow = 20;       // doubles per staged sample (16 + 4 pad => conflict-free fragment loads)
+// lanes per population: 16 for d <= 16 (two populations per warp), 32 for d in (16, 32] (one per warp)
+constexpr int v2_group(int d) { return d <= 16 ? 16 : 32; }
 
 template <int D>
 struct V2Smem {
-    static constexpr int GPB = kV2Threads / kV2G;
+    static constexpr int G = v2_group(D);
+    static constexpr int Slots = G + 1;       // doubles per tile row (G columns + 1 pad => conflict-free both ways)
+    static constexpr int StageRow = G + 4;    // doubles per staged sample (G + 4 pad => conflict-free fragment loads)
+    static constexpr int PW = 32 / G;         // populations per warp
+    static constexpr int SPF = 4 / PW;        // steps per DMMA flush (4 staged samples per warp)
+    static constexpr int NB = (D + 7) / 8;    // 8-wide blocks of the Gram matrix
+    static constexpr int NBLK = NB * (NB + 1) / 2;
+    static constexpr int GPB = kV2Threads / G;
     static constexpr int NW = kV2Threads / 32;
     static constexpr int NSLOT = D + 2;
     // offsets in doubles
-    static constexpr int tile = 0;                                  // [GPB][16][17] y_ij, double
-    static constexpr int pid = tile + GPB * kV2G * kV2Slots;        // [2][GPB][16] state, double
-    static constexpr int qv = pid + 2 * GPB * kV2G;                 // [GPB][16] q_i = pi_i / s_i
-    static constexpr int wl = qv + GPB * kV2G;                      // [NSLOT][16] critic slots
-    static constexpr int pif = wl + NSLOT * kV2G;                   // [2][GPB][16] state, float (GPB*16 doubles)
-    static constexpr int stage = pif + GPB * kV2G;                  // [NW][2][4][20] staged samples (A, B)
-    static constexpr int total = stage + NW * 2 * 4 * kV2StageRow;
-    // the end-of-kernel reduction reuses the tile: [NW][16][17] Gram tiles, [GPB][16] linear, [GPB] bias
+    static constexpr int tile = 0;                                  // [GPB][G][G+1] y_ij, double
+    static constexpr int pid = tile + GPB * G * Slots;              // [2][GPB][G] state, double
+    static constexpr int qv = pid + 2 * GPB * G;                    // [GPB][G] q_i = pi_i / s_i
+    static constexpr int wl = qv + GPB * G;                         // [NSLOT][G] critic slots
+    static constexpr int pif = wl + NSLOT * G;                      // [2][GPB][G] state, float (GPB*G doubles)
+    static constexpr int stage = pif + GPB * G;                     // [NW][2][4][G+4] staged samples (A, B)
+    static constexpr int total = stage + NW * 2 * 4 * StageRow;
+    // the end-of-kernel reduction reuses the tile ([NW][G][G+1] Gram tiles), the state ([GPB][G] linear) and q ([GPB] bias)
     static constexpr int gram = tile;
-    static constexpr int lin = gram + NW * kV2G * kV2Slots;
-    static constexpr int bias = lin + GPB * kV2G;
-    static_assert(bias + GPB <= pid, "reduction scratch must fit the tile");
+    static constexpr int lin = pid;
+    static constexpr int bias = qv;
+    static_assert(NW * G * Slots <= GPB * G * Slots, "reduction scratch must fit the tile");
+    static_assert(8 * NB <= StageRow && D <= G, "staged samples cover the Gram blocks");
 };
 
 // ---- explicit shared-window accesses (32-bit addresses from __cvta_generic_to_shared) -----------------
@@ -186,7 +194,7 @@ template <int D, int NOISE, bool REC, bool TRAIN, bool GRAD>
 __global__ void __launch_bounds__(kV2Threads, DMFG_V2_MINB)
 rollout_v2_kernel(const RolloutParams<float> p) {
     using S = V2Smem<D>;
-    constexpr int G = kV2G, NT = kV2Threads, GPB = S::GPB;
+    constexpr int G = S::G, NT = kV2Threads, GPB = S::GPB, kV2Slots = S::Slots, kV2StageRow = S::StageRow;
     constexpr int F = num_features_c(D);
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, r = tid & (G - 1), grp = tid / G, lane = tid & 31, warp = tid >> 5;
@@ -213,9 +221,11 @@ rollout_v2_kernel(const RolloutParams<float> p) {
     const bool has_reward = p.reward_kind != DMFG_REWARD_NONE;
     const double rew_scale = ac2 ? 1.0 : -0.5;
     double sum_dg = 0.0, sum_r = 0.0;            // per-LANE partial sums (reduced once, at the end)
-    double c00a = 0.0, c00b = 0.0, c01a = 0.0, c01b = 0.0, c11a = 0.0, c11b = 0.0;   // Gram tiles (warp-wide)
+    double gacc[S::NBLK][2];                     // Gram blocks (I <= J) of the warp, C fragments of m8n8k4
+#pragma unroll
+    for (int k = 0; k < S::NBLK; ++k) gacc[k][0] = gacc[k][1] = 0.0;
     double lin_acc = 0.0, bias_acc = 0.0;
-    const int half = (tid >> 4) & 1, gid = lane >> 2, tig = lane & 3;
+    const int sub = (tid / G) & (S::PW - 1), gid = lane >> 2, tig = lane & 3;   // sub: population of the warp
     const uint32_t a_frag = a_stage + 8u * (tig * kV2StageRow + gid);             // A[gid][tig] of the low tile
     const long long ntiles = (p.B + GPB - 1) / GPB;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -230,7 +240,7 @@ rollout_v2_kernel(const RolloutParams<float> p) {
         sts_f64(a_pid + 8 * r, pi_self);
         sts_f32(a_pif + 4 * r, (float)pi_self);
         warp_fence();
-        double vc_lane = td ? critic_partial_v2<D>(a_wl_r, a_pid, pi_self) : 0.0;
+        double vc_lane = td ? critic_partial_v2<D, G>(a_wl_r, a_pid, pi_self) : 0.0;
         double v_cur = (td && !TRAIN) ? group_sum<G>(vc_lane) : 0.0;
         double disc = 1.0;
         if (!TRAIN && p.states != nullptr && wr) p.states[b * D + r] = (float)pi_self;
@@ -299,7 +309,7 @@ rollout_v2_kernel(const RolloutParams<float> p) {
                 if (p.rewards_in != nullptr) rew = (double)p.rewards_in[tb];
             }
             if (td) {
-                const double vn_lane = critic_partial_v2<D>(a_wl_r, a_pid + nxt * kBufD, next_self);
+                const double vn_lane = critic_partial_v2<D, G>(a_wl_r, a_pid + nxt * kBufD, next_self);
                 const double gfac = p.discount_kind == DMFG_DISCOUNT_STEP ? p.gamma : disc;
                 double delta;
                 if (TRAIN) {
@@ -317,19 +327,31 @@ rollout_v2_kernel(const RolloutParams<float> p) {
                     sum_dg = fma(dl, glane, sum_dg);
                     lin_acc += dp;
                     bias_acc += dl;
-                    // stage sample k = 2 (t & 1) + half:  A[k][r] = delta pi_r,  B[k][r] = pi_r
-                    const uint32_t a_smp = a_stage + 8u * ((2 * (t & 1) + half) * kV2StageRow + r);
+                    // stage sample k = PW (t mod SPF) + sub:  A[k][r] = delta pi_r,  B[k][r] = pi_r
+                    const int ts = t & (S::SPF - 1);
+                    const uint32_t a_smp = a_stage + 8u * ((S::PW * ts + sub) * kV2StageRow + r);
                     sts_f64(a_smp, dp);
                     sts_f64(a_smp + kStageB, pi_self);
                     const bool last = t == p.T - 1;
-                    if ((t & 1) || last) {
-                        if (!(t & 1)) sts_f64(a_smp + 8u * 2 * kV2StageRow, 0.0);     // odd T: samples 2, 3 are empty
+                    if (ts == S::SPF - 1 || last) {
+#pragma unroll
+                        for (int e = 1; e < S::SPF; ++e)                           // T ends inside a flush group:
+                            if (ts + e < S::SPF) sts_f64(a_smp + 8u * S::PW * kV2StageRow * e, 0.0);   // the rest is empty
                         warp_fence();
-                        const double a_lo = lds_f64(a_frag), a_hi = lds_f64(a_frag + 64);
-                        const double b_lo = lds_f64(a_frag + kStageB), b_hi = lds_f64(a_frag + kStageB + 64);
-                        dmma884(c00a, c00b, a_lo, b_lo);       // rows 0-7  x cols 0-7
-                        dmma884(c01a, c01b, a_lo, b_hi);       // rows 0-7  x cols 8-15
-                        dmma884(c11a, c11b, a_hi, b_hi);       // rows 8-15 x cols 8-15   (rows 8-15 x cols 0-7 is below the diagonal)
+                        double af[S::NB], bf[S::NB];
+#pragma unroll
+                        for (int m = 0; m < S::NB; ++m) {
+                            af[m] = lds_f64(a_frag + 64 * m);
+                            bf[m] = lds_f64(a_frag + kStageB + 64 * m);
+                        }
+                        // blocks on or above the diagonal (rows 8I.. x cols 8J.., I <= J); below it is not a feature
+#pragma unroll
+                        for (int I = 0; I < S::NB; ++I)
+#pragma unroll
+                            for (int J = I; J < S::NB; ++J) {
+                                const int k = I * S::NB - (I * (I - 1)) / 2 + (J - I);
+                                dmma884(gacc[k][0], gacc[k][1], af[I], bf[J]);
+                            }
                         warp_fence();
                     }
                 }
@@ -363,12 +385,14 @@ rollout_v2_kernel(const RolloutParams<float> p) {
     __syncthreads();                                   // everyone is done with the tile: reuse it
     {
         double* gw = smem + S::gram + warp * (G * kV2Slots);
-        gw[gid * kV2Slots + 2 * tig] = c00a;
-        gw[gid * kV2Slots + 2 * tig + 1] = c00b;
-        gw[gid * kV2Slots + 8 + 2 * tig] = c01a;
-        gw[gid * kV2Slots + 8 + 2 * tig + 1] = c01b;
-        gw[(8 + gid) * kV2Slots + 8 + 2 * tig] = c11a;
-        gw[(8 + gid) * kV2Slots + 8 + 2 * tig + 1] = c11b;
+#pragma unroll
+        for (int I = 0; I < S::NB; ++I)
+#pragma unroll
+            for (int J = I; J < S::NB; ++J) {
+                const int k = I * S::NB - (I * (I - 1)) / 2 + (J - I);
+                gw[(8 * I + gid) * kV2Slots + 8 * J + 2 * tig] = gacc[k][0];
+                gw[(8 * I + gid) * kV2Slots + 8 * J + 2 * tig + 1] = gacc[k][1];
+            }
         smem[S::lin + grp * G + r] = lin_acc;
         if (r == 0) smem[S::bias + grp] = bias_acc;
     }

@@ -31,11 +31,14 @@ for d, dt in ((15, torch.float32), (16, torch.float32), (4, torch.float32), (15,
     engine.learners(th, ww, mat, 3, 5, shift=0.16, alpha_scale=12000.0, lr_critic=0.1, lr_actor=0.1, seed=1)
 pi0 = torch.as_tensor(rng.dirichlet(np.ones(64), size=5), dtype=torch.float32, device=dev)
 engine.rollout(pi0, 8.0, 0.1, 1e4, 3, seed=2, outputs=("states", "actions"))                                     # wide kernel, d = 64
-for dd in (21, 47, 130, 32, 64):                                                                                  # 32 / 64: TD pass on the DMMA kernels                                                                                          # odd d, 1 / 1 / 4 pairs per lane
+for dd, var in ((21, "auto"), (32, "auto"), (21, "generic"), (47, "auto"), (130, "auto"), (32, "generic"), (64, "auto")):
+    # auto at d = 21 / 32: the 32-lane v2 kernel; generic there and the other d: the wide kernel (1 / 1 / 4 pairs per
+    # lane), with the TD pass on the DMMA kernels at d = 32 / 64
     pw = torch.as_tensor(rng.dirichlet(np.ones(dd), size=6), dtype=torch.float32, device=dev)
     ww = torch.as_tensor(rng.rand(dd * (dd + 1) // 2 + dd + 1), dtype=torch.float64, device=dev)
-    engine.rollout(pw, 8.0, 0.1, 1e4, 2, w=ww, seed=2, want_acc=True,
+    engine.rollout(pw, 8.0, 0.1, 1e4, 3, w=ww, seed=2, want_acc=True, variant=var,
                    outputs=("states", "actions", "alpha", "alpha_deriv", "rewards", "deltas", "grads", "pi_final"))
+    engine.rollout(pw, 8.0, 0.1, 1e4, 3, w=ww, seed=2, want_acc=True, variant=var, outputs=())
 acts = engine.rollout(pi0[:, :15].contiguous(), 8.0, 0.1, 1e4, 3, seed=2, reward="none", outputs=("actions",))["actions"]
 engine.synthetic_check(acts)
 g = rng.standard_gamma(1.0, size=(8, 15))
