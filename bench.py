@@ -388,8 +388,9 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         pool = make_pool(cores)
-        v0, _ = cpu_throughput(40, cores, pool)                # calibration (also warms the workers)
-        episodes = int(os.environ.get("DMFG_BENCH_CPU_EPISODES", max(100, int(12.0 * v0 / (cores * T)))))   # ~12 s
+        cpu_throughput(5, cores, pool)                         # workers import the oracle
+        v0, _ = cpu_throughput(150, cores, pool)               # calibration
+        episodes = int(os.environ.get("DMFG_BENCH_CPU_EPISODES", max(100, int(15.0 * v0 / (cores * T)))))   # 10-15 s
         v, dt = cpu_throughput(episodes, cores, pool)
         pool.close()
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,

@@ -219,6 +219,37 @@ def test_train_batch_per_episode_matches_oracle(start_states):
     np.testing.assert_allclose(res["mean_reward"][0], r.sum() / B, rtol=1e-9)
 
 
+def test_train_batch_default_d21_float32_matches_oracle(start_states):
+    """The reference's default constructor (d = 21, mfg_ac2.py:25) on float streams: the batched train step runs the
+    32-lane v2 kernel (TD error and critic Gram in the kernel).  Its update equals the oracle's batch-mean update
+    evaluated in float64 on the recorded episode (same Philox draws); tolerances are relative to the sum of the
+    magnitudes of the summed terms (float32 streams, 441 terms of mixed sign per gradient)."""
+    rng = np.random.RandomState(3)
+    B, T = 203, 7                                                  # ragged tile, T ends inside a Gram flush group
+    ac = mfg_ac2.actor_critic(mat_pi0=start_states, dtype="float32", seed=5)
+    d = ac.d
+    assert d == 21
+    pi0 = rng.dirichlet(np.ones(d), size=B)
+    w0 = ac.w.ravel().astype(np.float64).copy()
+    rec = ac.rollout_batch(pi0, T=T, record=True, seed=5)
+    res = ac.train_batch(pi0, num_episodes=1, T=T, lr_critic=0.1, lr_actor=0.01, update="per_episode", seed=5)
+    S, P = np.float64(rec["states"]), np.float64(rec["actions"])
+    alpha, deriv = O.policy_alpha(S[:-1], 8.86349, 0.16)
+    g = O.log_policy_gradient(alpha, deriv, P)
+    r = O.reward_ac2(P, S[:-1])
+    phi = O.features(S)
+    v = phi @ w0
+    delta = r + v[1:] - v[:-1]
+    la, lc = O.actor_lr(0, 0.01, False) / B, O.critic_lr(0, 0.1, False) / B
+    th = 8.86349 + la * np.sum(delta * g)
+    w = w0 + lc * np.einsum("tb,tbf->f", delta, phi[:-1])
+    assert abs(res["theta"] - th) <= 1e-4 * la * np.sum(np.abs(delta * g)) + 1e-12, (res["theta"], th)
+    wscale = lc * np.einsum("tb,tbf->f", np.abs(delta), np.abs(phi[:-1]))
+    err = np.abs(ac.w.ravel().astype(np.float64) - w)
+    assert np.all(err <= 1e-5 * wscale + 1e-12), np.max(err / (wscale + 1e-300))
+    np.testing.assert_allclose(res["mean_reward"][0], r.sum() / B, rtol=1e-5)
+
+
 def test_mfg_synthetic_dropin(start_states):
     """mfg_synthetic.actor_critic: synthetic reward (mfg_synthetic.py:249-265) and the (shift, theta0) sweep of
     its __main__ (:902-925) as independent learners -- each learner equals a separate train() run."""
