@@ -537,7 +537,9 @@ def test_random_regimes_invariants_and_variant_agreement(dev):
         conc = float(rng.choice([0.05, 0.3, 1.0]))                       # sparse .. flat start states
         pi0 = T_(rng.dirichlet(np.ones(d) * conc, size=B), dev, torch.float32)
         w = T_(rng.rand(O.num_features(d)), dev, torch.float64)
-        kw = dict(w=w, seed=trial, outputs=("states", "actions", "rewards", "grads", "deltas"), want_acc=True)
+        reward = ("ac2", "synthetic")[trial % 2]                        # mfg_ac2.py:257-287 / mfg_synthetic.py:249-265
+        kw = dict(w=w, seed=trial, reward=reward, outputs=("states", "actions", "rewards", "grads", "deltas"),
+                  want_acc=True)
         a = eng.rollout(pi0, theta, shift, scale, T, **kw)
         tag = "trial %d: d=%d B=%d T=%d theta=%.2f shift=%.2f scale=%g" % (trial, d, B, T, theta, shift, scale)
         for k, v in a.items():
@@ -549,7 +551,7 @@ def test_random_regimes_invariants_and_variant_agreement(dev):
         assert float((torch.einsum("tbi,tbij->tbj", S[:-1], P) - S[1:]).abs().max()) <= 3e-7, tag
         if d in (15, 16, 21, 32):
             # the TRAIN specialisation (no per-step stream: one merged reduction per step) sums the same things
-            tr = eng.rollout(pi0, theta, shift, scale, T, w=w, seed=trial, outputs=(), want_acc=True)
+            tr = eng.rollout(pi0, theta, shift, scale, T, w=w, seed=trial, reward=reward, outputs=(), want_acc=True)
             sc = float(a["deltas"].double().abs().sum()) * max(1.0, float(a["grads"].double().abs().max()))
             assert float((tr["acc"] - a["acc"]).abs().max()) <= 1e-9 * max(sc, 1e-30) + 1e-12, tag
             g = eng.rollout(pi0, theta, shift, scale, T, variant="generic", **kw)
