@@ -97,6 +97,14 @@ class IrlLossArgs(C.Structure):
     ]
 
 
+class IrlGenArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("T", C.c_int32), ("M", C.c_int64),
+        ("gen_t_stride", C.c_int64), ("gen_j_stride", C.c_int64), ("n_demo", C.c_int64),
+        ("num_demo_traj", C.c_double), ("r_demo", C.c_void_p), ("loss_out", C.c_void_p),
+    ]
+
+
 # every symbol include/dmfg.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("dmfg_version", C.c_int, []),
@@ -124,6 +132,7 @@ SYMBOLS = [
     ("dmfg_rnet_backward", C.c_int, [C.POINTER(RnetArgs), C.c_void_p]),
     ("dmfg_irl_loss_workspace_bytes", C.c_uint64, [C.c_int64]),
     ("dmfg_irl_loss_grad", C.c_int, [C.POINTER(IrlLossArgs), C.c_void_p]),
+    ("dmfg_rnet_backward_gen", C.c_int, [C.POINTER(RnetArgs), C.POINTER(IrlGenArgs), C.c_void_p]),
     ("dmfg_adam_tf", C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64,
                                C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, C.c_void_p, C.c_void_p]),

@@ -78,6 +78,7 @@ class AC_IRL(_actor_critic):
         self.n_fc3 = n_fc3
         self.n_fc4 = n_fc4
         self.use_z = bool(use_z)
+        self.one_pass_reward_update = True    # generated half of update_reward_batch in one launch (z_j = 1 only)
         self.seed = int(np.random.randint(2 ** 31 - 1)) if seed is None else int(seed)
         self.net_seed = net_seed
         self._draws = 0
@@ -466,16 +467,26 @@ class AC_IRL(_actor_critic):
             self._d_demo_const = {(n_demo, float(num_demo_traj)): d_const}
         grad, r_demo = engine.rnet_backward(p.flat, demo_states, demo_actions, d_const, p.n_fc3, p.n_fc4,
                                             keep_prob=networks.KEEP_PROB, want_rewards=True, **kd)
-        r_gen = engine.rnet_forward(p.flat, gen_states, gen_actions, p.n_fc3, p.n_fc4, keep_prob=networks.KEEP_PROB, **kg)
-        log_z = None
-        if self.use_z:
-            thetas = torch.as_tensor(np.asarray(self.list_policies, dtype=np.float64), device=self.device)
-            lq = engine.dirichlet_logq(gen_states, gen_actions, thetas, self.shift)
-            log_z = engine.irl_log_z(lq, T_STEPS, self.num_start_samples, layout=layout)
         _, world = parallel.world_info(group)
-        res = engine.irl_loss_grad(r_demo, r_gen, T_STEPS, num_demo_traj, layout=layout, log_z=log_z)
-        engine.rnet_backward(p.flat, gen_states, gen_actions, res["d_gen"], p.n_fc3, p.n_fc4, grad=grad,
-                             accumulate=True, keep_prob=networks.KEEP_PROB, **kg)
+        if not self.use_z and self.one_pass_reward_update:
+            # z_j = 1 (upstream's ac_irl.py:406): the generated half runs in ONE reward-net launch -- trajectory by
+            # trajectory, weight exp(R_j), 1/sum_j exp(R_j) applied to the reduced gradient -- instead of
+            # forward -> loss / dL/dr -> backward.  3 -> 2 reward-net launches per update.
+            _, loss4 = engine.rnet_backward_gen(p.flat, gen_states, gen_actions, p.n_fc3, p.n_fc4, T_STEPS, r_demo,
+                                                num_demo_traj, layout=layout, grad=grad, accumulate=True,
+                                                keep_prob=networks.KEEP_PROB, **kg)
+            res = {"loss": loss4}
+        else:
+            r_gen = engine.rnet_forward(p.flat, gen_states, gen_actions, p.n_fc3, p.n_fc4, keep_prob=networks.KEEP_PROB,
+                                        **kg)
+            log_z = None
+            if self.use_z:
+                thetas = torch.as_tensor(np.asarray(self.list_policies, dtype=np.float64), device=self.device)
+                lq = engine.dirichlet_logq(gen_states, gen_actions, thetas, self.shift)
+                log_z = engine.irl_log_z(lq, T_STEPS, self.num_start_samples, layout=layout)
+            res = engine.irl_loss_grad(r_demo, r_gen, T_STEPS, num_demo_traj, layout=layout, log_z=log_z)
+            engine.rnet_backward(p.flat, gen_states, gen_actions, res["d_gen"], p.n_fc3, p.n_fc4, grad=grad,
+                                 accumulate=True, keep_prob=networks.KEEP_PROB, **kg)
         parallel.allreduce_sum_(grad, group)
         p.step += 1
         reg = engine.adam_tf(p.flat, p.m, p.v, grad, p.step, self.lr_reward, grad_scale=1.0 / world,

@@ -63,6 +63,10 @@ struct RnetParams {
     float* rewards;           // [N] or null
     const float* drewards;    // [N] (backward)
     float* partials;          // [grid][total] (backward)
+    // trajectory mode (TRAJ): tile = generated trajectory j, group = step t; transition (j, t) at t*t_stride + j*j_stride
+    long long traj_M, t_stride, j_stride;
+    int traj_T;
+    double* zpart;            // [grid] per-CTA sum_j exp(R_j)
 };
 
 // shared-memory map (in floats), identical on host and device
@@ -149,8 +153,17 @@ __device__ __forceinline__ void dropout_masks_philox(unsigned long long seed, un
 // computed (-10 % on the reward update).  Tried and rejected: 20-word row strides with LDS.128 row reads (4x fewer
 // load instructions, but 2-way conflicts on the row-strided stores and spills at 255 registers: +2 %).
 // N3S / N4S: the same for the two fully connected widths (0: from the arguments; 8 / 4 are the reference defaults).
-template <int G, int NP, bool BWD, int DS, int N3S, int N4S>
+// TRAJ (backward only): the generated half of the IRL reward update (ac_irl.py:390-418) in ONE pass.  A tile is one
+// trajectory (its <= 16 transitions on the 16 groups of the CTA), so after the forward part the CTA knows
+// R_j = sum_t r[j,t] and backpropagates with the UNNORMALISED weight u_j = exp(R_j) -- dL/dr[j,t] = u_j / Z with
+// Z = sum_j u_j is linear in the weight, so 1/Z is applied once to the reduced gradient (rnet_reduce_partials_kernel)
+// and the separate forward launch, the three loss kernels and the dL/dr stream disappear.  |r| < 1 (tanh) bounds
+// u_j by e^16: no max shift is needed.
+template <int G, int NP, bool BWD, int DS, int N3S, int N4S, bool TRAJ = false>
 __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const RnetParams p) {
+    static_assert(!TRAJ || BWD, "trajectory mode is a backward mode");
+    __shared__ float rtraj[kRnetThreads / G];
+    __shared__ double zsum;
     using SM = RnetSmem<G, NP, BWD>;
     constexpr int GPB = SM::GPB, SA = SM::SA, SC = SM::SC, RA = SM::RA, RC = SM::RC;
     extern __shared__ __align__(16) float smem[];
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 
     // ---- stage the parameters: one TMA bulk copy (+ <= 3 tail floats) ----------------------------
     const uint32_t bulk_floats = ((uintptr_t)p.params & 15) == 0 ? (uint32_t)(L.total / 4 * 4) : 0u;
-    if (tid == 0) mbar_init(&mbar, 1);
+    if (tid == 0) { mbar_init(&mbar, 1); zsum = 0.0; }
     __syncthreads();
     if (tid == 0 && bulk_floats) tma_bulk_load(wf, p.params, bulk_floats * 4u, &mbar);
     for (int i = bulk_floats + tid; i < L.total; i += kRnetThreads) wf[i] = p.params[i];
@@ -202,11 +215,15 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 #pragma unroll
         for (int i = 0; i < kK2 * kK2 * 2 + 2; ++i) gk2[i] = 0.f;
     }
-    const long long ntiles = (p.N + GPB - 1) / GPB;
+    const long long ntiles = TRAJ ? p.traj_M : (p.N + GPB - 1) / GPB;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         long long n = tile * GPB + grp;
-        const bool live = n < p.N;           // dead groups shadow the last transition (warp-wide syncs stay
+        bool live = n < p.N;                 // dead groups shadow the last transition (warp-wide syncs stay
         if (!live) n = p.N - 1;              // convergent); their writes are masked and their dr is 0
+        if (TRAJ) {
+            live = grp < p.traj_T;           // (dead groups shadow step 0 of the trajectory)
+            n = (live ? grp : 0) * p.t_stride + tile * p.j_stride;
+        }
         float dz3[NP];
 #pragma unroll
         for (int j = 0; j < NP; ++j) dz3[j] = 0.f;
@@ -350,7 +367,19 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
             if (BWD) {
                 float* Dt = Ct + RC * SC;                    // dz2 tile, 2 channels
                 float* gs = smem + S.gsmall + grp * SM::NSMALL;
-                const float dz5 = live ? p.drewards[n] * (1.f - r * r) : 0.f;
+                float dr;
+                if (TRAJ) {
+                    if (h == 0) rtraj[grp] = live ? r : 0.f;
+                    __syncthreads();         // (the two barriers of the fc3 gradient below order the next tile's writes)
+                    float R = 0.f;
+#pragma unroll
+                    for (int t = 0; t < GPB; ++t) R += rtraj[t];
+                    dr = expf(R);
+                    if (tid == 0) zsum += (double)dr;
+                } else {
+                    dr = p.drewards[n];
+                }
+                const float dz5 = live ? dr * (1.f - r * r) : 0.f;
                 float dz4[NP];
 #pragma unroll
                 for (int m = 0; m < NP; ++m)
@@ -509,6 +538,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
         }
     }
     if (!BWD) return;
+    if (TRAJ && tid == 0) p.zpart[blockIdx.x] = zsum;
     // ---- per-CTA partial gradient, fixed summation order ---------------------------------------------
     float* out = p.partials + (long long)blockIdx.x * L.total;
     {
@@ -573,25 +603,77 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     }
 }
 
-// grad[i] = (accumulate ? grad[i] : 0) + sum over CTAs of partials[cta][i]
-__global__ void rnet_reduce_partials_kernel(const float* __restrict__ partials, int ncta, int n, int accumulate,
-                                            float* __restrict__ grad) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    // four independent chains (fixed assignment c mod 4, fixed combination order): the loads pipeline instead of
-    // waiting on one serial add chain; still deterministic
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int c = 0;
-#pragma unroll 2
-    for (; c + 3 < ncta; c += 4) {
-        s0 += partials[(long long)c * n + i];
-        s1 += partials[(long long)(c + 1) * n + i];
-        s2 += partials[(long long)(c + 2) * n + i];
-        s3 += partials[(long long)(c + 3) * n + i];
+// grad[i] = (accumulate ? grad[i] : 0) + scale * sum over CTAs of partials[cta][i]
+// Block = 32 parameters x 8 slices of the CTA range: slice y sums CTAs y, y+8, ... (two independent chains), the 8
+// slice sums are combined in slice order -- fixed assignment and order, so still deterministic, but 8x the loads in
+// flight of the one-thread-per-parameter walk (14 us -> a few us for 3755 parameters x 148 CTAs).
+// (scale: optional device scalar multiplying the sum -- 1/Z of the trajectory mode)
+constexpr int kReduceSlices = 8;
+__global__ void __launch_bounds__(32 * kReduceSlices)
+rnet_reduce_partials_kernel(const float* __restrict__ partials, int ncta, int n, int accumulate,
+                            float* __restrict__ grad, const float* __restrict__ scale = nullptr) {
+    __shared__ float sh[kReduceSlices][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + x;
+    float s0 = 0.f, s1 = 0.f;
+    if (i < n) {
+        int c = y;
+        for (; c + kReduceSlices < ncta; c += 2 * kReduceSlices) {
+            s0 += partials[(long long)c * n + i];
+            s1 += partials[(long long)(c + kReduceSlices) * n + i];
+        }
+        if (c < ncta) s0 += partials[(long long)c * n + i];
     }
-    for (; c < ncta; ++c) s0 += partials[(long long)c * n + i];
-    const float s = (s0 + s1) + (s2 + s3);
-    grad[i] = accumulate ? grad[i] + s : s;
+    sh[y][x] = s0 + s1;
+    __syncthreads();
+    if (y == 0 && i < n) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < kReduceSlices; ++k) s += sh[k][x];
+        if (scale != nullptr) s *= *scale;
+        grad[i] = accumulate ? grad[i] + s : s;
+    }
+}
+
+// Loss terms of the trajectory mode (ac_irl.py:390-406 with z_j = 1): Z = sum of the per-CTA sums in CTA order,
+// first = -(1/num_demo_traj) sum r_demo, second = ln(Z / M); out[0..3] = {loss, first, second, ln Z}; *inv_z = 1/Z.
+__global__ void __launch_bounds__(1024) irl_gen_finalize_kernel(const double* __restrict__ zpart, int ncta,
+                                                               const float* __restrict__ r_demo, long long n_demo,
+                                                               double num_demo_traj, long long M,
+                                                               double* __restrict__ out, float* __restrict__ inv_z) {
+    __shared__ double sh[32], shz[32];
+    // four independent chains per thread (fixed assignment), then a fixed-order block sum
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+    long long i = threadIdx.x;
+    const long long st = blockDim.x;
+    for (; i + 3 * st < n_demo; i += 4 * st) {
+        d0 += (double)r_demo[i]; d1 += (double)r_demo[i + st];
+        d2 += (double)r_demo[i + 2 * st]; d3 += (double)r_demo[i + 3 * st];
+    }
+    for (; i < n_demo; i += st) d0 += (double)r_demo[i];
+    double sd = (d0 + d1) + (d2 + d3);
+    double z = 0.0;
+    for (int c = threadIdx.x; c < ncta; c += blockDim.x) z += zpart[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sd += __shfl_xor_sync(0xffffffffu, sd, o);
+        z += __shfl_xor_sync(0xffffffffu, z, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = sd; shz[threadIdx.x >> 5] = z; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sd = 0.0;
+        double Z = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { sd += sh[k]; Z += shz[k]; }
+        const double first = -sd / num_demo_traj;
+        const double lse = log(Z);
+        const double second = lse - log((double)M);
+        out[0] = first + second;
+        out[1] = first;
+        out[2] = second;
+        out[3] = lse;
+        *inv_z = (float)(1.0 / Z);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

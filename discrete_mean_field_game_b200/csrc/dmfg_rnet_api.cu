@@ -48,12 +48,13 @@ RnetParams make_params(const dmfg_rnet_args* a) {
     p.dropout = a->dropout; p.keep_prob = a->keep_prob; p.mask3 = a->mask3; p.mask4 = a->mask4;
     p.seed = a->seed; p.sample_offset = a->sample_offset;
     p.rewards = a->rewards; p.drewards = a->drewards; p.partials = nullptr;
+    p.traj_M = 0; p.t_stride = 0; p.j_stride = 0; p.traj_T = 0; p.zpart = nullptr;
     return p;
 }
 
-template <bool BWD, int DS, int N3S, int N4S>
-int rnet_grid(const dmfg_rnet_args* a, int* grid, size_t* smem_bytes) {
-    auto kern = rnet_kernel<kG, kNP, BWD, DS, N3S, N4S>;
+template <bool BWD, int DS, int N3S, int N4S, bool TRAJ = false>
+int rnet_grid(const dmfg_rnet_args* a, int* grid, size_t* smem_bytes, long long traj_M = 0) {
+    auto kern = rnet_kernel<kG, kNP, BWD, DS, N3S, N4S, TRAJ>;
     const RnetLayout L = rnet_layout(a->d, a->n_fc3, a->n_fc4);
     const RnetSmem<kG, kNP, BWD> S(a->d, L.total);
     const size_t smem = (size_t)S.total * sizeof(float);
@@ -64,7 +65,7 @@ int rnet_grid(const dmfg_rnet_args* a, int* grid, size_t* smem_bytes) {
     if (occ < 1) return fail(DMFG_ERR_CUDA, "rnet_kernel needs %zu bytes of shared memory: does not fit an SM", smem);
     long long g = (long long)sms * occ;
     if (g > kMaxRnetCtas) g = kMaxRnetCtas;
-    const long long ntiles = (a->N + kRnetThreads / kG - 1) / (kRnetThreads / kG);
+    const long long ntiles = TRAJ ? traj_M : (a->N + kRnetThreads / kG - 1) / (kRnetThreads / kG);
     if (g > ntiles) g = ntiles;
     if (g < 1) g = 1;
     *grid = (int)g;
@@ -100,7 +101,9 @@ int dmfg_rnet_param_offsets(int32_t d, int32_t n_fc3, int32_t n_fc4, int64_t* o)
 uint64_t dmfg_rnet_workspace_bytes(const dmfg_rnet_args* a) {
     if (!a || a->struct_size != sizeof(dmfg_rnet_args) || a->d < 1 || a->n_fc3 < 1 || a->n_fc4 < 1) return 0;
     if (!a->grad) return 0;
-    return align_up((uint64_t)kMaxRnetCtas * (uint64_t)rnet_layout(a->d, a->n_fc3, a->n_fc4).total * sizeof(float));
+    // per-CTA partial gradients, then (trajectory mode) the per-CTA sums of exp(R_j) and the 1/Z scalar
+    return align_up((uint64_t)kMaxRnetCtas * (uint64_t)rnet_layout(a->d, a->n_fc3, a->n_fc4).total * sizeof(float)) +
+           align_up((uint64_t)kMaxRnetCtas * 8) + 256;
 }
 
 int dmfg_rnet_forward(const dmfg_rnet_args* a, void* stream) {
@@ -149,7 +152,51 @@ int dmfg_rnet_backward(const dmfg_rnet_args* a, void* stream) {
         rnet_kernel<kG, kNP, true, 0, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
     }
     DMFG_CUDA(cudaGetLastError());
-    rnet_reduce_partials_kernel<<<(total + 127) / 128, 128, 0, st>>>(p.partials, grid, total, a->accumulate, a->grad);
+    rnet_reduce_partials_kernel<<<(total + 31) / 32, 32 * kReduceSlices, 0, st>>>(p.partials, grid, total, a->accumulate, a->grad);
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
+
+int dmfg_rnet_backward_gen(const dmfg_rnet_args* a, const dmfg_irl_gen_args* g, void* stream) {
+    if (!g) return fail(DMFG_ERR_INVALID, "gen args is NULL");
+    if (g->struct_size != sizeof(dmfg_irl_gen_args)) return fail(DMFG_ERR_INVALID, "dmfg_irl_gen_args.struct_size mismatch");
+    if (!a || a->struct_size != sizeof(dmfg_rnet_args)) return fail(DMFG_ERR_INVALID, "dmfg_rnet_args missing / struct_size mismatch");
+    if (g->T < 1 || g->T > kRnetThreads / kG)
+        return fail(DMFG_ERR_UNSUPPORTED, "the one-pass update holds a trajectory of T <= %d transitions per CTA (T = %d)",
+                    kRnetThreads / kG, g->T);
+    if (g->M < 1 || g->n_demo < 0 || !(g->num_demo_traj > 0)) return fail(DMFG_ERR_INVALID, "bad M/n_demo/num_demo_traj");
+    if (a->N != g->M * (int64_t)g->T) return fail(DMFG_ERR_INVALID, "N must be M*T");
+    if (!((g->gen_t_stride == g->M && g->gen_j_stride == 1) || (g->gen_t_stride == 1 && g->gen_j_stride == g->T)))
+        return fail(DMFG_ERR_INVALID, "strides must be (M,1) time-major or (1,T) trajectory-major");
+    if (!g->loss_out || (g->n_demo > 0 && !g->r_demo)) return fail(DMFG_ERR_INVALID, "loss_out / r_demo are required");
+    dmfg_rnet_args chk = *a;
+    chk.drewards = a->params;                       // (not read in this mode; keeps check_rnet's NULL test quiet)
+    if (int rc = check_rnet(&chk, true)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int total = rnet_layout(a->d, a->n_fc3, a->n_fc4).total;
+    const uint64_t need = dmfg_rnet_workspace_bytes(a);
+    if (!a->workspace || a->workspace_bytes < need)
+        return fail(DMFG_ERR_WORKSPACE, "workspace of %llu bytes needed, %llu given", (unsigned long long)need,
+                    (unsigned long long)(a->workspace ? a->workspace_bytes : 0));
+    RnetParams p = make_params(a);
+    p.partials = (float*)a->workspace;
+    char* tail = (char*)a->workspace + align_up((uint64_t)kMaxRnetCtas * (uint64_t)total * sizeof(float));
+    p.zpart = (double*)tail;
+    float* inv_z = (float*)(tail + align_up((uint64_t)kMaxRnetCtas * 8));
+    p.traj_M = g->M; p.traj_T = g->T; p.t_stride = g->gen_t_stride; p.j_stride = g->gen_j_stride;
+    int grid = 0;
+    size_t smem = 0;
+    if (a->d == 15) {
+        if (int rc = rnet_grid<true, 15, 0, 0, true>(a, &grid, &smem, g->M)) return rc;
+        rnet_kernel<kG, kNP, true, 15, 0, 0, true><<<grid, kRnetThreads, smem, st>>>(p);
+    } else {
+        if (int rc = rnet_grid<true, 0, 0, 0, true>(a, &grid, &smem, g->M)) return rc;
+        rnet_kernel<kG, kNP, true, 0, 0, 0, true><<<grid, kRnetThreads, smem, st>>>(p);
+    }
+    DMFG_CUDA(cudaGetLastError());
+    irl_gen_finalize_kernel<<<1, 1024, 0, st>>>(p.zpart, grid, g->r_demo, g->n_demo, g->num_demo_traj, g->M, g->loss_out, inv_z);
+    DMFG_CUDA(cudaGetLastError());
+    rnet_reduce_partials_kernel<<<(total + 31) / 32, 32 * kReduceSlices, 0, st>>>(p.partials, grid, total, a->accumulate, a->grad, inv_z);
     DMFG_CUDA(cudaGetLastError());
     return DMFG_OK;
 }

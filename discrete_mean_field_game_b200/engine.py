@@ -411,6 +411,50 @@ def rnet_backward(params, states, actions, drewards, n_fc3, n_fc4, *, grad=None,
     return (grad, r) if want_rewards else grad
 
 
+def rnet_backward_gen(params, states, actions, n_fc3, n_fc4, T, r_demo, num_demo_traj, *, layout="time_major",
+                      grad=None, accumulate=False, mask3=None, mask4=None, keep_prob=0.4, seed=None, sample_offset=0,
+                      want_rewards=False):
+    """The generated half of one reward update in one pass (ac_irl.py:390-418 with z_j = 1, T <= 16): forward,
+    R_j = sum_t r[j,t], backward with the weight exp(R_j), gradient scaled by 1 / sum_j exp(R_j) and written (or
+    added) to `grad`.  states [M*T, d], actions [M*T, d, d] in `layout` order; r_demo: rewards of the demonstration
+    batch.  Returns (grad, loss [4] float64 device = {first+second, first, second, ln sum_j e^{R_j}}[, r_gen])."""
+    from ._lib import IrlGenArgs
+    lib = _lib.load()
+    a, P = _rnet_args(params, states, actions, n_fc3, n_fc4, mask3, mask4, keep_prob, seed, sample_offset)
+    device = states.device
+    N = states.shape[0]
+    M = N // int(T)
+    if M * int(T) != N:
+        raise ValueError("%d transitions are not a multiple of T=%d" % (N, T))
+    g = IrlGenArgs()
+    g.struct_size = C.sizeof(IrlGenArgs)
+    g.T, g.M, g.n_demo = int(T), M, r_demo.numel()
+    if layout == "time_major":
+        g.gen_t_stride, g.gen_j_stride = M, 1
+    elif layout == "trajectory_major":
+        g.gen_t_stride, g.gen_j_stride = 1, int(T)
+    else:
+        raise ValueError("layout must be 'time_major' or 'trajectory_major'")
+    g.num_demo_traj = float(num_demo_traj)
+    g.r_demo = _ptr(_require(r_demo, "r_demo", device, torch.float32, tuple(r_demo.shape)))
+    with torch.cuda.device(device):
+        if grad is None:
+            grad = torch.zeros(P, dtype=torch.float32, device=device)
+        a.grad = _ptr(_require(grad, "grad", device, torch.float32, (P,)))
+        a.accumulate = 1 if accumulate else 0
+        r = None
+        if want_rewards:
+            r = torch.empty(N, dtype=torch.float32, device=device)
+            a.rewards = _ptr(r)
+        loss = torch.empty(4, dtype=torch.float64, device=device)
+        g.loss_out = _ptr(loss)
+        ws = _workspace(device, lib.dmfg_rnet_workspace_bytes(C.byref(a)))
+        if ws is not None:
+            a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        check(lib.dmfg_rnet_backward_gen(C.byref(a), C.byref(g), _stream_ptr(device)))
+    return (grad, loss, r) if want_rewards else (grad, loss)
+
+
 def irl_loss_grad(r_demo, r_gen, T, num_demo_traj, *, layout="time_major", log_z=None, want_grads=True):
     """IRL loss terms and dL/dr (ac_irl.py:390-406).  r_gen holds M*T rewards, time-major [T,M] (rollout
     record) or trajectory-major [M,T] (the reference's feed).  Returns dict(loss [4] float64 device =

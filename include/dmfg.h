@@ -321,6 +321,27 @@ typedef struct dmfg_irl_loss_args {
 uint64_t dmfg_irl_loss_workspace_bytes(int64_t M);
 int dmfg_irl_loss_grad(const dmfg_irl_loss_args* args, void* stream);
 
+/* ---- a11/a12: the generated half of one reward update in ONE pass ---------- *
+ * Replaces, for z_j = 1 (upstream's ac_irl.py:406) and T <= 16, the chain
+ *   dmfg_rnet_forward(gen) -> dmfg_irl_loss_grad -> dmfg_rnet_backward(gen, d_gen):
+ * one launch walks the generated batch trajectory by trajectory (net->states / actions, N = M*T, transition (j,t)
+ * at t*gen_t_stride + j*gen_j_stride), backpropagates with the unnormalised weight exp(R_j), R_j = sum_t r[j,t],
+ * and the reduced gradient is scaled by 1 / sum_j exp(R_j) before it is written / added to net->grad.
+ * net->drewards is ignored; net->rewards (optional) receives r_gen.  r_demo [n_demo] are the rewards of the
+ * demonstration batch (dmfg_rnet_backward(demo) with rewards != NULL hands them back).
+ * loss_out[4] (double, device) = {first+second, first, second, ln sum_j exp(R_j)} as in dmfg_irl_loss_grad. */
+typedef struct dmfg_irl_gen_args {
+    uint32_t struct_size;
+    int32_t  T;
+    int64_t  M;                   /* generated trajectories */
+    int64_t  gen_t_stride, gen_j_stride;
+    int64_t  n_demo;
+    double   num_demo_traj;
+    const float* r_demo;          /* [n_demo] */
+    double*  loss_out;            /* [4] out */
+} dmfg_irl_gen_args;
+int dmfg_rnet_backward_gen(const dmfg_rnet_args* net, const dmfg_irl_gen_args* gen, void* stream);
+
 /* ---- a11: one TF-style Adam step on the flat parameter vector -------------- *
  * tf.train.AdamOptimizer(lr).minimize (ac_irl.py:417-418): step counts from 1,
  * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t), p -= lr_t*m/(sqrt(v)+eps).  With l1l2 != 0

@@ -14,6 +14,7 @@ g = rng.standard_gamma(1.0, size=(64, D))
 with contextlib.redirect_stdout(sys.stderr):
     irl = AC_IRL(theta=8.64, shift=0, alpha_scale=1e4, d=D, reg="none", n_fc3=8, n_fc4=4,
                  mat_pi0=g / g.sum(1, keepdims=True), demonstrations=[], device=dev, seed=1, net_seed=2)
+irl.one_pass_reward_update = os.environ.get("DMFG_IRL_ONE_PASS", "1") != "0"      # A/B: the three-launch chain
 ds, da = irl.generate_batch(M, theta=8.06)
 gs, ga = irl.generate_batch(M)
 ds, da = ds[:15].reshape(-1, D), da.reshape(-1, D, D)

@@ -145,6 +145,28 @@ def test_update_reward_matches_oracle(data, reg):
         v = ac.reward_params.v.cpu().numpy().astype(np.float64)
 
 
+@pytest.mark.parametrize("reg", ["none", "dropout_l1l2"])
+def test_one_pass_reward_update_equals_the_three_launch_chain(data, reg):
+    """update_reward_batch with the generated half in one launch (weight exp(R_j), 1/Z afterwards) against the
+    forward -> loss -> backward chain on the same batch, same Philox dropout masks: loss terms, gradient and the
+    parameters after the Adam step agree to float accuracy."""
+    outs = []
+    for one_pass in (True, False):
+        irl = make(data, reg=reg)
+        irl.one_pass_reward_update = one_pass
+        ds, da = irl.generate_batch(37, theta=8.06)
+        gs, ga = irl.generate_batch(53)
+        T = 15
+        loss = irl.update_reward_batch(ds[:T].reshape(-1, 15), da.reshape(-1, 15, 15), gs[:T].reshape(-1, 15),
+                                       ga.reshape(-1, 15, 15), 37, "time_major", group=False)
+        outs.append((loss.cpu().numpy(), irl._last_grad.cpu().numpy(), irl.reward_params.flat.cpu().numpy()))
+    (l1, g1, p1), (l0, g0, p0) = outs
+    np.testing.assert_allclose(l1[:3], l0[:3], rtol=1e-5, atol=3e-5)
+    assert np.abs(g1 - g0).max() <= 2e-5 * np.abs(g0).max() + 1e-7
+    np.testing.assert_allclose(p1, p0, rtol=0, atol=2.1e-4)      # one Adam step moves every weight by <= lr = 1e-4
+    assert np.mean(np.abs(p1 - p0) <= 1e-6) > 0.99                # (sign flips of ~0 gradients aside)
+
+
 def test_update_reward_with_importance_weights(data):
     ac = make(data, use_z=True)
     ac.list_policies = list(np.linspace(6.0, 7.0, 10))

@@ -123,6 +123,56 @@ def test_irl_loss_and_derivatives(dev, layout, with_z):
     np.testing.assert_allclose(got, dg, rtol=1e-6)
 
 
+@pytest.mark.parametrize("layout", ["time_major", "trajectory_major"])
+@pytest.mark.parametrize("d,n3,n4,M,T,dropout", [(15, 8, 4, 53, 15, False), (15, 8, 4, 300, 15, True), (15, 6, 6, 7, 16, False),
+                                                 (4, 6, 8, 41, 3, True), (16, 8, 8, 1, 1, False)])
+def test_one_pass_generated_half_matches_oracle(dev, layout, d, n3, n4, M, T, dropout):
+    """dmfg_rnet_backward_gen (forward, R_j, backward with weight exp(R_j), 1/Z on the reduced gradient) against the
+    float64 oracle of the three-step chain it replaces (forward -> ac_irl.py:390-406 loss and dL/dr -> backward):
+    loss terms, r_gen and the gradient accumulated on top of an existing buffer; ragged trajectory counts, T up to
+    the 16 groups of a CTA, injected dropout masks, both layouts."""
+    from discrete_mean_field_game_b200 import engine
+    rng = np.random.RandomState(d * 100 + M)
+    n = M * T
+    p, s, a = make(rng, n, d, n3, n4, scale=0.3)                 # [M, T] trajectory-major reference view
+    m3 = (rng.rand(n, n3) < 0.4) if dropout else None
+    m4 = (rng.rand(n, n4) < 0.4) if dropout else None
+    rd = f32(rng.uniform(-1, 1, 75))
+    r_ref, cache = R.forward(p, s, a, n3, n4, m3, m4, cache=True)
+    first, second, _, dg = R.irl_loss(rd, r_ref.reshape(M, T), 5)
+    g_ref = R.backward(cache, dg.reshape(-1))
+
+    def order(x):                                                # trajectory-major [M*T, ...] -> the device layout
+        if x is None or layout == "trajectory_major":
+            return x
+        return np.ascontiguousarray(x.reshape((M, T) + x.shape[1:]).swapaxes(0, 1)).reshape(x.shape)
+
+    kw = dict(mask3=T_(order(m3), dev, torch.uint8), mask4=T_(order(m4), dev, torch.uint8)) if dropout else {}
+    g0 = f32(rng.randn(p.size))
+    g, loss, r = engine.rnet_backward_gen(T_(p, dev), T_(order(s), dev), T_(order(a), dev), n3, n4, T, T_(rd, dev), 5,
+                                          layout=layout, grad=T_(g0, dev), accumulate=True, want_rewards=True, **kw)
+    np.testing.assert_allclose(r.cpu().numpy(), order(r_ref), rtol=2e-5, atol=2e-6)
+    # R_j is a float sum of T float rewards: |err| ~ T * 2e-6 enters ln Z
+    np.testing.assert_allclose(loss.cpu().numpy()[:3], [first + second, first, second], rtol=1e-5, atol=3e-5)
+    g = g.cpu().numpy() - g0
+    for name, shp, off in R.layout(d, n3, n4):
+        sl = slice(off, off + int(np.prod(shp)))
+        scale = np.abs(g_ref[sl]).max() + 1e-6
+        assert np.abs(g[sl] - g_ref[sl]).max() <= 5e-5 * scale + 2e-6, name
+
+
+def test_one_pass_generated_half_argument_errors(dev):
+    from discrete_mean_field_game_b200 import engine
+    from discrete_mean_field_game_b200._lib import DmfgError
+    rng = np.random.RandomState(0)
+    p, s, a = make(rng, 34, 15, 8, 4)
+    rd = T_(f32(rng.rand(5)), dev)
+    with pytest.raises(DmfgError, match="T <= 16"):
+        engine.rnet_backward_gen(T_(p, dev), T_(s, dev), T_(a, dev), 8, 4, 17, rd, 5)
+    with pytest.raises(ValueError):
+        engine.rnet_backward_gen(T_(p, dev), T_(s, dev), T_(a, dev), 8, 4, 15, rd, 5)
+
+
 @pytest.mark.parametrize("l1l2", [False, True])
 def test_adam_tf_steps(dev, l1l2):
     from discrete_mean_field_game_b200 import engine
