@@ -396,7 +396,8 @@ def rnet_backward(params, states, actions, drewards, n_fc3, n_fc4, *, grad=None,
     N = states.shape[0]
     with torch.cuda.device(device):
         if grad is None:
-            grad = torch.zeros(P, dtype=torch.float32, device=device)
+            accumulate = False                               # every entry is written by the reduction
+            grad = torch.empty(P, dtype=torch.float32, device=device)
         a.grad = _ptr(_require(grad, "grad", device, torch.float32, (P,)))
         a.drewards = _ptr(_require(drewards, "drewards", device, torch.float32, (N,)))
         a.accumulate = 1 if accumulate else 0
@@ -439,7 +440,8 @@ def rnet_backward_gen(params, states, actions, n_fc3, n_fc4, T, r_demo, num_demo
     g.r_demo = _ptr(_require(r_demo, "r_demo", device, torch.float32, tuple(r_demo.shape)))
     with torch.cuda.device(device):
         if grad is None:
-            grad = torch.zeros(P, dtype=torch.float32, device=device)
+            accumulate = False
+            grad = torch.empty(P, dtype=torch.float32, device=device)
         a.grad = _ptr(_require(grad, "grad", device, torch.float32, (P,)))
         a.accumulate = 1 if accumulate else 0
         r = None
