@@ -47,7 +47,9 @@ with contextlib.redirect_stdout(sys.stderr):
                  mat_pi0=g / g.sum(1, keepdims=True), demonstrations=[], device=dev, seed=1, net_seed=2)
 ds, da = irl.generate_batch(24, theta=8.06)
 gs, ga = irl.generate_batch(24)
-irl.update_reward_batch(ds[:15].reshape(-1, 15), da.reshape(-1, 15, 15), gs[:15].reshape(-1, 15), ga.reshape(-1, 15, 15),
-                        24, "time_major", group=False)
+for one_pass in (True, False):            # generated half in one launch (rnet_kernel<TRAJ>) / forward -> loss -> backward
+    irl.one_pass_reward_update = one_pass
+    irl.update_reward_batch(ds[:15].reshape(-1, 15), da.reshape(-1, 15, 15), gs[:15].reshape(-1, 15),
+                            ga.reshape(-1, 15, 15), 24, "time_major", group=False)
 torch.cuda.synchronize()
 print("sanitize_small: done")
