@@ -17,7 +17,7 @@ constexpr int kLossBlocks = 148 * 4;
 
 inline uint64_t align_up(uint64_t x, uint64_t a = 256) { return (x + a - 1) / a * a; }
 
-int check_rnet(const dmfg_rnet_args* a, bool bwd) {
+int check_rnet(const dmfg_rnet_args* a, bool bwd, bool need_drewards = true) {
     if (!a) return fail(DMFG_ERR_INVALID, "args is NULL");
     if (a->struct_size != sizeof(dmfg_rnet_args))
         return fail(DMFG_ERR_INVALID, "dmfg_rnet_args.struct_size %u != %zu (header mismatch)", a->struct_size,
@@ -36,7 +36,7 @@ int check_rnet(const dmfg_rnet_args* a, bool bwd) {
     if (!bwd && a->N > 0 && !a->rewards) return fail(DMFG_ERR_INVALID, "rewards is NULL");
     if (bwd) {
         if (!a->grad) return fail(DMFG_ERR_INVALID, "grad is NULL");
-        if (a->N > 0 && !a->drewards) return fail(DMFG_ERR_INVALID, "drewards is NULL");
+        if (need_drewards && a->N > 0 && !a->drewards) return fail(DMFG_ERR_INVALID, "drewards is NULL");
     }
     return DMFG_OK;
 }
@@ -169,9 +169,7 @@ int dmfg_rnet_backward_gen(const dmfg_rnet_args* a, const dmfg_irl_gen_args* g, 
     if (!((g->gen_t_stride == g->M && g->gen_j_stride == 1) || (g->gen_t_stride == 1 && g->gen_j_stride == g->T)))
         return fail(DMFG_ERR_INVALID, "strides must be (M,1) time-major or (1,T) trajectory-major");
     if (!g->loss_out || (g->n_demo > 0 && !g->r_demo)) return fail(DMFG_ERR_INVALID, "loss_out / r_demo are required");
-    dmfg_rnet_args chk = *a;
-    chk.drewards = a->params;                       // (not read in this mode; keeps check_rnet's NULL test quiet)
-    if (int rc = check_rnet(&chk, true)) return rc;
+    if (int rc = check_rnet(a, true, /*need_drewards=*/false)) return rc;      // dL/dr is formed in the kernel
     cudaStream_t st = (cudaStream_t)stream;
     const int total = rnet_layout(a->d, a->n_fc3, a->n_fc4).total;
     const uint64_t need = dmfg_rnet_workspace_bytes(a);
