@@ -118,6 +118,25 @@ def test_irl_loss_terms_and_weights():
     assert np.allclose(dgz[:, 0], w / w.sum())
 
 
+def test_one_pass_form_of_the_generated_gradient():
+    """The algebra dmfg_rnet_backward_gen rests on: d second / d params = sum_j softmax_j(R) dR_j/dparams equals the
+    gradient backpropagated with the UNNORMALISED weights exp(R_j), divided by Z = sum_j exp(R_j) afterwards, and
+    second = ln(Z / M) (ac_irl.py:396-406 with z_j = 1).  |r| < 1 bounds exp(R_j) by e^T: no shift is needed."""
+    rng = np.random.RandomState(8)
+    d, n3, n4, M, Tt = 6, 5, 3, 7, 4
+    p = R.xavier_init(d, n3, n4, rng) + 0.3 * rng.randn(R.param_count(d, n3, n4))
+    s = rng.dirichlet(np.ones(d), size=M * Tt)
+    a = rng.dirichlet(np.ones(d) * 0.5, size=(M * Tt, d))
+    r, cache = R.forward(p, s, a, n3, n4, None, None, cache=True)
+    assert np.all(np.abs(r) < 1)
+    _, second, _, dg = R.irl_loss(np.zeros(1), r.reshape(M, Tt), 1)
+    g_ref = R.backward(cache, dg.reshape(-1))
+    u = np.exp(r.reshape(M, Tt).sum(1))
+    g_u = R.backward(cache, np.repeat(u, Tt))
+    np.testing.assert_allclose(g_u / u.sum(), g_ref, rtol=1e-11, atol=1e-15)
+    assert np.isclose(second, math.log(u.sum() / M), rtol=1e-13)
+
+
 def test_adam_tf_first_steps():
     rng = np.random.RandomState(4)
     p, g = rng.randn(10), rng.randn(10)
