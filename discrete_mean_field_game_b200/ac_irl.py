@@ -410,6 +410,74 @@ class AC_IRL(_actor_critic):
             out["states"], out["actions"] = rec["states"], rec["actions"]
         return out
 
+    def irl_step_batch(self, pi0, demo_states, demo_actions, num_demo_traj, episode=1, gamma=1, constant=False,
+                       lr_critic=0.1, lr_actor=0.001, seed=None, pop_offset=0, group=None):
+        """One data-parallel IRL training step (BASELINE config 5) = train_batch(num_episodes=1, keep_record=True)
+        followed by update_reward_batch on that record, with the shared work done once:
+          rollout + record of this rank's B populations  ->  reward-net backward over the demonstrations (-1/N)
+          ->  ONE reward-net pass over the generated record that hands back r_gen (the rewards of the forward solve)
+              AND the generated half of the reward gradient / loss (rnet_kernel<TRAJ>)
+          ->  TD sums from r_gen  ->  ONE all-reduce of the flat [2+F+|r_net|] double buffer (actor, critic and
+              reward gradients together)  ->  theta, w update and the Adam step.
+        Same numbers as the two calls in sequence (both evaluate the reward net with the parameters before the Adam
+        step); with dropout regularisers the two calls draw separate masks, so this method falls back to them.
+        demo_* : [N*15, d] / [N*15, d, d] device tensors.  Returns dict(theta, mean_reward, loss [4] device,
+        states, actions)."""
+        from . import parallel
+        if self._dropout or self.use_z or not self.one_pass_reward_update:
+            res = self.train_batch(pi0, 1, gamma, constant, lr_critic, lr_actor, seed, pop_offset, group, episode,
+                                   keep_record=True)
+            T = T_STEPS
+            res["loss"] = self.update_reward_batch(demo_states, demo_actions, res["states"][:T].reshape(-1, self.d),
+                                                   res["actions"].reshape(-1, self.d, self.d), num_demo_traj,
+                                                   "time_major", group=group)
+            res["mean_reward"] = res["mean_reward"][0]
+            return res
+        d, T = self.d, T_STEPS
+        seed = self.seed if seed is None else seed
+        theta = torch.tensor([float(self.theta)], dtype=torch.float64, device=self.device)
+        w = self._w_dev().clone()
+        pi = pi0 if isinstance(pi0, torch.Tensor) and pi0.is_cuda else self._dev(np.asarray(pi0, dtype=np.float32), torch.float32)
+        B = pi.shape[0]
+        _, world = parallel.world_info(group)
+        p = self.reward_params
+        lr_c = lr_critic if constant else lr_critic / (episode + 1.0)
+        lr_a = lr_actor if constant else lr_actor / ((episode + 1.0) * math.log(math.log(episode + 20.0)))
+        rec = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, T, theta_dev=theta, reward="none", seed=seed,
+                             pop_offset=pop_offset, step_offset=episode * T, outputs=("states", "actions", "grads"))
+        n_demo = demo_states.shape[0]
+        d_const = self._d_demo_const.get((n_demo, float(num_demo_traj)))
+        if d_const is None:
+            d_const = torch.full((n_demo,), -1.0 / float(num_demo_traj), dtype=torch.float32, device=self.device)
+            self._d_demo_const = {(n_demo, float(num_demo_traj)): d_const}
+        grad, r_demo = engine.rnet_backward(p.flat, demo_states, demo_actions, d_const, p.n_fc3, p.n_fc4,
+                                            keep_prob=networks.KEEP_PROB, want_rewards=True)
+        gs, ga = rec["states"][:T].reshape(-1, d), rec["actions"].reshape(-1, d, d)
+        _, loss, r_gen = engine.rnet_backward_gen(p.flat, gs, ga, p.n_fc3, p.n_fc4, T, r_demo, num_demo_traj,
+                                                  layout="time_major", grad=grad, accumulate=True,
+                                                  keep_prob=networks.KEEP_PROB, want_rewards=True)
+        td = engine.td_accumulate(rec["states"], r_gen.view(T, B), rec["grads"], w, gamma=gamma,
+                                  discount="cumulative", want_deltas=False)
+        acc = td["acc"]
+        if world > 1:
+            flat = torch.cat([acc, grad.double()])                       # [2+F] + [|r_net|]: one all-reduce
+            parallel.allreduce_sum_(flat, group)
+            acc = flat[:acc.numel()]
+            grad = flat[acc.numel():].float()
+        engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / (B * world))
+        p.step += 1
+        reg = engine.adam_tf(p.flat, p.m, p.v, grad, p.step, self.lr_reward, grad_scale=1.0 / world,
+                             l1l2=self._l1l2, net=(p.d, p.n_fc3, p.n_fc4), want_reg_loss=self._l1l2)
+        if reg is not None:
+            loss = loss.clone()
+            loss[0] += reg[0]
+        self._last_grad = grad
+        self.theta = float(theta[0])
+        self.w = w.cpu().numpy().reshape(-1, 1)
+        self.list_policies = (self.list_policies + [self.theta])[1:]
+        return dict(theta=self.theta, mean_reward=float(acc[-1]) / (B * world), loss=loss, states=rec["states"],
+                    actions=rec["actions"])
+
     def _philox_randint(self, counter, n):
         w0 = engine.philox((0, 0, counter & 0xFFFFFFFF, 0xC0000000), (self.seed & 0xFFFFFFFF, self.seed >> 32))[0]
         return (w0 * n) >> 32

@@ -5,11 +5,11 @@
 
 Every rank owns 2^k generated + 2^k demonstration trajectories (x 15 transitions).  One iteration =
   (a) the batched forward solve of ac_irl.py over the rank's populations with the reward net in the loop
-      (AC_IRL.train_batch: rollout + record -> r_net forward over all transitions -> TD sums) with ONE all-reduce
-      of the [2+F] double gradient buffer and the (theta, w) update on the device;
+      (rollout + record -> r_net over all transitions -> TD sums -> (theta, w) update on the device);
   (b) its record is the rank's generated batch (no second rollout);
-  (c) one reward update (reward-net backward over demo, forward + backward over generated, log-sum-exp loss over
-      the LOCAL generated trajectories) with ONE all-reduce of the [|r_net|] float gradient and TF-Adam.
+  (c) one reward update (reward-net backward over demo; ONE pass over the generated record that also hands back the
+      rewards (a) needs; log-sum-exp loss over the LOCAL generated trajectories) and TF-Adam;
+  with ONE all-reduce of the flat [2+F+|r_net|] buffer (AC_IRL.irl_step_batch).
 Timed on the device (CUDA events), max over ranks; rank 0 prints one JSON line.
 """
 import argparse
@@ -46,12 +46,11 @@ pi0 = ds[:M].contiguous()                                      # start states of
 
 
 def iteration(k):
-    # (a)+(b): batched forward solve with r = r_net(pi, P); its record IS the generated batch of the reward update
-    res = irl.train_batch(pi0, num_episodes=1, first_episode=1 + k, pop_offset=rank * M, group=None if world == 1 else dist.group.WORLD,
-                          keep_record=True)
-    gs, ga = res["states"][:T].reshape(-1, D), res["actions"].reshape(-1, D, D)
-    # (c): reward update, one all-reduce of the reward-net gradient
-    return irl.update_reward_batch(ds, da, gs, ga, M, "time_major")
+    # (a)+(b)+(c) in one call: the reward-net pass over the generated record serves the forward solve (r_gen) and
+    # the reward update (gradient, loss); one all-reduce of the flat [2+F+|r_net|] buffer
+    res = irl.irl_step_batch(pi0, ds, da, M, episode=1 + k, pop_offset=rank * M,
+                             group=None if world == 1 else dist.group.WORLD)
+    return res["loss"]
 
 
 for k in range(2):
@@ -76,7 +75,7 @@ if rank == 0:
         "n_gpus": world, "trajectories_per_gpu": M, "ms_per_iteration": ms, "irl_iters_per_s": 1e3 / ms,
         "population_steps_per_s": 1.0 * M * T * world / (ms * 1e-3),
         "reward_update_transitions_per_s": 2.0 * M * T * world / (ms * 1e-3),
-        "allreduces_per_iteration": 2 if world > 1 else 0, "loss": [float(x) for x in loss.cpu()],
+        "allreduces_per_iteration": 1 if world > 1 else 0, "loss": [float(x) for x in loss.cpu()],
         "theta": irl.theta,
     }))
 if world > 1:

@@ -167,6 +167,34 @@ def test_one_pass_reward_update_equals_the_three_launch_chain(data, reg):
     assert np.mean(np.abs(p1 - p0) <= 1e-6) > 0.99                # (sign flips of ~0 gradients aside)
 
 
+def test_irl_step_batch_equals_train_batch_then_update_reward_batch(data):
+    """irl_step_batch (one reward-net pass over the generated record serves the forward solve AND the reward update)
+    against train_batch(keep_record) followed by update_reward_batch: theta, w, loss and reward parameters."""
+    rng = np.random.RandomState(4)
+    pi0 = np.float32(rng.dirichlet(np.ones(D), size=45))
+    outs = []
+    for fused in (True, False):
+        irl = make(data, reg="l1l2")
+        ds, da = irl.generate_batch(21, theta=8.06)
+        ds, da = ds[:T].reshape(-1, D), da.reshape(-1, D, D)
+        for ep in (1, 2):
+            if fused:
+                res = irl.irl_step_batch(pi0, ds, da, 21, episode=ep, lr_critic=0.1, lr_actor=0.01, group=False)
+                loss = res["loss"]
+            else:
+                res = irl.train_batch(pi0, 1, lr_critic=0.1, lr_actor=0.01, first_episode=ep, keep_record=True, group=False)
+                loss = irl.update_reward_batch(ds, da, res["states"][:T].reshape(-1, D), res["actions"].reshape(-1, D, D),
+                                               21, "time_major", group=False)
+        outs.append((irl.theta, irl.w.ravel().copy(), loss.cpu().numpy(), irl.reward_params.flat.cpu().numpy(),
+                     irl._last_grad.cpu().numpy()))
+    (t1, w1, l1, p1, g1), (t0, w0, l0, p0, g0) = outs
+    np.testing.assert_allclose(t1, t0, rtol=1e-9)
+    np.testing.assert_allclose(w1, w0, rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(l1[:3], l0[:3], rtol=1e-5, atol=3e-5)
+    assert np.abs(g1 - g0).max() <= 2e-5 * np.abs(g0).max() + 1e-7
+    assert np.mean(np.abs(p1 - p0) <= 1e-6) > 0.99 and np.abs(p1 - p0).max() <= 4.2e-4     # two Adam steps of 1e-4
+
+
 def test_update_reward_with_importance_weights(data):
     ac = make(data, use_z=True)
     ac.list_policies = list(np.linspace(6.0, 7.0, 10))
