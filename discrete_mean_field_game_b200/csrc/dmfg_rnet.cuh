@@ -27,6 +27,10 @@ constexpr int kRnetThreads = 256;
 constexpr int kK1 = 5, kK2 = 3;
 #define DMFG_CTR_DROPOUT 0xA0000000u   // Philox counter word 3 of the dropout uniforms
 
+#ifndef DMFG_RNET_PREFETCH
+#define DMFG_RNET_PREFETCH 1
+#endif
+
 struct RnetLayout {
     int d, n3, n4;
     int k1, b1, k2, b2, w3, b3, w4, b4, w5, b5, total;
@@ -234,6 +238,25 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
             if (row_ok)
                 for (int i = 0; i < d; ++i) At[(i + 2) * SA + h + 2] = a[i * d + h];
             const float pi_h = row_ok ? p.states[n * d + h] : 0.f;
+#if DMFG_RNET_PREFETCH
+            // the next tile of this CTA: its d*d action block (<= 8 lines of 128 B) is asked for now, one line per
+            // lane, so the tile load above finds it in L1/L2 instead of waiting on DRAM with every warp of the
+            // CTA stalled at the same point (1 CTA/SM in the backward kernel: nothing else to switch to)
+            {
+                const long long tn = tile + gridDim.x;
+                if (tn < ntiles) {
+                    long long nn;
+                    if (TRAJ) nn = (grp < p.traj_T ? grp : 0) * p.t_stride + tn * p.j_stride;
+                    else { nn = tn * GPB + grp; if (nn >= p.N) nn = p.N - 1; }
+                    const char* nx = reinterpret_cast<const char*>(p.actions + nn * d * d);
+#if DMFG_RNET_PREFETCH == 2
+                    if (h * 128 < d * d * 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + h * 128));
+#else
+                    if (h * 128 < d * d * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + h * 128));
+#endif
+                }
+            }
+#endif
             __syncwarp();
             // ---- conv1 row h ----------------------------------------------------------------------
             float c1[G];
