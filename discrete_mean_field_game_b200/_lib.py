@@ -68,7 +68,7 @@ class LearnersArgs(C.Structure):
         ("lr_critic", C.c_double), ("lr_actor", C.c_double),
         ("constant_lr", C.c_int32), ("reward_kind", C.c_int32), ("discount_kind", C.c_int32),
         ("noise_kind", C.c_int32),
-        ("mat_pi0", C.c_void_p), ("S", C.c_int32), ("reserved", C.c_int32),
+        ("mat_pi0", C.c_void_p), ("S", C.c_int32), ("layout", C.c_int32),
         ("start_rows", C.c_void_p), ("noise_y", C.c_void_p), ("seed", C.c_uint64),
         ("noise_episode_offset", C.c_int64),
         ("theta_trace", C.c_void_p), ("delta_trace", C.c_void_p), ("total_reward", C.c_void_p),

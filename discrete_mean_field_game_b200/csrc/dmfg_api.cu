@@ -10,6 +10,7 @@
 #include "dmfg_error.h"
 #include "dmfg_rollout2.cuh"
 #include "dmfg_td_dmma.cuh"
+#include "dmfg_learner_cta.cuh"
 
 using namespace dmfg;
 
@@ -432,9 +433,31 @@ int launch_learners_v2(const LearnerParams<float>& p, cudaStream_t st) {
     DMFG_CUDA(cudaGetLastError());
     return DMFG_OK;
 }
+// float streams, d = 15 / 16 / 21, a few learners: one CTA per learner (latency form)
+template <int D, int NOISE>
+int launch_learner_cta(const LearnerParams<float>& p, cudaStream_t st) {
+    learner_cta_kernel<D, NOISE><<<(unsigned)p.L, LearnerCtaGeom<D>::NT, 0, st>>>(p, make_philox_keys(p.seed));
+    DMFG_CUDA(cudaGetLastError());
+    return DMFG_OK;
+}
 template <typename R, int NOISE>
-int dispatch_learners(const LearnerParams<R>& p, cudaStream_t st) {
+int dispatch_learners(const LearnerParams<R>& p, int layout, cudaStream_t st) {
     if constexpr (std::is_same<R, float>::value) {
+        if (p.d == 15 || p.d == 16 || p.d == 21) {
+            // up to ~8 learners per SM the CTA form wins (4x per step for one learner, 2.3x at 4 per SM); beyond that the
+            // 16-lane form does less work per learner-step
+            int sms = 0;
+            if (int rc = sm_count(&sms)) return rc;
+            const bool cta = layout == DMFG_LEARNERS_CTA ||
+                             (layout == DMFG_LEARNERS_AUTO && p.L <= (p.d == 21 ? 2LL : 8LL) * sms);
+            if (cta) {
+                if (p.d == 15) return launch_learner_cta<15, NOISE>(p, st);
+                if (p.d == 16) return launch_learner_cta<16, NOISE>(p, st);
+                return launch_learner_cta<21, NOISE>(p, st);
+            }
+        } else if (layout == DMFG_LEARNERS_CTA) {
+            return fail(DMFG_ERR_UNSUPPORTED, "the CTA-per-learner kernel is built for float streams, d in {15,16,21}");
+        }
         if (p.d == 15) return launch_learners_v2<15, 16, NOISE>(p, st);
         if (p.d == 16) return launch_learners_v2<16, 16, NOISE>(p, st);
         if (p.d == 21) return launch_learners_v2<21, 32, NOISE>(p, st);     // the reference's default d (mfg_ac2.py:25)
@@ -458,8 +481,11 @@ int learners_typed(const dmfg_learners_args* a, cudaStream_t st) {
     p.mat_pi0 = (const R*)a->mat_pi0; p.start_rows = a->start_rows; p.noise_y = (const R*)a->noise_y;
     p.seed = a->seed; p.noise_episode_offset = a->noise_episode_offset; p.theta_trace = a->theta_trace; p.delta_trace = a->delta_trace;
     p.total_reward = a->total_reward; p.pi_final = (R*)a->pi_final;
-    if (a->noise_kind == DMFG_NOISE_PHILOX) return dispatch_learners<R, DMFG_NOISE_PHILOX>(p, st);
-    return dispatch_learners<R, DMFG_NOISE_INJECTED>(p, st);
+    if (a->layout < DMFG_LEARNERS_AUTO || a->layout > DMFG_LEARNERS_CTA) return fail(DMFG_ERR_INVALID, "layout %d", a->layout);
+    if (a->layout == DMFG_LEARNERS_CTA && !std::is_same<R, float>::value)
+        return fail(DMFG_ERR_UNSUPPORTED, "the CTA-per-learner kernel is built for float streams, d in {15,16,21}");
+    if (a->noise_kind == DMFG_NOISE_PHILOX) return dispatch_learners<R, DMFG_NOISE_PHILOX>(p, a->layout, st);
+    return dispatch_learners<R, DMFG_NOISE_INJECTED>(p, a->layout, st);
 }
 
 // ---- testing aids ------------------------------------------------------------

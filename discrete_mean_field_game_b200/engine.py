@@ -244,11 +244,12 @@ def apply_update(d, theta_dev, w, acc, lr_critic_eff, lr_actor_eff, scale, lr_de
 
 def learners(theta, w, mat_pi0, E, T, *, shift, alpha_scale, episode0=0, gamma=1.0, lr_critic=0.1,
              lr_actor=0.001, constant=False, reward="ac2", discount="step", start_rows=None, noise_y=None,
-             seed=0, learner_offset=0, noise_episode_offset=0, trace=False, want_total_reward=True):
+             seed=0, learner_offset=0, noise_episode_offset=0, trace=False, want_total_reward=True, layout="auto"):
     """dmfg_ac_learners: L independent serial learners with per-step updates.
 
     theta [L] float64 and w [L,F] float64 are updated IN PLACE.  shift / alpha_scale may be
-    floats or [L] float64 tensors.  mat_pi0 [S,d] selects the stream dtype.
+    floats or [L] float64 tensors.  mat_pi0 [S,d] selects the stream dtype.  layout: "auto" | "groups" (16 / 32
+    lanes per learner, throughput form) | "cta" (a CTA per learner: latency form, float32, d = 15 / 16 / 21).
     """
     lib = _lib.load()
     device, dtype = mat_pi0.device, mat_pi0.dtype
@@ -276,6 +277,7 @@ def learners(theta, w, mat_pi0, E, T, *, shift, alpha_scale, episode0=0, gamma=1
     a.mat_pi0, a.S = _ptr(_require(mat_pi0, "mat_pi0", device, dtype, (S, d))), S
     a.seed = int(seed) & (2 ** 64 - 1)
     a.noise_episode_offset = int(noise_episode_offset)
+    a.layout = {"auto": 0, "groups": 1, "cta": 2}[layout]
     if noise_y is not None:
         a.noise_kind = NOISE_INJECTED
         a.noise_y = _ptr(_require(noise_y, "noise_y", device, dtype, (L, E, T, d, d)))

@@ -201,6 +201,9 @@ int dmfg_ac_apply_update_dev(int32_t d, double* theta_dev, double* w, const doub
  * episodes of T transitions: mfg_ac2.actor_critic.train (mfg_ac2.py:448-539),
  * AC_IRL.train with a closed-form reward (ac_irl.py:634-732) and the
  * (shift, theta0) sweep of mfg_synthetic.py:902-925.  L = 1 is config 1.    */
+#define DMFG_LEARNERS_AUTO   0
+#define DMFG_LEARNERS_GROUPS 1   /* 16 / 32 lanes per learner: throughput form (thousands of learners) */
+#define DMFG_LEARNERS_CTA    2   /* a CTA per learner (128 threads; 352 at d = 21): latency form (ONE learner = the reference's own run) */
 typedef struct dmfg_learners_args {
     uint32_t struct_size;
     int32_t  dtype;
@@ -226,7 +229,7 @@ typedef struct dmfg_learners_args {
 
     const void*    mat_pi0;     /* [S][d] start-state table (init_pi0, mfg_ac2.py:179-208) */
     int32_t        S;
-    int32_t        reserved;
+    int32_t        layout;      /* DMFG_LEARNERS_*: 0 = auto (CTA per learner for a few learners, float streams, d = 15/16/21) */
     const int32_t* start_rows;  /* [L][E] injected start rows, or NULL -> Philox randint */
     const void*    noise_y;     /* [L][E][T][d][d] (INJECTED) */
     uint64_t       seed;

@@ -184,11 +184,12 @@ def test_learners_are_independent_and_match_serial_oracle(dev, trace):
         np.testing.assert_allclose(N_(w)[l], ww, rtol=1e-10)
 
 
-@pytest.mark.parametrize("d", [15, 16, 21])
-def test_learners_v2_float_match_serial_oracle(dev, d):
+@pytest.mark.parametrize("d,layout", [(15, "groups"), (16, "groups"), (21, "groups"), (15, "cta"), (16, "cta"), (21, "cta")])
+def test_learners_v2_float_match_serial_oracle(dev, d, layout):
     """learners_v2_kernel (float streams; 16-lane groups at d = 15 / 16, 32-lane groups at the reference's default
-    d = 21): several learners with their own (theta0, shift), injected float32 Gamma variates and start rows, both
-    rewards / discount flavours, against the float64 serial oracle of mfg_ac2.train / AC_IRL.train."""
+    d = 21) and learner_cta_kernel (a CTA per learner, d = 15 / 16 / 21): several learners with their own
+    (theta0, shift), injected float32 Gamma variates and start rows, both rewards / discount flavours, against the
+    float64 serial oracle of mfg_ac2.train / AC_IRL.train."""
     E, T, L = 2, 15, 19                                   # 19 learners: not a multiple of the learners per CTA
     rng = np.random.RandomState(100 + d)
     mat = np.float32(rng.dirichlet(np.ones(d), size=9))
@@ -206,13 +207,42 @@ def test_learners_v2_float_match_serial_oracle(dev, d):
                            shift=torch.as_tensor(shifts, dtype=torch.float64, device=dev), alpha_scale=12000.0,
                            episode0=ep0, gamma=gamma, lr_critic=0.1, lr_actor=0.01, constant=False, reward=reward,
                            discount=discount, start_rows=torch.as_tensor(start, device=dev),
-                           noise_y=T_(y, dev, torch.float32))
+                           noise_y=T_(y, dev, torch.float32), layout=layout)
         for l in range(L):
             th, ww, info = O.train_serial(mat.astype(np.float64), theta0[l], w0[l], shifts[l], 12000.0, E, gamma=gamma,
                                           lr_critic=0.1, lr_actor=0.01, flavour=flavour, reward=reward,
                                           noise=O.InjectedNoise(start[l], y[l].astype(np.float64)), num_steps=T)
             np.testing.assert_allclose(N_(theta)[l], th, rtol=2e-6, err_msg="theta of learner %d" % l)
             np.testing.assert_allclose(N_(w)[l], ww, rtol=2e-5, atol=2e-6, err_msg="w of learner %d" % l)
+
+
+@pytest.mark.parametrize("d", [15, 16, 21])
+def test_learner_cta_and_group_kernels_agree_on_philox_draws(dev, d):
+    """The two layouts of dmfg_ac_learners key their draws identically (seed, learner, step, row, pair): with the
+    in-kernel sampler a learner follows the same trajectory in both, up to the order of the double sums -- theta and
+    delta after every step, episode rewards, final state and weights; AUTO picks the CTA form for a few learners."""
+    L, E, T = 5, 3, 15
+    rng = np.random.RandomState(d)
+    mat = T_(np.float32(rng.dirichlet(np.ones(d), size=11)), dev, torch.float32)
+    th0 = rng.uniform(6.0, 10.0, size=L)
+    w0 = rng.rand(L, O.num_features(d))
+    outs = {}
+    for layout in ("groups", "cta", "auto"):
+        theta = torch.as_tensor(th0, dtype=torch.float64, device=dev).clone()
+        w = torch.as_tensor(w0, dtype=torch.float64, device=dev).clone()
+        res = eng.learners(theta, w, mat, E, T, shift=0.16, alpha_scale=12000.0, lr_critic=0.1, lr_actor=0.01, seed=77,
+                           trace=True, layout=layout, learner_offset=3)
+        outs[layout] = (N_(theta), N_(w), N_(res["theta_trace"]), N_(res["delta_trace"]), N_(res["total_reward"]),
+                        N_(res["pi_final"]))
+    g, c, a = outs["groups"], outs["cta"], outs["auto"]
+    for x, y in zip(c, a):
+        np.testing.assert_array_equal(x, y)                     # AUTO == CTA at L = 5
+    np.testing.assert_allclose(c[0], g[0], rtol=1e-9)
+    np.testing.assert_allclose(c[1], g[1], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(c[2], g[2], rtol=1e-9)
+    np.testing.assert_allclose(c[3], g[3], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(c[4], g[4], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(c[5], g[5], rtol=1e-6)
 
 
 def test_generate_trajectory_d15(dev, traj15):
