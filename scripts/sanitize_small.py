@@ -22,13 +22,17 @@ for d, B, T in ((15, 37, 5), (16, 33, 4)):
                    outputs=("states", "actions", "alpha", "alpha_deriv", "rewards", "deltas", "grads", "pi_final"))  # record
     engine.rollout(pi0, 8.86349, 0.16, 12000.0, T, reward="none", seed=1, outputs=("pi_final",))                 # rollout only
 # independent serial learners (v2 math at d = 15 / 16, first-generation kernel at d = 4 and in float64)
-for d, dt in ((15, torch.float32), (16, torch.float32), (4, torch.float32), (15, torch.float64)):
+for d, dt in ((15, torch.float32), (16, torch.float32), (21, torch.float32), (4, torch.float32), (15, torch.float64)):
     F = d * (d + 1) // 2 + d + 1
     L = 19
     mat = torch.as_tensor(rng.dirichlet(np.ones(d), size=7), dtype=dt, device=dev)
     th = torch.full((L,), 8.0, dtype=torch.float64, device=dev)
     ww = torch.rand((L, F), dtype=torch.float64, device=dev)
-    engine.learners(th, ww, mat, 3, 5, shift=0.16, alpha_scale=12000.0, lr_critic=0.1, lr_actor=0.1, seed=1)
+    engine.learners(th, ww, mat, 3, 5, shift=0.16, alpha_scale=12000.0, lr_critic=0.1, lr_actor=0.1, seed=1,
+                    layout="groups")
+    if dt == torch.float32 and d in (15, 16, 21):                                                           # CTA per learner
+        engine.learners(th, ww, mat, 3, 5, shift=0.16, alpha_scale=12000.0, lr_critic=0.1, lr_actor=0.1, seed=1,
+                        layout="cta", trace=True)
 pi0 = torch.as_tensor(rng.dirichlet(np.ones(64), size=5), dtype=torch.float32, device=dev)
 engine.rollout(pi0, 8.0, 0.1, 1e4, 3, seed=2, outputs=("states", "actions"))                                     # wide kernel, d = 64
 for dd, var in ((21, "auto"), (32, "auto"), (21, "generic"), (47, "auto"), (130, "auto"), (32, "generic"), (64, "auto")):
