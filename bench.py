@@ -341,8 +341,24 @@ def run_ours(args):
                  "rollout_record": {"value": Br * T / (ms_rec * 1e-3), "unit": UNIT, "populations": Br,
                                     "hbm_gbs": Br * T * ALGO_BYTES_RECORD / (ms_rec * 1e-3) / 1e9}}
         del rec_out
+        # the reference's own run (BASELINE configs[0], what cpu_baseline / --impl reference time on the host): serial
+        # learners with per-step online updates, mfg_ac2.train semantics -- ONE learner, and one per host core
+        mat = torch.as_tensor(synthetic_pi0(21, seed=0), device=dev)
+        serial = {}
+        for L in (1, os.cpu_count() or 1):
+            th = torch.full((L,), THETA, dtype=torch.float64, device=dev)
+            ww = torch.rand((L, F), dtype=torch.float64, device=dev)
+            kw = dict(shift=SHIFT, alpha_scale=ALPHA_SCALE, lr_critic=LR_CRITIC, lr_actor=LR_ACTOR, seed=3)
+            E = 2000
+            ms = timed(lambda: engine.learners(th, ww, mat, E, T, episode0=2, **kw))
+            serial[L] = L * E * T / (ms * 1e-3)
+        modes["serial_learners"] = {"value": serial[1], "unit": UNIT, "learners": 1,
+                                    "one_per_host_core": {"learners": os.cpu_count() or 1,
+                                                          "value": serial[os.cpu_count() or 1]},
+                                    "kernel": "learner_cta_kernel<15,PHILOX>"}
         # IRL iterations/s (BASELINE config 2): 4096 demonstration + 4096 generated trajectories x 15 steps,
-        # one update_reward-equivalent = r_net forward (demo, gen) + loss + backward (demo, gen) + Adam
+        # one update_reward-equivalent = r_net backward over demo (hands back r_demo) + one pass over the generated
+        # batch (forward, loss weights, backward) + loss terms + Adam
         import contextlib
         from discrete_mean_field_game_b200.ac_irl import AC_IRL
         M = 4096
@@ -356,7 +372,7 @@ def run_ours(args):
         ms_irl = timed(lambda: irl.update_reward_batch(ds, da, gs, ga, M, "time_major", group=False), n=5)
         modes["irl_update"] = {"value": 1e3 / ms_irl, "unit": "IRL iters/s", "demo_trajectories": M,
                                "generated_trajectories": M, "transitions_per_iter": 2 * M * 15,
-                               "transitions_per_s": 2 * M * 15 / (ms_irl * 1e-3), "gpu_launches_per_iter": 9}
+                               "transitions_per_s": 2 * M * 15 / (ms_irl * 1e-3), "gpu_launches_per_iter": 6}
         del irl, ds, da, gs, ga
 
     if world > 1:
