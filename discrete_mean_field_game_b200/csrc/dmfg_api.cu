@@ -73,9 +73,9 @@ inline TdDmmaPlan td_dmma_plan(int dtype, int d, int T, long long B) {
 }
 
 
-// the throughput kernel: float streams, d = 15 / 16 (16-lane groups) and d = 21 / 32 (32-lane groups; 21 is the
-// default of mfg_ac2.py:25), sampled or injected Gamma variates
-bool v2_d(int d) { return d == 15 || d == 16 || d == 21 || d == 32; }
+// the throughput kernel: float streams, d = 15 / 16 (16-lane groups) and d = 20 / 21 / 32 (32-lane groups; 21 is the
+// default of mfg_ac2.py:25, 20 the size of test2.py:9), sampled or injected Gamma variates
+bool v2_d(int d) { return d == 15 || d == 16 || d == 20 || d == 21 || d == 32; }
 bool use_v2(const dmfg_rollout_args* a) {
     if (a->variant != DMFG_VARIANT_AUTO && a->variant != DMFG_VARIANT_V2) return false;
     return a->dtype == DMFG_F32 && v2_d(a->d) && a->noise_kind != DMFG_NOISE_ACTIONS;
@@ -130,7 +130,7 @@ int check_rollout(const dmfg_rollout_args* a) {
     if (a->variant < DMFG_VARIANT_AUTO || a->variant > DMFG_VARIANT_V2)
         return fail(DMFG_ERR_INVALID, "variant %d", a->variant);
     if (a->variant == DMFG_VARIANT_V2 && !use_v2(a))
-        return fail(DMFG_ERR_UNSUPPORTED, "the v2 kernel is built for float streams, d in {15,16,21,32}, sampled or injected noise");
+        return fail(DMFG_ERR_UNSUPPORTED, "the v2 kernel is built for float streams, d in {15,16,20,21,32}, sampled or injected noise");
     if (a->variant == DMFG_VARIANT_FAST && !fast_d(a->d))
         return fail(DMFG_ERR_UNSUPPORTED, "fast variant is built for d in {4,15,16}, not d=%d", a->d);
     if (a->B > 0 && !a->pi0) return fail(DMFG_ERR_INVALID, "pi0 is NULL");
@@ -221,6 +221,7 @@ int dispatch_v2(const RolloutParams<float>& p, int noise_kind, bool td, int* gri
     switch (p.d) {
         case 15: return dispatch_v2_d<15>(p, noise_kind, td, grid, st);
         case 16: return dispatch_v2_d<16>(p, noise_kind, td, grid, st);
+        case 20: return dispatch_v2_d<20>(p, noise_kind, td, grid, st);     // test2.py:9
         case 21: return dispatch_v2_d<21>(p, noise_kind, td, grid, st);
         case 32: return dispatch_v2_d<32>(p, noise_kind, td, grid, st);
     }

@@ -67,7 +67,7 @@ extern "C" {
 #define DMFG_VARIANT_AUTO    0
 #define DMFG_VARIANT_GENERIC 1   /* warp per population, any d <= DMFG_MAX_D         */
 #define DMFG_VARIANT_FAST    2   /* half-warp per population, compile-time d (4/15/16), float or double streams */
-#define DMFG_VARIANT_V2      3   /* throughput kernel: float streams, d = 15/16/21/32 (what AUTO picks when it applies) */
+#define DMFG_VARIANT_V2      3   /* throughput kernel: float streams, d = 15/16/20/21/32 (what AUTO picks when it applies) */
 
 #define DMFG_MAX_D 256
 
