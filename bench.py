@@ -15,8 +15,10 @@ Prints ONE JSON line (rank 0).  `value` is timed on the device with inputs resid
 `e2e` goes through the public NumPy-in/NumPy-out API (`actor_critic.train_batch`) with the
 start states copied from pinned host memory every step (double-buffered under the previous step's
 kernel) and theta/w/mean reward of every step read back into pinned host memory.
-`--impl reference` times the CPU restatement of the reference's train() loop (oracle port:
-the reference is Python and does not exist on the GPU box) on all host cores.
+`--impl reference` times the SAME workload on the box's host cores: the batched per-episode trainer restated in
+NumPy (`oracle.mfg_oracle.train_batch_port`, kind "port" -- the reference is Python and its checkout does not exist
+on the GPU box) on a bounded sample of the populations, one process per core; when the reference checkout IS present
+(the build container) the line also carries the unmodified reference's own `mfg_ac2.actor_critic.train` throughput.
 """
 from __future__ import annotations
 
@@ -40,6 +42,26 @@ LR_CRITIC, LR_ACTOR = 0.1, 0.1
 METRIC, UNIT = "population-steps/sec (d=15)", "population-steps/s"
 ALGO_BYTES_TRAIN = 16.0        # train, no recording: 2*4d/T + 8 B per population-step
 ALGO_BYTES_RECORD = 4.0 * (D + D * D) + 4.0 * D / T   # rollout + record: 963.75 B per population-step
+
+
+def bench_config(B, world):
+    """The ONE workload both arms are quoted on (BASELINE.json configs[2] at its largest size)."""
+    return {"workload": "configs[2]: batched actor-critic train step (a1-a7), %d populations/GPU x d=15 x "
+                        "16-step episodes, per-episode batch-mean update" % B,
+            "populations_per_gpu": B, "d": D, "T": T, "update": "per_episode",
+            "noise": "philox4x32-7 (in-kernel Gamma sampler)",
+            "l2": "flushed between timed iterations (256 MiB write)", "parallelism": "dp%d" % world}
+
+
+def source_sha():
+    """Hash of the sources the headline kernel is compiled from: profiles/kernel_constants.json records the hash its
+    instruction count was measured at, so a stale constant is detected instead of silently reported."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("dmfg_math.cuh", "dmfg_rollout.cuh", "dmfg_rollout2.cuh"):
+        with open(os.path.join(ROOT, "discrete_mean_field_game_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 def load_peaks():
@@ -167,7 +189,24 @@ def synthetic_pi0(B, seed):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def _cpu_worker(args):
+CPU_SAMPLE_POPS = 1024          # populations per process per CPU "step" (a bounded sample of the 2^20)
+
+
+def _cpu_worker_batch(args):
+    """the GPU arm's workload on one core: batched per-episode actor-critic over a sample of populations"""
+    seed, pops, episodes = args
+    from oracle import mfg_oracle as O
+    rng = np.random.RandomState(seed)
+    g = rng.standard_gamma(1.0, size=(pops, D))
+    pi0 = g / g.sum(1, keepdims=True)
+    w0 = rng.rand(O.num_features(D))
+    t0 = time.perf_counter()
+    O.train_batch_port(pi0, THETA, w0, SHIFT, ALPHA_SCALE, episodes, T=T, lr_critic=LR_CRITIC, lr_actor=LR_ACTOR, rng=rng)
+    return time.perf_counter() - t0
+
+
+def _cpu_worker_serial(args):
+    """the reference's own semantics (one population, per-step updates: mfg_ac2.py:448-539), oracle port"""
     seed, episodes = args
     from oracle import mfg_oracle as O
     np.random.seed(seed)
@@ -179,11 +218,50 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_throughput(episodes_per_worker, cores, pool):
+def _cpu_worker_reference(args):
+    """the UNMODIFIED reference (mfg_ac2.actor_critic.train, 15 transitions per episode) -- build container only"""
+    seed, episodes = args
+    from oracle import ref_runner
+    return ref_runner.time_train(episodes, d=D, theta=THETA, shift=SHIFT, alpha_scale=ALPHA_SCALE,
+                                 lr_critic=LR_CRITIC, lr_actor=LR_ACTOR, seed=seed)[0]
+
+
+def cpu_throughput(episodes, cores, pool, pops=CPU_SAMPLE_POPS):
+    """population-steps/s of the batched port over all cores"""
     t0 = time.perf_counter()
-    pool.map(_cpu_worker, [(100 + i, episodes_per_worker) for i in range(cores)])
+    pool.map(_cpu_worker_batch, [(100 + i, pops, episodes) for i in range(cores)])
     dt = time.perf_counter() - t0
-    return cores * episodes_per_worker * T / dt, dt
+    return cores * pops * episodes * T / dt, dt
+
+
+def cpu_serial_throughput(episodes, cores, pool):
+    t0 = time.perf_counter()
+    pool.map(_cpu_worker_serial, [(100 + i, episodes) for i in range(cores)])
+    dt = time.perf_counter() - t0
+    return cores * episodes * T / dt, dt
+
+
+def cpu_reference_throughput(episodes, cores, pool):
+    t0 = time.perf_counter()
+    pool.map(_cpu_worker_reference, [(100 + i, episodes) for i in range(cores)])
+    dt = time.perf_counter() - t0
+    return cores * episodes * 15 / dt, dt
+
+
+def reference_itself(cores, pool, seconds=4.0):
+    """Throughput of the reference's own train() when its checkout is present, else None."""
+    try:
+        from oracle import ref_runner
+        if not ref_runner.available():
+            return None
+        cpu_reference_throughput(5, cores, pool)
+        episodes = int(os.environ.get("DMFG_BENCH_REF_EPISODES", max(20, int(seconds * 1800 / 15))))
+        v, dt = cpu_reference_throughput(episodes, cores, pool)
+        return {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "seconds": dt,
+                "sample": "%d processes x %d episodes x 15 steps of the unmodified mfg_ac2.actor_critic.train "
+                          "(per-step updates, one population per process), d=15" % (cores, episodes)}
+    except Exception as exc:                                   # pragma: no cover
+        return {"unavailable": repr(exc)}
 
 
 def make_pool(cores):
@@ -199,27 +277,36 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    budget = 150.0 / (args.steps + args.warmup)                    # whole run within a few minutes
-    episodes = max(1, int(1400.0 * min(budget, 20.0) / T))         # ~1.4 k steps/s/core
-    episodes = int(os.environ.get("DMFG_BENCH_CPU_EPISODES", episodes))   # tests shrink the sample
+    # one CPU "step" = `episodes` batched episodes over CPU_SAMPLE_POPS populations per process; sized from a
+    # calibration run so that steps + warmup finish within ~2.5 minutes
     pool = make_pool(cores)
+    v0, _ = cpu_throughput(1, cores, pool)                                 # workers import the oracle; calibration
+    budget = min(150.0 / (args.steps + args.warmup), 20.0)
+    episodes = max(1, int(budget * v0 / (cores * CPU_SAMPLE_POPS * T)))
+    episodes = int(os.environ.get("DMFG_BENCH_CPU_EPISODES", episodes))    # tests shrink the sample
     for _ in range(args.warmup):
-        cpu_throughput(max(1, episodes // 8), cores, pool)
+        cpu_throughput(1, cores, pool)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_throughput(episodes, cores, pool)
     dt = time.perf_counter() - t0
+    value = args.steps * cores * CPU_SAMPLE_POPS * episodes * T / dt
+    serial, _ = cpu_serial_throughput(max(2, int(os.environ.get("DMFG_BENCH_CPU_EPISODES", 60))), cores, pool)
+    ref = reference_itself(cores, pool)
     pool.close()
-    value = args.steps * cores * episodes * T / dt
-    sample = "%d processes x %d episodes x %d steps of mfg_ac2.train per bench step (oracle port)" % (
-        cores, episodes, T)
+    sample = ("%d processes x %d episodes x %d populations x %d steps of the batched per-episode trainer per bench "
+              "step (oracle port train_batch_port, NumPy float64, np.random.gamma)" % (cores, episodes, CPU_SAMPLE_POPS, T))
+    B = 1 << args.log2_pops
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "mfg_ac2.train per-step actor-critic, d=15, T=16, single population per process",
-                   "d": D, "T": T},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": bench_config(B, max(1, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "reference_semantics_port": {"value": serial, "unit": UNIT,
+                                                      "what": "oracle port of mfg_ac2.train: ONE population per "
+                                                              "process, per-step updates"},
+                         "reference_itself": ref},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -229,7 +316,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from discrete_mean_field_game_b200 import engine
+    from discrete_mean_field_game_b200 import _lib, engine
     from discrete_mean_field_game_b200.mfg_ac2 import actor_critic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -282,6 +369,7 @@ def run_ours(args):
     step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    launches0 = int(_lib.load().dmfg_kernel_launches())
     t_wall = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                                     # L2 flush between timed iterations (untimed)
@@ -290,6 +378,7 @@ def run_ours(args):
         step_ev[k][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall
+    gpu_launches = int(_lib.load().dmfg_kernel_launches()) - launches0        # counted by the library's launch sites
     clocks = sampler.stop() if rank == 0 else None
     ms_steps = sum(a.elapsed_time(b) for a, b in step_ev)
     ms_kern = sum(a.elapsed_time(b) for a, b in kern_ev) / args.steps
@@ -318,6 +407,25 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = B * T * world * e2e_steps / float(te[0])
+
+    # ---- multi-GPU correctness inside the bench run: the summed [2+F] buffer of a small batch computed on the shards
+    # of all ranks (global population ids -> same Philox streams) against the same batch on ONE rank
+    dp_check = None
+    if world > 1:
+        Bc = 4096
+        pic = torch.as_tensor(synthetic_pi0(Bc, seed=11), device=dev)
+        lo, hi = rank * Bc // world, (rank + 1) * Bc // world
+        part = engine.rollout(pic[lo:hi].contiguous(), THETA, SHIFT, ALPHA_SCALE, T, w=w, seed=99, pop_offset=lo,
+                              outputs=(), want_acc=True)["acc"].clone()
+        dist.all_reduce(part)
+        full = engine.rollout(pic, THETA, SHIFT, ALPHA_SCALE, T, w=w, seed=99, pop_offset=0, outputs=(),
+                              want_acc=True)["acc"]
+        err = ((part - full).abs() / (full.abs() + 1e-300)).max()
+        err_abs = (part - full).abs().max()
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        dp_check = {"what": "sum over ranks of the sharded [2+F] accumulators vs the unsharded batch on one rank",
+                    "populations": Bc, "T": T, "max_rel_err": float(err), "max_abs_err": float(err_abs),
+                    "ok": bool(float(err) < 1e-9)}
 
     # ---- the other two modes of config 3 (single GPU numbers, for the roofline discussion)
     modes = {}
@@ -373,7 +481,66 @@ def run_ours(args):
         modes["irl_update"] = {"value": 1e3 / ms_irl, "unit": "IRL iters/s", "demo_trajectories": M,
                                "generated_trajectories": M, "transitions_per_iter": 2 * M * 15,
                                "transitions_per_s": 2 * M * 15 / (ms_irl * 1e-3), "gpu_launches_per_iter": 6}
-        del irl, ds, da, gs, ga
+        del ds, da, gs, ga
+        if not args.skip_big_modes:
+            # config 1's semantics at scale: 2^16 INDEPENDENT learners, each the reference's serial loop (private theta, w,
+            # per-step updates) -- the same algorithm the CPU reference runs, one population per process
+            L = 1 << 16
+            th = torch.full((L,), THETA, dtype=torch.float64, device=dev)
+            ww = torch.rand((L, F), dtype=torch.float64, device=dev)
+            E = 8
+            ms = timed(lambda: engine.learners(th, ww, mat, E, T, episode0=2, shift=SHIFT, alpha_scale=ALPHA_SCALE,
+                                               lr_critic=LR_CRITIC, lr_actor=LR_ACTOR, seed=3, want_total_reward=False))
+            modes["independent_learners"] = {"value": L * E * T / (ms * 1e-3), "unit": UNIT, "learners": L,
+                                             "episodes": E, "kernel": "learners_v2_kernel<15,16,PHILOX>",
+                                             "semantics": "mfg_ac2.train per learner (per-step updates of w, theta)"}
+            del th, ww
+            # BASELINE config 4 as stated: d = 64 / 256, 2^20 populations on one GPU, full train step (rollout + TD sums)
+            for dw in (64, 256):
+                try:
+                    Bw = 1 << 20
+                    Fw = dw * (dw + 1) // 2 + dw + 1
+                    rw = np.random.RandomState(dw)
+                    gw = rw.standard_gamma(1.0, size=(1 << 14, dw)).astype(np.float32)
+                    piw = torch.as_tensor(gw / gw.sum(1, keepdims=True), device=dev).repeat(Bw >> 14, 1).contiguous()
+                    wd = torch.as_tensor(rw.rand(Fw), dtype=torch.float64, device=dev)
+                    fn = lambda n=Bw: engine.rollout(piw[:n], THETA, SHIFT, ALPHA_SCALE, T, w=wd, seed=5, outputs=(),
+                                                     want_acc=True)
+                    fn(1 << 12); torch.cuda.synchronize()
+                    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a_.record(); fn(); b_.record(); torch.cuda.synchronize()
+                    ms = a_.elapsed_time(b_)
+                    modes["wide_d%d" % dw] = {"value": Bw * T / (ms * 1e-3), "unit": UNIT, "populations": Bw, "d": dw,
+                                              "ms": ms, "sampled_elements_per_s": Bw * T * dw * dw / (ms * 1e-3),
+                                              "what": "train step: rollout_wide_kernel + TD pass (DMMA), one launch chain"}
+                    del piw, wd
+                    engine._workspaces.clear()
+                    torch.cuda.empty_cache()
+                except Exception as exc:                       # pragma: no cover
+                    modes["wide_d%d" % dw] = {"error": repr(exc)[:200]}
+            # BASELINE config 5 per-GPU step at its stated size: one data-parallel IRL training step over 2^20 trajectories
+            try:
+                Bi = 1 << 20
+                pii = torch.as_tensor(synthetic_pi0(1 << 14, seed=9), device=dev).repeat(Bi >> 14, 1).contiguous()
+                Md = 4096
+                dsd, dad = irl.generate_batch(Md, theta=8.06)
+                dsd, dad = dsd[:15].reshape(-1, D).contiguous(), dad.reshape(-1, D, D)
+                with contextlib.redirect_stdout(sys.stderr):
+                    irl.irl_step_batch(pii[:1 << 12], dsd, dad, Md, episode=1)
+                    torch.cuda.synchronize()
+                    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a_.record(); irl.irl_step_batch(pii, dsd, dad, Md, episode=2); b_.record(); torch.cuda.synchronize()
+                ms = a_.elapsed_time(b_)
+                modes["irl_dp_step"] = {"value": Bi * 15 / (ms * 1e-3), "unit": UNIT, "trajectories_per_gpu": Bi,
+                                        "ms": ms, "demo_trajectories": Md,
+                                        "what": "AC_IRL.irl_step_batch: rollout+record, reward net fwd/bwd over the "
+                                                "record, TD sums, (all-reduce), theta/w update, Adam"}
+                del pii, dsd, dad
+            except Exception as exc:                           # pragma: no cover
+                modes["irl_dp_step"] = {"error": repr(exc)[:200]}
+        del irl
+        engine._workspaces.clear()
+        torch.cuda.empty_cache()
 
     if world > 1:
         dist.barrier()
@@ -385,46 +552,61 @@ def run_ours(args):
     peak, peak_src = load_peaks()
     achieved = B * T * ALGO_BYTES_TRAIN / (ms_kern * 1e-3) / 1e9
     consts = load_profile_constants()
-    roofline = {"bound": "hbm", "kernel": "rollout_v2_kernel<15,PHILOX,train>", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": consts.get("train_dram_bytes_per_launch"),
-                "peak_source": peak_src, "kernel_ms": ms_kern,
-                "algorithmic_bytes_per_population_step": ALGO_BYTES_TRAIN,
-                "note": "train step without recording moves 16 B per population-step: the kernel is "
-                        "instruction-issue bound (Gamma sampling, digamma), not HBM bound -- see `issue`"}
-    ipp = consts.get("train_inst_per_population_step")
+    sha = source_sha()
+    fresh = consts.get("source_sha") == sha
+    ipp = consts.get("train_inst_per_population_step") if fresh else None
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    hbm = {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+           "algorithmic_bytes_per_population_step": ALGO_BYTES_TRAIN,
+           "traffic": consts.get("train_dram_bytes_per_launch") if fresh else None}
+    # the binding roof of this kernel is instruction issue (4 warp instructions / clock / SM): the train step moves
+    # 16 B per population-step (0.2 % of HBM) and executes ~800 warp instructions for it
+    roofline = {"bound": "issue", "kernel": "rollout_v2_kernel<15,PHILOX,train>", "kernel_ms": ms_kern,
+                "unit": "warp-inst/clk/SM", "peak": 4.0, "achieved": None, "frac": None,
+                "traffic": hbm["traffic"], "hbm": hbm,
+                "warp_inst_per_population_step": ipp, "source_sha": sha,
+                "inst_count_source": consts.get("source") if fresh else
+                "STALE: profiles/kernel_constants.json was measured at source_sha %s" % consts.get("source_sha")}
     if ipp and clocks and clocks.get("sm_mhz"):
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
         ipc = ipp * (B * T / (ms_kern * 1e-3)) / (sms * clocks["sm_mhz"] * 1e6)
-        roofline["issue"] = {"warp_inst_per_population_step": ipp, "achieved_ipc_per_sm": ipc,
-                             "peak_ipc_per_sm": 4.0, "frac": ipc / 4.0}
+        roofline["achieved"], roofline["frac"] = ipc, ipc / 4.0
     if "rollout_record" in modes:
         modes["rollout_record"]["hbm_frac"] = modes["rollout_record"]["hbm_gbs"] / peak
+    for k in ("wide_d64", "wide_d256"):
+        if k in modes and "ms" in modes[k]:
+            dw = modes[k]["d"]
+            modes[k]["hbm_gbs"] = modes[k]["populations"] * T * 4.0 * (dw + 2) / (modes[k]["ms"] * 1e-3) / 1e9
+            modes[k]["hbm_frac"] = modes[k]["hbm_gbs"] / peak
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         pool = make_pool(cores)
-        cpu_throughput(5, cores, pool)                         # workers import the oracle
-        v0, _ = cpu_throughput(150, cores, pool)               # calibration
-        episodes = int(os.environ.get("DMFG_BENCH_CPU_EPISODES", max(100, int(15.0 * v0 / (cores * T)))))   # 10-15 s
+        v0, _ = cpu_throughput(1, cores, pool)                 # workers import the oracle; calibration
+        episodes = int(os.environ.get("DMFG_BENCH_CPU_EPISODES",
+                                      max(1, int(12.0 * v0 / (cores * CPU_SAMPLE_POPS * T)))))   # ~10-15 s
         v, dt = cpu_throughput(episodes, cores, pool)
+        serial, _ = cpu_serial_throughput(max(2, int(os.environ.get("DMFG_BENCH_CPU_EPISODES", 60))), cores, pool)
+        ref = reference_itself(cores, pool)
         pool.close()
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
-                        "sample": "%d processes x %d episodes x %d steps of the oracle port of mfg_ac2.train "
-                                  "(per-step updates, one population per process), d=15" % (cores, episodes, T)}
+                        "sample": "%d processes x %d episodes x %d populations x %d steps of the batched per-episode "
+                                  "trainer (oracle port train_batch_port: the GPU arm's workload on a sample of its "
+                                  "populations), d=15" % (cores, episodes, CPU_SAMPLE_POPS, T),
+                        "reference_semantics_port": {"value": serial, "unit": UNIT,
+                                                     "what": "oracle port of mfg_ac2.train: ONE population per process, "
+                                                             "per-step updates (compare modes.independent_learners)"},
+                        "reference_itself": ref}
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (transcendentals) + f64 (state, reductions)", "data": "synthetic",
-        "config": {"workload": "configs[2]: batched actor-critic train step (a1-a7), %d populations/GPU x d=15 x "
-                               "16-step episodes, per-episode batch-mean update" % B,
-                   "populations_per_gpu": B, "d": D, "T": T, "update": "per_episode", "noise": "philox4x32-7 (in-kernel Gamma sampler)",
-                   "l2": "flushed between timed iterations (256 MiB write)", "parallelism": "dp%d" % world},
+        "config": bench_config(B, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 4,
                 "d2h_bytes_per_step": (F + 1) * 8 + 8, "steps": e2e_steps},
-        "gpu_launches": 3 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "modes": modes, "wall_s": t_wall,
+        "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "dp_check": dp_check, "modes": modes, "wall_s": t_wall,
     }))
     if world > 1:
         dist.destroy_process_group()
@@ -444,6 +626,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-pops", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-big-modes", action="store_true", help="skip the 2^20-population side modes (configs 4, 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

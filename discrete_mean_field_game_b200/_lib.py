@@ -102,6 +102,7 @@ class IrlGenArgs(C.Structure):
         ("struct_size", C.c_uint32), ("T", C.c_int32), ("M", C.c_int64),
         ("gen_t_stride", C.c_int64), ("gen_j_stride", C.c_int64), ("n_demo", C.c_int64),
         ("num_demo_traj", C.c_double), ("r_demo", C.c_void_p), ("loss_out", C.c_void_p),
+        ("local_sums", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -109,6 +110,7 @@ class IrlGenArgs(C.Structure):
 SYMBOLS = [
     ("dmfg_version", C.c_int, []),
     ("dmfg_last_error", C.c_char_p, []),
+    ("dmfg_kernel_launches", C.c_uint64, []),
     ("dmfg_num_features", C.c_int64, [C.c_int32]),
     ("dmfg_acc_len", C.c_int64, [C.c_int32]),
     ("dmfg_rollout_workspace_bytes", C.c_uint64, [C.POINTER(RolloutArgs)]),
@@ -133,6 +135,7 @@ SYMBOLS = [
     ("dmfg_irl_loss_workspace_bytes", C.c_uint64, [C.c_int64]),
     ("dmfg_irl_loss_grad", C.c_int, [C.POINTER(IrlLossArgs), C.c_void_p]),
     ("dmfg_rnet_backward_gen", C.c_int, [C.POINTER(RnetArgs), C.POINTER(IrlGenArgs), C.c_void_p]),
+    ("dmfg_irl_dp_finalize", C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dmfg_adam_tf", C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64,
                                C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, C.c_void_p, C.c_void_p]),

@@ -79,10 +79,12 @@ class AC_IRL(_actor_critic):
         self.n_fc4 = n_fc4
         self.use_z = bool(use_z)
         self.one_pass_reward_update = True    # generated half of update_reward_batch in one launch (z_j = 1 only)
+        self.rank_invariant_reward_step = False   # force the data-parallel (raw sums) form on ONE rank (tests)
         self.seed = int(np.random.randint(2 ** 31 - 1)) if seed is None else int(seed)
         self.net_seed = net_seed
         self._draws = 0
         self._episodes = 0
+        self._batch_episodes = 0
         self._dropout_calls = 0
         self.mat_alpha = np.zeros([d, d])
         self.mat_alpha_deriv = np.zeros([d, d])
@@ -264,8 +266,6 @@ class AC_IRL(_actor_critic):
         One serial learner: every transition is a dmfg_rollout (sample P, pi', gradient) -> dmfg_rnet_forward
         -> dmfg_td_accumulate -> dmfg_ac_apply_update chain on the device; theta is read back once per
         episode only when stop_criteria != -1.  ``start_rows`` [E] / ``noise_y`` [E,15,d,d] replay draws."""
-        if write_all:
-            raise NotImplementedError("write_all (dump of every P to temp.csv) is not supported")
         if verbose:
             print("----- Starting train -----")
         d, T = self.d, T_STEPS
@@ -285,6 +285,9 @@ class AC_IRL(_actor_critic):
                 out = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, 1, theta_dev=theta, reward="none",
                                      noise_y=noise, seed=self.seed, step_offset=step_base + t, step_offset_dev=step_dev,
                                      outputs=("states", "actions", "grads"))
+                if write_all:                                     # ac_irl.py:670-676
+                    self.write_all_step('temp.csv', t + 1, out["states"][0, 0].double().cpu().numpy(),
+                                        out["actions"][0, 0].double().cpu().numpy())
                 r = self._reward(out["states"][0], out["actions"][0])
                 td = engine.td_accumulate(out["states"], r.reshape(1, 1), out["grads"], w, gamma=disc,
                                           discount="step", want_deltas=False)
@@ -298,7 +301,8 @@ class AC_IRL(_actor_critic):
         # advance it is captured ONCE as a CUDA graph and replayed per episode -- the start state, the two step sizes
         # and the Philox position live in device buffers refreshed before each replay (about 6x faster per step).
         graph = None
-        if use_graph and noise_y is None and not self._dropout and max_episodes >= 4:
+        scratch_streams = []       # streams whose cached workspaces (one of them owned by the graph's pool) die with train()
+        if use_graph and noise_y is None and not self._dropout and max_episodes >= 4 and not write_all:
             try:
                 pi_static = torch.empty((1, d), dtype=torch.float32, device=self.device)
                 lr_dev = torch.zeros(2, dtype=torch.float64, device=self.device)
@@ -313,7 +317,9 @@ class AC_IRL(_actor_critic):
                 torch.cuda.current_stream(self.device).wait_stream(side)
                 theta.copy_(theta0); w.copy_(w0)
                 graph = torch.cuda.CUDAGraph()
+                scratch_streams.append(side)
                 with torch.cuda.graph(graph):
+                    scratch_streams.append(torch.cuda.current_stream(self.device))
                     pi_end, total_static = run_episode(pi_static, 0.0, 0.0, 0, None, lr_dev=lr_dev, step_dev=step_dev)
                 theta.copy_(theta0); w.copy_(w0)              # capture does not execute, but keep the state explicit
             except Exception as exc:                          # pragma: no cover - eager launches are the same kernels
@@ -328,6 +334,9 @@ class AC_IRL(_actor_critic):
             lr_c = lr_critic if constant else lr_critic / (episode + 1.0)
             lr_a = lr_actor if constant else lr_actor / ((episode + 1.0) * math.log(math.log(episode + 20.0)))
             step_base = (self._episodes + episode) * T
+            if write_all:                                         # ac_irl.py:651-653
+                with open('temp.csv', 'a') as f:
+                    f.write('Episode %d \n\n' % episode)
             if graph is not None:
                 pi_static.copy_(mat[row:row + 1])
                 lr_dev.copy_(torch.tensor([lr_c, lr_a], dtype=torch.float64), non_blocking=False)
@@ -359,6 +368,9 @@ class AC_IRL(_actor_critic):
         self.theta = float(theta[0])
         self.w = w.cpu().numpy().reshape(-1, 1)
         self._episodes += max_episodes
+        del graph
+        for st in scratch_streams:
+            engine.drop_workspace(self.device, st)
         self.list_policies = (self.list_policies + [self.theta])[1:]                    # ac_irl.py:731
         if verbose:
             print("----- Exiting train at episode %d with theta %f -----" % (episode, self.theta))
@@ -381,7 +393,7 @@ class AC_IRL(_actor_critic):
         w = self._w_dev().clone()
         pi = pi0 if isinstance(pi0, torch.Tensor) and pi0.is_cuda else self._dev(np.asarray(pi0, dtype=np.float32), torch.float32)
         B = pi.shape[0]
-        _, world = parallel.world_info(group)
+        total_pops = parallel.total_count(B, group, self.device)
         p = self.reward_params
         mean_rewards, rec = [], None
         for e in range(num_episodes):
@@ -390,7 +402,8 @@ class AC_IRL(_actor_critic):
             lr_a = lr_actor if constant else lr_actor / ((episode + 1.0) * math.log(math.log(episode + 20.0)))
             noise = None if noise_y is None else self._dev(np.asarray(noise_y[e], dtype=np.float32), torch.float32)
             rec = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, T, theta_dev=theta, reward="none",
-                                 noise_y=noise, seed=seed, pop_offset=pop_offset, step_offset=episode * T,
+                                 noise_y=noise, seed=seed, pop_offset=pop_offset,
+                                 step_offset=(episode + self._batch_episodes) * T,
                                  outputs=("states", "actions", "grads"))
             kd = {}
             if self._dropout:
@@ -400,8 +413,9 @@ class AC_IRL(_actor_critic):
             td = engine.td_accumulate(rec["states"], r.view(T, B), rec["grads"], w, gamma=gamma,
                                       discount="cumulative", want_deltas=False)
             acc = parallel.allreduce_sum_(td["acc"], group)
-            engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / (B * world))
-            mean_rewards.append(acc[-1] / (B * world))
+            engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / total_pops)
+            mean_rewards.append(acc[-1] / total_pops)
+        self._batch_episodes += num_episodes        # first_episode restarts the step sizes, never the noise
         self.theta = float(theta[0])
         self.w = w.cpu().numpy().reshape(-1, 1)
         self.list_policies = (self.list_policies + [self.theta])[1:]
@@ -444,29 +458,42 @@ class AC_IRL(_actor_critic):
         lr_c = lr_critic if constant else lr_critic / (episode + 1.0)
         lr_a = lr_actor if constant else lr_actor / ((episode + 1.0) * math.log(math.log(episode + 20.0)))
         rec = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, T, theta_dev=theta, reward="none", seed=seed,
-                             pop_offset=pop_offset, step_offset=episode * T, outputs=("states", "actions", "grads"))
-        n_demo = demo_states.shape[0]
-        d_const = self._d_demo_const.get((n_demo, float(num_demo_traj)))
-        if d_const is None:
-            d_const = torch.full((n_demo,), -1.0 / float(num_demo_traj), dtype=torch.float32, device=self.device)
-            self._d_demo_const = {(n_demo, float(num_demo_traj)): d_const}
-        grad, r_demo = engine.rnet_backward(p.flat, demo_states, demo_actions, d_const, p.n_fc3, p.n_fc4,
-                                            keep_prob=networks.KEEP_PROB, want_rewards=True)
+                             pop_offset=pop_offset, step_offset=(episode + self._batch_episodes) * T,
+                             outputs=("states", "actions", "grads"))
+        self._batch_episodes += 1
         gs, ga = rec["states"][:T].reshape(-1, d), rec["actions"].reshape(-1, d, d)
-        _, loss, r_gen = engine.rnet_backward_gen(p.flat, gs, ga, p.n_fc3, p.n_fc4, T, r_demo, num_demo_traj,
-                                                  layout="time_major", grad=grad, accumulate=True,
-                                                  keep_prob=networks.KEEP_PROB, want_rewards=True)
-        td = engine.td_accumulate(rec["states"], r_gen.view(T, B), rec["grads"], w, gamma=gamma,
-                                  discount="cumulative", want_deltas=False)
-        acc = td["acc"]
-        if world > 1:
-            flat = torch.cat([acc, grad.double()])                       # [2+F] + [|r_net|]: one all-reduce
+        if world > 1 or self.rank_invariant_reward_step:
+            # data-parallel form: every rank contributes RAW sums -- the demonstration gradient for dL/dr = -1, the
+            # unnormalised generated gradient sum_j e^{R_j} dR_j, Z = sum_j e^{R_j}, sum r_demo, the trajectory and
+            # population counts -- next to its actor / critic sums; 1/N_demo, 1/Z and 1/B are applied AFTER the ONE
+            # all-reduce of the flat double buffer, so the step equals the single-rank step on the concatenated batch
+            terms, r_gen = self._dp_reward_terms(demo_states, demo_actions, gs, ga, num_demo_traj, "time_major",
+                                                 want_rewards=True)
+            td = engine.td_accumulate(rec["states"], r_gen.view(T, B), rec["grads"], w, gamma=gamma,
+                                      discount="cumulative", want_deltas=False)
+            nacc = td["acc"].numel()
+            flat = torch.cat([td["acc"], torch.full((1,), float(B), dtype=torch.float64, device=self.device), terms])
             parallel.allreduce_sum_(flat, group)
-            acc = flat[:acc.numel()]
-            grad = flat[acc.numel():].float()
-        engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / (B * world))
+            acc, total_b = flat[:nacc], flat[nacc:nacc + 1]
+            lr_dev = torch.tensor([lr_c, lr_a], dtype=torch.float64, device=self.device) / total_b
+            engine.apply_update(d, theta, w, acc, 0.0, 0.0, 1.0, lr_dev=lr_dev)
+            grad, loss = engine.irl_dp_finalize(flat[nacc + 1:].contiguous(), p.flat.numel())
+            mean_reward = acc[-1] / total_b[0]
+        else:
+            n_demo = demo_states.shape[0]
+            d_const = self._demo_weight(n_demo, -1.0 / float(num_demo_traj))
+            grad, r_demo = engine.rnet_backward(p.flat, demo_states, demo_actions, d_const, p.n_fc3, p.n_fc4,
+                                                keep_prob=networks.KEEP_PROB, want_rewards=True)
+            _, loss, r_gen = engine.rnet_backward_gen(p.flat, gs, ga, p.n_fc3, p.n_fc4, T, r_demo, num_demo_traj,
+                                                      layout="time_major", grad=grad, accumulate=True,
+                                                      keep_prob=networks.KEEP_PROB, want_rewards=True)
+            td = engine.td_accumulate(rec["states"], r_gen.view(T, B), rec["grads"], w, gamma=gamma,
+                                      discount="cumulative", want_deltas=False)
+            acc = td["acc"]
+            engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / B)
+            mean_reward = acc[-1] / B
         p.step += 1
-        reg = engine.adam_tf(p.flat, p.m, p.v, grad, p.step, self.lr_reward, grad_scale=1.0 / world,
+        reg = engine.adam_tf(p.flat, p.m, p.v, grad, p.step, self.lr_reward,
                              l1l2=self._l1l2, net=(p.d, p.n_fc3, p.n_fc4), want_reg_loss=self._l1l2)
         if reg is not None:
             loss = loss.clone()
@@ -475,8 +502,33 @@ class AC_IRL(_actor_critic):
         self.theta = float(theta[0])
         self.w = w.cpu().numpy().reshape(-1, 1)
         self.list_policies = (self.list_policies + [self.theta])[1:]
-        return dict(theta=self.theta, mean_reward=float(acc[-1]) / (B * world), loss=loss, states=rec["states"],
+        return dict(theta=self.theta, mean_reward=float(mean_reward), loss=loss, states=rec["states"],
                     actions=rec["actions"])
+
+    def _demo_weight(self, n_demo, value):
+        """constant dL/dr of the demonstration transitions (cached device vector)"""
+        d_const = self._d_demo_const.get((n_demo, float(value)))
+        if d_const is None:
+            d_const = torch.full((n_demo,), float(value), dtype=torch.float32, device=self.device)
+            self._d_demo_const = {(n_demo, float(value)): d_const}
+        return d_const
+
+    def _dp_reward_terms(self, demo_states, demo_actions, gen_states, gen_actions, num_demo_traj, layout,
+                         want_rewards=False):
+        """This rank's RAW contribution to a data-parallel reward step (ac_irl.py:390-406 over the union of all ranks'
+        trajectories): float64 [2|r_net|+4] = {d/dparams sum_demo (-r), sum_j e^{R_j} dR_j/dparams, sum_j e^{R_j},
+        sum r_demo, demonstration trajectories, generated trajectories}.  Sum over ranks -> engine.irl_dp_finalize."""
+        p = self.reward_params
+        grad_demo, r_demo = engine.rnet_backward(p.flat, demo_states, demo_actions,
+                                                 self._demo_weight(demo_states.shape[0], -1.0), p.n_fc3, p.n_fc4,
+                                                 keep_prob=networks.KEEP_PROB, want_rewards=True)
+        out = engine.rnet_backward_gen(p.flat, gen_states, gen_actions, p.n_fc3, p.n_fc4, T_STEPS, r_demo, 1.0,
+                                       layout=layout, keep_prob=networks.KEEP_PROB, want_rewards=want_rewards,
+                                       local_sums=True)
+        counts = torch.tensor([float(num_demo_traj), float(gen_states.shape[0] // T_STEPS)], dtype=torch.float64,
+                              device=self.device)
+        terms = torch.cat([grad_demo.double(), out[0].double(), out[1][:2], counts])
+        return terms, (out[2] if want_rewards else None)
 
     def _philox_randint(self, counter, n):
         w0 = engine.philox((0, 0, counter & 0xFFFFFFFF, 0xC0000000), (self.seed & 0xFFFFFFFF, self.seed >> 32))[0]
@@ -528,14 +580,24 @@ class AC_IRL(_actor_critic):
         # dL/dr of a demonstration transition is the constant -1/N (first term of ac_irl.py:390), so the
         # demonstrations need no separate forward pass: their backward launch recomputes the forward anyway
         # and hands back r_demo for the loss value.  4 -> 3 reward-net launches per update.
+        _, world = parallel.world_info(group)
+        if (world > 1 or self.rank_invariant_reward_step) and not self.use_z and self.one_pass_reward_update \
+                and masks is None and not self._dropout:
+            # rank-count invariant data-parallel step: raw sums are all-reduced, 1/N_demo and 1/Z applied afterwards
+            terms, _ = self._dp_reward_terms(demo_states, demo_actions, gen_states, gen_actions, num_demo_traj, layout)
+            parallel.allreduce_sum_(terms, group)
+            grad, loss = engine.irl_dp_finalize(terms, p.flat.numel())
+            p.step += 1
+            reg = engine.adam_tf(p.flat, p.m, p.v, grad, p.step, self.lr_reward, l1l2=self._l1l2,
+                                 net=(p.d, p.n_fc3, p.n_fc4), want_reg_loss=self._l1l2)
+            if reg is not None:
+                loss[0] += reg[0]
+            self._last_grad = grad
+            return loss
         n_demo = demo_states.shape[0]
-        d_const = self._d_demo_const.get((n_demo, float(num_demo_traj)))
-        if d_const is None:
-            d_const = torch.full((n_demo,), -1.0 / float(num_demo_traj), dtype=torch.float32, device=self.device)
-            self._d_demo_const = {(n_demo, float(num_demo_traj)): d_const}
+        d_const = self._demo_weight(n_demo, -1.0 / float(num_demo_traj))
         grad, r_demo = engine.rnet_backward(p.flat, demo_states, demo_actions, d_const, p.n_fc3, p.n_fc4,
                                             keep_prob=networks.KEEP_PROB, want_rewards=True, **kd)
-        _, world = parallel.world_info(group)
         if not self.use_z and self.one_pass_reward_update:
             # z_j = 1 (upstream's ac_irl.py:406): the generated half runs in ONE reward-net launch -- trajectory by
             # trajectory, weight exp(R_j), 1/sum_j exp(R_j) applied to the reduced gradient -- instead of

@@ -3,6 +3,7 @@
 // state: every call works on caller-owned device pointers and a caller stream.
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -16,6 +17,7 @@ using namespace dmfg;
 
 namespace {
 thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
 }
 
 namespace dmfg {
@@ -28,6 +30,7 @@ int fail(int code, const char* fmt, ...) {
     g_last_error = buf;
     return code;
 }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int sm_count(int* out) {
     int dev = 0;
     DMFG_CUDA(cudaGetDevice(&dev));
@@ -177,7 +180,7 @@ int launch_fast(RolloutParams<R> p, bool td, int* grid_out, cudaStream_t st) {
     if (grid > ntiles) grid = ntiles;
     *grid_out = (int)grid;
     kern<<<(unsigned)grid, kFastThreads, smem, st>>>(p);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -197,7 +200,7 @@ int launch_v2(RolloutParams<float> p, bool td, int* grid_out, cudaStream_t st) {
     if (grid > ntiles) grid = ntiles;
     *grid_out = (int)grid;
     kern<<<(unsigned)grid, kV2Threads, smem, st>>>(p);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 template <int D>
@@ -254,7 +257,7 @@ int launch_wide_n(const RolloutParams<float>& p, cudaStream_t st) {
     const long long need = (p.B + WPB - 1) / WPB;
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, kWideThreads, smem, st>>>(p);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 template <int NOISE>
@@ -281,7 +284,7 @@ int launch_generic(const RolloutParams<R>& p, cudaStream_t st) {
     const long long need = (p.B + WPB - 1) / WPB;
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, kGenericThreads, smem, st>>>(p);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -301,16 +304,16 @@ int run_td(const TdParams<R>& p0, double* acc, double* partials, cudaStream_t st
             double* vbuf = (double*)(dmma_ws + plan.off_v);
             const long long N = (long long)(p.T + 1) * p.B, Nt = (long long)p.T * p.B;
             td_unpack_w_kernel<<<(p.d * p.d + 255) / 256, 256, 0, st>>>(p.d, p.w, U);
-            DMFG_CUDA(cudaGetLastError());
+            DMFG_LAUNCHED();
             const size_t smem = (size_t)(kTdDmmaThreads / 32) * 8 * (p.d + 4) * sizeof(double);
             DMFG_CUDA(cudaFuncSetAttribute(td_values_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             long long grid = ((N + 7) / 8 + 3) / 4;
             if (grid > (long long)sms * 8) grid = (long long)sms * 8;
             td_values_dmma_kernel<<<(unsigned)grid, kTdDmmaThreads, smem, st>>>(p.d, N, p.states, U, p.w, vbuf);
-            DMFG_CUDA(cudaGetLastError());
+            DMFG_LAUNCHED();
             td_delta_from_values_kernel<<<(unsigned)((Nt + 255) / 256), 256, 0, st>>>(p.T, p.B, p.gamma, p.discount_kind,
                                                                                      p.rewards, vbuf, p.deltas, p.delta_buf);
-            DMFG_CUDA(cudaGetLastError());
+            DMFG_LAUNCHED();
         }
     }
     if (!plan.use) {
@@ -318,7 +321,7 @@ int run_td(const TdParams<R>& p0, double* acc, double* partials, cudaStream_t st
         long long grid = (warps_needed + 3) / 4;
         if (grid > (long long)sms * 16) grid = (long long)sms * 16;
         td_delta_kernel<R><<<(unsigned)grid, 128, 0, st>>>(p);
-        DMFG_CUDA(cudaGetLastError());
+        DMFG_LAUNCHED();
     }
     if (acc) {
         const long long N = (long long)p.T * p.B;
@@ -328,9 +331,9 @@ int run_td(const TdParams<R>& p0, double* acc, double* partials, cudaStream_t st
         const size_t smem = (size_t)kTdChunk * (p.d + 3) * sizeof(double);
         DMFG_CUDA(cudaFuncSetAttribute(td_gw_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         td_gw_kernel<R><<<(unsigned)grid, 256, smem, st>>>(p, kTdChunk, plan.use ? 1 : 0);
-        DMFG_CUDA(cudaGetLastError());
+        DMFG_LAUNCHED();
         reduce_partials_kernel<<<(F + 2 + 127) / 128, 128, 0, st>>>(partials, (int)grid, F + 2, acc);
-        DMFG_CUDA(cudaGetLastError());
+        DMFG_LAUNCHED();
         if constexpr (std::is_same<R, float>::value) {
             if (plan.use) {
                 // the quadratic features: Gram blocks on the FP64 tensor cores, split-K partials summed in fixed order
@@ -338,10 +341,10 @@ int run_td(const TdParams<R>& p0, double* acc, double* partials, cudaStream_t st
                 const long long warps = (long long)plan.nblk * plan.ksplit;
                 td_gram_dmma_kernel<<<(unsigned)((warps + 3) / 4), kTdDmmaThreads, 0, st>>>(
                     p.d, N, p.states, p.delta_buf, plan.nblk, plan.ksplit, plan.kchunk, gpart);
-                DMFG_CUDA(cudaGetLastError());
+                DMFG_LAUNCHED();
                 const int Q = p.d * (p.d + 1) / 2;
                 td_gram_reduce_kernel<<<(Q + 127) / 128, 128, 0, st>>>(p.d, plan.nblk, plan.ksplit, gpart, acc);
-                DMFG_CUDA(cudaGetLastError());
+                DMFG_LAUNCHED();
             }
         }
     }
@@ -372,7 +375,7 @@ int rollout_typed(const dmfg_rollout_args* a, cudaStream_t st) {
                 if (rc) return rc;
                 if (accum) {
                     reduce_partials_kernel<<<(F + 2 + 127) / 128, 128, 0, st>>>(p.partials, grid, F + 2, a->acc);
-                    DMFG_CUDA(cudaGetLastError());
+                    DMFG_LAUNCHED();
                 }
                 return DMFG_OK;
             }
@@ -383,7 +386,7 @@ int rollout_typed(const dmfg_rollout_args* a, cudaStream_t st) {
         if (rc) return rc;
         if (accum) {
             reduce_partials_kernel<<<(F + 2 + 127) / 128, 128, 0, st>>>(p.partials, grid, F + 2, a->acc);
-            DMFG_CUDA(cudaGetLastError());
+            DMFG_LAUNCHED();
         }
         return DMFG_OK;
     }
@@ -419,7 +422,7 @@ int launch_learners(const LearnerParams<R>& p, cudaStream_t st) {
     const long long gpb = kFastThreads / G;
     const long long grid = (p.L + gpb - 1) / gpb;
     kern<<<(unsigned)grid, kFastThreads, smem, st>>>(p);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 // float streams, d = 15 / 16: the learners on the v2 math (single-pass packed row walk)
@@ -431,14 +434,14 @@ int launch_learners_v2(const LearnerParams<float>& p, cudaStream_t st) {
     const long long gpb = kV2Threads / G;
     const long long grid = (p.L + gpb - 1) / gpb;
     kern<<<(unsigned)grid, kV2Threads, smem, st>>>(p, make_philox_keys(p.seed));
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 // float streams, d = 15 / 16 / 21, a few learners: one CTA per learner (latency form)
 template <int D, int NOISE>
 int launch_learner_cta(const LearnerParams<float>& p, cudaStream_t st) {
     learner_cta_kernel<D, NOISE><<<(unsigned)p.L, LearnerCtaGeom<D>::NT, 0, st>>>(p, make_philox_keys(p.seed));
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 template <typename R, int NOISE>
@@ -512,6 +515,7 @@ extern "C" {
 
 int dmfg_version(void) { return DMFG_VERSION; }
 const char* dmfg_last_error(void) { return g_last_error.c_str(); }
+uint64_t dmfg_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 int64_t dmfg_num_features(int32_t d) { return num_features_c(d); }
 int64_t dmfg_acc_len(int32_t d) { return 2 + (int64_t)num_features_c(d); }
 
@@ -581,13 +585,13 @@ int dmfg_critic_eval(int32_t dtype, int32_t d, int64_t N, const void* states, co
         const unsigned grid = (unsigned)((N * F + 255) / 256);
         if (dtype == DMFG_F64) critic_features_kernel<double><<<grid, 256, 0, st>>>(d, N, (const double*)states, (double*)features);
         else critic_features_kernel<float><<<grid, 256, 0, st>>>(d, N, (const float*)states, (float*)features);
-        DMFG_CUDA(cudaGetLastError());
+        DMFG_LAUNCHED();
     }
     if (values) {
         const unsigned grid = (unsigned)((N + 3) / 4);
         if (dtype == DMFG_F64) critic_value_kernel<double><<<grid, 128, 0, st>>>(d, N, (const double*)states, w, (double*)values);
         else critic_value_kernel<float><<<grid, 128, 0, st>>>(d, N, (const float*)states, w, (float*)values);
-        DMFG_CUDA(cudaGetLastError());
+        DMFG_LAUNCHED();
     }
     return DMFG_OK;
 }
@@ -607,7 +611,7 @@ int dmfg_traj_metrics(int32_t dtype, int32_t d, int64_t B, int32_t H, const void
     else
         traj_metrics_kernel<float><<<grid, 128, 0, st>>>(d, B, H, (const float*)generated, gen_stride_b, gen_stride_h,
                                                        (const float*)empirical, emp_stride_b, emp_stride_h, l1, jsd);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -624,7 +628,7 @@ int dmfg_synthetic_check(int32_t dtype, int32_t d, int64_t B, int32_t T, const v
         synthetic_check_kernel<double><<<grid, 128, smem, st>>>(d, B, T, (const double*)actions, l1, jsd);
     else
         synthetic_check_kernel<float><<<grid, 128, smem, st>>>(d, B, T, (const float*)actions, l1, jsd);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -634,7 +638,7 @@ int dmfg_ac_apply_update(int32_t d, double* theta_dev, double* w, const double* 
     const int F = num_features_c(d);
     ac_apply_update_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(F, theta_dev, w, acc, lr_critic_eff,
                                                                             lr_actor_eff, scale);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -643,7 +647,7 @@ int dmfg_ac_apply_update_dev(int32_t d, double* theta_dev, double* w, const doub
     if (d < 1 || d > DMFG_MAX_D || !w || !acc || !lr_dev) return fail(DMFG_ERR_INVALID, "dmfg_ac_apply_update_dev: bad argument");
     const int F = num_features_c(d);
     ac_apply_update_dev_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(F, theta_dev, w, acc, lr_dev, scale);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -743,7 +747,7 @@ int dmfg_gamma_sample(const float* shape, int64_t n, uint64_t seed, uint64_t pop
     const long long pairs = (n + 1) / 2;
     gamma_sample_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         shape, n, make_noise_key(seed, pop), out);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -754,7 +758,7 @@ int dmfg_digamma(int32_t dtype, const void* x, int64_t n, void* out, void* strea
     if (dtype == DMFG_F64) digamma_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x, n, (double*)out);
     else if (dtype == DMFG_F32) digamma_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, n, (float*)out);
     else return fail(DMFG_ERR_INVALID, "dtype %d", dtype);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 

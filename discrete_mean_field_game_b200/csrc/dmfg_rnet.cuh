@@ -663,7 +663,8 @@ rnet_reduce_partials_kernel(const float* __restrict__ partials, int ncta, int n,
 __global__ void __launch_bounds__(1024) irl_gen_finalize_kernel(const double* __restrict__ zpart, int ncta,
                                                                const float* __restrict__ r_demo, long long n_demo,
                                                                double num_demo_traj, long long M,
-                                                               double* __restrict__ out, float* __restrict__ inv_z) {
+                                                               double* __restrict__ out, float* __restrict__ inv_z,
+                                                               int normalise = 1) {
     __shared__ double sh[32], shz[32];
     // four independent chains per thread (fixed assignment), then a fixed-order block sum
     double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
@@ -688,6 +689,13 @@ __global__ void __launch_bounds__(1024) irl_gen_finalize_kernel(const double* __
         sd = 0.0;
         double Z = 0.0;
         for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { sd += sh[k]; Z += shz[k]; }
+        if (!normalise) {
+            // data-parallel form: this rank's LOCAL sums go out raw; the caller all-reduces them together with the
+            // unnormalised gradient and applies 1/Z afterwards (dmfg_irl_dp_finalize) -- rank-count invariant
+            out[0] = Z; out[1] = sd; out[2] = 0.0; out[3] = 0.0;
+            *inv_z = 1.0f;
+            return;
+        }
         const double first = -sd / num_demo_traj;
         const double lse = log(Z);
         const double second = lse - log((double)M);
@@ -696,6 +704,20 @@ __global__ void __launch_bounds__(1024) irl_gen_finalize_kernel(const double* __
         out[2] = second;
         out[3] = lse;
         *inv_z = (float)(1.0 / Z);
+    }
+}
+
+// Data-parallel reward step, after the all-reduce: red = [grad_demo for dL/dr = -1 (n), grad_gen_unnormalised (n),
+// Z = sum_j exp(R_j), sum r_demo, demonstration trajectories, generated trajectories] (doubles, summed over ranks).
+// grad = grad_demo / N_demo + grad_gen / Z; loss terms of ac_irl.py:390-406 from the global sums.
+__global__ void irl_dp_finalize_kernel(int n, const double* __restrict__ red, float* __restrict__ grad,
+                                       double* __restrict__ loss_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double Z = red[2 * n], sd = red[2 * n + 1], nd = red[2 * n + 2], M = red[2 * n + 3];
+    if (i < n) grad[i] = (float)(red[i] / nd + red[n + i] / Z);
+    if (i == 0 && loss_out != nullptr) {
+        const double first = -sd / nd, lse = log(Z), second = lse - log(M);
+        loss_out[0] = first + second; loss_out[1] = first; loss_out[2] = second; loss_out[3] = lse;
     }
 }
 

@@ -123,7 +123,7 @@ int dmfg_rnet_forward(const dmfg_rnet_args* a, void* stream) {
         if (int rc = rnet_grid<false, 0, 0, 0>(a, &grid, &smem)) return rc;
         rnet_kernel<kG, kNP, false, 0, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
     }
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -151,9 +151,9 @@ int dmfg_rnet_backward(const dmfg_rnet_args* a, void* stream) {
         if (int rc = rnet_grid<true, 0, 0, 0>(a, &grid, &smem)) return rc;
         rnet_kernel<kG, kNP, true, 0, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
     }
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     rnet_reduce_partials_kernel<<<(total + 31) / 32, 32 * kReduceSlices, 0, st>>>(p.partials, grid, total, a->accumulate, a->grad);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -191,11 +191,19 @@ int dmfg_rnet_backward_gen(const dmfg_rnet_args* a, const dmfg_irl_gen_args* g, 
         if (int rc = rnet_grid<true, 0, 0, 0, true>(a, &grid, &smem, g->M)) return rc;
         rnet_kernel<kG, kNP, true, 0, 0, 0, true><<<grid, kRnetThreads, smem, st>>>(p);
     }
-    DMFG_CUDA(cudaGetLastError());
-    irl_gen_finalize_kernel<<<1, 1024, 0, st>>>(p.zpart, grid, g->r_demo, g->n_demo, g->num_demo_traj, g->M, g->loss_out, inv_z);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
+    irl_gen_finalize_kernel<<<1, 1024, 0, st>>>(p.zpart, grid, g->r_demo, g->n_demo, g->num_demo_traj, g->M, g->loss_out, inv_z,
+                                                g->local_sums ? 0 : 1);
+    DMFG_LAUNCHED();
     rnet_reduce_partials_kernel<<<(total + 31) / 32, 32 * kReduceSlices, 0, st>>>(p.partials, grid, total, a->accumulate, a->grad, inv_z);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
+    return DMFG_OK;
+}
+
+int dmfg_irl_dp_finalize(int64_t n, const double* reduced, float* grad, double* loss_out, void* stream) {
+    if (n < 1 || n > INT32_MAX || !reduced || !grad) return fail(DMFG_ERR_INVALID, "dmfg_irl_dp_finalize: bad argument");
+    irl_dp_finalize_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((int)n, reduced, grad, loss_out);
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -229,14 +237,14 @@ int dmfg_irl_loss_grad(const dmfg_irl_loss_args* a, void* stream) {
     if (blocks > kLossBlocks) blocks = kLossBlocks;
     if (blocks < 1) blocks = 1;
     irl_loss_stage1_kernel<<<blocks, 256, 0, st>>>(p);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     irl_loss_stage2_kernel<<<1, 256, 0, st>>>(p, blocks);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     if (a->d_gen) {
         long long b3 = (a->M * a->T + 255) / 256;
         if (b3 > kLossBlocks) b3 = kLossBlocks;
         irl_loss_stage3_kernel<<<(int)b3, 256, 0, st>>>(p);
-        DMFG_CUDA(cudaGetLastError());
+        DMFG_LAUNCHED();
     }
     return DMFG_OK;
 }
@@ -256,7 +264,7 @@ int dmfg_adam_tf(int64_t n, float* params, float* m, float* v, const float* grad
     cudaStream_t st = (cudaStream_t)stream;
     if (reg_loss_out) {
         reg_loss_kernel<<<1, 256, 0, st>>>(params, b0, e0, b1, e1, reg_loss_out);
-        DMFG_CUDA(cudaGetLastError());
+        DMFG_LAUNCHED();
     }
     if (!l1l2) b0 = e0 = b1 = e1 = 0;
     if (n == 0) return DMFG_OK;
@@ -264,7 +272,7 @@ int dmfg_adam_tf(int64_t n, float* params, float* m, float* v, const float* grad
     adam_tf_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>((int)n, params, m, v, grad, (float)grad_scale, (float)lr_t,
                                                         (float)beta1, (float)beta2, (float)(1.0 - beta1),
                                                         (float)(1.0 - beta2), (float)eps, b0, e0, b1, e1);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -276,7 +284,7 @@ int dmfg_dirichlet_logq(int32_t d, int64_t N, int32_t K, const float* states, co
     const long long warps = N * K;
     dirichlet_logq_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, (cudaStream_t)stream>>>(d, N, K, states, actions, thetas,
                                                                                         shift, logq);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -287,7 +295,7 @@ int dmfg_irl_log_z(int64_t M, int32_t T, int32_t K, int64_t t_stride, int64_t j_
     if (M == 0) return DMFG_OK;
     irl_log_z_kernel<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(M, T, K, t_stride, j_stride, logq,
                                                                                   num_start_samples, log_z);
-    DMFG_CUDA(cudaGetLastError());
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 

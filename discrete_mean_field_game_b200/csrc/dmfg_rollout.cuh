@@ -40,7 +40,12 @@ template <typename R> struct StreamMath;
 template <> struct StreamMath<float> {
     static __device__ __forceinline__ void alpha(float th, float x, float& a, float& d) { policy_alpha_fast(th, x, a, d); }
     static __device__ __forceinline__ float psi(float x) { return digamma_fast(x); }
-    static __device__ __forceinline__ float lnp(float p) { return p > 0.0f ? lg2_approx(p) * DMFG_LN2 : -230.25850929940458f; }
+    // lg2.approx.ftz flushes a denormal argument to zero (-inf): a denormal P > 0 (a Gamma variate far below the row
+    // sum, shapes << 1) is scaled into the normal range first -- ln(p) = ln(p 2^64) - 64 ln 2
+    static __device__ __forceinline__ float lnp(float p) {
+        if (p >= 1.17549435e-38f) return lg2_approx(p) * DMFG_LN2;
+        return p > 0.0f ? (lg2_approx(p * 1.8446744073709552e19f) - 64.0f) * DMFG_LN2 : -230.25850929940458f;
+    }
 };
 template <> struct StreamMath<double> {
     static __device__ __forceinline__ void alpha(double th, double x, double& a, double& d) { policy_alpha<double>(th, x, a, d); }

@@ -5,6 +5,7 @@ scalars [T,B]); nothing falls back to the host.
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 
 import torch
@@ -15,7 +16,8 @@ from ._lib import (DISCOUNT_CUMULATIVE, DISCOUNT_STEP, F32, F64, NOISE_ACTIONS, 
 
 ROLLOUT_OUTPUTS = ("states", "actions", "alpha", "alpha_deriv", "rewards", "deltas", "grads", "pi_final")
 
-_workspaces = {}
+_workspaces = collections.OrderedDict()      # (device index, stream handle) -> scratch tensor, least recently used first
+_MAX_WORKSPACES = 16
 
 
 def _dtype_code(dtype):
@@ -57,7 +59,15 @@ def _workspace(device, nbytes):
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
+    _workspaces.move_to_end(key)
+    while len(_workspaces) > _MAX_WORKSPACES:            # short-lived side streams must not pin scratch forever
+        _workspaces.popitem(last=False)
     return ws
+
+
+def drop_workspace(device, stream):
+    """Forget the scratch cached for `stream` (a side / capture stream that is going away)."""
+    _workspaces.pop((torch.device(device).index, stream.cuda_stream), None)
 
 
 def require_cuda():
@@ -416,11 +426,13 @@ def rnet_backward(params, states, actions, drewards, n_fc3, n_fc4, *, grad=None,
 
 def rnet_backward_gen(params, states, actions, n_fc3, n_fc4, T, r_demo, num_demo_traj, *, layout="time_major",
                       grad=None, accumulate=False, mask3=None, mask4=None, keep_prob=0.4, seed=None, sample_offset=0,
-                      want_rewards=False):
+                      want_rewards=False, local_sums=False):
     """The generated half of one reward update in one pass (ac_irl.py:390-418 with z_j = 1, T <= 16): forward,
     R_j = sum_t r[j,t], backward with the weight exp(R_j), gradient scaled by 1 / sum_j exp(R_j) and written (or
     added) to `grad`.  states [M*T, d], actions [M*T, d, d] in `layout` order; r_demo: rewards of the demonstration
-    batch.  Returns (grad, loss [4] float64 device = {first+second, first, second, ln sum_j e^{R_j}}[, r_gen])."""
+    batch.  Returns (grad, loss [4] float64 device = {first+second, first, second, ln sum_j e^{R_j}}[, r_gen]).
+    local_sums=True (data-parallel form): grad is the UNNORMALISED sum_j e^{R_j} dR_j/dparams of these trajectories and
+    loss[0:2] = {sum_j e^{R_j}, sum r_demo}; reduce over ranks, then irl_dp_finalize."""
     from ._lib import IrlGenArgs
     lib = _lib.load()
     a, P = _rnet_args(params, states, actions, n_fc3, n_fc4, mask3, mask4, keep_prob, seed, sample_offset)
@@ -439,6 +451,7 @@ def rnet_backward_gen(params, states, actions, n_fc3, n_fc4, T, r_demo, num_demo
     else:
         raise ValueError("layout must be 'time_major' or 'trajectory_major'")
     g.num_demo_traj = float(num_demo_traj)
+    g.local_sums = 1 if local_sums else 0
     g.r_demo = _ptr(_require(r_demo, "r_demo", device, torch.float32, tuple(r_demo.shape)))
     with torch.cuda.device(device):
         if grad is None:
@@ -457,6 +470,20 @@ def rnet_backward_gen(params, states, actions, n_fc3, n_fc4, T, r_demo, num_demo
             a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
         check(lib.dmfg_rnet_backward_gen(C.byref(a), C.byref(g), _stream_ptr(device)))
     return (grad, loss, r) if want_rewards else (grad, loss)
+
+
+def irl_dp_finalize(reduced, n):
+    """After the all-reduce of a data-parallel reward step: reduced [2n+4] float64 = {grad_demo for dL/dr = -1,
+    unnormalised generated gradient, Z, sum r_demo, demo trajectories, generated trajectories} summed over ranks.
+    Returns (grad [n] float32 = grad_demo / N_demo + grad_gen / Z, loss [4] float64)."""
+    lib = _lib.load()
+    device = reduced.device
+    _require(reduced, "reduced", device, torch.float64, (2 * n + 4,))
+    with torch.cuda.device(device):
+        grad = torch.empty(n, dtype=torch.float32, device=device)
+        loss = torch.empty(4, dtype=torch.float64, device=device)
+        check(lib.dmfg_irl_dp_finalize(int(n), _ptr(reduced), _ptr(grad), _ptr(loss), _stream_ptr(device)))
+    return grad, loss
 
 
 def irl_loss_grad(r_demo, r_gen, T, num_demo_traj, *, layout="time_major", log_z=None, want_grads=True):

@@ -28,6 +28,10 @@ from . import engine
 from ._lib import num_features
 
 _FAST_D = (4, 15, 16)
+# sample_action / generate_trajectory / evaluate draw from their OWN Philox populations: train() uses learner ids
+# 0.. and train_batch population ids pop_offset + b at the same (seed, step) positions, and the reference draws
+# fresh noise for every call (AC_IRL.generate_batch sits at 1 << 32)
+HELPER_POP_OFFSET = 1 << 33
 
 
 def _torch_dtype(dtype):
@@ -65,6 +69,7 @@ class actor_critic:
         self.seed = int(np.random.randint(2 ** 31 - 1)) if seed is None else int(seed)
         self._draws = 0          # Philox step counter of the single-population methods
         self._episodes = 0       # episodes consumed by train() so far (Philox stream position)
+        self._batch_episodes = 0  # episodes consumed by train_batch() so far: repeated calls never replay noise
 
     # ------------------------------------------------------------------ set-up
     def init_w(self, d):
@@ -101,7 +106,7 @@ class actor_critic:
         pi = np.asarray(pi, dtype=np.float64).reshape(1, self.d)
         noise = None if y is None else self._dev(np.asarray(y).reshape(1, 1, self.d, self.d))
         out = engine.rollout(self._dev(pi), self.theta, self.shift, self.alpha_scale, 1, reward="none",
-                             noise_y=noise, seed=self.seed, step_offset=self._draws,
+                             noise_y=noise, seed=self.seed, pop_offset=HELPER_POP_OFFSET, step_offset=self._draws,
                              outputs=("actions", "alpha", "alpha_deriv"))
         if y is None:
             self._draws += 1
@@ -172,9 +177,6 @@ class actor_critic:
         """
         T = 15                                       # mfg_ac2.py:478
         d = self.d
-        if write_all:
-            raise NotImplementedError("write_all (dump of every P to temp.csv) is a debugging aid of the "
-                                      "reference and is not supported; use rollout_batch(record=True)")
         theta = torch.tensor([float(self.theta)], dtype=torch.float64, device=self.device)
         w = self._w_dev().reshape(1, -1).clone()
         mat = self._dev(self.mat_pi0)
@@ -189,8 +191,12 @@ class actor_critic:
                 kw["noise_y"] = self._dev(np.asarray(noise_y)[e:e + n].reshape(1, n, T, d, d))
             if start_rows is not None:
                 kw["start_rows"] = self._dev(np.asarray(start_rows)[e:e + n].reshape(1, n), torch.int32)
-            res = self._run_learner(theta, w, mat, n, T, self.first_episode + e, self._episodes,
-                                    gamma, constant, lr_critic, lr_actor, kw)
+            if write_all:      # mfg_ac2.py:461-463,488-494: every (pi, P) goes to temp.csv -- the host-driven per-step path
+                res = self._run_learner_generic(theta, w, mat, n, T, self.first_episode + e, self._episodes,
+                                                gamma, constant, lr_critic, lr_actor, kw, dump="temp.csv")
+            else:
+                res = self._run_learner(theta, w, mat, n, T, self.first_episode + e, self._episodes,
+                                        gamma, constant, lr_critic, lr_actor, kw)
             list_reward += res["total_reward"][0].cpu().tolist()
             e += n
             if (e - 1) % consecutive == 0:
@@ -221,8 +227,18 @@ class actor_critic:
         return self._run_learner_generic(theta, w, mat, n, T, episode0, noise_ep, gamma, constant, lr_critic,
                                          lr_actor, kw)
 
+    @staticmethod
+    def write_all_step(path, num_steps, pi, P):
+        """The per-step block the reference appends to temp.csv with write_all=1 (mfg_ac2.py:488-494)."""
+        with open(path, 'ab') as f:
+            np.savetxt(f, np.array(['num_steps = %d' % num_steps]), fmt='%s')
+            np.savetxt(f, np.array(['distribution']), fmt='%s')
+            np.savetxt(f, np.asarray(pi).reshape(1, -1), delimiter=',', fmt='%.6f')
+            np.savetxt(f, np.array(['Action']), fmt='%s')
+            np.savetxt(f, np.asarray(P), delimiter=',', fmt='%.3f')
+
     def _run_learner_generic(self, theta, w, mat, n, T, episode0, noise_ep, gamma, constant, lr_critic, lr_actor,
-                             kw):
+                             kw, dump=None):
         """Any d: the same per-step semantics driven from the host -- one transition launch (generic
         kernel), then the device-side update; parameters never leave the GPU."""
         d = self.d
@@ -241,12 +257,18 @@ class actor_critic:
             lr_c = lr_critic if constant else lr_critic / (episode + 1.0)
             lr_a = lr_actor if constant else lr_actor / ((episode + 1.0) * math.log(math.log(episode + 20.0)))
             disc = 1.0
+            if dump:
+                with open(dump, 'a') as f:
+                    f.write('Episode %d \n\n' % episode)
             for t in range(T):
                 noise = kw["noise_y"][0, e, t].reshape(1, 1, d, d) if "noise_y" in kw else None
                 g_next = gamma if self.discount_kind == "step" else disc
                 out = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, 1, w=w1, theta_dev=theta,
                                      gamma=g_next, reward=self.reward_kind, noise_y=noise, seed=self.seed,
-                                     step_offset=(episode + noise_ep) * T + t, outputs=("pi_final",), want_acc=True)
+                                     step_offset=(episode + noise_ep) * T + t,
+                                     outputs=("pi_final", "actions") if dump else ("pi_final",), want_acc=True)
+                if dump:
+                    self.write_all_step(dump, t + 1, pi[0].double().cpu().numpy(), out["actions"][0, 0].double().cpu().numpy())
                 engine.apply_update(d, theta, w1, out["acc"], lr_c, lr_a, 1.0)
                 total[0, e] += out["acc"][-1]
                 disc *= gamma
@@ -260,7 +282,7 @@ class actor_critic:
         T = int(total_hours) - 1
         noise = None if y is None else self._dev(np.asarray(y).reshape(T, 1, self.d, self.d))
         out = engine.rollout(self._dev(pi0), self.theta, self.shift, self.alpha_scale, T, reward="none",
-                             noise_y=noise, seed=self.seed, step_offset=self._draws, outputs=("states",))
+                             noise_y=noise, seed=self.seed, pop_offset=HELPER_POP_OFFSET, step_offset=self._draws, outputs=("states",))
         if y is None:
             self._draws += T
         return out["states"][:, 0].double().cpu().numpy()
@@ -289,7 +311,7 @@ class actor_critic:
         n, T = emp.shape[0], episode_length - 1
         noise = None if y is None else self._dev(np.ascontiguousarray(np.transpose(np.asarray(y), (1, 0, 2, 3))))
         out = engine.rollout(self._dev(emp[:, 0]), theta, shift, alpha_scale, T, reward="none", noise_y=noise,
-                             seed=self.seed, step_offset=self._draws, outputs=("states",))
+                             seed=self.seed, pop_offset=HELPER_POP_OFFSET, step_offset=self._draws, outputs=("states",))
         if y is None:
             self._draws += T
         l1, js = engine.traj_metrics(out["states"], self._dev(emp))
@@ -373,9 +395,12 @@ class actor_critic:
         theta = torch.tensor([float(self.theta)], dtype=torch.float64, device=self.device)
         w = self._w_dev().clone()
         _, world = parallel.world_info(group)
-        first = self.first_episode if first_episode is None else first_episode
+        first = self.first_episode if first_episode is None else first_episode      # step-size schedule only
+        noise0 = first + self._batch_episodes      # Philox position: moves on across calls (like train()'s _episodes)
         mean_rewards = []
         F = w.numel()
+        B_local = -1
+        total_pops = None                  # populations over ALL ranks (shards may differ by one): set at episode 0
 
         def source(e):
             if callable(pi0):
@@ -425,31 +450,33 @@ class actor_critic:
             else:
                 pi = self._to_device(source(e))
             B = pi.shape[0]
+            if total_pops is None or B != B_local:
+                B_local, total_pops = B, parallel.total_count(B, group, self.device)
             lr_c = lr_critic if constant else lr_critic / (episode + 1.0)
             lr_a = lr_actor if constant else lr_actor / ((episode + 1.0) * math.log(math.log(episode + 20.0)))
             if update == "per_episode":
                 out = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, T, w=w, theta_dev=theta, gamma=gamma,
                                      reward=self.reward_kind, discount=self.discount_kind, seed=seed,
-                                     pop_offset=pop_offset, step_offset=episode * T, outputs=(), want_acc=True)
+                                     pop_offset=pop_offset, step_offset=(noise0 + e) * T, outputs=(), want_acc=True)
                 if copy_stream is not None:
                     ev_free[e & 1] = torch.cuda.Event()
                     ev_free[e & 1].record(compute)
                 acc = parallel.allreduce_sum_(out["acc"], group)
-                engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / (B * world))
-                mean_rewards.append(acc[-1] / (B * world))
+                engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / total_pops)
+                mean_rewards.append(acc[-1] / total_pops)
             elif update == "per_step":
                 disc, tot = 1.0, torch.zeros((), dtype=torch.float64, device=self.device)
                 for t in range(T):
                     g_next = gamma if self.discount_kind == "step" else disc
                     out = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, 1, w=w, theta_dev=theta,
                                          gamma=g_next, reward=self.reward_kind, seed=seed, pop_offset=pop_offset,
-                                         step_offset=episode * T + t, outputs=("pi_final",), want_acc=True)
+                                         step_offset=(noise0 + e) * T + t, outputs=("pi_final",), want_acc=True)
                     if t == 0 and copy_stream is not None:
                         ev_free[e & 1] = torch.cuda.Event()
                         ev_free[e & 1].record(compute)
                     acc = parallel.allreduce_sum_(out["acc"], group)
-                    engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / (B * world))
-                    tot = tot + acc[-1] / (B * world)
+                    engine.apply_update(d, theta, w, acc, lr_c, lr_a, 1.0 / total_pops)
+                    tot = tot + acc[-1] / total_pops
                     disc *= gamma
                     pi = out["pi_final"]
                 mean_rewards.append(tot)
@@ -462,6 +489,7 @@ class actor_critic:
         if hist is not None:
             torch.cuda.current_stream(self.device).synchronize()
             extra = dict(theta_history=hist[:, 0].numpy().copy(), w_history=hist[:, 1:1 + F].numpy().copy())
+        self._batch_episodes += num_episodes
         self.theta = float(theta[0])                       # the device->host read of the step's result
         self.w = w.cpu().numpy().reshape(-1, 1)
         return dict(theta=self.theta, mean_reward=torch.stack(mean_rewards).cpu().numpy()

@@ -16,7 +16,7 @@ import torch
 
 from . import engine
 from ._lib import num_features
-from .mfg_ac2 import actor_critic as _actor_critic
+from .mfg_ac2 import HELPER_POP_OFFSET, actor_critic as _actor_critic
 
 
 class actor_critic(_actor_critic):
@@ -53,7 +53,7 @@ class actor_critic(_actor_critic):
         T = int(total_hours) - 1
         noise = None if y is None else self._dev(np.asarray(y).reshape(T, 1, self.d, self.d))
         out = engine.rollout(self._dev(pi0), self.theta, self.shift, self.alpha_scale, T, reward="none",
-                             noise_y=noise, seed=self.seed, step_offset=self._draws, outputs=("states", "actions"))
+                             noise_y=noise, seed=self.seed, pop_offset=HELPER_POP_OFFSET, step_offset=self._draws, outputs=("states", "actions"))
         if y is None:
             self._draws += T
         return out["states"][:, 0].double().cpu().numpy(), out["actions"][:, 0].double().cpu().numpy()
@@ -69,7 +69,7 @@ class actor_critic(_actor_critic):
         if actions is None:
             pi0 = self._dev(self.mat_pi0[day_first - 1:day_last])
             out = engine.rollout(pi0, self.theta, self.shift, self.alpha_scale, 15, reward="none", seed=self.seed,
-                                 step_offset=self._draws, outputs=("actions",))
+                                 pop_offset=HELPER_POP_OFFSET, step_offset=self._draws, outputs=("actions",))
             self._draws += 15
             acts = out["actions"]
         else:

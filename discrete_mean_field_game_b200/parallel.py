@@ -44,6 +44,20 @@ def allreduce_sum_(buf, group=None):
     return buf
 
 
+def total_count(n, group=None, device=None):
+    """Sum of the per-rank counts `n` as a Python int (one tiny blocking all-reduce, done ONCE per train call):
+    shard_range hands out shards whose sizes differ by one when total % world != 0, so the batch-mean scale must
+    come from the TOTAL, not from local_count * world."""
+    _, world = world_info(group)
+    if world == 1:
+        return int(n)
+    backend = dist.get_backend(group)
+    dev = device if (device is not None and backend == "nccl") else torch.device("cpu")
+    t = torch.tensor([int(n)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(t[0])
+
+
 def allreduce_max_(buf, group=None):
     _, world = world_info(group)
     if world > 1:

@@ -74,6 +74,9 @@ extern "C" {
 /* ---- library ---------------------------------------------------------- */
 int         dmfg_version(void);
 const char* dmfg_last_error(void);
+/* kernels launched through this library by the calling process so far (every launch site counts itself);
+ * bench.py reports the difference over its timed region as `gpu_launches` */
+uint64_t    dmfg_kernel_launches(void);
 /* number of critic features for d topics (mfg_ac2.py:175) */
 int64_t     dmfg_num_features(int32_t d);
 /* length of the reduced accumulator written by dmfg_rollout / dmfg_td_accumulate: 2 + F doubles
@@ -342,8 +345,19 @@ typedef struct dmfg_irl_gen_args {
     double   num_demo_traj;
     const float* r_demo;          /* [n_demo] */
     double*  loss_out;            /* [4] out */
+    int32_t  local_sums;          /* 0: as above.  1 (data-parallel form): net->grad receives the UNNORMALISED gradient
+                                     sum_j exp(R_j) dR_j/dparams of THIS rank's trajectories and loss_out[0..1] its local
+                                     sums {sum_j exp(R_j), sum r_demo}; all-reduce [grad_demo, grad, sums] over the ranks
+                                     and hand the result to dmfg_irl_dp_finalize -- the step then does not depend on how
+                                     the trajectories were sharded */
+    int32_t  reserved;
 } dmfg_irl_gen_args;
 int dmfg_rnet_backward_gen(const dmfg_rnet_args* net, const dmfg_irl_gen_args* gen, void* stream);
+/* reduced [2n+4] doubles = {demonstration gradient for dL/dr = -1 per transition (n), unnormalised generated gradient
+ * (n), Z = sum_j exp(R_j), sum r_demo, demonstration trajectories, generated trajectories}, each summed over all
+ * ranks; grad[n] (float) = grad_demo / N_demo + grad_gen / Z -- the gradient of ac_irl.py:390-406 on the WHOLE batch --
+ * and loss_out[4] as in dmfg_irl_loss_grad (optional). */
+int dmfg_irl_dp_finalize(int64_t n, const double* reduced, float* grad, double* loss_out, void* stream);
 
 /* ---- a11: one TF-style Adam step on the flat parameter vector -------------- *
  * tf.train.AdamOptimizer(lr).minimize (ac_irl.py:417-418): step counts from 1,

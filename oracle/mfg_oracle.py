@@ -406,3 +406,33 @@ def synthetic_start_states(n_rows=21, n_cols=20, d=15, seed=0):
     rows = rng.dirichlet(np.ones(n_cols), size=n_rows)
     rows = np.array([[float("%.3e" % v) for v in row] for row in rows])
     return rows[:, :d].copy()
+
+
+# --------------------------------------------------------------------------
+# the batched ("per-episode batch-mean") trainer of the GPU path, restated on the CPU with NumPy noise:
+# what bench.py --impl reference times when it is asked for the SAME workload as the GPU arm
+# --------------------------------------------------------------------------
+def train_batch_port(pi0, theta, w, shift, alpha_scale, num_episodes, *, T=16, gamma=1.0, lr_critic=0.1,
+                     lr_actor=0.1, first_episode=0, reward="ac2", rng=None):
+    """B populations share (theta, w), frozen within an episode; after every episode
+    theta += lr_a(e)/B sum delta*g, w += lr_c(e)/B sum delta*phi (the reference's updates, mfg_ac2.py:505-522,
+    applied to the batch mean).  Gamma variates from ``rng`` (vectorised np.random.gamma).  Returns (theta, w)."""
+    rng = rng or np.random
+    pi0 = np.asarray(pi0, dtype=np.float64)
+    B = pi0.shape[0]
+    w = np.array(w, dtype=np.float64).reshape(-1)
+    theta = float(theta)
+    for e in range(num_episodes):
+        episode = first_episode + e
+        pi = pi0
+        G_theta, G_w = 0.0, np.zeros_like(w)
+        for _ in range(T):
+            alpha, _ = policy_alpha(pi, theta, shift)
+            y = rng.gamma(shape=alpha * alpha_scale, scale=1.0)
+            o = transition(pi, theta, shift, alpha_scale, y, w, gamma, reward)
+            G_theta += float((o["delta"] * o["grad"]).sum())
+            G_w += (o["delta"][:, None] * o["phi"]).sum(axis=0)
+            pi = o["pi_next"]
+        theta += actor_lr(episode, lr_actor, False) / B * G_theta
+        w = w + critic_lr(episode, lr_critic, False) / B * G_w
+    return theta, w

@@ -195,6 +195,64 @@ def test_irl_step_batch_equals_train_batch_then_update_reward_batch(data):
     assert np.mean(np.abs(p1 - p0) <= 1e-6) > 0.99 and np.abs(p1 - p0).max() <= 4.2e-4     # two Adam steps of 1e-4
 
 
+def test_data_parallel_reward_step_is_rank_count_invariant(data):
+    """The data-parallel reward step (ac_irl.py:390-406 over the union of all ranks' trajectories): every "rank"
+    contributes RAW sums (demonstration gradient for dL/dr = -1, unnormalised generated gradient sum_j e^{R_j} dR_j,
+    Z, sum r_demo, counts); 1/N_demo and 1/Z are applied after the sum.  Two and three virtual ranks on one GPU must
+    give the single-batch gradient, loss and Adam step (1e-6), whatever the (uneven) sharding."""
+    from discrete_mean_field_game_b200 import engine
+    irl = make(data, reg="none")
+    ds, da = irl.generate_batch(37, theta=8.06)
+    gs, ga = irl.generate_batch(53)
+    P = irl.reward_params.flat.numel()
+
+    def shard(x, lo, hi, tail):
+        return x[:T, lo:hi].reshape((-1,) + tail).contiguous()
+
+    ref_irl = make(data, reg="none")
+    loss_ref = ref_irl.update_reward_batch(shard(ds, 0, 37, (D,)), shard(da, 0, 37, (D, D)), shard(gs, 0, 53, (D,)),
+                                           shard(ga, 0, 53, (D, D)), 37, "time_major", group=False).cpu().numpy()
+    g_ref = ref_irl._last_grad.cpu().numpy()
+    for cuts_d, cuts_g in (((0, 20, 37), (0, 11, 53)), ((0, 1, 30, 37), (0, 25, 26, 53))):
+        total = torch.zeros(2 * P + 4, dtype=torch.float64, device=irl.device)
+        for k in range(len(cuts_d) - 1):
+            terms, _ = irl._dp_reward_terms(shard(ds, cuts_d[k], cuts_d[k + 1], (D,)), shard(da, cuts_d[k], cuts_d[k + 1], (D, D)),
+                                            shard(gs, cuts_g[k], cuts_g[k + 1], (D,)), shard(ga, cuts_g[k], cuts_g[k + 1], (D, D)),
+                                            cuts_d[k + 1] - cuts_d[k], "time_major")
+            total += terms
+        grad, loss = engine.irl_dp_finalize(total, P)
+        assert float(total[2 * P + 2]) == 37 and float(total[2 * P + 3]) == 53
+        np.testing.assert_allclose(loss.cpu().numpy()[:3], loss_ref[:3], rtol=1e-6, atol=1e-6)
+        assert np.abs(grad.cpu().numpy() - g_ref).max() <= 1e-6 * np.abs(g_ref).max() + 1e-8
+    # the forced single-rank form of the public call takes the same path and lands on the same parameters
+    irl2 = make(data, reg="none")
+    irl2.rank_invariant_reward_step = True
+    irl2.update_reward_batch(shard(ds, 0, 37, (D,)), shard(da, 0, 37, (D, D)), shard(gs, 0, 53, (D,)),
+                             shard(ga, 0, 53, (D, D)), 37, "time_major", group=False)
+    np.testing.assert_allclose(irl2.reward_params.flat.cpu().numpy(), ref_irl.reward_params.flat.cpu().numpy(), rtol=0,
+                               atol=1e-6)
+
+
+def test_write_all_dumps_every_step_like_the_reference(data, tmp_path, monkeypatch):
+    """write_all=1 appends 'Episode k', then per step the state and the sampled P to temp.csv (ac_irl.py:651-676,
+    mfg_ac2.py:461-494)."""
+    from discrete_mean_field_game_b200.mfg_ac2 import actor_critic
+    monkeypatch.chdir(tmp_path)
+    ac = actor_critic(theta=8.0, shift=0.1, alpha_scale=1e4, d=D, mat_pi0=data[0], seed=3)
+    ac.train(num_episodes=2, lr_critic=0.1, lr_actor=0.01, write_all=1, verbose=False)
+    txt = open(tmp_path / "temp.csv").read()
+    assert txt.count("Episode") == 2 and txt.count("num_steps = ") == 2 * T and txt.count("Action") == 2 * T
+    assert "Episode 0 \n\n" in txt and "num_steps = 15" in txt
+    block = txt.split("Action\n")[1].split("num_steps")[0].strip().splitlines()
+    rows = np.array([[float(v) for v in ln.split(",")] for ln in block[:D]])
+    assert rows.shape == (D, D) and np.allclose(rows.sum(1), 1.0, atol=0.01)
+    os.remove(tmp_path / "temp.csv")
+    irl = make(data)
+    irl.train(max_episodes=2, stop_criteria=-1, write_all=1, verbose=False)
+    txt = open(tmp_path / "temp.csv").read()
+    assert txt.count("Episode") == 2 and txt.count("distribution") == 2 * T and "Episode 1 \n\n" in txt
+
+
 def test_update_reward_with_importance_weights(data):
     ac = make(data, use_z=True)
     ac.list_policies = list(np.linspace(6.0, 7.0, 10))

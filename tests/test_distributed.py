@@ -104,29 +104,53 @@ th1, w1, mr1 = run(False, 0, B)                       # every rank alone on all 
 np.testing.assert_allclose(th2, th1, rtol=1e-12)
 np.testing.assert_allclose(w2, w1, rtol=1e-11)
 np.testing.assert_allclose(mr2, mr1, rtol=1e-10)
-# reward step: every rank's shard is one minibatch of update_reward (the log-sum-exp of the loss is over the
-# LOCAL generated trajectories); the data-parallel step applies the MEAN of the per-rank gradients
-def irl(group, shards):
+# uneven shards (B not a multiple of the world): the batch-mean scale comes from the all-reduced TOTAL
+Bu = 4095
+def run_u(group, lo, hi):
+    ac = actor_critic(theta=8.0, shift=0.1, alpha_scale=1e4, d=d, mat_pi0=pi0[:4], device=dev, seed=78)
+    ac.w = w0.copy()
+    ac.train_batch(pi0[lo:hi], num_episodes=2, T=T, lr_critic=0.1, lr_actor=0.01, pop_offset=lo, group=group)
+    return ac.theta, ac.w.ravel().copy()
+bu, eu = parallel.shard_range(Bu, rank, world)
+thu2, wu2 = run_u(None, bu, eu)
+thu1, wu1 = run_u(False, 0, Bu)
+np.testing.assert_allclose(thu2, thu1, rtol=1e-12)
+np.testing.assert_allclose(wu2, wu1, rtol=1e-11)
+# reward step: RANK-COUNT INVARIANT -- the ranks all-reduce raw sums (demonstration gradient for dL/dr = -1, the
+# unnormalised generated gradient sum_j e^{R_j} dR_j, Z, sum r_demo, the counts) and apply 1/N_demo and 1/Z afterwards:
+# the 2-rank step equals the 1-rank step on the concatenated batch (ac_irl.py:390-406 over ALL trajectories)
+def irl(group, lo, hi):
     ac = AC_IRL(theta=6.5, d=d, reg="none", mat_pi0=pi0[:21], demonstrations=[], device=dev, seed=5, net_seed=2)
     ds, da = ac.generate_batch(64, theta=8.0)
     gs, ga = ac.generate_batch(64)
-    grads = []
-    for lo, hi in shards:
-        p0 = ac.reward_params.flat.clone()
-        ac.update_reward_batch(ds[:15, lo:hi].reshape(-1, d).contiguous(), da[:, lo:hi].reshape(-1, d, d).contiguous(),
-                               gs[:15, lo:hi].reshape(-1, d).contiguous(), ga[:, lo:hi].reshape(-1, d, d).contiguous(),
-                               hi - lo, "time_major", group=group)
-        grads.append(ac._last_grad.clone())
-        params = ac.reward_params.flat.clone()
-        ac.reward_params.load_flat(p0.cpu().numpy())
-    return grads, params
-lo, hi = parallel.shard_range(64, rank, world)
-(g_dp,), p_dp = irl(None, [(lo, hi)])                                   # 2 ranks: summed gradient, Adam on the mean
-(g0, g1), _ = irl(False, [parallel.shard_range(64, 0, 2), parallel.shard_range(64, 1, 2)])
-np.testing.assert_allclose(g_dp.cpu().numpy(), (g0 + g1).cpu().numpy(), rtol=1e-5, atol=1e-7)
+    loss = ac.update_reward_batch(ds[:15, lo:hi].reshape(-1, d).contiguous(), da[:, lo:hi].reshape(-1, d, d).contiguous(),
+                                  gs[:15, lo:hi].reshape(-1, d).contiguous(), ga[:, lo:hi].reshape(-1, d, d).contiguous(),
+                                  hi - lo, "time_major", group=group)
+    return ac._last_grad.clone(), ac.reward_params.flat.clone(), loss.clone()
+lo, hi = parallel.shard_range(63, rank, world)                           # 32 + 31 trajectories
+g_dp, p_dp, l_dp = irl(None, lo, hi)
+g_1, p_1, l_1 = irl(False, 0, 63)
+np.testing.assert_allclose(g_dp.cpu().numpy(), g_1.cpu().numpy(), rtol=2e-5, atol=1e-7)
+np.testing.assert_allclose(p_dp.cpu().numpy(), p_1.cpu().numpy(), rtol=0, atol=1e-6)
+np.testing.assert_allclose(l_dp.cpu().numpy(), l_1.cpu().numpy(), rtol=1e-6)
 gathered = [torch.empty_like(p_dp) for _ in range(world)]
 dist.all_gather(gathered, p_dp)
 assert torch.equal(gathered[0], gathered[1])                            # replicas stay identical
+# the whole IRL training step (forward solve + reward update on its record, ONE all-reduce)
+def irl_step(group, lo, hi):
+    ac = AC_IRL(theta=6.5, d=d, reg="none", mat_pi0=pi0[:21], demonstrations=[], device=dev, seed=5, net_seed=2)
+    ac.w = w0.copy()
+    ds, da = ac.generate_batch(64, theta=8.0)
+    res = ac.irl_step_batch(torch.as_tensor(pi0[lo:hi], device=dev), ds[:15, lo:hi].reshape(-1, d).contiguous(),
+                            da[:, lo:hi].reshape(-1, d, d).contiguous(), hi - lo, episode=1, lr_critic=0.1,
+                            lr_actor=0.01, pop_offset=lo, group=group)
+    return ac.theta, ac.w.ravel().copy(), ac.reward_params.flat.clone(), res["loss"].clone()
+t2, ww2, pp2, ll2 = irl_step(None, lo, hi)
+t1, ww1, pp1, ll1 = irl_step(False, 0, 63)
+np.testing.assert_allclose(t2, t1, rtol=1e-9)
+np.testing.assert_allclose(ww2, ww1, rtol=1e-8)
+np.testing.assert_allclose(pp2.cpu().numpy(), pp1.cpu().numpy(), rtol=0, atol=1e-6)
+np.testing.assert_allclose(ll2.cpu().numpy(), ll1.cpu().numpy(), rtol=1e-6)
 dist.barrier(); dist.destroy_process_group()
 print("rank %%d ok" %% rank)
 '''
