@@ -228,19 +228,56 @@ class AC_IRL(_actor_critic):
         a = self._dev(np.asarray(a, dtype=np.float32).reshape(-1, self.d, self.d), torch.float32)
         return self._reward(s, a).cpu().numpy().reshape(-1, 1)
 
+    def _named_slots(self, flat):
+        p = self.reward_params
+        flat = flat.cpu().numpy()
+        return {n: flat[o:o + int(np.prod(sh))].reshape(sh).copy() for n, sh, o in zip(p.NAMES, p.shapes, p.offsets)}
+
     def save(self, path):
-        """Reward-net checkpoint (stands in for tf.train.Saver.save, ac_irl.py:948): an .npz of the
-        named tensors reward/{conv1,conv2,fc3,fc4,out}/{weights,biases} plus the Adam state."""
+        """tf.train.Saver.save (ac_irl.py:948): writes a TF1 "V2" checkpoint bundle -- ``path.index`` +
+        ``path.data-00000-of-00001`` -- with the variables a Saver of the reference's graph holds:
+        reward/{conv1,conv2,fc3,fc4,out}/{weights,biases}, their Adam slots (``.../Adam``, ``.../Adam_1``) and
+        beta1_power / beta2_power (tf_checkpoint.py, no TensorFlow involved).  A ``.npz`` with the same tensors is
+        written next to it (round 1's format, still restorable)."""
+        from . import tf_checkpoint
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
         p = self.reward_params
         tensors = {"reward/" + k: v for k, v in p.named().items()}
+        bundle = dict(tensors)
+        for k, v in self._named_slots(p.m).items():
+            bundle["reward/%s/Adam" % k] = v
+        for k, v in self._named_slots(p.v).items():
+            bundle["reward/%s/Adam_1" % k] = v
+        bundle["beta1_power"] = np.float32(0.9 ** (p.step + 1))          # TF stores beta^t for the NEXT step
+        bundle["beta2_power"] = np.float32(0.999 ** (p.step + 1))
+        tf_checkpoint.write_bundle(path, bundle)
         np.savez(path, adam_m=p.m.cpu().numpy(), adam_v=p.v.cpu().numpy(), adam_step=p.step, **tensors)
 
     def restore(self, path):
+        """tf.train.Saver.restore (ac_irl.py:110-111): ``path`` is the checkpoint prefix.  Reads a TF1 V2 bundle
+        (written by TensorFlow or by save()) through the TF-free reader; falls back to round 1's ``.npz``."""
+        from . import tf_checkpoint
+        p = self.reward_params
+        if os.path.exists(path + ".index"):
+            z = tf_checkpoint.read_bundle(path)
+            missing = [n for n in p.NAMES if "reward/" + n not in z]
+            if missing:
+                raise KeyError("checkpoint %s lacks reward-net variables %s (has: %s)" % (path, missing, sorted(z)))
+            p.load_named({k[len("reward/"):]: v for k, v in z.items() if k.startswith("reward/")})
+            if all("reward/%s/Adam" % n in z and "reward/%s/Adam_1" % n in z for n in p.NAMES):
+                flat_m, flat_v = p.m.cpu().numpy(), p.v.cpu().numpy()
+                for n, sh, o in zip(p.NAMES, p.shapes, p.offsets):
+                    k = int(np.prod(sh))
+                    flat_m[o:o + k] = np.asarray(z["reward/%s/Adam" % n], dtype=np.float32).reshape(-1)
+                    flat_v[o:o + k] = np.asarray(z["reward/%s/Adam_1" % n], dtype=np.float32).reshape(-1)
+                p.m.copy_(torch.as_tensor(flat_m, device=p.device))
+                p.v.copy_(torch.as_tensor(flat_v, device=p.device))
+                if "beta1_power" in z:                        # beta1^(t+1) -> steps taken so far
+                    p.step = max(0, int(round(math.log(float(z["beta1_power"])) / math.log(0.9))) - 1)
+            return
         if not path.endswith(".npz"):
             path = path + ".npz"
         z = np.load(path)
-        p = self.reward_params
         p.load_named({k[len("reward/"):]: z[k] for k in z.files if k.startswith("reward/")})
         if "adam_m" in z.files:
             p.m.copy_(torch.as_tensor(z["adam_m"], device=p.device))

@@ -104,3 +104,63 @@ def test_td_errors_telescope_at_full_size(dev):
     np.testing.assert_allclose(float(acc[-1]), float(out["rewards"].double().sum()), rtol=1e-6)
     # bias feature of the critic gradient = sum of all TD errors
     np.testing.assert_allclose(float(acc[O.num_features(D)]), float(out["deltas"].double().sum()), rtol=1e-5, atol=1e-3)
+
+
+def test_config2_shape_4096_populations_vs_oracle(dev):
+    """BASELINE config 2's shape -- AC_IRL defaults (theta 8.64, shift 0, alpha_scale 1e4, ac_irl.py:33), 4096
+    populations x 15 steps -- on injected Gamma variates against the float64 oracle at north_star's 1e-5."""
+    B, T2, th, sh, sc = 4096, 15, 8.64, 0.0, 1e4
+    rng = np.random.RandomState(2)
+    pi0 = np.float32(rng.dirichlet(np.ones(D), size=B))
+    w = rng.rand(O.num_features(D))
+    y = np.zeros((T2, B, D, D), np.float32)
+    pi = pi0.astype(np.float64)
+    for t in range(T2):
+        alpha, _ = O.policy_alpha(pi, th, sh)
+        y[t] = np.float32(rng.gamma(alpha * sc))
+        pi = O.mean_field_step(O.normalise_gamma(y[t].astype(np.float64)), pi)
+    ref = O.rollout_frozen(pi0.astype(np.float64), th, sh, sc, y.astype(np.float64), w=w, gamma=0.95, discount="cumulative")
+    out = eng.rollout(torch.as_tensor(pi0, device=dev), th, sh, sc, T2, w=torch.as_tensor(w, device=dev), gamma=0.95,
+                      discount="cumulative", noise_y=torch.as_tensor(y, device=dev),
+                      outputs=("states", "actions", "alpha", "alpha_deriv", "rewards", "deltas", "grads"), want_acc=True)
+    N = lambda t: t.double().cpu().numpy()
+    for k in ("states", "actions", "alpha"):
+        np.testing.assert_allclose(N(out[k]), ref[k], rtol=1e-5, atol=1e-30, err_msg=k)
+    np.testing.assert_allclose(N(out["alpha_deriv"]), ref["alpha_deriv"], rtol=1e-5, atol=3e-8)   # float32 rounding of x
+    np.testing.assert_allclose(N(out["grads"]), ref["grads"], rtol=1e-5, atol=2e-6 * D)           # mixed-sign sum of d^2 terms
+    v = np.abs(O.features(ref["states"]) @ w)
+    scale = np.abs(ref["rewards"]) + v[1:] + v[:-1]
+    assert np.all(np.abs(N(out["rewards"]) - ref["rewards"]) <= 1e-6 * np.maximum(scale, 1e-3))
+    assert np.all(np.abs(N(out["deltas"]) - ref["deltas"]) <= 1e-6 * scale)
+    acc = N(out["acc"])
+    F = O.num_features(D)
+    np.testing.assert_allclose(acc[0], ref["G_theta"], rtol=1e-5)
+    wscale = np.sum(np.abs(ref["deltas"])[..., None] * np.abs(O.features(ref["states"][:-1])), axis=(0, 1))
+    assert np.all(np.abs(acc[1:1 + F] - ref["G_w"]) <= 1e-6 * wscale + 1e-12)
+    np.testing.assert_allclose(acc[1 + F], ref["R"], rtol=1e-5)
+
+
+def test_config3_sample_of_2_16_populations_vs_oracle(dev):
+    """A 2^16-population launch of config 3 (in-kernel Philox, 16 steps, recorded): 2048 randomly chosen populations are
+    re-evaluated by the float64 oracle from the RECORDED (pi_t, P_t) -- alpha, alpha', pi', reward, TD error, gradient
+    -- at 1e-5.  (The record's float32 rows sum to 1 only to 1e-7, which bounds how close r and delta can be.)"""
+    B = 1 << 16
+    w = _w(dev)
+    out = eng.rollout(_pi0(B, dev, seed=5), THETA, SHIFT, SCALE, T, w=w, seed=4321,
+                      outputs=("states", "actions", "alpha", "alpha_deriv", "rewards", "deltas", "grads"), want_acc=True)
+    idx = torch.as_tensor(np.random.RandomState(1).choice(B, 2048, replace=False), device=dev)
+    S = out["states"][:, idx].double().cpu().numpy()
+    P = out["actions"][:, idx].double().cpu().numpy()
+    alpha, deriv = O.policy_alpha(S[:-1], THETA, SHIFT)
+    np.testing.assert_allclose(out["alpha"][:, idx].double().cpu().numpy(), alpha, rtol=1e-5)
+    np.testing.assert_allclose(out["alpha_deriv"][:, idx].double().cpu().numpy(), deriv, rtol=1e-5, atol=3e-8)
+    np.testing.assert_allclose(np.einsum("tbi,tbij->tbj", S[:-1], P), S[1:], rtol=1e-5, atol=1e-9)
+    g = O.log_policy_gradient(alpha, deriv, P)
+    np.testing.assert_allclose(out["grads"][:, idx].double().cpu().numpy(), g, rtol=1e-5, atol=2e-6 * D)
+    r = O.reward_ac2(P, S[:-1])
+    wn = w.cpu().numpy()
+    v = O.features(S) @ wn
+    delta = r + v[1:] - v[:-1]
+    scale = np.abs(r) + np.abs(v[1:]) + np.abs(v[:-1])
+    assert np.all(np.abs(out["rewards"][:, idx].double().cpu().numpy() - r) <= 1e-6 * np.maximum(scale, 1e-3))
+    assert np.all(np.abs(out["deltas"][:, idx].double().cpu().numpy() - delta) <= 1e-6 * scale)

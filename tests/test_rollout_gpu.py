@@ -3,10 +3,14 @@ the oracle and the reference-generated golden fixtures.
 
 Tolerances (stated here, used below)
   float64 streams : rtol 1e-10 everywhere (libm-level differences only)
-  float32 streams : pi', P, alpha, g      rtol 2e-5  (transcendentals in fp32)
-                    r, delta, sums        |err| <= 1e-5 * operand scale; the kernels
-                                          accumulate them in float64, so the error is
-                                          the fp32 rounding of P / alpha only
+  float32 streams : pi', P, alpha, g      rtol 1e-5  (north_star's tolerance; achieved maxima over 2^16 populations:
+                                          pi' 6e-8, P 1.2e-7, alpha 1.9e-6 -- profiles/r2_parity_maxerr.md)
+                    alpha', g             quantities that cross zero (alpha' = x sigma(theta x), x = pi_j - pi_i - shift;
+                                          g sums d^2 terms of mixed sign): rtol 1e-5 plus an absolute floor from the
+                                          float32 rounding of x (|err(x)| <= 3e-8), stated at each use
+                    r, delta, sums        |err| <= 1e-6 * operand scale; the kernels accumulate them in float64, so
+                                          the error is the fp32 rounding of P / alpha only
+                    G_theta               rtol 1e-5 of the sum plus 1e-7 of sum |delta g| (cancellation)
 """
 import numpy as np
 import pytest
@@ -35,7 +39,7 @@ def N_(t):
     return t.detach().cpu().numpy().astype(np.float64)
 
 
-RT = {torch.float64: 1e-10, torch.float32: 2e-5}
+RT = {torch.float64: 1e-10, torch.float32: 1e-5}
 ALL_OUT = ("states", "actions", "alpha", "alpha_deriv", "rewards", "deltas", "grads", "pi_final")
 
 
@@ -440,21 +444,21 @@ def test_v2_random_batch_vs_oracle(dev, d, T):
     out = eng.rollout(T_(pi0, dev, torch.float32), 8.64, 0.05, 1e4, T, w=T_(w, dev, torch.float64),
                       noise_y=T_(y, dev, torch.float32), outputs=ALL_OUT, want_acc=True, variant="v2")
     for k in ("states", "alpha"):
-        np.testing.assert_allclose(N_(out[k]), ref[k], rtol=2e-5, err_msg=k)
+        np.testing.assert_allclose(N_(out[k]), ref[k], rtol=1e-5, err_msg=k)
     # alpha' = x sigma(theta x) crosses zero with x = pi_j - pi_i - shift: float32 inputs bound |err(x)| by ~1e-8
-    np.testing.assert_allclose(N_(out["alpha_deriv"]), ref["alpha_deriv"], rtol=2e-5, atol=3e-8)
-    np.testing.assert_allclose(N_(out["actions"]), ref["actions"], rtol=2e-5, atol=1e-30)
+    np.testing.assert_allclose(N_(out["alpha_deriv"]), ref["alpha_deriv"], rtol=1e-5, atol=3e-8)
+    np.testing.assert_allclose(N_(out["actions"]), ref["actions"], rtol=1e-5, atol=1e-30)
     # g sums d^2 terms of mixed sign: bound relative to the sum of their magnitudes (~ d for these inputs)
-    np.testing.assert_allclose(N_(out["grads"]), ref["grads"], rtol=2e-5, atol=max(2e-5, 2e-6 * d))
+    np.testing.assert_allclose(N_(out["grads"]), ref["grads"], rtol=1e-5, atol=max(2e-5, 2e-6 * d))
     v = np.abs(O.features(ref["states"]) @ w)
     scale = np.abs(ref["rewards"]) + v[1:] + v[:-1]
     assert np.all(np.abs(N_(out["deltas"]) - ref["deltas"]) <= 1e-6 * scale)
     assert np.all(np.abs(N_(out["rewards"]) - ref["rewards"]) <= 1e-6 * np.maximum(scale, 1e-3))
     acc = N_(out["acc"])
-    np.testing.assert_allclose(acc[0], ref["G_theta"], rtol=1e-4)
+    assert abs(acc[0] - ref["G_theta"]) <= 1e-5 * abs(ref["G_theta"]) + 1e-7 * np.sum(np.abs(ref["deltas"] * ref["grads"]))
     wscale = np.sum(np.abs(ref["deltas"])[..., None] * np.abs(O.features(ref["states"][:-1])), axis=(0, 1))
     assert np.all(np.abs(acc[1:1 + F] - ref["G_w"]) <= 1e-5 * wscale + 1e-12)
-    np.testing.assert_allclose(acc[1 + F], ref["R"], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(acc[1 + F], ref["R"], rtol=1e-5, atol=1e-9)
     # the TRAIN specialisation (no per-step stream) on the same variates: same sums
     tr = eng.rollout(T_(pi0, dev, torch.float32), 8.64, 0.05, 1e4, T, w=T_(w, dev, torch.float64),
                      noise_y=T_(y, dev, torch.float32), outputs=(), want_acc=True, variant="v2")
@@ -537,12 +541,12 @@ def test_wide_kernel_vs_oracle(dev, d):
     out = eng.rollout(T_(pi0, dev, torch.float32), 8.64, 0.05, 1e4, T, w=T_(w, dev, torch.float64),
                       noise_y=T_(y, dev, torch.float32), outputs=ALL_OUT, want_acc=True, variant="generic")
     for k in ("states", "alpha"):
-        np.testing.assert_allclose(N_(out[k]), ref[k], rtol=2e-5, err_msg=k)
-    np.testing.assert_allclose(N_(out["alpha_deriv"]), ref["alpha_deriv"], rtol=2e-5, atol=3e-8)
-    np.testing.assert_allclose(N_(out["actions"]), ref["actions"], rtol=2e-5, atol=1e-30)
-    np.testing.assert_allclose(N_(out["pi_final"]), ref["states"][-1], rtol=2e-5)
+        np.testing.assert_allclose(N_(out[k]), ref[k], rtol=1e-5, err_msg=k)
+    np.testing.assert_allclose(N_(out["alpha_deriv"]), ref["alpha_deriv"], rtol=1e-5, atol=3e-8)
+    np.testing.assert_allclose(N_(out["actions"]), ref["actions"], rtol=1e-5, atol=1e-30)
+    np.testing.assert_allclose(N_(out["pi_final"]), ref["states"][-1], rtol=1e-5)
     # g sums d^2 terms of mixed sign: bound relative to the sum of their magnitudes (~ d for these inputs)
-    np.testing.assert_allclose(N_(out["grads"]), ref["grads"], rtol=2e-5, atol=2e-6 * d)
+    np.testing.assert_allclose(N_(out["grads"]), ref["grads"], rtol=1e-5, atol=2e-6 * d)
     v = np.abs(O.features(ref["states"]) @ w)
     scale = np.abs(ref["rewards"]) + v[1:] + v[:-1]
     assert np.all(np.abs(N_(out["deltas"]) - ref["deltas"]) <= 1e-6 * scale)
@@ -550,7 +554,7 @@ def test_wide_kernel_vs_oracle(dev, d):
     acc = N_(out["acc"])
     wscale = np.sum(np.abs(ref["deltas"])[..., None] * np.abs(O.features(ref["states"][:-1])), axis=(0, 1))
     assert np.all(np.abs(acc[1:1 + F] - ref["G_w"]) <= 1e-5 * wscale + 1e-12)
-    np.testing.assert_allclose(acc[1 + F], ref["R"], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(acc[1 + F], ref["R"], rtol=1e-5, atol=1e-9)
 
 
 def test_random_regimes_invariants_and_variant_agreement(dev):
