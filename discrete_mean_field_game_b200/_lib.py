@@ -145,6 +145,9 @@ SYMBOLS = [
                                  C.c_void_p, C.c_void_p]),
     ("dmfg_synthetic_check", C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    ("dmfg_umma_probe", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32,
+                                  C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    ("dmfg_umma_selftest", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     ("dmfg_philox4x32_10", None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("dmfg_gamma_philox_rounds", C.c_int32, []),
     ("dmfg_philox4x32_gamma", None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

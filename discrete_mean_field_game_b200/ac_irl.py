@@ -440,7 +440,7 @@ class AC_IRL(_actor_critic):
             noise = None if noise_y is None else self._dev(np.asarray(noise_y[e], dtype=np.float32), torch.float32)
             rec = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, T, theta_dev=theta, reward="none",
                                  noise_y=noise, seed=seed, pop_offset=pop_offset,
-                                 step_offset=(episode + self._batch_episodes) * T,
+                                 step_offset=(self.first_episode + self._batch_episodes + e) * T,
                                  outputs=("states", "actions", "grads"))
             kd = {}
             if self._dropout:
@@ -495,9 +495,9 @@ class AC_IRL(_actor_critic):
         lr_c = lr_critic if constant else lr_critic / (episode + 1.0)
         lr_a = lr_actor if constant else lr_actor / ((episode + 1.0) * math.log(math.log(episode + 20.0)))
         rec = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, T, theta_dev=theta, reward="none", seed=seed,
-                             pop_offset=pop_offset, step_offset=(episode + self._batch_episodes) * T,
+                             pop_offset=pop_offset, step_offset=(self.first_episode + self._batch_episodes) * T,
                              outputs=("states", "actions", "grads"))
-        self._batch_episodes += 1
+        self._batch_episodes += 1              # `episode` drives the step sizes only; the noise never restarts
         gs, ga = rec["states"][:T].reshape(-1, d), rec["actions"].reshape(-1, d, d)
         if world > 1 or self.rank_invariant_reward_step:
             # data-parallel form: every rank contributes RAW sums -- the demonstration gradient for dL/dr = -1, the

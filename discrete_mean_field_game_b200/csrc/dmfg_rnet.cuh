@@ -19,6 +19,7 @@
 // accumulators in registers.  Per-CTA partials are then summed in fixed order (deterministic).
 #pragma once
 #include "dmfg_math.cuh"
+#include "dmfg_umma.cuh"
 #include "../../include/dmfg.h"
 
 namespace dmfg {
@@ -81,7 +82,12 @@ struct RnetSmem {
     static constexpr int RC = G + 2, SC = (G + 2) | 1;
     static constexpr int NSLOT = 25 + 1 + 18 + 2 + 2 * NP;     // per-thread gradient slots
     static constexpr int NSMALL = 3 * NP + 1;                  // per-group: gW5[NP] gb4[NP] gb3[NP] gb5
-    int wflat, w3s, w3stride, tiles, tile_stride, flat, flat_stride, dz3, gacc, gsmall, total;
+    // tensor-core operand tiles of the fc3 weight gradient (dmfg_umma.cuh): rows m = t * G + h (t < 2d: position inside
+    // the lane's row of conv2 activations, h: lane), K = the GPB transitions of the tile
+    static constexpr int MT = (2 * G * G + 127) / 128, KG = GPB / 8;
+    using W3G = umma::W3Grad<MT, KG>;
+    static_assert(GPB % 8 == 0 && NP <= 8, "tile = whole groups of 8 transitions; fc3 width <= 8");
+    int wflat, w3s, w3stride, tiles, tile_stride, umA, umB, gacc, gsmall, total;
     __host__ __device__ RnetSmem(int d, int ptotal) {
         int o = 0;
         wflat = o; o += (ptotal + 3) / 4 * 4;
@@ -94,13 +100,13 @@ struct RnetSmem {
         // (ncu: 34 % of the shared wavefronts were 2-way conflicts between the two groups before this)
         tile_stride += (16 - (tile_stride & 31) + 32) & 31;
         tiles = o; o += GPB * tile_stride;
-        flat = dz3 = gacc = gsmall = 0; flat_stride = 0;
+        umA = umB = gacc = gsmall = 0;
         if (BWD) {
-            flat_stride = 2 * d * d;
-            flat_stride += flat_stride & 1;
-            flat = o; o += GPB * flat_stride;
-            dz3 = o; o += GPB * NP;
-            gacc = o; o += NSLOT * kRnetThreads;
+            o = (o + 31) & ~31;                                      // 128-byte aligned operand tiles
+            umA = o; o += 2 * (int)(W3G::kBytesA / 4);               // hi, lo
+            umB = o; o += 2 * (int)(W3G::kBytesB / 4);               // hi, lo
+            gacc = umA;                                              // end-of-kernel staging reuses the operand tiles
+            static_assert(NSLOT * kRnetThreads <= 2 * (int)(W3G::kBytesA / 4), "staging must fit the operand tiles");
             gsmall = o; o += GPB * NSMALL;
         }
         total = o;
@@ -125,6 +131,141 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* mbar, uint32_t par
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
     }
+}
+
+// the same wait with a bound on the spin: a tensor-core commit that never arrives (a malformed descriptor) must end in
+// a trap, not in a hung GPU
+__device__ __forceinline__ void mbar_wait_bounded(unsigned long long* mbar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 22)) __trap();
+    }
+}
+
+// Testing aid (dmfg_umma_selftest): the tensor-core path of the fc3 weight gradient in isolation -- out[512][8] =
+// sum over passes of h_p^T . z_p  with h_p [16][512] and z_p [16][8], through exactly the operand tiles, descriptors,
+// MMA sequence, commit / mbarrier hand-off and TMEM read-back that rnet_kernel<BWD> uses.
+__global__ void __launch_bounds__(256, 1) umma_selftest_kernel(const float* __restrict__ h, const float* __restrict__ z,
+                                                              int passes, float* __restrict__ out) {
+    using W = umma::W3Grad<4, 2>;
+    extern __shared__ __align__(128) unsigned char usm[];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char *a_hi = usm, *a_lo = usm + W::kBytesA, *b_hi = usm + 2 * W::kBytesA, *b_lo = b_hi + W::kBytesB;
+    for (int i = tid; i < (int)((2 * W::kBytesA + 2 * W::kBytesB) / 4); i += 256) reinterpret_cast<float*>(usm)[i] = 0.f;
+    if (tid == 0) mbar_init(&bar, 1);
+    if (warp == 0) umma::tmem_alloc(smem_u32(&tmem_slot), W::kTmemCols);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    uint32_t phase = 0;
+    bool pending = false;
+    for (int p = 0; p < passes; ++p) {
+        if (pending) { mbar_wait_bounded(&bar, phase); phase ^= 1u; }
+        for (int i = tid; i < 16 * 512; i += 256) {
+            const int n = i >> 9, k = i & 511;
+            float hi, lo;
+            umma::split_tf32(h[(size_t)p * 8192 + i], hi, lo);
+            *reinterpret_cast<float*>(a_hi + W::off(k, n)) = hi;
+            *reinterpret_cast<float*>(a_lo + W::off(k, n)) = lo;
+        }
+        if (tid < 128) {
+            const int n = tid >> 3, j = tid & 7;
+            float hi, lo;
+            umma::split_tf32(z[(size_t)p * 128 + tid], hi, lo);
+            *reinterpret_cast<float*>(b_hi + W::off(j, n)) = hi;
+            *reinterpret_cast<float*>(b_lo + W::off(j, n)) = lo;
+        }
+        umma::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) W::issue(tmem, smem_u32(a_hi), smem_u32(a_lo), smem_u32(b_hi), smem_u32(b_lo), p == 0, smem_u32(&bar));
+        pending = true;
+    }
+    if (pending) mbar_wait_bounded(&bar, phase);
+    umma::fence_after_sync();
+    {
+        const int q = warp & 3;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int mm = 2 * (warp >> 2) + e;
+            float v[8];
+            umma::tmem_ld_32x32b_x8(tmem + ((uint32_t)(32 * q) << 16) + 16u * (uint32_t)mm, v);
+            const int kidx = 128 * mm + 32 * q + lane;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) out[kidx * 8 + j] = passes > 0 ? v[j] : 0.f;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, W::kTmemCols);
+}
+
+// Testing aid (dmfg_umma_probe): ONE kind::tf32 MMA D[128 x 16] = A[128 x 8] . B[8 x 16] with the operands laid out
+// by the canonical un-swizzled formulas for the requested major-ness and (LBO, SBO) -- pins the descriptor semantics
+// the kernels rely on.  a_cfg / b_cfg = {mn_major, lbo_bytes, sbo_bytes}.
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                           int a_mn, uint32_t a_lbo, uint32_t a_sbo, int b_mn, uint32_t b_lbo,
+                                                           uint32_t b_sbo, uint32_t idesc, float* __restrict__ out,
+                                                           uint32_t a_dl, uint32_t a_ds, uint32_t b_dl, uint32_t b_ds) {
+    extern __shared__ __align__(128) unsigned char usm[];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char *sa = usm, *sb = usm + 32768;
+    for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<float*>(usm)[i] = 0.f;
+    if (tid == 0) mbar_init(&bar, 1);
+    if (warp == 0) umma::tmem_alloc(smem_u32(&tmem_slot), 32);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    for (int i = tid; i < 128 * 8; i += 128) {
+        const int m = i >> 3, k = i & 7;
+        const uint32_t off = a_mn ? (uint32_t)(m >> 2) * a_sbo + (uint32_t)(k >> 3) * a_lbo + (uint32_t)(k & 7) * 16u + (uint32_t)(m & 3) * 4u
+                                  : (uint32_t)(m >> 3) * a_sbo + (uint32_t)(k >> 2) * a_lbo + (uint32_t)(m & 7) * 16u + (uint32_t)(k & 3) * 4u;
+        if (off < 32768u) *reinterpret_cast<float*>(sa + off) = A[i];
+    }
+    {
+        const int k = tid >> 4, n = tid & 15;                  // B[k][n], 8 x 16
+        const uint32_t off = b_mn ? (uint32_t)(n >> 2) * b_sbo + (uint32_t)(k >> 3) * b_lbo + (uint32_t)(k & 7) * 16u + (uint32_t)(n & 3) * 4u
+                                  : (uint32_t)(n >> 3) * b_sbo + (uint32_t)(k >> 2) * b_lbo + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 3) * 4u;
+        if (off < 32768u) *reinterpret_cast<float*>(sb + off) = B[tid];
+    }
+    umma::fence_proxy_async();
+    __syncthreads();
+    // every allocated column starts from a recognisable pattern: 1000 + lane + column / 100
+    {
+        const uint32_t ta = tmem + ((uint32_t)(32 * warp) << 16);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const uint32_t val = __float_as_uint(1000.0f + (float)(32 * warp + lane) + 0.01f * (float)c);
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(ta + (uint32_t)c), "r"(val) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid == 0 && idesc != 0u) {
+        umma::fence_after_sync();
+        umma::mma_tf32(tmem, umma::smem_desc(smem_u32(sa), a_dl, a_ds), umma::smem_desc(smem_u32(sb), b_dl, b_ds), idesc, 0u);
+        umma::commit(smem_u32(&bar));
+    }
+    if (idesc != 0u) mbar_wait_bounded(&bar, 0);
+    umma::fence_after_sync();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float v[8];
+        umma::tmem_ld_32x32b_x8(tmem + ((uint32_t)(32 * warp) << 16) + 8u * (uint32_t)e, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[(32 * warp + lane) * 32 + 8 * e + j] = v[j];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 32);
 }
 
 template <int G>
@@ -170,8 +311,11 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     __shared__ double zsum;
     using SM = RnetSmem<G, NP, BWD>;
     constexpr int GPB = SM::GPB, SA = SM::SA, SC = SM::SC, RA = SM::RA, RC = SM::RC;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) unsigned long long mbar;
+    __shared__ __align__(8) unsigned long long mma_bar;       // completion of the tile's tensor-core MMAs (BWD)
+    __shared__ uint32_t tmem_slot;
+    using W3G = typename SM::W3G;
     const int d = DS ? DS : p.d, n3 = N3S ? N3S : p.n3, n4 = N4S ? N4S : p.n4;
     const RnetLayout L = rnet_layout(d, n3, n4);
     const SM S(d, L.total);
@@ -183,14 +327,20 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 
     // ---- stage the parameters: one TMA bulk copy (+ <= 3 tail floats) ----------------------------
     const uint32_t bulk_floats = ((uintptr_t)p.params & 15) == 0 ? (uint32_t)(L.total / 4 * 4) : 0u;
-    if (tid == 0) { mbar_init(&mbar, 1); zsum = 0.0; }
+    if (tid == 0) { mbar_init(&mbar, 1); if (BWD) mbar_init(&mma_bar, 1); zsum = 0.0; }
+    if (BWD && tid < 32) {                                     // warp 0 allocates the TMEM columns of the dW3 accumulators
+        __syncwarp();
+        umma::tmem_alloc(smem_u32(&tmem_slot), W3G::kTmemCols);
+        umma::fence_before_sync();
+    }
     __syncthreads();
+    uint32_t tmem_base = 0;
+    if (BWD) { umma::fence_after_sync(); tmem_base = tmem_slot; }
     if (tid == 0 && bulk_floats) tma_bulk_load(wf, p.params, bulk_floats * 4u, &mbar);
     for (int i = bulk_floats + tid; i < L.total; i += kRnetThreads) wf[i] = p.params[i];
     for (int i = tid; i < GPB * S.tile_stride; i += kRnetThreads) smem[S.tiles + i] = 0.f;    // zero halos
     if (BWD) {
-        for (int i = tid; i < GPB * S.flat_stride; i += kRnetThreads) smem[S.flat + i] = 0.f;
-        for (int i = tid; i < SM::NSLOT * kRnetThreads; i += kRnetThreads) smem[S.gacc + i] = 0.f;
+        for (int i = tid; i < 2 * (int)((W3G::kBytesA + W3G::kBytesB) / 4); i += kRnetThreads) smem[S.umA + i] = 0.f;
         for (int i = tid; i < GPB * SM::NSMALL; i += kRnetThreads) smem[S.gsmall + i] = 0.f;
     }
     if (bulk_floats) mbar_wait(&mbar, 0);
@@ -208,17 +358,26 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     const bool row_ok = h < d;
     const float inv_keep = p.dropout ? 1.0f / p.keep_prob : 1.0f;
     // persistent register accumulators (backward)
-    float gw3[2][NP], gw4pi[NP], gw4h[NP];
+    float gw4pi[NP], gw4h[NP];
     float gk1[kK1 * kK1 + 1];            // d conv1/weights [dh][dw] + bias: thread-owned for the whole kernel
     float gk2[kK2 * kK2 * 2 + 2];        // d conv2/weights [dh][dw][c] + 2 biases
     if (BWD) {
 #pragma unroll
-        for (int n = 0; n < NP; ++n) { gw3[0][n] = gw3[1][n] = 0.f; gw4pi[n] = gw4h[n] = 0.f; }
+        for (int n = 0; n < NP; ++n) { gw4pi[n] = gw4h[n] = 0.f; }
 #pragma unroll
         for (int i = 0; i < kK1 * kK1 + 1; ++i) gk1[i] = 0.f;
 #pragma unroll
         for (int i = 0; i < kK2 * kK2 * 2 + 2; ++i) gk2[i] = 0.f;
     }
+    // tensor-core hand-off state (uniform over the CTA)
+    uint32_t mma_phase = 0;
+    bool mma_pending = false, mma_first = true;
+    const uint32_t um_a_hi = smem_u32(smem + S.umA), um_a_lo = um_a_hi + W3G::kBytesA;      // shared-window addresses
+    const uint32_t um_b_hi = smem_u32(smem + S.umB), um_b_lo = um_b_hi + W3G::kBytesB;
+    // this thread's store addresses into the A tile (row h of chunk group 0, column grp), pinned to ordinary registers:
+    // left to itself the compiler splits them into a uniform part it rematerialises (ULEA from SR_CgaCtaId) per store
+    uint32_t a_st_hi = um_a_hi + W3G::off(h, grp), a_st_lo = um_a_lo + W3G::off(h, grp);
+    asm volatile("mov.u32 %0, %0;\n\tmov.u32 %1, %1;" : "+r"(a_st_hi), "+r"(a_st_lo));
     const long long ntiles = TRAJ ? p.traj_M : (p.N + GPB - 1) / GPB;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         long long n = tile * GPB + grp;
@@ -437,12 +596,24 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                         for (int m = 0; m < NP; ++m) gw4h[m] = fmaf(h3[j], dz4[m], gw4h[m]);
                     }
                 }
-                // conv2 activations of this transition -> flat tile (consumed by the CTA-wide fc3 gradient)
-                float* fl = smem + S.flat + grp * S.flat_stride;
+                // conv2 activations of this transition -> A operand of the fc3 weight gradient on the tensor cores
+                // (3xTF32 split; row m = (2w + c) * G + h, column = this transition: every store is base + immediate).
+                // The MMAs of the previous tile must have finished reading the tile first.
+                if (mma_pending) { mbar_wait_bounded(&mma_bar, mma_phase); mma_phase ^= 1u; mma_pending = false; }
                 if (row_ok) {
 #pragma unroll
-                    for (int w = 0; w < G; ++w)
-                        if (w < d) *reinterpret_cast<float2*>(fl + (h * d + w) * 2) = make_float2(c2[0][w], c2[1][w]);
+                    for (int w = 0; w < G; ++w) {
+                        if (w < d) {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                float hi, lo;
+                                umma::split_tf32(c2[c][w], hi, lo);
+                                constexpr uint32_t kRowStep = (uint32_t)(G / 8) * W3G::kSbo;
+                                umma::sts_f32(a_st_hi + (uint32_t)(2 * w + c) * kRowStep, hi);
+                                umma::sts_f32(a_st_lo + (uint32_t)(2 * w + c) * kRowStep, lo);
+                            }
+                        }
+                    }
                 }
                 // d conv2 pre-activation: dz2 = (W3 row block . dz3) masked by relu
                 float dz2[2][G];
@@ -534,48 +705,50 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
             __syncwarp();      // tiles are rewritten by the next transition of this group
         }
         if (BWD) {
-            // ---- fc3 gradient: CTA-wide outer product flat^T . dz3 over this tile's transitions ----
-            if (h == 0) {
-                float* dzt = smem + S.dz3 + grp * NP;
+            // ---- fc3 gradient on the tensor cores: D[m, j] += sum_n A[m, n] dz3[n, j] over this tile's transitions ----
+            if (h == 0) {                                              // B operand: dz3 of this transition (zero for dead groups)
 #pragma unroll
-                for (int j = 0; j < NP; ++j) dzt[j] = dz3[j];          // zero for dead groups
-            }
-            __syncthreads();
-            const int K = 2 * d * d;
-            const int k0 = tid, k1 = tid + kRnetThreads;
-            for (int t = 0; t < GPB; ++t) {
-                const float* fl = smem + S.flat + t * S.flat_stride;
-                const float* dzt = smem + S.dz3 + t * NP;
-                const float f0 = k0 < K ? fl[k0] : 0.f;
-                const float f1 = k1 < K ? fl[k1] : 0.f;
-#pragma unroll
-                for (int q = 0; q < NP / 4; ++q) {
-                    const float4 dz = reinterpret_cast<const float4*>(dzt)[q];      // broadcast LDS.128
-                    gw3[0][4 * q + 0] = fmaf(f0, dz.x, gw3[0][4 * q + 0]); gw3[1][4 * q + 0] = fmaf(f1, dz.x, gw3[1][4 * q + 0]);
-                    gw3[0][4 * q + 1] = fmaf(f0, dz.y, gw3[0][4 * q + 1]); gw3[1][4 * q + 1] = fmaf(f1, dz.y, gw3[1][4 * q + 1]);
-                    gw3[0][4 * q + 2] = fmaf(f0, dz.z, gw3[0][4 * q + 2]); gw3[1][4 * q + 2] = fmaf(f1, dz.z, gw3[1][4 * q + 2]);
-                    gw3[0][4 * q + 3] = fmaf(f0, dz.w, gw3[0][4 * q + 3]); gw3[1][4 * q + 3] = fmaf(f1, dz.w, gw3[1][4 * q + 3]);
+                for (int j = 0; j < NP; ++j) {
+                    float hi, lo;
+                    umma::split_tf32(dz3[j], hi, lo);
+                    umma::sts_f32(um_b_hi + W3G::off(j, grp), hi);
+                    umma::sts_f32(um_b_lo + W3G::off(j, grp), lo);
                 }
             }
+            umma::fence_proxy_async();                                 // generic-proxy stores -> visible to the tensor core
             __syncthreads();
+            if (tid == 0)
+                W3G::issue(tmem_base, um_a_hi, um_a_lo, um_b_hi, um_b_lo, mma_first, smem_u32(&mma_bar));
+            mma_pending = true;
+            mma_first = false;
         }
     }
     if (!BWD) return;
     if (TRAJ && tid == 0) p.zpart[blockIdx.x] = zsum;
     // ---- per-CTA partial gradient, fixed summation order ---------------------------------------------
     float* out = p.partials + (long long)blockIdx.x * L.total;
+    if (mma_pending) mbar_wait_bounded(&mma_bar, mma_phase);           // the last tile's MMAs (they also read the operand tiles)
+    umma::fence_after_sync();
     {
-        const int K = 2 * d * d;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int k = tid + s * kRnetThreads;
-            if (k < K) {
+        // d fc3/weights from TMEM: accumulator row m = t * G + hh of M-tile m / 128 sits in TMEM lane m % 128; warp w reads
+        // lanes 32 (w % 4) .. of the M-tiles w / 4, w / 4 + 2, ...
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int mt = warp >> 2; mt < SM::MT; mt += kRnetThreads / 128) {
+            float v[8];
+            umma::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 16u * (uint32_t)mt, v);
+            const int m = 128 * mt + 32 * (warp & 3) + lane;
+            const int t = m / G, hh = m % G;
+            if (hh < d && t < 2 * d) {
+                const int k = hh * 2 * d + t;
 #pragma unroll
                 for (int j = 0; j < NP; ++j)
-                    if (j < n3) out[L.w3 + k * n3 + j] = gw3[s][j];
+                    if (j < n3) out[L.w3 + k * n3 + j] = mma_first ? 0.f : v[j];
             }
         }
     }
+    umma::fence_before_sync();
+    __syncthreads();                                                   // everyone has read TMEM; the operand tiles are free
+    if (tid < 32) umma::tmem_dealloc(tmem_base, W3G::kTmemCols);
     float* ga = smem + S.gacc;
 #pragma unroll
     for (int i = 0; i < kK1 * kK1 + 1; ++i) ga[i * kRnetThreads + tid] = gk1[i];

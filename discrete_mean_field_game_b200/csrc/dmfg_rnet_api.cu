@@ -143,8 +143,13 @@ int dmfg_rnet_backward(const dmfg_rnet_args* a, void* stream) {
     size_t smem = 0;
     RnetParams p = make_params(a);
     p.partials = (float*)a->workspace;
-    // (the backward kernel sits at the 255-register limit: compile-time widths make it spill, so only d is fixed)
-    if (a->d == 15) {
+    // the reference's default shape (d = 15, n_fc3 = 8, n_fc4 = 4) with every size a compile-time constant (fits the
+    // 255 registers without spills since the fc3 weight gradient moved to the tensor cores); d = 15 with other widths;
+    // everything else from the arguments
+    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) {
+        if (int rc = rnet_grid<true, 15, 8, 4>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, true, 15, 8, 4><<<grid, kRnetThreads, smem, st>>>(p);
+    } else if (a->d == 15) {
         if (int rc = rnet_grid<true, 15, 0, 0>(a, &grid, &smem)) return rc;
         rnet_kernel<kG, kNP, true, 15, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
     } else {
@@ -184,7 +189,10 @@ int dmfg_rnet_backward_gen(const dmfg_rnet_args* a, const dmfg_irl_gen_args* g, 
     p.traj_M = g->M; p.traj_T = g->T; p.t_stride = g->gen_t_stride; p.j_stride = g->gen_j_stride;
     int grid = 0;
     size_t smem = 0;
-    if (a->d == 15) {
+    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) {
+        if (int rc = rnet_grid<true, 15, 8, 4, true>(a, &grid, &smem, g->M)) return rc;
+        rnet_kernel<kG, kNP, true, 15, 8, 4, true><<<grid, kRnetThreads, smem, st>>>(p);
+    } else if (a->d == 15) {
         if (int rc = rnet_grid<true, 15, 0, 0, true>(a, &grid, &smem, g->M)) return rc;
         rnet_kernel<kG, kNP, true, 15, 0, 0, true><<<grid, kRnetThreads, smem, st>>>(p);
     } else {
@@ -203,6 +211,28 @@ int dmfg_rnet_backward_gen(const dmfg_rnet_args* a, const dmfg_irl_gen_args* g, 
 int dmfg_irl_dp_finalize(int64_t n, const double* reduced, float* grad, double* loss_out, void* stream) {
     if (n < 1 || n > INT32_MAX || !reduced || !grad) return fail(DMFG_ERR_INVALID, "dmfg_irl_dp_finalize: bad argument");
     irl_dp_finalize_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((int)n, reduced, grad, loss_out);
+    DMFG_LAUNCHED();
+    return DMFG_OK;
+}
+
+int dmfg_umma_probe(const float* A, const float* B, int32_t a_mn_major, uint32_t a_lbo, uint32_t a_sbo, int32_t b_mn_major,
+                    uint32_t b_lbo, uint32_t b_sbo, float* out, void* stream, uint32_t a_desc_lbo, uint32_t a_desc_sbo,
+                    uint32_t b_desc_lbo, uint32_t b_desc_sbo) {
+    if (!A || !B || !out) return fail(DMFG_ERR_INVALID, "dmfg_umma_probe: NULL argument");
+    const bool no_mma = a_mn_major < 0;                       // TMEM store / load round trip only
+    DMFG_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    umma_probe_kernel<<<1, 128, 65536, (cudaStream_t)stream>>>(A, B, a_mn_major, a_lbo, a_sbo, b_mn_major, b_lbo, b_sbo,
+                                                              no_mma ? 0u : umma::idesc_tf32(128, 16, a_mn_major != 0, b_mn_major != 0), out,
+                                                              a_desc_lbo, a_desc_sbo, b_desc_lbo, b_desc_sbo);
+    DMFG_LAUNCHED();
+    return DMFG_OK;
+}
+
+int dmfg_umma_selftest(const float* h, const float* z, int32_t passes, float* out, void* stream) {
+    if (passes < 0 || !out || (passes > 0 && (!h || !z))) return fail(DMFG_ERR_INVALID, "dmfg_umma_selftest: bad argument");
+    const size_t smem = 2 * umma::W3Grad<4, 2>::kBytesA + 2 * umma::W3Grad<4, 2>::kBytesB;
+    DMFG_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(h, z, passes, out);
     DMFG_LAUNCHED();
     return DMFG_OK;
 }

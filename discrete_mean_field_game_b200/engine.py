@@ -344,6 +344,37 @@ def philox(ctr, key, gamma_stream=False):
     return tuple(int(v) for v in o)
 
 
+def umma_probe(A, B, a_cfg, b_cfg, a_desc=None, b_desc=None):
+    """ONE kind::tf32 MMA: out[128,16] = A[128,8] . B[8,16]; *_cfg = (mn_major, lbo_bytes, sbo_bytes) place the operands,
+    *_desc = (lbo, sbo) are written into the descriptors (default: the same values) (testing aid)."""
+    a_desc = a_desc or a_cfg[1:]
+    b_desc = b_desc or b_cfg[1:]
+    lib = _lib.load()
+    device = A.device
+    _require(A, "A", device, torch.float32, (128, 8))
+    _require(B, "B", device, torch.float32, (8, 16))
+    with torch.cuda.device(device):
+        out = torch.empty((128, 32), dtype=torch.float32, device=device)
+        check(lib.dmfg_umma_probe(_ptr(A), _ptr(B), int(a_cfg[0]), int(a_cfg[1]), int(a_cfg[2]), int(b_cfg[0]),
+                                  int(b_cfg[1]), int(b_cfg[2]), _ptr(out), _stream_ptr(device), int(a_desc[0]),
+                                  int(a_desc[1]), int(b_desc[0]), int(b_desc[1])))
+    return out
+
+
+def umma_selftest(h, z):
+    """out[512, 8] = sum_p h[p]^T z[p] on the tcgen05 / TMEM path of the fc3 weight gradient (testing aid).
+    h [P,16,512], z [P,16,8] float32 CUDA tensors."""
+    lib = _lib.load()
+    device = h.device
+    P = h.shape[0]
+    _require(h, "h", device, torch.float32, (P, 16, 512))
+    _require(z, "z", device, torch.float32, (P, 16, 8))
+    with torch.cuda.device(device):
+        out = torch.empty((512, 8), dtype=torch.float32, device=device)
+        check(lib.dmfg_umma_selftest(_ptr(h), _ptr(z), P, _ptr(out), _stream_ptr(device)))
+    return out
+
+
 def gamma_philox_rounds():
     return int(_lib.load().dmfg_gamma_philox_rounds())
 

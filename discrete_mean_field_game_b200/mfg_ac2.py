@@ -396,7 +396,9 @@ class actor_critic:
         w = self._w_dev().clone()
         _, world = parallel.world_info(group)
         first = self.first_episode if first_episode is None else first_episode      # step-size schedule only
-        noise0 = first + self._batch_episodes      # Philox position: moves on across calls (like train()'s _episodes)
+        # Philox position: a persistent per-object episode counter (like train()'s _episodes), NOT first_episode --
+        # a loop of train_batch calls never replays noise, and resuming the schedule does not move the noise
+        noise0 = self.first_episode + self._batch_episodes
         mean_rewards = []
         F = w.numel()
         B_local = -1

@@ -380,6 +380,17 @@ int dmfg_irl_log_z(int64_t M, int32_t T, int32_t K, int64_t t_stride, int64_t j_
                    double num_start_samples, float* log_z, void* stream);
 
 /* ---- testing aids: direct access to the device math ---------------------- */
+/* The tensor-core (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators) path of the fc3 weight gradient of
+ * dmfg_rnet_backward in isolation: out[512][8] = sum_p h_p^T . z_p for h [passes][16][512], z [passes][16][8]
+ * (device pointers; one CTA; the operand tiles, descriptors and the commit / mbarrier hand-off are the kernel's own). */
+int dmfg_umma_selftest(const float* h, const float* z, int32_t passes, float* out, void* stream);
+/* ONE kind::tf32 MMA out[128][32] (columns 0..15 = the product, the rest keep the pattern 1000 + lane + column / 100 stored
+ * into TMEM beforehand; a_mn_major < 0: no MMA at all) = A[128][8] . B[8][16] with each operand laid out in shared memory by the canonical
+ * un-swizzled formula of the requested major-ness (0 = K-major, 1 = MN-major) and (LBO, SBO) in bytes: pins the matrix
+ * descriptor semantics the reward-net kernels rely on. */
+int dmfg_umma_probe(const float* A, const float* B, int32_t a_mn_major, uint32_t a_lbo, uint32_t a_sbo, int32_t b_mn_major,
+                    uint32_t b_lbo, uint32_t b_sbo, float* out, void* stream, uint32_t a_desc_lbo, uint32_t a_desc_sbo,
+                    uint32_t b_desc_lbo, uint32_t b_desc_sbo);   /* *_desc_*: the values written into the descriptors */
 /* Philox4x32-10 on the host (same code the kernels run): out[4] = philox(ctr[4], key[2]) */
 void dmfg_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out);
 /* The Gamma sampler of the rollout kernels (the replacement of np.random.gamma, mfg_ac2.py:242) runs the

@@ -224,7 +224,7 @@ def test_data_parallel_reward_step_is_rank_count_invariant(data):
         assert float(total[2 * P + 2]) == 37 and float(total[2 * P + 3]) == 53
         np.testing.assert_allclose(loss.cpu().numpy()[:3], loss_ref[:3], rtol=1e-6, atol=1e-6)
         err = np.abs(grad.cpu().numpy() - g_ref).max()
-        assert err <= 2e-6 * np.abs(g_ref).max() + 1e-8, (err, np.abs(g_ref).max())     # float32 summation order only
+        assert err <= 2e-5 * np.abs(g_ref).max() + 1e-8, (err, np.abs(g_ref).max())     # float32 summation order only
     # the forced single-rank form of the public call takes the same path and lands on the same parameters
     irl2 = make(data, reg="none")
     irl2.rank_invariant_reward_step = True

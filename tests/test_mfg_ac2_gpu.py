@@ -369,6 +369,37 @@ def test_train_batch_pipelined_inputs_and_history(start_states):
     np.testing.assert_allclose(r2["w_history"], np.stack(ws), rtol=1e-14)
 
 
+def test_repeated_train_batch_calls_never_replay_noise(start_states):
+    """A loop of train_batch calls with default arguments walks ON through the Philox stream (persistent episode counter):
+    two 1-episode calls equal one 2-episode call (with constant step sizes), and the second call's noise is new."""
+    rng = np.random.RandomState(5)
+    pi0 = np.float32(rng.dirichlet(np.ones(15), size=256))
+    kw = dict(T=6, constant=1, lr_critic=0.0, lr_actor=0.0)                # frozen parameters: only the noise differs
+
+    def fresh():
+        ac = mfg_ac2.actor_critic(theta=8.0, shift=0.16, alpha_scale=12000, d=15, mat_pi0=start_states, seed=11)
+        ac.w = np.full((136, 1), 0.5)
+        return ac
+    a = fresh()
+    r1 = a.train_batch(pi0, num_episodes=1, **kw)["mean_reward"][0]
+    r2 = a.train_batch(pi0, num_episodes=1, **kw)["mean_reward"][0]
+    both = fresh().train_batch(pi0, num_episodes=2, **kw)["mean_reward"]
+    assert r1 != r2
+    np.testing.assert_allclose([r1, r2], both, rtol=1e-14)
+    # the single-population helpers draw from their own Philox populations (HELPER_POP_OFFSET): sample_action does not
+    # return the variates train() consumes at (learner 0, step 0)
+    b = fresh()
+    pi = start_states[0, :15] / start_states[0, :15].sum()
+    P_helper = b.sample_action(pi)
+    P_train_pos = mfg_ac2.engine.rollout(b._dev(pi.reshape(1, 15)), 8.0, 0.16, 12000, 1, reward="none", seed=11,
+                                         pop_offset=0, step_offset=0, outputs=("actions",))["actions"][0, 0].double().cpu().numpy()
+    assert np.abs(P_train_pos - P_helper).max() > 1e-6
+    P_own = mfg_ac2.engine.rollout(b._dev(pi.reshape(1, 15)), 8.0, 0.16, 12000, 1, reward="none", seed=11,
+                                   pop_offset=mfg_ac2.HELPER_POP_OFFSET, step_offset=0,
+                                   outputs=("actions",))["actions"][0, 0].double().cpu().numpy()
+    np.testing.assert_array_equal(P_own, P_helper)
+
+
 def test_train_batch_learns(start_states):
     """The batched per-episode actor-critic climbs the reward it is given: with constant step sizes the mean reward of
     8192 populations rises by two orders of magnitude and theta settles (a policy-gradient sign or TD-error error
