@@ -127,6 +127,9 @@ SYMBOLS = [
     ("dmfg_ac_apply_update_dev", C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                            C.c_void_p]),
     ("dmfg_ac_learners", C.c_int, [C.POINTER(LearnersArgs), C.c_void_p]),
+    ("dmfg_ac_step_workspace_bytes", C.c_uint64, [C.POINTER(RolloutArgs)]),
+    ("dmfg_ac_step", C.c_int, [C.POINTER(RolloutArgs), C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                               C.c_void_p, C.c_void_p]),
     ("dmfg_rnet_param_count", C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     ("dmfg_rnet_param_offsets", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     ("dmfg_rnet_workspace_bytes", C.c_uint64, [C.POINTER(RnetArgs)]),

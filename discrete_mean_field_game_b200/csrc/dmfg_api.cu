@@ -161,6 +161,8 @@ RolloutParams<R> make_params(const dmfg_rollout_args* a) {
     p.grads = (R*)a->grads; p.pi_final = (R*)a->pi_final; p.partials = nullptr;
     p.rk = make_philox_keys(a->seed);
     p.shift_f = (float)a->shift; p.scale_f = (float)a->alpha_scale;
+    p.fuse_counter = nullptr; p.fuse_theta = nullptr; p.fuse_w = nullptr; p.fuse_acc = nullptr; p.fuse_lr_dev = nullptr;
+    p.fuse_lr_c = p.fuse_lr_a = p.fuse_scale = 0.0;
     return p;
 }
 
@@ -184,9 +186,9 @@ int launch_fast(RolloutParams<R> p, bool td, int* grid_out, cudaStream_t st) {
     return DMFG_OK;
 }
 
-template <int D, int NOISE, bool REC, bool TRAIN, bool GRAD>
+template <int D, int NOISE, bool REC, bool TRAIN, bool GRAD, bool FUSE = false>
 int launch_v2(RolloutParams<float> p, bool td, int* grid_out, cudaStream_t st) {
-    auto kern = rollout_v2_kernel<D, NOISE, REC, TRAIN, GRAD>;
+    auto kern = rollout_v2_kernel<D, NOISE, REC, TRAIN, GRAD, FUSE>;
     const size_t smem = (size_t)V2Smem<D>::total * sizeof(double);
     DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0, sms = 0;
@@ -219,6 +221,20 @@ int dispatch_v2_d(const RolloutParams<float>& p, int noise_kind, bool td, int* g
                    : launch_v2<D, DMFG_NOISE_PHILOX, false, false, false>(p, td, grid, st);
     }
     return launch_v2<D, DMFG_NOISE_INJECTED, true, false, true>(p, td, grid, st);
+}
+// dmfg_ac_step: one transition + TD sums + in-launch update (no per-element stream)
+template <int D>
+int dispatch_v2_step_d(const RolloutParams<float>& p, int noise_kind, int* grid, cudaStream_t st) {
+    if (noise_kind == DMFG_NOISE_PHILOX) return launch_v2<D, DMFG_NOISE_PHILOX, false, false, true, true>(p, true, grid, st);
+    return launch_v2<D, DMFG_NOISE_INJECTED, false, false, true, true>(p, true, grid, st);
+}
+int dispatch_v2_step(const RolloutParams<float>& p, int noise_kind, int* grid, cudaStream_t st) {
+    switch (p.d) {
+        case 15: return dispatch_v2_step_d<15>(p, noise_kind, grid, st);
+        case 16: return dispatch_v2_step_d<16>(p, noise_kind, grid, st);
+        case 21: return dispatch_v2_step_d<21>(p, noise_kind, grid, st);     // mfg_ac2.py:25
+    }
+    return fail(DMFG_ERR_UNSUPPORTED, "dmfg_ac_step is built for float streams, d in {15,16,21} (got d=%d)", p.d);
 }
 int dispatch_v2(const RolloutParams<float>& p, int noise_kind, bool td, int* grid, cudaStream_t st) {
     switch (p.d) {
@@ -649,6 +665,43 @@ int dmfg_ac_apply_update_dev(int32_t d, double* theta_dev, double* w, const doub
     ac_apply_update_dev_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(F, theta_dev, w, acc, lr_dev, scale);
     DMFG_LAUNCHED();
     return DMFG_OK;
+}
+
+uint64_t dmfg_ac_step_workspace_bytes(const dmfg_rollout_args* a) {
+    if (!a || a->struct_size != sizeof(dmfg_rollout_args) || a->d < 1 || a->d > DMFG_MAX_D) return 0;
+    return align_up((uint64_t)kMaxPartialCtas * (2 + (uint64_t)num_features_c(a->d)) * 8) + 256;
+}
+
+int dmfg_ac_step(const dmfg_rollout_args* a, double* theta_dev, double* w, double lr_critic_eff, double lr_actor_eff,
+                 double scale, const double* lr_dev, void* stream) {
+    if (int rc = check_rollout(a)) return rc;
+    if (!theta_dev || !w) return fail(DMFG_ERR_INVALID, "dmfg_ac_step: theta_dev and w are required (updated in place)");
+    if (a->T != 1) return fail(DMFG_ERR_INVALID, "dmfg_ac_step runs ONE transition (T = %d)", a->T);
+    if (a->dtype != DMFG_F32 || a->noise_kind == DMFG_NOISE_ACTIONS || !(a->d == 15 || a->d == 16 || a->d == 21))
+        return fail(DMFG_ERR_UNSUPPORTED, "dmfg_ac_step is built for float streams, d in {15,16,21}, sampled or injected noise");
+    if (a->states || a->actions || a->alpha || a->alpha_deriv || a->rewards || a->deltas || a->grads || a->rewards_in)
+        return fail(DMFG_ERR_UNSUPPORTED, "dmfg_ac_step writes pi_final and acc only");
+    const uint64_t need = dmfg_ac_step_workspace_bytes(a);
+    if (!a->workspace || a->workspace_bytes < need)
+        return fail(DMFG_ERR_WORKSPACE, "workspace of %llu bytes needed, %llu given", (unsigned long long)need,
+                    (unsigned long long)(a->workspace ? a->workspace_bytes : 0));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = num_features_c(a->d);
+    if (a->B == 0) {
+        if (a->acc) DMFG_CUDA(cudaMemsetAsync(a->acc, 0, (size_t)(2 + F) * 8, st));
+        return DMFG_OK;
+    }
+    RolloutParams<float> p = make_params<float>(a);
+    p.theta_dev = theta_dev;
+    p.w = w;
+    p.partials = (double*)a->workspace;
+    p.fuse_counter = (unsigned int*)((char*)a->workspace + need - 256);
+    p.fuse_theta = theta_dev; p.fuse_w = w; p.fuse_acc = a->acc; p.fuse_lr_dev = lr_dev;
+    p.fuse_lr_c = lr_critic_eff; p.fuse_lr_a = lr_actor_eff; p.fuse_scale = scale;
+    // the ticket counter resets itself after every step; the memset covers a workspace that has never been used
+    DMFG_CUDA(cudaMemsetAsync(p.fuse_counter, 0, sizeof(unsigned int), st));
+    int grid = 0;
+    return dispatch_v2_step(p, a->noise_kind, &grid, st);
 }
 
 int dmfg_ac_learners(const dmfg_learners_args* a, void* stream) {

@@ -71,6 +71,14 @@ struct RolloutParams {
     double* partials;      // [gridDim.x][2+F] per-CTA sums (fast variant with w)
     PhiloxKeys rk;         // round keys of `seed` (v2 kernel)
     float shift_f, scale_f;
+    // fused per-step update (dmfg_ac_step): the last CTA to finish reduces the per-CTA partials in fixed order and
+    // applies theta += lr_a * scale * sum delta g, w += lr_c * scale * sum delta phi in the same launch
+    unsigned int* fuse_counter;
+    double* fuse_theta;
+    double* fuse_w;
+    double* fuse_acc;              // optional [2+F]: the step's reduced sums
+    const double* fuse_lr_dev;     // optional {lr_critic_eff, lr_actor_eff} on the device
+    double fuse_lr_c, fuse_lr_a, fuse_scale;
 };
 
 // first Philox step index of this launch: the by-value offset plus the optional device-side one

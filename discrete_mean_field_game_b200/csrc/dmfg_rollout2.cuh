@@ -190,7 +190,8 @@ __device__ __forceinline__ V2RowSums v2_row_walk(float theta, float xi, float sc
 // output test is compiled out of the step loop.  REC = some per-element stream (actions / alpha) is written.
 // GRAD = d log F / d theta is wanted (critic attached or a grads stream): without it -- the IRL sampler and
 // evaluate() only want states and actions -- psi(alpha), lg2 y and the alpha' sums are compiled out (-20 %).
-template <int D, int NOISE, bool REC, bool TRAIN, bool GRAD>
+// FUSE = dmfg_ac_step: the batch-mean update of (theta, w) is applied by the last CTA of the SAME launch.
+template <int D, int NOISE, bool REC, bool TRAIN, bool GRAD, bool FUSE = false>
 __global__ void __launch_bounds__(kV2Threads, DMFG_V2_MINB)
 rollout_v2_kernel(const RolloutParams<float> p) {
     using S = V2Smem<D>;
@@ -419,6 +420,29 @@ rollout_v2_kernel(const RolloutParams<float> p) {
         for (int wv = 0; wv < NT / 32; ++wv) { a += red[0][wv]; c += red[1][wv]; }
         out[0] = a;
         out[1 + F] = c;
+    }
+    if (FUSE) {
+        // ---- one launch per step: whoever finishes last sums the per-CTA partials (CTA order: deterministic) and
+        // updates the parameters in place; every other CTA has long finished reading theta and w
+        __shared__ unsigned int ticket;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) ticket = atomicAdd(p.fuse_counter, 1u);
+        __syncthreads();
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            const double lr_c = p.fuse_lr_dev ? p.fuse_lr_dev[0] : p.fuse_lr_c;
+            const double lr_a = p.fuse_lr_dev ? p.fuse_lr_dev[1] : p.fuse_lr_a;
+            for (int f = tid; f < F + 2; f += NT) {
+                double s = 0.0;
+                for (unsigned int c = 0; c < gridDim.x; ++c) s += __ldcg(p.partials + (long long)c * (2 + F) + f);
+                if (p.fuse_acc != nullptr) p.fuse_acc[f] = s;
+                // (the arithmetic of ac_apply_update_kernel, so the fused step equals the three-launch chain bit for bit)
+                if (f == 0) p.fuse_theta[0] = fma(lr_a * p.fuse_scale, s, p.fuse_theta[0]);
+                else if (f <= F) p.fuse_w[f - 1] = fma(lr_c * p.fuse_scale, s, p.fuse_w[f - 1]);
+            }
+            if (tid == 0) *p.fuse_counter = 0u;                          // ready for the next step's launch
+        }
     }
 }
 

@@ -148,6 +148,50 @@ def rollout(pi0, theta, shift, alpha_scale, T, *, w=None, gamma=1.0, reward="ac2
     return res
 
 
+AC_STEP_D = (15, 16, 21)
+
+
+def ac_step(pi, theta_dev, w, shift, alpha_scale, lr_critic_eff, lr_actor_eff, scale, *, gamma=1.0, reward="ac2",
+            noise_y=None, seed=0, pop_offset=0, step_offset=0, lr_dev=None, out=None, step_offset_dev=None):
+    """dmfg_ac_step: ONE transition of B populations + the batch-mean update of (theta_dev, w) in a single launch
+    (float32 streams, d in AC_STEP_D).  Returns dict(pi_final [B,d], acc [2+F])."""
+    lib = _lib.load()
+    device = pi.device
+    B, d = pi.shape
+    F = num_features(d)
+    a = RolloutArgs()
+    a.struct_size = C.sizeof(RolloutArgs)
+    a.dtype, a.d, a.T, a.B, a.pop_offset = _dtype_code(pi.dtype), d, 1, B, int(pop_offset)
+    a.shift, a.alpha_scale, a.gamma = float(shift), float(alpha_scale), float(gamma)
+    a.reward_kind, a.discount_kind = REWARD_KINDS[reward], DISCOUNT_STEP
+    a.seed, a.step_offset = int(seed) & (2 ** 64 - 1), int(step_offset)
+    if step_offset_dev is not None:
+        a.step_offset_dev = _ptr(_require(step_offset_dev, "step_offset_dev", device, torch.int64, (1,)))
+    if noise_y is not None:
+        a.noise_kind = NOISE_INJECTED
+        a.noise_y = _ptr(_require(noise_y, "noise_y", device, pi.dtype, (1, B, d, d)))
+    else:
+        a.noise_kind = NOISE_PHILOX
+    a.pi0 = _ptr(_require(pi, "pi", device, pi.dtype, (B, d)))
+    _require(theta_dev, "theta_dev", device, torch.float64, (1,))
+    _require(w, "w", device, torch.float64, (F,))
+    a.w = _ptr(w)
+    res = {}
+    with torch.cuda.device(device):
+        res["pi_final"] = (out or {}).get("pi_final")
+        if res["pi_final"] is None:
+            res["pi_final"] = torch.empty((B, d), dtype=pi.dtype, device=device)
+        res["acc"] = (out or {}).get("acc")
+        if res["acc"] is None:
+            res["acc"] = torch.empty(2 + F, dtype=torch.float64, device=device)
+        a.pi_final, a.acc = _ptr(res["pi_final"]), _ptr(res["acc"])
+        ws = _workspace(device, lib.dmfg_ac_step_workspace_bytes(C.byref(a)))
+        a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        check(lib.dmfg_ac_step(C.byref(a), _ptr(theta_dev), _ptr(w), float(lr_critic_eff), float(lr_actor_eff),
+                               float(scale), _ptr(lr_dev) if lr_dev is not None else None, _stream_ptr(device)))
+    return res
+
+
 def td_accumulate(states, rewards, grads, w, *, gamma=1.0, discount="step", want_deltas=True, want_acc=True):
     """dmfg_td_accumulate: TD errors / accumulators from a recorded batch of trajectories."""
     lib = _lib.load()

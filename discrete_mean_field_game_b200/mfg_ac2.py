@@ -374,7 +374,8 @@ class actor_critic:
         return self._dev(x)
 
     def train_batch(self, pi0, num_episodes=1, T=15, gamma=1, constant=0, lr_critic=0.1, lr_actor=0.001,
-                    update="per_episode", seed=None, pop_offset=0, group=None, first_episode=None, history=False):
+                    update="per_episode", seed=None, pop_offset=0, group=None, first_episode=None, history=False,
+                    fuse_step=True):
         """Batched actor-critic: B populations share (theta, w).
 
         update="per_episode": parameters frozen within an episode, one batch-mean update
@@ -468,8 +469,22 @@ class actor_critic:
                 mean_rewards.append(acc[-1] / total_pops)
             elif update == "per_step":
                 disc, tot = 1.0, torch.zeros((), dtype=torch.float64, device=self.device)
+                # one rank, float streams, d in {15, 16, 21}: ONE launch per transition (dmfg_ac_step: sampling, TD sums
+                # and the batch-mean update fused); otherwise rollout(T=1) -> (all-reduce) -> apply_update
+                fused = fuse_step and world == 1 and self.dtype == torch.float32 and d in engine.AC_STEP_D
                 for t in range(T):
                     g_next = gamma if self.discount_kind == "step" else disc
+                    if fused:
+                        out = engine.ac_step(pi, theta, w, self.shift, self.alpha_scale, lr_c, lr_a, 1.0 / total_pops,
+                                             gamma=g_next, reward=self.reward_kind, seed=seed, pop_offset=pop_offset,
+                                             step_offset=(noise0 + e) * T + t)
+                        if t == 0 and copy_stream is not None:
+                            ev_free[e & 1] = torch.cuda.Event()
+                            ev_free[e & 1].record(compute)
+                        tot = tot + out["acc"][-1] / total_pops
+                        disc *= gamma
+                        pi = out["pi_final"]
+                        continue
                     out = engine.rollout(pi, 0.0, self.shift, self.alpha_scale, 1, w=w, theta_dev=theta,
                                          gamma=g_next, reward=self.reward_kind, seed=seed, pop_offset=pop_offset,
                                          step_offset=(noise0 + e) * T + t, outputs=("pi_final",), want_acc=True)

@@ -199,6 +199,18 @@ int dmfg_ac_apply_update(int32_t d, double* theta_dev, double* w, const double* 
 int dmfg_ac_apply_update_dev(int32_t d, double* theta_dev, double* w, const double* acc, const double* lr_dev,
                              double scale, void* stream);
 
+/* ---- a1..a7 for update="per_step": ONE fused launch per transition ------------ *
+ * The synchronous batch-mean step of B populations sharing (theta, w) -- what mfg_ac2.py:497-522 does for its one
+ * population, reduced over the batch: sample P, pi' = P^T pi, reward, TD error, sum delta*g and sum delta*phi, THEN
+ * theta += lr_actor_eff * scale * sum delta*g and w += lr_critic_eff * scale * sum delta*phi, all in one kernel (the
+ * last CTA to finish reduces the per-CTA partial sums in CTA order and applies the update).  `args` as for dmfg_rollout
+ * with T = 1, float streams, d in {15, 16, 21}; args->theta_dev / args->w are ignored in favour of the in/out pointers
+ * below; outputs: args->pi_final (the next states) and args->acc (optional).  lr_dev (optional, device) = {lr_critic_eff,
+ * lr_actor_eff} overrides the by-value step sizes (CUDA-graph replays).  Replaces rollout(T=1) -> reduce -> apply_update. */
+uint64_t dmfg_ac_step_workspace_bytes(const dmfg_rollout_args* args);
+int dmfg_ac_step(const dmfg_rollout_args* args, double* theta_dev, double* w, double lr_critic_eff, double lr_actor_eff,
+                 double scale, const double* lr_dev, void* stream);
+
 /* ---- a8: independent serial learners (exact reference semantics) -------- *
  * L learners, each with its OWN (theta, w) and per-step online updates, run E
  * episodes of T transitions: mfg_ac2.actor_critic.train (mfg_ac2.py:448-539),

@@ -369,6 +369,27 @@ def test_train_batch_pipelined_inputs_and_history(start_states):
     np.testing.assert_allclose(r2["w_history"], np.stack(ws), rtol=1e-14)
 
 
+@pytest.mark.parametrize("d", [15, 21])
+def test_per_step_update_fused_launch_equals_three_launch_chain(start_states, d):
+    """update="per_step": dmfg_ac_step (sampling + TD sums + batch-mean update of theta, w in ONE launch per transition;
+    the last CTA reduces the per-CTA partials in CTA order) against rollout(T=1) -> reduce -> apply_update: the same
+    parameters bit for bit, at B = 1 (the reference's own semantics, mfg_ac2.py:497-522) and at a ragged batch."""
+    rng = np.random.RandomState(d)
+    mat = O.synthetic_start_states(n_rows=21, n_cols=30, d=d, seed=4)
+    for B in (1, 777):
+        pi0 = np.float32(rng.dirichlet(np.ones(d), size=B))
+        outs = []
+        for fuse in (True, False):
+            ac = mfg_ac2.actor_critic(theta=8.0, shift=0.16, alpha_scale=12000, d=d, mat_pi0=mat, dtype="float32", seed=21)
+            ac.w = np.linspace(0.1, 0.9, O.num_features(d)).reshape(-1, 1)
+            res = ac.train_batch(pi0, num_episodes=2, T=5, lr_critic=0.1, lr_actor=0.01, update="per_step", fuse_step=fuse)
+            outs.append((ac.theta, ac.w.ravel().copy(), res["mean_reward"]))
+        (t1, w1, m1), (t0, w0, m0) = outs
+        assert t1 == t0 and np.array_equal(w1, w0)
+        np.testing.assert_allclose(m1, m0, rtol=1e-13)
+        assert t1 != 8.0
+
+
 def test_repeated_train_batch_calls_never_replay_noise(start_states):
     """A loop of train_batch calls with default arguments walks ON through the Philox stream (persistent episode counter):
     two 1-episode calls equal one 2-episode call (with constant step sizes), and the second call's noise is new."""
