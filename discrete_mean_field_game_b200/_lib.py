@@ -87,6 +87,14 @@ class RnetArgs(C.Structure):
     ]
 
 
+class IrlNetArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("n_fc3", C.c_int32), ("n_fc4", C.c_int32), ("dropout", C.c_int32),
+        ("keep_prob", C.c_float), ("reserved", C.c_int32), ("params", C.c_void_p),
+        ("seed", C.c_uint64), ("sample_offset", C.c_uint64), ("reward_trace", C.c_void_p),
+    ]
+
+
 class IrlLossArgs(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("T", C.c_int32), ("n_demo", C.c_int64), ("M", C.c_int64),
@@ -127,6 +135,7 @@ SYMBOLS = [
     ("dmfg_ac_apply_update_dev", C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                            C.c_void_p]),
     ("dmfg_ac_learners", C.c_int, [C.POINTER(LearnersArgs), C.c_void_p]),
+    ("dmfg_irl_learners", C.c_int, [C.POINTER(LearnersArgs), C.POINTER(IrlNetArgs), C.c_void_p]),
     ("dmfg_ac_step_workspace_bytes", C.c_uint64, [C.POINTER(RolloutArgs)]),
     ("dmfg_ac_step", C.c_int, [C.POINTER(RolloutArgs), C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
                                C.c_void_p, C.c_void_p]),

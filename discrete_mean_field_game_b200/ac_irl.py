@@ -297,12 +297,14 @@ class AC_IRL(_actor_critic):
     def train(self, max_episodes=4000, stop_criteria=0.01, gamma=1, constant=False, lr_critic=0.1, lr_actor=0.001,
               consecutive=100, file_theta='results/theta.csv', file_pi='results/pi.csv',
               file_reward='results/reward.csv', write_file=0, write_all=0, start_rows=None, noise_y=None,
-              verbose=True, use_graph=True):
+              verbose=True, use_graph=True, fused=True):
         """Actor-critic with r = r_net(pi, P), per-step online updates of w then theta (ac_irl.py:634-732).
 
-        One serial learner: every transition is a dmfg_rollout (sample P, pi', gradient) -> dmfg_rnet_forward
-        -> dmfg_td_accumulate -> dmfg_ac_apply_update chain on the device; theta is read back once per
-        episode only when stop_criteria != -1.  ``start_rows`` [E] / ``noise_y`` [E,15,d,d] replay draws."""
+        d = 15 / 16 (``fused=True``): the whole learner -- sampling, pi', the reward net on (pi_t, P_t), TD error and the
+        two updates, for all episodes up to the next report -- is ONE kernel (dmfg_irl_learners, a CTA per learner).
+        Otherwise one serial learner driven from the host: every transition is a dmfg_rollout (sample P, pi', gradient)
+        -> dmfg_rnet_forward -> dmfg_td_accumulate -> dmfg_ac_apply_update chain on the device.
+        ``start_rows`` [E] / ``noise_y`` [E,15,d,d] replay draws."""
         if verbose:
             print("----- Starting train -----")
         d, T = self.d, T_STEPS
@@ -312,6 +314,17 @@ class AC_IRL(_actor_critic):
         list_reward = []
         prev_theta = float(self.theta)
         episode = 0
+        if fused and d in (15, 16) and not write_all:
+            episode = self._train_fused(theta, w, mat, max_episodes, stop_criteria, gamma, constant, lr_critic, lr_actor,
+                                        consecutive, file_theta, file_pi, file_reward, write_file, start_rows, noise_y,
+                                        verbose)
+            self.theta = float(theta[0])
+            self.w = w.cpu().numpy().reshape(-1, 1)
+            self._episodes += max_episodes
+            self.list_policies = (self.list_policies + [self.theta])[1:]                    # ac_irl.py:731
+            if verbose:
+                print("----- Exiting train at episode %d with theta %f -----" % (episode, self.theta))
+            return
 
         def run_episode(pi, lr_c, lr_a, step_base, noise_ep, lr_dev=None, step_dev=None):
             """the 15-transition chain of one episode: 4 launches per transition, parameters on the device"""
@@ -411,6 +424,72 @@ class AC_IRL(_actor_critic):
         self.list_policies = (self.list_policies + [self.theta])[1:]                    # ac_irl.py:731
         if verbose:
             print("----- Exiting train at episode %d with theta %f -----" % (episode, self.theta))
+
+    def _train_fused(self, theta, w, mat, max_episodes, stop_criteria, gamma, constant, lr_critic, lr_actor, consecutive,
+                     file_theta, file_pi, file_reward, write_file, start_rows, noise_y, verbose):
+        """train() on dmfg_irl_learners: chunks that end at the reference's report episodes (multiples of
+        ``consecutive``); with a stop criterion theta after every episode comes back with the chunk, and a chunk in which
+        |theta_e - theta_{e-1}| < stop_criteria fires is re-run up to that episode (draws are counter-based, so the
+        re-run is identical).  Returns the last episode run (1-based)."""
+        d, T = self.d, T_STEPS
+        p = self.reward_params
+        w2 = w.reshape(1, -1)
+        prev_theta = float(self.theta)
+        list_reward = []
+        e = 0
+        while e < max_episodes:
+            n = min(consecutive - (e % consecutive), max_episodes - e)
+
+            def run(n_run, trace):
+                kw = {}
+                if noise_y is not None:
+                    kw["noise_y"] = self._dev(np.asarray(noise_y)[e:e + n_run].reshape(1, n_run, T, d, d), torch.float32)
+                if start_rows is not None:
+                    kw["start_rows"] = self._dev(np.asarray(start_rows)[e:e + n_run].reshape(1, n_run), torch.int32)
+                if self._dropout:
+                    kw.update(dropout_seed=self.seed ^ 0x5DEECE66D, sample_offset=self._dropout_calls)
+                return engine.irl_learners(theta, w2, mat, n_run, T, p.flat, p.n_fc3, p.n_fc4, shift=self.shift,
+                                           alpha_scale=self.alpha_scale, episode0=1 + e, gamma=gamma, lr_critic=lr_critic,
+                                           lr_actor=lr_actor, constant=bool(constant), discount="cumulative",
+                                           seed=self.seed, noise_episode_offset=self._episodes,
+                                           keep_prob=networks.KEEP_PROB, trace=trace, **kw)
+            stop_at = None
+            if stop_criteria != -1:
+                theta0, w0 = theta.clone(), w2.clone()
+                res = run(n, True)
+                th = [prev_theta] + res["theta_trace"][0, :, -1].cpu().tolist()
+                for k in range(n):
+                    if abs(th[k + 1] - th[k]) < stop_criteria:
+                        stop_at = k + 1
+                        break
+                if stop_at is not None and stop_at < n:
+                    theta.copy_(theta0); w2.copy_(w0)
+                    res = run(stop_at, False)
+                n_done = stop_at if stop_at is not None else n
+                prev_theta = th[n_done]
+            else:
+                res = run(n, False)
+                n_done = n
+            if self._dropout:
+                self._dropout_calls += n_done * T
+            list_reward += res["total_reward"][0, :n_done].cpu().tolist()
+            e += n_done
+            if e % consecutive == 0:
+                self.theta = float(theta[0])
+                pi_host = res["pi_final"][0].double().cpu().numpy()
+                reward_avg = sum(list_reward) / consecutive
+                if verbose:
+                    print("Theta\n", self.theta)
+                    print("pi\n", pi_host)
+                    print("Average reward during previous %d episodes: " % consecutive, str(reward_avg))
+                list_reward = []
+                if write_file:
+                    self.train_log(np.array([self.theta]), file_theta, "%.5e")
+                    self.train_log(pi_host, file_pi, "%.3e")
+                    self.train_log(np.array([reward_avg]), file_reward, "%.3e")
+            if stop_at is not None:
+                break
+        return e
 
     def train_batch(self, pi0, num_episodes=1, gamma=1, constant=False, lr_critic=0.1, lr_actor=0.001, seed=None,
                     pop_offset=0, group=None, first_episode=1, noise_y=None, keep_record=False):

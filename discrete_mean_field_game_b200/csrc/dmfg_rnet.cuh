@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     __shared__ double zsum;
     using SM = RnetSmem<G, NP, BWD>;
     constexpr int GPB = SM::GPB, SA = SM::SA, SC = SM::SC, RA = SM::RA, RC = SM::RC;
-    extern __shared__ __align__(128) float smem[];
+    extern __shared__ __align__(128) float rnet_smem[];      // (own name: other kernels of the library declare a double array)
+    float* const smem = rnet_smem;
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ __align__(8) unsigned long long mma_bar;       // completion of the tile's tensor-core MMAs (BWD)
     __shared__ uint32_t tmem_slot;

@@ -5,6 +5,7 @@
 
 #include "dmfg_error.h"
 #include "dmfg_rnet.cuh"
+#include "dmfg_irl_learner.cuh"
 
 using namespace dmfg;
 
@@ -70,6 +71,21 @@ int rnet_grid(const dmfg_rnet_args* a, int* grid, size_t* smem_bytes, long long 
     if (g < 1) g = 1;
     *grid = (int)g;
     *smem_bytes = smem;
+    return DMFG_OK;
+}
+
+template <int D>
+int launch_irl_learner(const LearnerParams<float>& p, const IrlLearnerNet& net, int noise_kind, cudaStream_t st) {
+    const RnetLayout L = rnet_layout(D, net.n3, net.n4);
+    const size_t smem = (size_t)(IrlLearnerSmem<D>::w3a + 2 * D * D * 8 + L.total) * sizeof(float);
+    if (noise_kind == DMFG_NOISE_PHILOX) {
+        DMFG_CUDA(cudaFuncSetAttribute(irl_learner_cta_kernel<D, DMFG_NOISE_PHILOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        irl_learner_cta_kernel<D, DMFG_NOISE_PHILOX><<<(unsigned)p.L, 128, smem, st>>>(p, make_philox_keys(p.seed), net);
+    } else {
+        DMFG_CUDA(cudaFuncSetAttribute(irl_learner_cta_kernel<D, DMFG_NOISE_INJECTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        irl_learner_cta_kernel<D, DMFG_NOISE_INJECTED><<<(unsigned)p.L, 128, smem, st>>>(p, make_philox_keys(p.seed), net);
+    }
+    DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
@@ -213,6 +229,40 @@ int dmfg_irl_dp_finalize(int64_t n, const double* reduced, float* grad, double* 
     irl_dp_finalize_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((int)n, reduced, grad, loss_out);
     DMFG_LAUNCHED();
     return DMFG_OK;
+}
+
+int dmfg_irl_learners(const dmfg_learners_args* a, const dmfg_irl_net_args* n, void* stream) {
+    if (!a || !n) return fail(DMFG_ERR_INVALID, "args is NULL");
+    if (a->struct_size != sizeof(dmfg_learners_args)) return fail(DMFG_ERR_INVALID, "dmfg_learners_args.struct_size mismatch");
+    if (n->struct_size != sizeof(dmfg_irl_net_args)) return fail(DMFG_ERR_INVALID, "dmfg_irl_net_args.struct_size mismatch");
+    if (a->dtype != DMFG_F32) return fail(DMFG_ERR_UNSUPPORTED, "dmfg_irl_learners is built for float streams");
+    if (a->d != 15 && a->d != 16) return fail(DMFG_ERR_UNSUPPORTED, "dmfg_irl_learners is built for d in {15,16} (got %d)", a->d);
+    if (n->n_fc3 < 1 || n->n_fc4 < 1 || n->n_fc3 > 8 || n->n_fc4 > 8)
+        return fail(DMFG_ERR_UNSUPPORTED, "reward-net widths must be in 1..8 (got %d, %d)", n->n_fc3, n->n_fc4);
+    if (a->L < 0 || a->E < 0 || a->T < 0 || a->S < 1) return fail(DMFG_ERR_INVALID, "bad L/E/T/S");
+    if (!a->theta || !a->w || !a->mat_pi0 || !n->params) return fail(DMFG_ERR_INVALID, "theta, w, mat_pi0 and net params are required");
+    if (a->noise_kind == DMFG_NOISE_INJECTED && (!a->noise_y || !a->start_rows))
+        return fail(DMFG_ERR_INVALID, "noise_kind=INJECTED needs noise_y and start_rows");
+    if (n->dropout != DMFG_DROPOUT_NONE && n->dropout != DMFG_DROPOUT_PHILOX)
+        return fail(DMFG_ERR_UNSUPPORTED, "dropout must be NONE or PHILOX");
+    if (n->dropout != DMFG_DROPOUT_NONE && !(n->keep_prob > 0.f && n->keep_prob <= 1.f))
+        return fail(DMFG_ERR_INVALID, "keep_prob must be in (0,1]");
+    if (a->L == 0 || a->E == 0) return DMFG_OK;
+    LearnerParams<float> p;
+    p.d = a->d; p.T = a->T; p.E = a->E; p.episode0 = a->episode0; p.S = a->S;
+    p.L = a->L; p.learner_offset = a->learner_offset;
+    p.theta = a->theta; p.w = a->w; p.shift = a->shift; p.alpha_scale = a->alpha_scale;
+    p.shift_scalar = a->shift_scalar; p.alpha_scale_scalar = a->alpha_scale_scalar;
+    p.gamma = a->gamma; p.lr_critic = a->lr_critic; p.lr_actor = a->lr_actor;
+    p.constant_lr = a->constant_lr; p.reward_kind = DMFG_REWARD_NONE; p.discount_kind = a->discount_kind;
+    p.mat_pi0 = (const float*)a->mat_pi0; p.start_rows = a->start_rows; p.noise_y = (const float*)a->noise_y;
+    p.seed = a->seed; p.noise_episode_offset = a->noise_episode_offset; p.theta_trace = a->theta_trace;
+    p.delta_trace = a->delta_trace; p.total_reward = a->total_reward; p.pi_final = (float*)a->pi_final;
+    IrlLearnerNet net;
+    net.params = n->params; net.n3 = n->n_fc3; net.n4 = n->n_fc4; net.dropout = n->dropout; net.keep_prob = n->keep_prob;
+    net.seed = n->seed; net.sample_offset = n->sample_offset; net.reward_trace = n->reward_trace;
+    cudaStream_t st = (cudaStream_t)stream;
+    return a->d == 15 ? launch_irl_learner<15>(p, net, a->noise_kind, st) : launch_irl_learner<16>(p, net, a->noise_kind, st);
 }
 
 int dmfg_umma_probe(const float* A, const float* B, int32_t a_mn_major, uint32_t a_lbo, uint32_t a_sbo, int32_t b_mn_major,

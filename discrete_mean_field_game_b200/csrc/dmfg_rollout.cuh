@@ -341,7 +341,7 @@ rollout_fast_kernel(const RolloutParams<R> p) {
 }
 
 // acc[f] = sum over CTAs of partials[cta][f], in CTA order
-__global__ void reduce_partials_kernel(const double* __restrict__ partials, int ncta, int n, double* __restrict__ acc) {
+static __global__ void reduce_partials_kernel(const double* __restrict__ partials, int ncta, int n, double* __restrict__ acc) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;
     // four independent chains with a fixed assignment and combination order: deterministic, loads pipelined
@@ -726,7 +726,7 @@ __global__ void __launch_bounds__(128) synthetic_check_kernel(int d, long long B
 }
 
 // theta += lr_a*scale*acc[0];  w[f] += lr_c*scale*acc[1+f]   (mfg_ac2.py:511-522)
-__global__ void ac_apply_update_kernel(int F, double* theta, double* w, const double* __restrict__ acc,
+static __global__ void ac_apply_update_kernel(int F, double* theta, double* w, const double* __restrict__ acc,
                                        double lr_c, double lr_a, double scale) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f < F) w[f] = fma(lr_c * scale, acc[1 + f], w[f]);
@@ -735,7 +735,7 @@ __global__ void ac_apply_update_kernel(int F, double* theta, double* w, const do
 
 // the same update with the two effective step sizes read from device memory (lr[0] critic, lr[1] actor): the
 // launch arguments do not change between replays of a captured CUDA graph
-__global__ void ac_apply_update_dev_kernel(int F, double* theta, double* w, const double* __restrict__ acc,
+static __global__ void ac_apply_update_dev_kernel(int F, double* theta, double* w, const double* __restrict__ acc,
                                            const double* __restrict__ lr, double scale) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f < F) w[f] = fma(lr[0] * scale, acc[1 + f], w[f]);

@@ -356,6 +356,68 @@ def learners(theta, w, mat_pi0, E, T, *, shift, alpha_scale, episode0=0, gamma=1
     return res
 
 
+def irl_learners(theta, w, mat_pi0, E, T, params, n_fc3, n_fc4, *, shift, alpha_scale, episode0=1, gamma=1.0,
+                 lr_critic=0.1, lr_actor=0.001, constant=False, discount="cumulative", start_rows=None, noise_y=None,
+                 seed=0, learner_offset=0, noise_episode_offset=0, dropout_seed=None, keep_prob=0.4, sample_offset=0,
+                 trace=False):
+    """dmfg_irl_learners: AC_IRL.train (ac_irl.py:634-732) as ONE kernel -- L serial learners (a CTA each) whose reward
+    is r_net(pi_t, P_t) evaluated inside the loop.  theta [L] / w [L,F] float64 are updated in place; `params` is the flat
+    float32 reward net; float32 streams, d in {15, 16}.  dropout_seed keys the in-kernel Philox dropout masks
+    (None: no dropout); transition (l, e, t) uses sample id sample_offset + (l*E + e)*T + t."""
+    from ._lib import DROPOUT_NONE, DROPOUT_PHILOX, IrlNetArgs
+    lib = _lib.load()
+    device, dtype = mat_pi0.device, mat_pi0.dtype
+    S, d = mat_pi0.shape
+    L = theta.shape[0]
+    F = num_features(d)
+    a = LearnersArgs()
+    a.struct_size = C.sizeof(LearnersArgs)
+    a.dtype, a.d, a.T, a.L, a.E = _dtype_code(dtype), d, int(T), L, int(E)
+    a.learner_offset, a.episode0 = int(learner_offset), int(episode0)
+    a.theta = _ptr(_require(theta, "theta", device, torch.float64, (L,)))
+    a.w = _ptr(_require(w, "w", device, torch.float64, (L, F)))
+    a.shift_scalar, a.alpha_scale_scalar = float(shift), float(alpha_scale)
+    a.gamma, a.lr_critic, a.lr_actor = float(gamma), float(lr_critic), float(lr_actor)
+    a.constant_lr = 1 if constant else 0
+    a.reward_kind = REWARD_KINDS["none"]
+    a.discount_kind = DISCOUNT_STEP if discount == "step" else DISCOUNT_CUMULATIVE
+    a.mat_pi0, a.S = _ptr(_require(mat_pi0, "mat_pi0", device, dtype, (S, d))), S
+    a.seed = int(seed) & (2 ** 64 - 1)
+    a.noise_episode_offset = int(noise_episode_offset)
+    if noise_y is not None:
+        a.noise_kind = NOISE_INJECTED
+        a.noise_y = _ptr(_require(noise_y, "noise_y", device, dtype, (L, E, T, d, d)))
+        if start_rows is None:
+            raise ValueError("injected noise needs start_rows [L,E]")
+    else:
+        a.noise_kind = NOISE_PHILOX
+    if start_rows is not None:
+        a.start_rows = _ptr(_require(start_rows, "start_rows", device, torch.int32, (L, E)))
+    n = IrlNetArgs()
+    n.struct_size = C.sizeof(IrlNetArgs)
+    n.n_fc3, n.n_fc4 = int(n_fc3), int(n_fc4)
+    n.params = _ptr(_require(params, "params", device, torch.float32, (rnet_param_count(d, n_fc3, n_fc4),)))
+    n.keep_prob = float(keep_prob)
+    if dropout_seed is None:
+        n.dropout = DROPOUT_NONE
+    else:
+        n.dropout, n.seed, n.sample_offset = DROPOUT_PHILOX, int(dropout_seed) & (2 ** 64 - 1), int(sample_offset)
+    res = {}
+    with torch.cuda.device(device):
+        if trace:
+            res["theta_trace"] = torch.empty((L, E, T), dtype=torch.float64, device=device)
+            res["delta_trace"] = torch.empty((L, E, T), dtype=torch.float64, device=device)
+            res["reward_trace"] = torch.empty((L, E, T), dtype=torch.float32, device=device)
+            a.theta_trace, a.delta_trace = _ptr(res["theta_trace"]), _ptr(res["delta_trace"])
+            n.reward_trace = _ptr(res["reward_trace"])
+        res["total_reward"] = torch.empty((L, E), dtype=torch.float64, device=device)
+        a.total_reward = _ptr(res["total_reward"])
+        res["pi_final"] = torch.empty((L, d), dtype=dtype, device=device)
+        a.pi_final = _ptr(res["pi_final"])
+        check(lib.dmfg_irl_learners(C.byref(a), C.byref(n), _stream_ptr(device)))
+    return res
+
+
 def gamma_sample(shape, seed=0, pop=0):
     """Gamma(shape,1) variates from the kernels' own sampler (testing aid)."""
     lib = _lib.load()

@@ -259,6 +259,25 @@ typedef struct dmfg_learners_args {
 } dmfg_learners_args;
 int dmfg_ac_learners(const dmfg_learners_args* args, void* stream);
 
+/* ---- a8 with the reward network in the loop: AC_IRL.train as ONE kernel ------ *
+ * AC_IRL.train (ac_irl.py:634-732): the serial actor-critic learner whose reward is r_net(pi_t, P_t), queried through
+ * sess.run for every transition upstream (ac_irl.py:683).  `args` as for dmfg_ac_learners (reward_kind is ignored, float
+ * streams, d <= 16, one CTA per learner; use episode0 = 1 and DMFG_DISCOUNT_CUMULATIVE for the reference's semantics);
+ * `net` gives the reward net shared by all learners.  Dropout: DMFG_DROPOUT_NONE or DMFG_DROPOUT_PHILOX -- transition
+ * t of episode e of learner l draws the masks of sample id sample_offset + (l*E + e)*T + t, exactly as
+ * dmfg_rnet_forward would for that id (the reference's dropout is active whenever the net is evaluated). */
+typedef struct dmfg_irl_net_args {
+    uint32_t struct_size;
+    int32_t  n_fc3, n_fc4;
+    int32_t  dropout;
+    float    keep_prob;
+    int32_t  reserved;
+    const float* params;          /* [dmfg_rnet_param_count(d, n_fc3, n_fc4)] */
+    uint64_t seed, sample_offset;
+    float*   reward_trace;        /* optional [L][E][T] */
+} dmfg_irl_net_args;
+int dmfg_irl_learners(const dmfg_learners_args* args, const dmfg_irl_net_args* net, void* stream);
+
 /* ---- host-buffer convenience wrapper (the end-to-end path) --------------- *
  * Same as dmfg_rollout but pi0 / noise_y / w and every output are HOST
  * pointers; the call allocates device buffers, copies in, runs, copies out

@@ -389,7 +389,7 @@ def test_train_cuda_graph_replay_equals_eager_launches(data):
     step sizes and Philox position refreshed in device buffers: bit-identical to launching the chain eagerly."""
     a, b = make(data), make(data)
     b.w = a.w.copy()
-    kw = dict(max_episodes=6, stop_criteria=-1, lr_critic=0.1, lr_actor=0.01, verbose=False)
+    kw = dict(max_episodes=6, stop_criteria=-1, lr_critic=0.1, lr_actor=0.01, verbose=False, fused=False)
     a.train(use_graph=True, **kw)
     b.train(use_graph=False, **kw)
     assert a.theta == b.theta and a.theta != 6.5
@@ -398,6 +398,53 @@ def test_train_cuda_graph_replay_equals_eager_launches(data):
     b.train(use_graph=False, **kw)
     assert a.theta == b.theta
     np.testing.assert_array_equal(a.w, b.w)
+
+
+@pytest.mark.parametrize("reg", ["none", "dropout_l1l2"])
+def test_train_fused_kernel_equals_host_driven_chain(data, reg, capsys):
+    """AC_IRL.train as ONE kernel (dmfg_irl_learners: a CTA per learner, the reward net evaluated inside the loop, Philox
+    dropout masks keyed by the transition id) against the host-driven chain of 4 launches per transition on the same
+    Philox draws: same start rows, same rewards and TD errors to float32 accuracy, same theta / w after 7 episodes,
+    same reports; and the |delta theta| stop criterion fires at the same episode."""
+    outs = []
+    for fused in (True, False):
+        ac = make(data, reg=reg)
+        rng = np.random.RandomState(3)
+        ac.reward_params.load_flat(ac.reward_params.flat.cpu().numpy() + np.float32(0.2 * rng.randn(3755)))
+        ac.w = np.linspace(0.2, 0.8, 136).reshape(-1, 1)
+        ac.train(max_episodes=7, stop_criteria=-1, lr_critic=0.1, lr_actor=0.01, consecutive=3, verbose=True, fused=fused,
+                 use_graph=False)
+        first = (ac.theta, ac.w.ravel().copy(), capsys.readouterr().out)
+        ac.train(max_episodes=40, stop_criteria=2e-3, lr_critic=0.1, lr_actor=0.01, verbose=True, fused=fused, use_graph=False)
+        outs.append(first + (ac.theta, capsys.readouterr().out.strip().splitlines()[-1]))
+    (t1, w1, o1, s1, e1), (t0, w0, o0, s0, e0) = outs
+    assert t1 != 6.5
+    np.testing.assert_allclose(t1, t0, rtol=2e-5)
+    np.testing.assert_allclose(w1, w0, rtol=2e-5, atol=1e-6)
+    assert o1.count("Average reward during previous 3 episodes") == 2 == o0.count("Average reward during previous 3 episodes")
+    assert e1.split("with theta")[0] == e0.split("with theta")[0] and "Exiting train at episode" in e1   # same stop episode
+    np.testing.assert_allclose(s1, s0, rtol=1e-4)
+
+
+def test_train_fused_many_learners_and_traces(data):
+    """dmfg_irl_learners with several learners (a CTA each): learner l equals a single-learner launch with learner_offset l;
+    the reward trace equals dmfg_rnet_forward on the recorded transitions is implied by the previous test -- here the
+    per-step traces are finite and tanh-bounded."""
+    from discrete_mean_field_game_b200 import engine
+    ac = make(data)
+    dev = ac.device
+    mat = torch.as_tensor(np.float32(data[0][:, :D]), device=dev)
+    L, E = 5, 4
+    th = torch.full((L,), 6.5, dtype=torch.float64, device=dev)
+    w = torch.rand((L, 136), dtype=torch.float64, device=dev)
+    th1, w1 = th.clone(), w.clone()
+    kw = dict(shift=0.0, alpha_scale=1e4, episode0=1, lr_critic=0.1, lr_actor=0.01, seed=9)
+    res = engine.irl_learners(th, w, mat, E, T, ac.reward_params.flat, N3, N4, trace=True, **kw)
+    assert torch.isfinite(res["theta_trace"]).all() and res["reward_trace"].abs().max() <= 1.0
+    for l in (0, 3):
+        tl, wl = th1[l:l + 1].clone(), w1[l:l + 1].clone()
+        engine.irl_learners(tl, wl, mat, E, T, ac.reward_params.flat, N3, N4, learner_offset=l, **kw)
+        assert tl[0] == th[l] and torch.equal(wl[0], w[l])
 
 
 def test_gridsearch_dropin(data, tmp_path, monkeypatch):
