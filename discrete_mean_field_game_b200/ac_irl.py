@@ -554,7 +554,7 @@ class AC_IRL(_actor_critic):
         demo_* : [N*15, d] / [N*15, d, d] device tensors.  Returns dict(theta, mean_reward, loss [4] device,
         states, actions)."""
         from . import parallel
-        if self._dropout or self.use_z or not self.one_pass_reward_update:
+        if self._dropout or self.use_z or not self.one_pass_reward_update or self.d > 16:
             res = self.train_batch(pi0, 1, gamma, constant, lr_critic, lr_actor, seed, pop_offset, group, episode,
                                    keep_record=True)
             T = T_STEPS
@@ -698,7 +698,7 @@ class AC_IRL(_actor_critic):
         # and hands back r_demo for the loss value.  4 -> 3 reward-net launches per update.
         _, world = parallel.world_info(group)
         if (world > 1 or self.rank_invariant_reward_step) and not self.use_z and self.one_pass_reward_update \
-                and masks is None and not self._dropout:
+                and masks is None and not self._dropout and self.d <= 16:
             # rank-count invariant data-parallel step: raw sums are all-reduced, 1/N_demo and 1/Z applied afterwards
             terms, _ = self._dp_reward_terms(demo_states, demo_actions, gen_states, gen_actions, num_demo_traj, layout)
             parallel.allreduce_sum_(terms, group)
@@ -714,7 +714,7 @@ class AC_IRL(_actor_critic):
         d_const = self._demo_weight(n_demo, -1.0 / float(num_demo_traj))
         grad, r_demo = engine.rnet_backward(p.flat, demo_states, demo_actions, d_const, p.n_fc3, p.n_fc4,
                                             keep_prob=networks.KEEP_PROB, want_rewards=True, **kd)
-        if not self.use_z and self.one_pass_reward_update:
+        if not self.use_z and self.one_pass_reward_update and self.d <= 16:
             # z_j = 1 (upstream's ac_irl.py:406): the generated half runs in ONE reward-net launch -- trajectory by
             # trajectory, weight exp(R_j), 1/sum_j exp(R_j) applied to the reduced gradient -- instead of
             # forward -> loss / dL/dr -> backward.  3 -> 2 reward-net launches per update.

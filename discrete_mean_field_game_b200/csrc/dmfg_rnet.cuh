@@ -75,16 +75,20 @@ struct RnetParams {
 };
 
 // shared-memory map (in floats), identical on host and device
-template <int G, int NP, bool BWD>
+// DS: compile-time state dimension (0 = the maximum of the lane group, G) -- the tiles are sized for it, which is what lets
+// d = 20 / 21 (32-lane groups) fit: tiles of 36 x 37 words per group would not.
+template <int G, int NP, bool BWD, int DS = 0>
 struct RnetSmem {
     static constexpr int GPB = kRnetThreads / G;
-    static constexpr int RA = G + 4, SA = (G + 4) | 1;
-    static constexpr int RC = G + 2, SC = (G + 2) | 1;
+    static constexpr int DT = DS ? DS : G;                     // widest d this instantiation serves
+    static constexpr int RA = DT + 4, SA = (DT + 4) | 1;
+    static constexpr int RC = DT + 2, SC = (DT + 2) | 1;
     static constexpr int NSLOT = 25 + 1 + 18 + 2 + 2 * NP;     // per-thread gradient slots
     static constexpr int NSMALL = 3 * NP + 1;                  // per-group: gW5[NP] gb4[NP] gb3[NP] gb5
     // tensor-core operand tiles of the fc3 weight gradient (dmfg_umma.cuh): rows m = t * G + h (t < 2d: position inside
     // the lane's row of conv2 activations, h: lane), K = the GPB transitions of the tile
-    static constexpr int MT = (2 * G * G + 127) / 128, KG = GPB / 8;
+    static constexpr int GM = (DT + 7) & ~7;                   // rows per activation slot t (a multiple of the 8-row group)
+    static constexpr int MT = (2 * DT * GM + 127) / 128, KG = GPB / 8;
     using W3G = umma::W3Grad<MT, KG>;
     static_assert(GPB % 8 == 0 && NP <= 8, "tile = whole groups of 8 transitions; fc3 width <= 8");
     int wflat, w3s, w3stride, tiles, tile_stride, umA, umB, gacc, gsmall, total;
@@ -93,7 +97,7 @@ struct RnetSmem {
         wflat = o; o += (ptotal + 3) / 4 * 4;
         w3stride = 2 * d * NP;
         if (((w3stride / 4) & 1) == 0) w3stride += 4;
-        w3s = o; o += G * w3stride;
+        w3s = o; o += d * w3stride;                                  // one block per row of the action (lane h < d)
         tile_stride = RA * SA + RC * SC + (BWD ? 2 * RC * SC : 0);
         // a warp holds two groups (transitions): with odd row strides the 16 lanes of a group hit 16 distinct
         // banks, and a tile offset of 16 (mod 32) words puts the other group on exactly the other 16
@@ -309,8 +313,9 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     static_assert(!TRAJ || BWD, "trajectory mode is a backward mode");
     __shared__ float rtraj[kRnetThreads / G];
     __shared__ double zsum;
-    using SM = RnetSmem<G, NP, BWD>;
+    using SM = RnetSmem<G, NP, BWD, DS>;
     constexpr int GPB = SM::GPB, SA = SM::SA, SC = SM::SC, RA = SM::RA, RC = SM::RC;
+    constexpr int W = SM::DT;                                   // columns walked by the unrolled row loops (d <= W)
     extern __shared__ __align__(128) float rnet_smem[];      // (own name: other kernels of the library declare a double array)
     float* const smem = rnet_smem;
     __shared__ __align__(8) unsigned long long mbar;
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     if (bulk_floats) mbar_wait(&mbar, 0);
     __syncthreads();
     // fc3 weights into per-row blocks [h][2d][NP] (zero padded columns), conflict-free stride
-    for (int i = tid; i < G * S.w3stride; i += kRnetThreads) w3s[i] = 0.f;
+    for (int i = tid; i < d * S.w3stride; i += kRnetThreads) w3s[i] = 0.f;
     __syncthreads();
     for (int i = tid; i < 2 * d * d * n3; i += kRnetThreads) {
         const int k = i / n3, n = i - k * n3;
@@ -357,6 +362,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     __syncthreads();
 
     const bool row_ok = h < d;
+    const int hs = row_ok ? h : 0;           // tile row of this lane: idle lanes (h >= d) re-read row 0, their results are masked
     const float inv_keep = p.dropout ? 1.0f / p.keep_prob : 1.0f;
     // persistent register accumulators (backward)
     float gw4pi[NP], gw4h[NP];
@@ -391,7 +397,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
         float dz3[NP];
 #pragma unroll
         for (int j = 0; j < NP; ++j) dz3[j] = 0.f;
-        float c2[2][G];
+        float c2[2][W];
         {
             // ---- action tile -> shared (interior of the zero-haloed tile) ------------------------
             const float* a = p.actions + n * d * d;
@@ -419,31 +425,31 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 #endif
             __syncwarp();
             // ---- conv1 row h ----------------------------------------------------------------------
-            float c1[G];
+            float c1[W];
             {
                 const float b1 = wf[L.b1];
 #pragma unroll
-                for (int w = 0; w < G; ++w) c1[w] = b1;
+                for (int w = 0; w < W; ++w) c1[w] = b1;
 #pragma unroll
                 for (int dh = 0; dh < kK1; ++dh) {
-                    const float* row = At + (h + dh) * SA;
+                    const float* row = At + (hs + dh) * SA;
                     float k[kK1];
 #pragma unroll
                     for (int dw = 0; dw < kK1; ++dw) k[dw] = wf[L.k1 + dh * kK1 + dw];
 #pragma unroll
-                    for (int wp = 0; wp < G + 4; ++wp) {
+                    for (int wp = 0; wp < W + 4; ++wp) {
                         const float v = row[wp];
 #pragma unroll
                         for (int dw = 0; dw < kK1; ++dw) {
                             const int w = wp - dw;
-                            if (w >= 0 && w < G) c1[w] = fmaf(v, k[dw], c1[w]);
+                            if (w >= 0 && w < W) c1[w] = fmaf(v, k[dw], c1[w]);
                         }
                     }
                 }
 #pragma unroll
-                for (int w = 0; w < G; ++w) {
+                for (int w = 0; w < W; ++w) {
                     c1[w] = (row_ok && w < d) ? fmaxf(c1[w], 0.f) : 0.f;
-                    Ct[(h + 1) * SC + w + 1] = c1[w];
+                    if (row_ok) Ct[(h + 1) * SC + w + 1] = c1[w];
                 }
             }
             __syncwarp();
@@ -453,11 +459,11 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                 for (int c = 0; c < 2; ++c) {
                     const float b2 = wf[L.b2 + c];
 #pragma unroll
-                    for (int w = 0; w < G; ++w) c2[c][w] = b2;
+                    for (int w = 0; w < W; ++w) c2[c][w] = b2;
                 }
 #pragma unroll
                 for (int dh = 0; dh < kK2; ++dh) {
-                    const float* row = Ct + (h + dh) * SC;
+                    const float* row = Ct + (hs + dh) * SC;
                     float k[kK2][2];
 #pragma unroll
                     for (int dw = 0; dw < kK2; ++dw) {
@@ -465,12 +471,12 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                         k[dw][1] = wf[L.k2 + (dh * kK2 + dw) * 2 + 1];
                     }
 #pragma unroll
-                    for (int wp = 0; wp < G + 2; ++wp) {
+                    for (int wp = 0; wp < W + 2; ++wp) {
                         const float v = row[wp];
 #pragma unroll
                         for (int dw = 0; dw < kK2; ++dw) {
                             const int w = wp - dw;
-                            if (w >= 0 && w < G) {
+                            if (w >= 0 && w < W) {
                                 c2[0][w] = fmaf(v, k[dw][0], c2[0][w]);
                                 c2[1][w] = fmaf(v, k[dw][1], c2[1][w]);
                             }
@@ -480,7 +486,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
-                    for (int w = 0; w < G; ++w) c2[c][w] = (row_ok && w < d) ? fmaxf(c2[c][w], 0.f) : 0.f;
+                    for (int w = 0; w < W; ++w) c2[c][w] = (row_ok && w < d) ? fmaxf(c2[c][w], 0.f) : 0.f;
             }
             // ---- fc3: this row's 2d activations x W3 row block, then all-reduce over the group ----
             float z3[NP];
@@ -488,7 +494,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
             for (int j = 0; j < NP; ++j) z3[j] = 0.f;
             const float* wrow = w3s + (row_ok ? h : 0) * S.w3stride;
 #pragma unroll
-            for (int w = 0; w < G; ++w) {
+            for (int w = 0; w < W; ++w) {
                 if (w < d) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -598,18 +604,18 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                     }
                 }
                 // conv2 activations of this transition -> A operand of the fc3 weight gradient on the tensor cores
-                // (3xTF32 split; row m = (2w + c) * G + h, column = this transition: every store is base + immediate).
+                // (3xTF32 split; row m = (2w + c) * GM + h, column = this transition: every store is base + immediate).
                 // The MMAs of the previous tile must have finished reading the tile first.
                 if (mma_pending) { mbar_wait_bounded(&mma_bar, mma_phase); mma_phase ^= 1u; mma_pending = false; }
                 if (row_ok) {
 #pragma unroll
-                    for (int w = 0; w < G; ++w) {
+                    for (int w = 0; w < W; ++w) {
                         if (w < d) {
 #pragma unroll
                             for (int c = 0; c < 2; ++c) {
                                 float hi, lo;
                                 umma::split_tf32(c2[c][w], hi, lo);
-                                constexpr uint32_t kRowStep = (uint32_t)(G / 8) * W3G::kSbo;
+                                constexpr uint32_t kRowStep = (uint32_t)(SM::GM / 8) * W3G::kSbo;
                                 umma::sts_f32(a_st_hi + (uint32_t)(2 * w + c) * kRowStep, hi);
                                 umma::sts_f32(a_st_lo + (uint32_t)(2 * w + c) * kRowStep, lo);
                             }
@@ -617,9 +623,9 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                     }
                 }
                 // d conv2 pre-activation: dz2 = (W3 row block . dz3) masked by relu
-                float dz2[2][G];
+                float dz2[2][W];
 #pragma unroll
-                for (int w = 0; w < G; ++w) {
+                for (int w = 0; w < W; ++w) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         float s = 0.f;
@@ -633,7 +639,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                             }
                         }
                         dz2[c][w] = c2[c][w] > 0.f ? s : 0.f;
-                        Dt[c * RC * SC + (h + 1) * SC + w + 1] = dz2[c][w];
+                        if (row_ok) Dt[c * RC * SC + (h + 1) * SC + w + 1] = dz2[c][w];
                     }
                 }
                 // d conv2/weights [dh][dw][c] and biases
@@ -641,14 +647,14 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                     float* gk = gk2;
 #pragma unroll
                     for (int dh = 0; dh < kK2; ++dh) {
-                        const float* row = Ct + (h + dh) * SC;
+                        const float* row = Ct + (hs + dh) * SC;
 #pragma unroll
-                        for (int wp = 0; wp < G + 2; ++wp) {
+                        for (int wp = 0; wp < W + 2; ++wp) {
                             const float v = row[wp];
 #pragma unroll
                             for (int dw = 0; dw < kK2; ++dw) {
                                 const int w = wp - dw;
-                                if (w >= 0 && w < G) {
+                                if (w >= 0 && w < W) {
                                     gk[(dh * kK2 + dw) * 2] = fmaf(v, dz2[0][w], gk[(dh * kK2 + dw) * 2]);
                                     gk[(dh * kK2 + dw) * 2 + 1] = fmaf(v, dz2[1][w], gk[(dh * kK2 + dw) * 2 + 1]);
                                 }
@@ -656,51 +662,51 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                         }
                     }
 #pragma unroll
-                    for (int w = 0; w < G; ++w) { gk2[18] += dz2[0][w]; gk2[19] += dz2[1][w]; }
+                    for (int w = 0; w < W; ++w) { gk2[18] += dz2[0][w]; gk2[19] += dz2[1][w]; }
                 }
                 __syncwarp();
                 // d conv1 output row h: full correlation of dz2 with the flipped conv2 kernel
-                float dz1[G];
+                float dz1[W];
 #pragma unroll
-                for (int w = 0; w < G; ++w) dz1[w] = 0.f;
+                for (int w = 0; w < W; ++w) dz1[w] = 0.f;
 #pragma unroll
                 for (int e = 0; e < kK2; ++e) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
-                        const float* row = Dt + c * RC * SC + (h + e) * SC;
+                        const float* row = Dt + c * RC * SC + (hs + e) * SC;
                         float k[kK2];
 #pragma unroll
                         for (int f = 0; f < kK2; ++f) k[f] = wf[L.k2 + ((2 - e) * kK2 + (2 - f)) * 2 + c];
 #pragma unroll
-                        for (int wp = 0; wp < G + 2; ++wp) {
+                        for (int wp = 0; wp < W + 2; ++wp) {
                             const float v = row[wp];
 #pragma unroll
                             for (int f = 0; f < kK2; ++f) {
                                 const int w = wp - f;
-                                if (w >= 0 && w < G) dz1[w] = fmaf(v, k[f], dz1[w]);
+                                if (w >= 0 && w < W) dz1[w] = fmaf(v, k[f], dz1[w]);
                             }
                         }
                     }
                 }
 #pragma unroll
-                for (int w = 0; w < G; ++w) dz1[w] = c1[w] > 0.f ? dz1[w] : 0.f;
+                for (int w = 0; w < W; ++w) dz1[w] = c1[w] > 0.f ? dz1[w] : 0.f;
                 // d conv1/weights [dh][dw] and bias
                 {
 #pragma unroll
                     for (int dh = 0; dh < kK1; ++dh) {
-                        const float* row = At + (h + dh) * SA;
+                        const float* row = At + (hs + dh) * SA;
 #pragma unroll
-                        for (int wp = 0; wp < G + 4; ++wp) {
+                        for (int wp = 0; wp < W + 4; ++wp) {
                             const float v = row[wp];
 #pragma unroll
                             for (int dw = 0; dw < kK1; ++dw) {
                                 const int w = wp - dw;
-                                if (w >= 0 && w < G) gk1[dh * kK1 + dw] = fmaf(v, dz1[w], gk1[dh * kK1 + dw]);
+                                if (w >= 0 && w < W) gk1[dh * kK1 + dw] = fmaf(v, dz1[w], gk1[dh * kK1 + dw]);
                             }
                         }
                     }
 #pragma unroll
-                    for (int w = 0; w < G; ++w) gk1[kK1 * kK1] += dz1[w];
+                    for (int w = 0; w < W; ++w) gk1[kK1 * kK1] += dz1[w];
                 }
             }
             __syncwarp();      // tiles are rewritten by the next transition of this group
@@ -731,14 +737,14 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     if (mma_pending) mbar_wait_bounded(&mma_bar, mma_phase);           // the last tile's MMAs (they also read the operand tiles)
     umma::fence_after_sync();
     {
-        // d fc3/weights from TMEM: accumulator row m = t * G + hh of M-tile m / 128 sits in TMEM lane m % 128; warp w reads
+        // d fc3/weights from TMEM: accumulator row m = t * GM + hh of M-tile m / 128 sits in TMEM lane m % 128; warp w reads
         // lanes 32 (w % 4) .. of the M-tiles w / 4, w / 4 + 2, ...
         const int warp = tid >> 5, lane = tid & 31;
         for (int mt = warp >> 2; mt < SM::MT; mt += kRnetThreads / 128) {
             float v[8];
             umma::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 16u * (uint32_t)mt, v);
             const int m = 128 * mt + 32 * (warp & 3) + lane;
-            const int t = m / G, hh = m % G;
+            const int t = m / SM::GM, hh = m % SM::GM;
             if (hh < d && t < 2 * d) {
                 const int k = hh * 2 * d + t;
 #pragma unroll

@@ -11,7 +11,8 @@ using namespace dmfg;
 
 namespace {
 
-constexpr int kG = 16;           // lanes per transition: d <= 16
+constexpr int kG = 16;           // lanes per transition: 16 for d <= 16 (two transitions per warp), 32 for d <= 32
+constexpr int kGmax = 32;
 constexpr int kNP = 8;           // padded width of fc3 / fc4: n_fc3, n_fc4 <= 8
 constexpr int kMaxRnetCtas = 148 * 2;
 constexpr int kLossBlocks = 148 * 4;
@@ -24,9 +25,12 @@ int check_rnet(const dmfg_rnet_args* a, bool bwd, bool need_drewards = true) {
         return fail(DMFG_ERR_INVALID, "dmfg_rnet_args.struct_size %u != %zu (header mismatch)", a->struct_size,
                     sizeof(dmfg_rnet_args));
     if (a->d < 1 || a->n_fc3 < 1 || a->n_fc4 < 1 || a->N < 0) return fail(DMFG_ERR_INVALID, "bad d/n_fc3/n_fc4/N");
-    if (a->d > kG || a->n_fc3 > kNP || a->n_fc4 > kNP)
+    if (a->d > kGmax || a->n_fc3 > kNP || a->n_fc4 > kNP)
         return fail(DMFG_ERR_UNSUPPORTED, "reward-net kernels are built for d <= %d, n_fc3, n_fc4 <= %d (got %d, %d, %d)",
-                    kG, kNP, a->d, a->n_fc3, a->n_fc4);
+                    kGmax, kNP, a->d, a->n_fc3, a->n_fc4);
+    if (bwd && a->d > kG && a->d != 20 && a->d != 21)
+        return fail(DMFG_ERR_UNSUPPORTED, "the reward-net backward kernel is built for d <= 16 and d = 20, 21 (got %d): "
+                    "its per-transition tiles are compile-time sized", a->d);
     if (!a->params) return fail(DMFG_ERR_INVALID, "params is NULL");
     if (a->N > 0 && (!a->states || !a->actions)) return fail(DMFG_ERR_INVALID, "states/actions are NULL");
     if (a->dropout < DMFG_DROPOUT_NONE || a->dropout > DMFG_DROPOUT_PHILOX) return fail(DMFG_ERR_INVALID, "dropout %d", a->dropout);
@@ -53,20 +57,22 @@ RnetParams make_params(const dmfg_rnet_args* a) {
     return p;
 }
 
-template <bool BWD, int DS, int N3S, int N4S, bool TRAJ = false>
+template <bool BWD, int DS, int N3S, int N4S, bool TRAJ = false, int G = kG>
 int rnet_grid(const dmfg_rnet_args* a, int* grid, size_t* smem_bytes, long long traj_M = 0) {
-    auto kern = rnet_kernel<kG, kNP, BWD, DS, N3S, N4S, TRAJ>;
+    auto kern = rnet_kernel<G, kNP, BWD, DS, N3S, N4S, TRAJ>;
     const RnetLayout L = rnet_layout(a->d, a->n_fc3, a->n_fc4);
-    const RnetSmem<kG, kNP, BWD> S(a->d, L.total);
+    const RnetSmem<G, kNP, BWD, DS> S(a->d, L.total);
     const size_t smem = (size_t)S.total * sizeof(float);
+    if (smem > 227 * 1024)
+        return fail(DMFG_ERR_UNSUPPORTED, "the reward-net kernel needs %zu bytes of shared memory at d = %d: does not fit an SM", smem, a->d);
     DMFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0, sms = 0;
     DMFG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRnetThreads, smem));
     if (int rc = sm_count(&sms)) return rc;
-    if (occ < 1) return fail(DMFG_ERR_CUDA, "rnet_kernel needs %zu bytes of shared memory: does not fit an SM", smem);
+    if (occ < 1) return fail(DMFG_ERR_UNSUPPORTED, "rnet_kernel needs %zu bytes of shared memory: does not fit an SM", smem);
     long long g = (long long)sms * occ;
     if (g > kMaxRnetCtas) g = kMaxRnetCtas;
-    const long long ntiles = TRAJ ? traj_M : (a->N + kRnetThreads / kG - 1) / (kRnetThreads / kG);
+    const long long ntiles = TRAJ ? traj_M : (a->N + kRnetThreads / G - 1) / (kRnetThreads / G);
     if (g > ntiles) g = ntiles;
     if (g < 1) g = 1;
     *grid = (int)g;
@@ -135,9 +141,18 @@ int dmfg_rnet_forward(const dmfg_rnet_args* a, void* stream) {
     } else if (a->d == 15) {
         if (int rc = rnet_grid<false, 15, 0, 0>(a, &grid, &smem)) return rc;
         rnet_kernel<kG, kNP, false, 15, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
-    } else {
+    } else if (a->d <= kG) {
         if (int rc = rnet_grid<false, 0, 0, 0>(a, &grid, &smem)) return rc;
         rnet_kernel<kG, kNP, false, 0, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
+    } else if (a->d == 20) {      // the reference's action files are 20 x 20 (ac_irl.py:164-200)
+        if (int rc = rnet_grid<false, 20, 0, 0, false, 32>(a, &grid, &smem)) return rc;
+        rnet_kernel<32, kNP, false, 20, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
+    } else if (a->d == 21) {      // mfg_ac2.py:25 default d
+        if (int rc = rnet_grid<false, 21, 0, 0, false, 32>(a, &grid, &smem)) return rc;
+        rnet_kernel<32, kNP, false, 21, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
+    } else {                      // 16 < d <= 32: 32 lanes per transition, sizes from the arguments
+        if (int rc = rnet_grid<false, 0, 0, 0, false, 32>(a, &grid, &smem)) return rc;
+        rnet_kernel<32, kNP, false, 0, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
     }
     DMFG_LAUNCHED();
     return DMFG_OK;
@@ -168,9 +183,15 @@ int dmfg_rnet_backward(const dmfg_rnet_args* a, void* stream) {
     } else if (a->d == 15) {
         if (int rc = rnet_grid<true, 15, 0, 0>(a, &grid, &smem)) return rc;
         rnet_kernel<kG, kNP, true, 15, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
-    } else {
+    } else if (a->d <= kG) {
         if (int rc = rnet_grid<true, 0, 0, 0>(a, &grid, &smem)) return rc;
         rnet_kernel<kG, kNP, true, 0, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
+    } else if (a->d == 20) {
+        if (int rc = rnet_grid<true, 20, 0, 0, false, 32>(a, &grid, &smem)) return rc;
+        rnet_kernel<32, kNP, true, 20, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
+    } else {
+        if (int rc = rnet_grid<true, 21, 0, 0, false, 32>(a, &grid, &smem)) return rc;
+        rnet_kernel<32, kNP, true, 21, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
     }
     DMFG_LAUNCHED();
     rnet_reduce_partials_kernel<<<(total + 31) / 32, 32 * kReduceSlices, 0, st>>>(p.partials, grid, total, a->accumulate, a->grad);
@@ -185,6 +206,9 @@ int dmfg_rnet_backward_gen(const dmfg_rnet_args* a, const dmfg_irl_gen_args* g, 
     if (g->T < 1 || g->T > kRnetThreads / kG)
         return fail(DMFG_ERR_UNSUPPORTED, "the one-pass update holds a trajectory of T <= %d transitions per CTA (T = %d)",
                     kRnetThreads / kG, g->T);
+    if (a && a->d > kG)
+        return fail(DMFG_ERR_UNSUPPORTED, "the one-pass update is built for d <= %d (16 lanes per transition, a trajectory per CTA): "
+                    "use dmfg_rnet_forward -> dmfg_irl_loss_grad -> dmfg_rnet_backward at d = %d", kG, a->d);
     if (g->M < 1 || g->n_demo < 0 || !(g->num_demo_traj > 0)) return fail(DMFG_ERR_INVALID, "bad M/n_demo/num_demo_traj");
     if (a->N != g->M * (int64_t)g->T) return fail(DMFG_ERR_INVALID, "N must be M*T");
     if (!((g->gen_t_stride == g->M && g->gen_j_stride == 1) || (g->gen_t_stride == 1 && g->gen_j_stride == g->T)))

@@ -8,8 +8,8 @@ when it is fetched through ``Session.run`` or called directly.  Inputs may be ``
 tensors (eager).  Variables live in a ``variable_scope``: a second ``r_net*`` call in the same scope
 shares the parameters of the first (``scope.reuse_variables()``, ac_irl.py:251).
 
-Only the instantiation the reference uses is built on the GPU: f1=1, k1=5, f2=2, k2=3, d <= 16,
-n_fc3, n_fc4 <= 8; ``n_fc5`` is accepted and ignored exactly like upstream (fc5 is commented out,
+Only the instantiation the reference uses is built on the GPU: f1=1, k1=5, f2=2, k2=3, n_fc3, n_fc4 <= 8, forward for
+d <= 32, backward for d <= 16 and d = 20, 21; ``n_fc5`` is accepted and ignored exactly like upstream (fc5 is commented out,
 networks.py:39,76,115,152).
 """
 from __future__ import annotations

@@ -294,7 +294,9 @@ int dmfg_rollout_host(const dmfg_rollout_args* args_with_host_pointers, void* st
  *   fc3/weights[2d^2,n3] fc3/biases[n3] fc4/weights[n3+d,n4] fc4/biases[n4]
  *   out/weights[n4,1] out/biases[1]
  * Transitions are rows of states [N][d] / actions [N][d][d]; a time-major rollout
- * record [T][B].. is such an array with N = T*B.  Built for d <= 16, n3,n4 <= 8. */
+ * record [T][B].. is such an array with N = T*B.  n3, n4 <= 8.  Forward: d <= 32 (16 lanes per transition up to d = 16,
+ * 32 above); backward: d <= 16 and d = 20, 21 (the 20 x 20 action files of ac_irl.py:164-200 and mfg_ac2.py:25's
+ * default); dmfg_rnet_backward_gen: d <= 16. */
 #define DMFG_DROPOUT_NONE   0   /* reg = 'none' | 'l1l2'                                       */
 #define DMFG_DROPOUT_MASKS  1   /* caller supplies 0/1 keep masks (parity)                     */
 #define DMFG_DROPOUT_PHILOX 2   /* in-kernel Philox keep masks keyed by (seed, sample_offset+n) */

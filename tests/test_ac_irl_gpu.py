@@ -478,3 +478,30 @@ def test_evaluate_surface_of_ac_irl(data, tmp_path, evalm):
     np.testing.assert_allclose(ac.JSD(evalm["jsd_P"].copy(), evalm["jsd_Q"].copy()), float(evalm["jsd_value"]), rtol=1e-12)
     traj = ac.generate_trajectory(data[0][0], 16)
     assert traj.shape == (16, D)
+
+
+def test_ac_irl_runs_at_d21_on_20x20_style_data(tmp_path, monkeypatch):
+    """AC_IRL at d = 21 / 20 (round 1 returned DMFG_ERR_UNSUPPORTED): the reward net runs on the 32-lane kernels, the reward
+    update takes the forward -> loss -> backward chain (the one-pass launch holds a trajectory per CTA at d <= 16 only),
+    train() runs host-driven; one outer-loop-style sequence stays finite and moves theta and the reward parameters."""
+    from discrete_mean_field_game_b200.ac_irl import AC_IRL
+    monkeypatch.chdir(tmp_path)
+    for d in (21, 20):
+        rng = np.random.RandomState(d)
+        mat = rng.dirichlet(np.ones(d), size=12)
+        ac = AC_IRL(theta=6.5, d=d, reg="none", mat_pi0=mat, demonstrations=[], seed=3, net_seed=4)
+        ds, da = ac.generate_batch(9, theta=8.0)
+        gs, ga = ac.generate_batch(11)
+        p0 = ac.reward_params.flat.clone()
+        loss = ac.update_reward_batch(ds[:15].reshape(-1, d).contiguous(), da.reshape(-1, d, d), gs[:15].reshape(-1, d).contiguous(),
+                                      ga.reshape(-1, d, d), 9, "time_major", group=False).cpu().numpy()
+        assert np.isfinite(loss).all() and not torch.equal(p0, ac.reward_params.flat)
+        # against the oracle: loss and gradient of the same batch
+        g_ref = R.loss_and_grad(p0.cpu().numpy(), ds[:15].reshape(-1, d).cpu().numpy(), da.reshape(-1, d, d).cpu().numpy(),
+                                gs[:15].permute(1, 0, 2).reshape(-1, d).cpu().numpy(),
+                                ga.permute(1, 0, 2, 3).reshape(-1, d, d).cpu().numpy(), 8, 4, 9, 15)
+        np.testing.assert_allclose(loss[0], g_ref[0], rtol=1e-4, atol=1e-5)
+        g = ac._last_grad.cpu().numpy()
+        assert np.abs(g - g_ref[2]).max() <= 3e-5 * np.abs(g_ref[2]).max() + 1e-6
+        ac.train(max_episodes=2, stop_criteria=-1, lr_critic=0.1, lr_actor=0.01, verbose=False)
+        assert np.isfinite(ac.theta) and ac.theta != 6.5 and np.isfinite(ac.w).all()

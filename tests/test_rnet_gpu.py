@@ -262,3 +262,54 @@ def test_random_shapes_forward_backward_vs_oracle(dev):
             sl = slice(off, off + int(np.prod(shp)))
             scale = np.abs(g_ref[sl]).max() + 1e-6
             assert np.abs(g[sl] - g_ref[sl]).max() <= 2e-5 * scale + 1e-6, tag + " " + name
+
+
+@pytest.mark.parametrize("d", [20, 21])
+def test_reward_net_d20_d21_forward_backward_vs_oracle(dev, d):
+    """The 32-lanes-per-transition instantiations: d = 20 (the reference's action files are 20 x 20, ac_irl.py:164-200)
+    and d = 21 (mfg_ac2.py:25's default), forward and backward (fc3 weight gradient on the tensor cores with 8 M-tiles)."""
+    from discrete_mean_field_game_b200 import engine
+    rng = np.random.RandomState(d)
+    for n3, n4, n, dropout in ((8, 4, 77, False), (5, 7, 8, True), (8, 4, 1, False)):
+        p = f32(R.xavier_init(d, n3, n4, rng) + 0.1 * rng.randn(R.param_count(d, n3, n4)))
+        s = f32(rng.dirichlet(np.ones(d) * 0.3, size=n))
+        a = f32(rng.dirichlet(np.ones(d) * 0.5, size=(n, d)))
+        m3 = (rng.rand(n, n3) < 0.4) if dropout else None
+        m4 = (rng.rand(n, n4) < 0.4) if dropout else None
+        dr = f32(rng.randn(n))
+        r_ref, cache = R.forward(p, s, a, n3, n4, m3, m4, cache=True)
+        g_ref = R.backward(cache, dr)
+        kw = dict(mask3=T_(m3, dev, torch.uint8), mask4=T_(m4, dev, torch.uint8)) if dropout else {}
+        tag = "d=%d n3=%d n4=%d N=%d dropout=%s" % (d, n3, n4, n, dropout)
+        r_f = engine.rnet_forward(T_(p, dev), T_(s, dev), T_(a, dev), n3, n4, **kw).cpu().numpy()
+        g, r_b = engine.rnet_backward(T_(p, dev), T_(s, dev), T_(a, dev), T_(dr, dev), n3, n4, want_rewards=True, **kw)
+        np.testing.assert_allclose(r_f, r_ref, rtol=2e-5, atol=2e-6, err_msg=tag)
+        np.testing.assert_array_equal(r_b.cpu().numpy(), r_f, err_msg=tag)
+        g = g.cpu().numpy()
+        for name, shp, off in R.layout(d, n3, n4):
+            sl = slice(off, off + int(np.prod(shp)))
+            scale = np.abs(g_ref[sl]).max() + 1e-6
+            assert np.abs(g[sl] - g_ref[sl]).max() <= 2e-5 * scale + 1e-6, tag + " " + name
+
+
+def test_reward_net_forward_generic_wide_d_and_limits(dev):
+    """16 < d <= 32 runs the generic 32-lane forward kernel; the backward kernel is built for d <= 16 and d = 20 / 21 and
+    says so; d > 32 is refused."""
+    from discrete_mean_field_game_b200 import engine
+    from discrete_mean_field_game_b200._lib import DmfgError, ERR_UNSUPPORTED
+    rng = np.random.RandomState(2)
+    for d in (17, 27, 32):
+        n = 9
+        p = f32(R.xavier_init(d, 6, 3, rng))
+        s = f32(rng.dirichlet(np.ones(d), size=n))
+        a = f32(rng.dirichlet(np.ones(d), size=(n, d)))
+        r = engine.rnet_forward(T_(p, dev), T_(s, dev), T_(a, dev), 6, 3).cpu().numpy()
+        np.testing.assert_allclose(r, R.forward(p, s, a, 6, 3), rtol=2e-5, atol=2e-6)
+    with pytest.raises(DmfgError) as e:
+        engine.rnet_backward(T_(p, dev), T_(s, dev), T_(a, dev), T_(f32(rng.randn(n)), dev), 6, 3)
+    assert e.value.code == ERR_UNSUPPORTED
+    d = 33
+    with pytest.raises(DmfgError) as e:
+        engine.rnet_forward(T_(f32(R.xavier_init(d, 6, 3, rng)), dev), T_(f32(rng.dirichlet(np.ones(d), size=2)), dev),
+                            T_(f32(rng.dirichlet(np.ones(d), size=(2, d))), dev), 6, 3)
+    assert e.value.code == ERR_UNSUPPORTED
