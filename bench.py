@@ -482,6 +482,35 @@ def run_ours(args):
                                "generated_trajectories": M, "transitions_per_iter": 2 * M * 15,
                                "transitions_per_s": 2 * M * 15 / (ms_irl * 1e-3), "gpu_launches_per_iter": 6}
         del ds, da, gs, ga
+        # AC_IRL.train (ac_irl.py:634-732: ONE learner, the reward net queried at every transition, the reference's default
+        # regulariser with dropout active) as one kernel -- dmfg_irl_learners -- and the reference's own 5 + 5 trajectory
+        # reward update (ac_irl.py:804-846) through the class
+        with contextlib.redirect_stdout(sys.stderr):
+            one = AC_IRL(theta=8.64, shift=0, alpha_scale=1e4, d=D, reg="dropout_l1l2", n_fc3=8, n_fc4=4,
+                         mat_pi0=synthetic_pi0(21, seed=5), demonstrations=[], device=dev, seed=1, net_seed=2)
+            one.train(max_episodes=20, stop_criteria=-1, verbose=False)
+            torch.cuda.synchronize()
+            E = 2000
+            t0 = time.perf_counter()
+            one.train(max_episodes=E, stop_criteria=-1, consecutive=1000, verbose=False)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            modes["irl_learner"] = {"value": E * 15 / dt, "unit": UNIT, "learners": 1, "episodes": E,
+                                    "kernel": "irl_learner_cta_kernel<15,PHILOX> (reward net + dropout in the loop)",
+                                    "us_per_transition": 1e6 * dt / (E * 15)}
+            one.list_demonstrations = one.generate_trajectories(20)
+            one.list_generated = one.generate_trajectories(50)
+            for _ in range(5):
+                one.update_reward()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(100):
+                one.update_reward()
+            torch.cuda.synchronize()
+            modes["irl_update_minibatch"] = {"value": 100 / (time.perf_counter() - t0), "unit": "IRL iters/s",
+                                             "demo_trajectories": 5, "generated_trajectories": 5,
+                                             "what": "AC_IRL.update_reward as the reference calls it (host lists in, e2e)"}
+        del one
         if not args.skip_big_modes:
             # config 1's semantics at scale: 2^16 INDEPENDENT learners, each the reference's serial loop (private theta, w,
             # per-step updates) -- the same algorithm the CPU reference runs, one population per process

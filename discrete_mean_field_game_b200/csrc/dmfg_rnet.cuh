@@ -367,14 +367,14 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     // persistent register accumulators (backward)
     float gw4pi[NP], gw4h[NP];
     float gk1[kK1 * kK1 + 1];            // d conv1/weights [dh][dw] + bias: thread-owned for the whole kernel
-    float gk2[kK2 * kK2 * 2 + 2];        // d conv2/weights [dh][dw][c] + 2 biases
+    float2 gk2v[kK2 * kK2 + 1];          // d conv2/weights [dh][dw] as (channel 0, channel 1) + the two biases
     if (BWD) {
 #pragma unroll
         for (int n = 0; n < NP; ++n) { gw4pi[n] = gw4h[n] = 0.f; }
 #pragma unroll
         for (int i = 0; i < kK1 * kK1 + 1; ++i) gk1[i] = 0.f;
 #pragma unroll
-        for (int i = 0; i < kK2 * kK2 * 2 + 2; ++i) gk2[i] = 0.f;
+        for (int i = 0; i < kK2 * kK2 + 1; ++i) gk2v[i] = make_float2(0.f, 0.f);
     }
     // tensor-core hand-off state (uniform over the CTA)
     uint32_t mma_phase = 0;
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
         float dz3[NP];
 #pragma unroll
         for (int j = 0; j < NP; ++j) dz3[j] = 0.f;
-        float c2[2][W];
+        float2 c2v[W];                 // conv2 activations of this lane's row: (channel 0, channel 1) per column
         {
             // ---- action tile -> shared (interior of the zero-haloed tile) ------------------------
             const float* a = p.actions + n * d * d;
@@ -453,62 +453,57 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                 }
             }
             __syncwarp();
-            // ---- conv2 row h, both channels -------------------------------------------------------
+            // ---- conv2 row h, both channels: one packed FFMA2 per tap updates (channel 0, channel 1) of an output --------
             {
+                const float2 b2v = make_float2(wf[L.b2], wf[L.b2 + 1]);
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const float b2 = wf[L.b2 + c];
-#pragma unroll
-                    for (int w = 0; w < W; ++w) c2[c][w] = b2;
-                }
+                for (int w = 0; w < W; ++w) c2v[w] = b2v;
 #pragma unroll
                 for (int dh = 0; dh < kK2; ++dh) {
                     const float* row = Ct + (hs + dh) * SC;
-                    float k[kK2][2];
+                    float2 k[kK2];                                   // (channel 0, channel 1) weights of tap (dh, dw)
 #pragma unroll
-                    for (int dw = 0; dw < kK2; ++dw) {
-                        k[dw][0] = wf[L.k2 + (dh * kK2 + dw) * 2];
-                        k[dw][1] = wf[L.k2 + (dh * kK2 + dw) * 2 + 1];
-                    }
+                    for (int dw = 0; dw < kK2; ++dw)
+                        k[dw] = make_float2(wf[L.k2 + (dh * kK2 + dw) * 2], wf[L.k2 + (dh * kK2 + dw) * 2 + 1]);
 #pragma unroll
                     for (int wp = 0; wp < W + 2; ++wp) {
                         const float v = row[wp];
 #pragma unroll
                         for (int dw = 0; dw < kK2; ++dw) {
                             const int w = wp - dw;
-                            if (w >= 0 && w < W) {
-                                c2[0][w] = fmaf(v, k[dw][0], c2[0][w]);
-                                c2[1][w] = fmaf(v, k[dw][1], c2[1][w]);
+                            if (w >= 0 && w < W) c2v[w] = __ffma2_rn(make_float2(v, v), k[dw], c2v[w]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < W; ++w)
+                    c2v[w] = (row_ok && w < d) ? make_float2(fmaxf(c2v[w].x, 0.f), fmaxf(c2v[w].y, 0.f)) : make_float2(0.f, 0.f);
+            }
+            // ---- fc3: this row's 2d activations x W3 row block (packed over pairs of units), all-reduce over the group ----
+            float z3[NP];
+            const float* wrow = w3s + (row_ok ? h : 0) * S.w3stride;
+            {
+                float2 z3v[NP / 2];
+#pragma unroll
+                for (int j = 0; j < NP / 2; ++j) z3v[j] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    if (w < d) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const float a = c ? c2v[w].y : c2v[w].x;
+                            const float4* wq = reinterpret_cast<const float4*>(wrow + (w * 2 + c) * NP);
+#pragma unroll
+                            for (int q = 0; q < NP / 4; ++q) {
+                                const float4 ww = wq[q];
+                                z3v[2 * q] = __ffma2_rn(make_float2(a, a), make_float2(ww.x, ww.y), z3v[2 * q]);
+                                z3v[2 * q + 1] = __ffma2_rn(make_float2(a, a), make_float2(ww.z, ww.w), z3v[2 * q + 1]);
                             }
                         }
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int w = 0; w < W; ++w) c2[c][w] = (row_ok && w < d) ? fmaxf(c2[c][w], 0.f) : 0.f;
-            }
-            // ---- fc3: this row's 2d activations x W3 row block, then all-reduce over the group ----
-            float z3[NP];
-#pragma unroll
-            for (int j = 0; j < NP; ++j) z3[j] = 0.f;
-            const float* wrow = w3s + (row_ok ? h : 0) * S.w3stride;
-#pragma unroll
-            for (int w = 0; w < W; ++w) {
-                if (w < d) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const float4* wq = reinterpret_cast<const float4*>(wrow + (w * 2 + c) * NP);
-#pragma unroll
-                        for (int q = 0; q < NP / 4; ++q) {
-                            const float4 ww = wq[q];
-                            z3[4 * q + 0] = fmaf(c2[c][w], ww.x, z3[4 * q + 0]);
-                            z3[4 * q + 1] = fmaf(c2[c][w], ww.y, z3[4 * q + 1]);
-                            z3[4 * q + 2] = fmaf(c2[c][w], ww.z, z3[4 * q + 2]);
-                            z3[4 * q + 3] = fmaf(c2[c][w], ww.w, z3[4 * q + 3]);
-                        }
-                    }
-                }
+                for (int j = 0; j < NP / 2; ++j) { z3[2 * j] = z3v[j].x; z3[2 * j + 1] = z3v[j].y; }
             }
             float m3[NP], m4[NP];
 #pragma unroll
@@ -614,7 +609,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 #pragma unroll
                             for (int c = 0; c < 2; ++c) {
                                 float hi, lo;
-                                umma::split_tf32(c2[c][w], hi, lo);
+                                umma::split_tf32(c ? c2v[w].y : c2v[w].x, hi, lo);
                                 constexpr uint32_t kRowStep = (uint32_t)(SM::GM / 8) * W3G::kSbo;
                                 umma::sts_f32(a_st_hi + (uint32_t)(2 * w + c) * kRowStep, hi);
                                 umma::sts_f32(a_st_lo + (uint32_t)(2 * w + c) * kRowStep, lo);
@@ -622,29 +617,38 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                         }
                     }
                 }
-                // d conv2 pre-activation: dz2 = (W3 row block . dz3) masked by relu
-                float dz2[2][W];
+                // d conv2 pre-activation: dz2 = (W3 row block . dz3) masked by relu -- packed partial sums over unit pairs
+                float2 dz2v[W];                                        // (channel 0, channel 1) per column
+                {
+                    float2 dz3v[NP / 2];
 #pragma unroll
-                for (int w = 0; w < W; ++w) {
+                    for (int j = 0; j < NP / 2; ++j) dz3v[j] = make_float2(dz3[2 * j], dz3[2 * j + 1]);
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        float s = 0.f;
+                    for (int w = 0; w < W; ++w) {
+                        float sc[2] = {0.f, 0.f};
                         if (w < d) {
-                            const float4* wq = reinterpret_cast<const float4*>(wrow + (w * 2 + c) * NP);
 #pragma unroll
-                            for (int q = 0; q < NP / 4; ++q) {
-                                const float4 ww = wq[q];
-                                s = fmaf(dz3[4 * q + 0], ww.x, s); s = fmaf(dz3[4 * q + 1], ww.y, s);
-                                s = fmaf(dz3[4 * q + 2], ww.z, s); s = fmaf(dz3[4 * q + 3], ww.w, s);
+                            for (int c = 0; c < 2; ++c) {
+                                const float4* wq = reinterpret_cast<const float4*>(wrow + (w * 2 + c) * NP);
+                                float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+                                for (int q = 0; q < NP / 4; ++q) {
+                                    const float4 ww = wq[q];
+                                    s2 = __ffma2_rn(dz3v[2 * q], make_float2(ww.x, ww.y), s2);
+                                    s2 = __ffma2_rn(dz3v[2 * q + 1], make_float2(ww.z, ww.w), s2);
+                                }
+                                sc[c] = s2.x + s2.y;
                             }
                         }
-                        dz2[c][w] = c2[c][w] > 0.f ? s : 0.f;
-                        if (row_ok) Dt[c * RC * SC + (h + 1) * SC + w + 1] = dz2[c][w];
+                        dz2v[w] = make_float2(c2v[w].x > 0.f ? sc[0] : 0.f, c2v[w].y > 0.f ? sc[1] : 0.f);
+                        if (row_ok) {
+                            Dt[(h + 1) * SC + w + 1] = dz2v[w].x;
+                            Dt[RC * SC + (h + 1) * SC + w + 1] = dz2v[w].y;
+                        }
                     }
                 }
-                // d conv2/weights [dh][dw][c] and biases
+                // d conv2/weights [dh][dw][c] and biases: one FFMA2 per tap updates the (channel 0, channel 1) gradients
                 {
-                    float* gk = gk2;
 #pragma unroll
                     for (int dh = 0; dh < kK2; ++dh) {
                         const float* row = Ct + (hs + dh) * SC;
@@ -654,42 +658,42 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 #pragma unroll
                             for (int dw = 0; dw < kK2; ++dw) {
                                 const int w = wp - dw;
-                                if (w >= 0 && w < W) {
-                                    gk[(dh * kK2 + dw) * 2] = fmaf(v, dz2[0][w], gk[(dh * kK2 + dw) * 2]);
-                                    gk[(dh * kK2 + dw) * 2 + 1] = fmaf(v, dz2[1][w], gk[(dh * kK2 + dw) * 2 + 1]);
-                                }
+                                if (w >= 0 && w < W) gk2v[dh * kK2 + dw] = __ffma2_rn(make_float2(v, v), dz2v[w], gk2v[dh * kK2 + dw]);
                             }
                         }
                     }
 #pragma unroll
-                    for (int w = 0; w < W; ++w) { gk2[18] += dz2[0][w]; gk2[19] += dz2[1][w]; }
+                    for (int w = 0; w < W; ++w) gk2v[kK2 * kK2] = __fadd2_rn(gk2v[kK2 * kK2], dz2v[w]);
                 }
                 __syncwarp();
-                // d conv1 output row h: full correlation of dz2 with the flipped conv2 kernel
+                // d conv1 output row h: full correlation of dz2 with the flipped conv2 kernel; the two channels are the two
+                // halves of a packed accumulator, added at the end
                 float dz1[W];
+                {
+                    float2 dz1v[W];
 #pragma unroll
-                for (int w = 0; w < W; ++w) dz1[w] = 0.f;
+                    for (int w = 0; w < W; ++w) dz1v[w] = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int e = 0; e < kK2; ++e) {
+                    for (int e = 0; e < kK2; ++e) {
+                        const float* row0 = Dt + (hs + e) * SC;
+                        const float* row1 = Dt + RC * SC + (hs + e) * SC;
+                        float2 k[kK2];
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const float* row = Dt + c * RC * SC + (hs + e) * SC;
-                        float k[kK2];
-#pragma unroll
-                        for (int f = 0; f < kK2; ++f) k[f] = wf[L.k2 + ((2 - e) * kK2 + (2 - f)) * 2 + c];
+                        for (int f = 0; f < kK2; ++f)
+                            k[f] = make_float2(wf[L.k2 + ((2 - e) * kK2 + (2 - f)) * 2], wf[L.k2 + ((2 - e) * kK2 + (2 - f)) * 2 + 1]);
 #pragma unroll
                         for (int wp = 0; wp < W + 2; ++wp) {
-                            const float v = row[wp];
+                            const float2 v = make_float2(row0[wp], row1[wp]);
 #pragma unroll
                             for (int f = 0; f < kK2; ++f) {
                                 const int w = wp - f;
-                                if (w >= 0 && w < W) dz1[w] = fmaf(v, k[f], dz1[w]);
+                                if (w >= 0 && w < W) dz1v[w] = __ffma2_rn(v, k[f], dz1v[w]);
                             }
                         }
                     }
-                }
 #pragma unroll
-                for (int w = 0; w < W; ++w) dz1[w] = c1[w] > 0.f ? dz1[w] : 0.f;
+                    for (int w = 0; w < W; ++w) dz1[w] = c1[w] > 0.f ? dz1v[w].x + dz1v[w].y : 0.f;
+                }
                 // d conv1/weights [dh][dw] and bias
                 {
 #pragma unroll
@@ -760,7 +764,10 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 #pragma unroll
     for (int i = 0; i < kK1 * kK1 + 1; ++i) ga[i * kRnetThreads + tid] = gk1[i];
 #pragma unroll
-    for (int i = 0; i < kK2 * kK2 * 2 + 2; ++i) ga[(26 + i) * kRnetThreads + tid] = gk2[i];
+    for (int i = 0; i < kK2 * kK2 + 1; ++i) {
+        ga[(26 + 2 * i) * kRnetThreads + tid] = gk2v[i].x;
+        ga[(26 + 2 * i + 1) * kRnetThreads + tid] = gk2v[i].y;
+    }
 #pragma unroll
     for (int m = 0; m < NP; ++m) {
         ga[(46 + m) * kRnetThreads + tid] = gw4pi[m];

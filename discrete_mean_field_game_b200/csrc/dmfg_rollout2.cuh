@@ -123,20 +123,33 @@ struct V2RowSums {
     float asum, dsum, g1, g2;
 };
 
+// The walk is written as two phases per column pair so that several pairs can be in flight at once:
+//   phase A (branch-free): alpha, alpha', psi(alpha) and the alpha sums -- long MUFU / FFMA2 chains the compiler can
+//                          interleave freely across the pairs of a chunk;
+//   phase B: the Gamma pair (one rarely taken out-of-line branch per pair), lg2 y, the row sums, the tile store.
+// DMFG_V2_CHUNK pairs run phase A back to back (their alpha / alpha' stay in registers), then phase B; chunk = 1 is the
+// plain interleaved loop.  The order of every accumulation is the same for every chunk size: results do not depend on it.
+#ifndef DMFG_V2_CHUNK
+#define DMFG_V2_CHUNK 1
+#endif
 template <int D, int NOISE, bool GRAD, bool REC>
-__device__ __forceinline__ V2RowSums v2_row_walk(float theta, float xi, float scale, double c0, double c1, bool has_reward,
-                                                 uint32_t a_pfc, uint32_t a_pic, uint32_t a_row, const NoiseKey& nk,
-                                                 const PhiloxKeys& rk, uint32_t slot0, const float* __restrict__ noise_row,
-                                                 bool row_ok, float* __restrict__ alpha_row, float* __restrict__ deriv_row) {
-    constexpr int PD = (D + 1) / 2;
-    float2 asum2 = make_float2(0.f, 0.f), dsum2 = asum2, g12 = asum2, g22 = asum2;
-    double ysum0 = 0.0, ysum1 = 0.0, racc0 = 0.0, racc1 = 0.0;
-    float a_last = 0.0f;
-#pragma unroll kV2Unroll
-    for (int pp = 0; pp < PD; ++pp) {
+struct V2Walk {
+    static constexpr int PD = (D + 1) / 2;
+    float theta, xi, scale;
+    double c0, c1;
+    bool has_reward, row_ok;
+    uint32_t a_pfc, a_pic, a_row, slot0;
+    const float* __restrict__ noise_row;
+    float* __restrict__ alpha_row;
+    float* __restrict__ deriv_row;
+    float2 asum2, dsum2, g12, g22;
+    double ysum0, ysum1, racc0, racc1;
+    float a_last;
+
+    __device__ __forceinline__ void phase_a(int pp, float2& a, float2& dv) {
         const float2 pj = lds_f32x2(a_pfc + 8 * pp);
         const bool ok1 = (2 * pp + 1) < D;                     // only the last pair of an odd D
-        float2 a, dv, psi;
+        float2 psi;
         if (GRAD) {
             alpha_psi_fast2(theta, __fadd2_rn(pj, splat2(-xi)), a, dv, psi);
         } else {
@@ -152,6 +165,14 @@ __device__ __forceinline__ V2RowSums v2_row_walk(float theta, float xi, float sc
             asum2 = __fadd2_rn(asum2, a);
             dsum2 = __fadd2_rn(dsum2, dv);
         }
+        if (REC && alpha_row != nullptr) {
+            alpha_row[2 * pp] = a.x;
+            deriv_row[2 * pp] = dv.x;
+            if (ok1) { alpha_row[2 * pp + 1] = a.y; deriv_row[2 * pp + 1] = dv.y; }
+        }
+    }
+    __device__ __forceinline__ void phase_b(int pp, const float2 a, const float2 dv, const NoiseKey& nk, const PhiloxKeys& rk) {
+        const bool ok1 = (2 * pp + 1) < D;
         float y0, y1;
         if (NOISE == DMFG_NOISE_PHILOX) {
             gamma_pair_fast(nk, rk, slot0 + (uint32_t)pp, a, scale, y0, y1);   // never returns 0
@@ -170,19 +191,47 @@ __device__ __forceinline__ V2RowSums v2_row_walk(float theta, float xi, float sc
         }
         sts_f64(a_row + 16 * pp, yd0);
         sts_f64(a_row + 16 * pp + 8, yd1);
-        if (REC && alpha_row != nullptr) {
-            alpha_row[2 * pp] = a.x;
-            deriv_row[2 * pp] = dv.x;
-            if (ok1) { alpha_row[2 * pp + 1] = a.y; deriv_row[2 * pp + 1] = dv.y; }
-        }
+    }
+    template <int N>
+    __device__ __forceinline__ void chunk(int p0, const NoiseKey& nk, const PhiloxKeys& rk) {
+        float2 a[N], dv[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) phase_a(p0 + c, a[c], dv[c]);
+#pragma unroll
+        for (int c = 0; c < N; ++c) phase_b(p0 + c, a[c], dv[c], nk, rk);
+    }
+};
+
+template <int D, int NOISE, bool GRAD, bool REC>
+__device__ __forceinline__ V2RowSums v2_row_walk(float theta, float xi, float scale, double c0, double c1, bool has_reward,
+                                                 uint32_t a_pfc, uint32_t a_pic, uint32_t a_row, const NoiseKey& nk,
+                                                 const PhiloxKeys& rk, uint32_t slot0, const float* __restrict__ noise_row,
+                                                 bool row_ok, float* __restrict__ alpha_row, float* __restrict__ deriv_row) {
+    constexpr int PD = (D + 1) / 2;
+    V2Walk<D, NOISE, GRAD, REC> wk;
+    wk.theta = theta; wk.xi = xi; wk.scale = scale; wk.c0 = c0; wk.c1 = c1; wk.has_reward = has_reward; wk.row_ok = row_ok;
+    wk.a_pfc = a_pfc; wk.a_pic = a_pic; wk.a_row = a_row; wk.slot0 = slot0;
+    wk.noise_row = noise_row; wk.alpha_row = alpha_row; wk.deriv_row = deriv_row;
+    wk.asum2 = wk.dsum2 = wk.g12 = wk.g22 = make_float2(0.f, 0.f);
+    wk.ysum0 = wk.ysum1 = wk.racc0 = wk.racc1 = 0.0;
+    wk.a_last = 0.0f;
+    constexpr int CH = DMFG_V2_CHUNK;
+    if (CH <= 1) {
+#pragma unroll kV2Unroll
+        for (int pp = 0; pp < PD; ++pp) wk.template chunk<1>(pp, nk, rk);
+    } else {
+        constexpr int NFULL = PD / CH, REM = PD % CH;
+#pragma unroll kV2Unroll
+        for (int k = 0; k < NFULL; ++k) wk.template chunk<CH>(k * CH, nk, rk);
+        if (REM > 0) wk.template chunk<(REM > 0 ? REM : 1)>(NFULL * CH, nk, rk);
     }
     V2RowSums o;
-    o.ysum = ysum0 + ysum1;
-    o.racc = racc0 + racc1;
-    o.asum = asum2.x + ((D & 1) ? asum2.y - a_last : asum2.y);
-    o.dsum = dsum2.x + dsum2.y;
-    o.g1 = g12.x + g12.y;
-    o.g2 = g22.x + g22.y;
+    o.ysum = wk.ysum0 + wk.ysum1;
+    o.racc = wk.racc0 + wk.racc1;
+    o.asum = wk.asum2.x + ((D & 1) ? wk.asum2.y - wk.a_last : wk.asum2.y);
+    o.dsum = wk.dsum2.x + wk.dsum2.y;
+    o.g1 = wk.g12.x + wk.g12.y;
+    o.g2 = wk.g22.x + wk.g22.y;
     return o;
 }
 

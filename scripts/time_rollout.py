@@ -39,4 +39,6 @@ for name, fn in modes.items():
     ms = float(np.median([x.elapsed_time(y) for x, y in ev]))
     n = (Br if name == "record" else B) * T
     res[name] = (ms, n / ms / 1e3)
-print(os.environ.get("DMFG_LIB_PATH", "default"), " ".join("%s %.3f ms %.1f Mps/s" % (k, v[0], v[1] / 1e3) for k, v in res.items()))
+chk = engine.rollout(pi0[:4096], 8.86349, 0.16, 12000.0, T, w=w, seed=1234, outputs=(), want_acc=True)["acc"].cpu().numpy()
+import hashlib
+print(os.environ.get("DMFG_LIB_PATH", "default"), "acc-sha", hashlib.sha1(chk.tobytes()).hexdigest()[:10], " ".join("%s %.3f ms %.1f Mps/s" % (k, v[0], v[1] / 1e3) for k, v in res.items()))
