@@ -257,6 +257,14 @@ static __device__ __noinline__ float2 gamma_pair_redo(uint32_t p0, uint32_t p1, 
     return make_float2(y0, y1);
 }
 // packed single precision (Blackwell FFMA2 / FMUL2 / FADD2: two lanes of math per issue slot)
+#ifdef DMFG_AB_SCALAR_ALL   // A/B probe: every packed operation as two scalar ones (same roundings)
+__device__ __forceinline__ float2 ab_ffma2(float2 a, float2 b, float2 c) { return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 ab_fmul2(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 ab_fadd2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+#define __ffma2_rn ab_ffma2
+#define __fmul2_rn ab_fmul2
+#define __fadd2_rn ab_fadd2
+#endif
 __device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
@@ -439,6 +447,24 @@ __device__ __forceinline__ float digamma_fast(float x) {
 
 // packed log1p(e), same fma chain as the scalar form (bit-identical per element)
 __device__ __forceinline__ float2 log1p_poly2(float2 e) {
+#ifdef DMFG_AB_SCALAR_L1P
+    float2 o;                       // A/B probe: the same chain as two scalar FFMA streams (FMA-lite can take them)
+    {
+        float pl = fmaf(DMFG_L1P_C8, e.x, DMFG_L1P_C7);
+        pl = fmaf(pl, e.x, DMFG_L1P_C6); pl = fmaf(pl, e.x, DMFG_L1P_C5); pl = fmaf(pl, e.x, DMFG_L1P_C4);
+        pl = fmaf(pl, e.x, DMFG_L1P_C3); pl = fmaf(pl, e.x, DMFG_L1P_C2); pl = fmaf(pl, e.x, DMFG_L1P_C1);
+        pl = fmaf(pl, e.x, DMFG_L1P_C0);
+        o.x = __fmul_rn(pl, e.x);
+    }
+    {
+        float pl = fmaf(DMFG_L1P_C8, e.y, DMFG_L1P_C7);
+        pl = fmaf(pl, e.y, DMFG_L1P_C6); pl = fmaf(pl, e.y, DMFG_L1P_C5); pl = fmaf(pl, e.y, DMFG_L1P_C4);
+        pl = fmaf(pl, e.y, DMFG_L1P_C3); pl = fmaf(pl, e.y, DMFG_L1P_C2); pl = fmaf(pl, e.y, DMFG_L1P_C1);
+        pl = fmaf(pl, e.y, DMFG_L1P_C0);
+        o.y = __fmul_rn(pl, e.y);
+    }
+    return o;
+#endif
     float2 pl = __ffma2_rn(splat2(DMFG_L1P_C8), e, splat2(DMFG_L1P_C7));
     pl = __ffma2_rn(pl, e, splat2(DMFG_L1P_C6));
     pl = __ffma2_rn(pl, e, splat2(DMFG_L1P_C5));

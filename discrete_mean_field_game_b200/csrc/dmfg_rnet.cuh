@@ -29,7 +29,7 @@ constexpr int kK1 = 5, kK2 = 3;
 #define DMFG_CTR_DROPOUT 0xA0000000u   // Philox counter word 3 of the dropout uniforms
 
 #ifndef DMFG_RNET_PREFETCH
-#define DMFG_RNET_PREFETCH 1
+#define DMFG_RNET_PREFETCH 3      // 0: none, 1 / 2: L2 / L1 prefetch hints for the next tile, 3: register-pipelined loads
 #endif
 
 struct RnetLayout {
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     for (int i = tid; i < 2 * d * d * n3; i += kRnetThreads) {
         const int k = i / n3, n = i - k * n3;
         const int row = k / (2 * d), kk = k - row * 2 * d;
-        w3s[row * S.w3stride + kk * NP + n] = wf[L.w3 + i];
+        w3s[row * S.w3stride + (kk >> 1) * 2 * NP + n * 2 + (kk & 1)] = wf[L.w3 + i];      // [w][unit][channel]
     }
     __syncthreads();
 
@@ -386,25 +386,56 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     uint32_t a_st_hi = um_a_hi + W3G::off(h, grp), a_st_lo = um_a_lo + W3G::off(h, grp);
     asm volatile("mov.u32 %0, %0;\n\tmov.u32 %1, %1;" : "+r"(a_st_hi), "+r"(a_st_lo));
     const long long ntiles = TRAJ ? p.traj_M : (p.N + GPB - 1) / GPB;
+    // transition served by this group in tile `tl` (dead groups shadow a live one: warp-wide syncs stay convergent)
+    auto transition_of = [&](long long tl) -> long long {
+        if (TRAJ) return (grp < p.traj_T ? grp : 0) * p.t_stride + tl * p.j_stride;
+        const long long nn = tl * GPB + grp;
+        return nn < p.N ? nn : p.N - 1;
+    };
+#if DMFG_RNET_PREFETCH == 3
+    // software pipeline over tiles: this lane's column of the NEXT transition's action (d global loads), its state entry
+    // and dL/dr travel to registers while the current tile computes -- with one CTA per SM there is nothing else to hide
+    // the DRAM latency behind (ncu: 6.5 % of the samples sat on the tile load, 57 % of them long-scoreboard)
+    float a_next[W], pi_next = 0.f, dr_next = 0.f;
+    auto fetch = [&](long long tl) {
+        const long long nn = transition_of(tl);
+        const float* a = p.actions + nn * d * d;
+#pragma unroll
+        for (int i = 0; i < W; ++i) a_next[i] = (row_ok && i < d) ? a[i * d + h] : 0.f;
+        pi_next = row_ok ? p.states[nn * d + h] : 0.f;
+        if (BWD && !TRAJ) dr_next = p.drewards[nn];
+    };
+    if ((long long)blockIdx.x < ntiles) fetch(blockIdx.x);
+#endif
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        long long n = tile * GPB + grp;
-        bool live = n < p.N;                 // dead groups shadow the last transition (warp-wide syncs stay
-        if (!live) n = p.N - 1;              // convergent); their writes are masked and their dr is 0
-        if (TRAJ) {
-            live = grp < p.traj_T;           // (dead groups shadow step 0 of the trajectory)
-            n = (live ? grp : 0) * p.t_stride + tile * p.j_stride;
-        }
+        const long long n = transition_of(tile);
+        const bool live = TRAJ ? grp < p.traj_T : tile * GPB + grp < p.N;      // writes of dead groups are masked, their dr is 0
         float dz3[NP];
 #pragma unroll
         for (int j = 0; j < NP; ++j) dz3[j] = 0.f;
         float2 c2v[W];                 // conv2 activations of this lane's row: (channel 0, channel 1) per column
+        // ReLU patterns of this lane's conv1 / conv2 rows as bit masks (backward): the activations themselves are dead
+        // once fc3 and the tensor-core operand store have consumed them, which frees 45 registers for the backward phases
+        uint32_t relu1 = 0u, relu2x = 0u, relu2y = 0u;      // (bit w: column w; W <= 32)
         {
             // ---- action tile -> shared (interior of the zero-haloed tile) ------------------------
+#if DMFG_RNET_PREFETCH == 3
+            if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < W; ++i)
+                    if (i < d) At[(i + 2) * SA + h + 2] = a_next[i];
+            }
+            const float pi_h = pi_next;
+            const float dr_in = dr_next;
+            if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);
+#else
             const float* a = p.actions + n * d * d;
             if (row_ok)
                 for (int i = 0; i < d; ++i) At[(i + 2) * SA + h + 2] = a[i * d + h];
             const float pi_h = row_ok ? p.states[n * d + h] : 0.f;
-#if DMFG_RNET_PREFETCH
+            const float dr_in = (BWD && !TRAJ) ? p.drewards[n] : 0.f;
+#endif
+#if DMFG_RNET_PREFETCH == 1 || DMFG_RNET_PREFETCH == 2
             // the next tile of this CTA: its d*d action block (<= 8 lines of 128 B) is asked for now, one line per
             // lane, so the tile load above finds it in L1/L2 instead of waiting on DRAM with every warp of the
             // CTA stalled at the same point (1 CTA/SM in the backward kernel: nothing else to switch to)
@@ -450,6 +481,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                 for (int w = 0; w < W; ++w) {
                     c1[w] = (row_ok && w < d) ? fmaxf(c1[w], 0.f) : 0.f;
                     if (row_ok) Ct[(h + 1) * SC + w + 1] = c1[w];
+                    if (BWD && c1[w] > 0.f) relu1 |= 1u << w;
                 }
             }
             __syncwarp();
@@ -476,34 +508,58 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                     }
                 }
 #pragma unroll
-                for (int w = 0; w < W; ++w)
+                for (int w = 0; w < W; ++w) {
                     c2v[w] = (row_ok && w < d) ? make_float2(fmaxf(c2v[w].x, 0.f), fmaxf(c2v[w].y, 0.f)) : make_float2(0.f, 0.f);
+                    if (BWD) {
+                        if (c2v[w].x > 0.f) relu2x |= 1u << w;
+                        if (c2v[w].y > 0.f) relu2y |= 1u << w;
+                    }
+                }
             }
-            // ---- fc3: this row's 2d activations x W3 row block (packed over pairs of units), all-reduce over the group ----
+            // ---- fc3: this row's 2d activations x W3 row block [w][unit][channel]: the (channel 0, channel 1) pair of a column
+            // times the matching weight pair is ONE packed FFMA2 per unit; the two halves are added once at the end;
+            // then all-reduce over the group ----
             float z3[NP];
             const float* wrow = w3s + (row_ok ? h : 0) * S.w3stride;
             {
-                float2 z3v[NP / 2];
+                float2 z3v[NP];
 #pragma unroll
-                for (int j = 0; j < NP / 2; ++j) z3v[j] = make_float2(0.f, 0.f);
+                for (int j = 0; j < NP; ++j) z3v[j] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int w = 0; w < W; ++w) {
                     if (w < d) {
+                        const float4* wq = reinterpret_cast<const float4*>(wrow + w * 2 * NP);
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const float a = c ? c2v[w].y : c2v[w].x;
-                            const float4* wq = reinterpret_cast<const float4*>(wrow + (w * 2 + c) * NP);
-#pragma unroll
-                            for (int q = 0; q < NP / 4; ++q) {
-                                const float4 ww = wq[q];
-                                z3v[2 * q] = __ffma2_rn(make_float2(a, a), make_float2(ww.x, ww.y), z3v[2 * q]);
-                                z3v[2 * q + 1] = __ffma2_rn(make_float2(a, a), make_float2(ww.z, ww.w), z3v[2 * q + 1]);
-                            }
+                        for (int q = 0; q < NP / 2; ++q) {
+                            const float4 ww = wq[q];                       // units 2q, 2q+1: (c0, c1), (c0, c1)
+                            z3v[2 * q] = __ffma2_rn(c2v[w], make_float2(ww.x, ww.y), z3v[2 * q]);
+                            z3v[2 * q + 1] = __ffma2_rn(c2v[w], make_float2(ww.z, ww.w), z3v[2 * q + 1]);
                         }
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < NP / 2; ++j) { z3[2 * j] = z3v[j].x; z3[2 * j + 1] = z3v[j].y; }
+                for (int j = 0; j < NP; ++j) z3[j] = z3v[j].x + z3v[j].y;
+            }
+            if (BWD) {
+                // conv2 activations of this transition -> A operand of the fc3 weight gradient on the tensor cores
+                // (3xTF32 split; row m = (2w + c) * GM + h, column = this transition: every store is base + immediate).
+                // The MMAs of the previous tile must have finished reading the tile first.
+                if (mma_pending) { mbar_wait_bounded(&mma_bar, mma_phase); mma_phase ^= 1u; mma_pending = false; }
+                if (row_ok) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        if (w < d) {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                float hi, lo;
+                                umma::split_tf32(c ? c2v[w].y : c2v[w].x, hi, lo);
+                                constexpr uint32_t kRowStep = (uint32_t)(SM::GM / 8) * W3G::kSbo;
+                                umma::sts_f32(a_st_hi + (uint32_t)(2 * w + c) * kRowStep, hi);
+                                umma::sts_f32(a_st_lo + (uint32_t)(2 * w + c) * kRowStep, lo);
+                            }
+                        }
+                    }
+                }
             }
             float m3[NP], m4[NP];
 #pragma unroll
@@ -561,7 +617,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                     dr = expf(R);
                     if (tid == 0) zsum += (double)dr;
                 } else {
-                    dr = p.drewards[n];
+                    dr = dr_in;
                 }
                 const float dz5 = live ? dr * (1.f - r * r) : 0.f;
                 float dz4[NP];
@@ -591,56 +647,30 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                 // d fc4/weights: row n3+h (state part) on every lane, row h (h3 part) on lanes h < n3
 #pragma unroll
                 for (int m = 0; m < NP; ++m) gw4pi[m] = fmaf(pi_h, dz4[m], gw4pi[m]);
+                {
+                    float h3h = 0.f;                                   // h3[h] by selects (a switch on the lane index compiled to
+#pragma unroll                                                         // an indexed branch: 8 % of the samples sat on it)
+                    for (int j = 0; j < NP; ++j) h3h = (j == h) ? h3[j] : h3h;
 #pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    if (j == h) {
-#pragma unroll
-                        for (int m = 0; m < NP; ++m) gw4h[m] = fmaf(h3[j], dz4[m], gw4h[m]);
-                    }
+                    for (int m = 0; m < NP; ++m) gw4h[m] = fmaf(h3h, dz4[m], gw4h[m]);
                 }
-                // conv2 activations of this transition -> A operand of the fc3 weight gradient on the tensor cores
-                // (3xTF32 split; row m = (2w + c) * GM + h, column = this transition: every store is base + immediate).
-                // The MMAs of the previous tile must have finished reading the tile first.
-                if (mma_pending) { mbar_wait_bounded(&mma_bar, mma_phase); mma_phase ^= 1u; mma_pending = false; }
-                if (row_ok) {
-#pragma unroll
-                    for (int w = 0; w < W; ++w) {
-                        if (w < d) {
-#pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                float hi, lo;
-                                umma::split_tf32(c ? c2v[w].y : c2v[w].x, hi, lo);
-                                constexpr uint32_t kRowStep = (uint32_t)(SM::GM / 8) * W3G::kSbo;
-                                umma::sts_f32(a_st_hi + (uint32_t)(2 * w + c) * kRowStep, hi);
-                                umma::sts_f32(a_st_lo + (uint32_t)(2 * w + c) * kRowStep, lo);
-                            }
-                        }
-                    }
-                }
-                // d conv2 pre-activation: dz2 = (W3 row block . dz3) masked by relu -- packed partial sums over unit pairs
+                // d conv2 pre-activation: dz2 = (W3 row block . dz3) masked by relu -- the (channel 0, channel 1) pair of a
+                // column accumulates in one packed register, one FFMA2 per unit
                 float2 dz2v[W];                                        // (channel 0, channel 1) per column
                 {
-                    float2 dz3v[NP / 2];
-#pragma unroll
-                    for (int j = 0; j < NP / 2; ++j) dz3v[j] = make_float2(dz3[2 * j], dz3[2 * j + 1]);
 #pragma unroll
                     for (int w = 0; w < W; ++w) {
-                        float sc[2] = {0.f, 0.f};
+                        float2 s2 = make_float2(0.f, 0.f);
                         if (w < d) {
+                            const float4* wq = reinterpret_cast<const float4*>(wrow + w * 2 * NP);
 #pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                const float4* wq = reinterpret_cast<const float4*>(wrow + (w * 2 + c) * NP);
-                                float2 s2 = make_float2(0.f, 0.f);
-#pragma unroll
-                                for (int q = 0; q < NP / 4; ++q) {
-                                    const float4 ww = wq[q];
-                                    s2 = __ffma2_rn(dz3v[2 * q], make_float2(ww.x, ww.y), s2);
-                                    s2 = __ffma2_rn(dz3v[2 * q + 1], make_float2(ww.z, ww.w), s2);
-                                }
-                                sc[c] = s2.x + s2.y;
+                            for (int q = 0; q < NP / 2; ++q) {
+                                const float4 ww = wq[q];
+                                s2 = __ffma2_rn(make_float2(dz3[2 * q], dz3[2 * q]), make_float2(ww.x, ww.y), s2);
+                                s2 = __ffma2_rn(make_float2(dz3[2 * q + 1], dz3[2 * q + 1]), make_float2(ww.z, ww.w), s2);
                             }
                         }
-                        dz2v[w] = make_float2(c2v[w].x > 0.f ? sc[0] : 0.f, c2v[w].y > 0.f ? sc[1] : 0.f);
+                        dz2v[w] = make_float2((relu2x >> w) & 1u ? s2.x : 0.f, (relu2y >> w) & 1u ? s2.y : 0.f);
                         if (row_ok) {
                             Dt[(h + 1) * SC + w + 1] = dz2v[w].x;
                             Dt[RC * SC + (h + 1) * SC + w + 1] = dz2v[w].y;
@@ -692,7 +722,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                         }
                     }
 #pragma unroll
-                    for (int w = 0; w < W; ++w) dz1[w] = c1[w] > 0.f ? dz1v[w].x + dz1v[w].y : 0.f;
+                    for (int w = 0; w < W; ++w) dz1[w] = (relu1 >> w) & 1u ? dz1v[w].x + dz1v[w].y : 0.f;
                 }
                 // d conv1/weights [dh][dw] and bias
                 {
