@@ -28,6 +28,11 @@ constexpr int kRnetThreads = 256;
 constexpr int kK1 = 5, kK2 = 3;
 #define DMFG_CTR_DROPOUT 0xA0000000u   // Philox counter word 3 of the dropout uniforms
 
+// 1: the conv-weight gradient accumulators of a thread (26 + 20 floats) live in its private strip of tensor memory between
+// the two phases that update them (tcgen05.ld / .st, 32 columns each) instead of in registers for the whole kernel
+#ifndef DMFG_RNET_TMEM_ACC
+#define DMFG_RNET_TMEM_ACC 1
+#endif
 #ifndef DMFG_RNET_PREFETCH
 #define DMFG_RNET_PREFETCH 3      // 0: none, 1 / 2: L2 / L1 prefetch hints for the next tile, 3: register-pipelined loads
 #endif
@@ -322,6 +327,12 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     __shared__ __align__(8) unsigned long long mma_bar;       // completion of the tile's tensor-core MMAs (BWD)
     __shared__ uint32_t tmem_slot;
     using W3G = typename SM::W3G;
+    // TMEM columns: the dW3 accumulators (W3G::kTmemCols), then one 64-column strip per warp of a quadrant for the parked
+    // per-thread accumulators (warps w and w + 4 share the lanes of quadrant w % 4)
+    constexpr uint32_t kTmemAcc = DMFG_RNET_TMEM_ACC ? 64u * (kRnetThreads / 128) : 0u;
+    constexpr uint32_t kTmemAlloc = W3G::kTmemCols + kTmemAcc <= 32 ? 32 : W3G::kTmemCols + kTmemAcc <= 64 ? 64
+                                  : W3G::kTmemCols + kTmemAcc <= 128 ? 128 : W3G::kTmemCols + kTmemAcc <= 256 ? 256 : 512;
+    static_assert(W3G::kTmemCols + kTmemAcc <= 512, "tensor memory has 512 columns");
     const int d = DS ? DS : p.d, n3 = N3S ? N3S : p.n3, n4 = N4S ? N4S : p.n4;
     const RnetLayout L = rnet_layout(d, n3, n4);
     const SM S(d, L.total);
@@ -336,7 +347,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     if (tid == 0) { mbar_init(&mbar, 1); if (BWD) mbar_init(&mma_bar, 1); zsum = 0.0; }
     if (BWD && tid < 32) {                                     // warp 0 allocates the TMEM columns of the dW3 accumulators
         __syncwarp();
-        umma::tmem_alloc(smem_u32(&tmem_slot), W3G::kTmemCols);
+        umma::tmem_alloc(smem_u32(&tmem_slot), kTmemAlloc);
         umma::fence_before_sync();
     }
     __syncthreads();
@@ -366,6 +377,20 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     const float inv_keep = p.dropout ? 1.0f / p.keep_prob : 1.0f;
     // persistent register accumulators (backward)
     float gw4pi[NP], gw4h[NP];
+#if DMFG_RNET_TMEM_ACC
+    // this thread's strip: columns [0, 32) d conv1/weights [dh][dw] + bias, [32, 64) d conv2/weights as (channel 0,
+    // channel 1) pairs + the two biases
+    const uint32_t acc_t = tmem_base + ((uint32_t)(32 * ((tid >> 5) & 3)) << 16) + W3G::kTmemCols + 64u * (uint32_t)(tid >> 7);
+    if (BWD) {
+#pragma unroll
+        for (int n = 0; n < NP; ++n) { gw4pi[n] = gw4h[n] = 0.f; }
+        float zero[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) zero[i] = 0.f;
+        umma::tmem_st_32x32b_x32(acc_t, zero);
+        umma::tmem_st_32x32b_x32(acc_t + 32u, zero);
+    }
+#else
     float gk1[kK1 * kK1 + 1];            // d conv1/weights [dh][dw] + bias: thread-owned for the whole kernel
     float2 gk2v[kK2 * kK2 + 1];          // d conv2/weights [dh][dw] as (channel 0, channel 1) + the two biases
     if (BWD) {
@@ -376,6 +401,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 #pragma unroll
         for (int i = 0; i < kK2 * kK2 + 1; ++i) gk2v[i] = make_float2(0.f, 0.f);
     }
+#endif
     // tensor-core hand-off state (uniform over the CTA)
     uint32_t mma_phase = 0;
     bool mma_pending = false, mma_first = true;
@@ -679,6 +705,13 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                 }
                 // d conv2/weights [dh][dw][c] and biases: one FFMA2 per tap updates the (channel 0, channel 1) gradients
                 {
+#if DMFG_RNET_TMEM_ACC
+                    float tb[32];
+                    umma::tmem_ld_32x32b_x32(acc_t + 32u, tb);
+                    float2 gk2v[kK2 * kK2 + 1];
+#pragma unroll
+                    for (int i = 0; i < kK2 * kK2 + 1; ++i) gk2v[i] = make_float2(tb[2 * i], tb[2 * i + 1]);
+#endif
 #pragma unroll
                     for (int dh = 0; dh < kK2; ++dh) {
                         const float* row = Ct + (hs + dh) * SC;
@@ -694,6 +727,11 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                     }
 #pragma unroll
                     for (int w = 0; w < W; ++w) gk2v[kK2 * kK2] = __fadd2_rn(gk2v[kK2 * kK2], dz2v[w]);
+#if DMFG_RNET_TMEM_ACC
+#pragma unroll
+                    for (int i = 0; i < kK2 * kK2 + 1; ++i) { tb[2 * i] = gk2v[i].x; tb[2 * i + 1] = gk2v[i].y; }
+                    umma::tmem_st_32x32b_x32(acc_t + 32u, tb);
+#endif
                 }
                 __syncwarp();
                 // d conv1 output row h: full correlation of dz2 with the flipped conv2 kernel; the two channels are the two
@@ -726,6 +764,10 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                 }
                 // d conv1/weights [dh][dw] and bias
                 {
+#if DMFG_RNET_TMEM_ACC
+                    float gk1[32];
+                    umma::tmem_ld_32x32b_x32(acc_t, gk1);
+#endif
 #pragma unroll
                     for (int dh = 0; dh < kK1; ++dh) {
                         const float* row = At + (hs + dh) * SA;
@@ -741,6 +783,9 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                     }
 #pragma unroll
                     for (int w = 0; w < W; ++w) gk1[kK1 * kK1] += dz1[w];
+#if DMFG_RNET_TMEM_ACC
+                    umma::tmem_st_32x32b_x32(acc_t, gk1);
+#endif
                 }
             }
             __syncwarp();      // tiles are rewritten by the next transition of this group
@@ -787,16 +832,26 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
             }
         }
     }
+#if DMFG_RNET_TMEM_ACC
+    float gk1[32], gk2f[32];
+    umma::tmem_ld_32x32b_x32(acc_t, gk1);
+    umma::tmem_ld_32x32b_x32(acc_t + 32u, gk2f);
+#endif
     umma::fence_before_sync();
     __syncthreads();                                                   // everyone has read TMEM; the operand tiles are free
-    if (tid < 32) umma::tmem_dealloc(tmem_base, W3G::kTmemCols);
+    if (tid < 32) umma::tmem_dealloc(tmem_base, kTmemAlloc);
     float* ga = smem + S.gacc;
 #pragma unroll
     for (int i = 0; i < kK1 * kK1 + 1; ++i) ga[i * kRnetThreads + tid] = gk1[i];
 #pragma unroll
     for (int i = 0; i < kK2 * kK2 + 1; ++i) {
+#if DMFG_RNET_TMEM_ACC
+        ga[(26 + 2 * i) * kRnetThreads + tid] = gk2f[2 * i];
+        ga[(26 + 2 * i + 1) * kRnetThreads + tid] = gk2f[2 * i + 1];
+#else
         ga[(26 + 2 * i) * kRnetThreads + tid] = gk2v[i].x;
         ga[(26 + 2 * i + 1) * kRnetThreads + tid] = gk2v[i].y;
+#endif
     }
 #pragma unroll
     for (int m = 0; m < NP; ++m) {
