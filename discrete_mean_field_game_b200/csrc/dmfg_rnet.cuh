@@ -377,6 +377,9 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     const float inv_keep = p.dropout ? 1.0f / p.keep_prob : 1.0f;
     // persistent register accumulators (backward)
     float gw4pi[NP], gw4h[NP];
+    float gsm[3 * NP + 1];               // d out/weights [NP], d fc4/biases [NP], d fc3/biases [NP], d out/biases (uniform over the group)
+#pragma unroll
+    for (int i = 0; i < 3 * NP + 1; ++i) gsm[i] = 0.f;
 #if DMFG_RNET_TMEM_ACC
     // this thread's strip: columns [0, 32) d conv1/weights [dh][dw] + bias, [32, 64) d conv2/weights as (channel 0,
     // channel 1) pairs + the two biases
@@ -632,7 +635,6 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 
             if (BWD) {
                 float* Dt = Ct + RC * SC;                    // dz2 tile, 2 channels
-                float* gs = smem + S.gsmall + grp * SM::NSMALL;
                 float dr;
                 if (TRAJ) {
                     if (h == 0) rtraj[grp] = live ? r : 0.f;
@@ -650,14 +652,17 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 #pragma unroll
                 for (int m = 0; m < NP; ++m)
                     dz4[m] = (m < n4 && z4[m] > 0.f) ? dz5 * wf[L.w5 + m] * m4[m] * inv_keep : 0.f;
-                if (h == 0) {
+                // the head's small gradients are uniform over the group: every lane keeps its own running copy in registers
+                // (lane 0's is written out at the end) -- the one-lane read-modify-write of 25 shared-memory slots per
+                // transition was a divergent branch with a serial LDS -> FADD -> STS chain behind it
 #pragma unroll
-                    for (int m = 0; m < NP; ++m) {
-                        gs[m] = fmaf(h4[m], dz5, gs[m]);                    // d out/weights
-                        gs[NP + m] += dz4[m];                               // d fc4/biases
+                for (int m = 0; m < NP; ++m) {
+                    if (m < n4) {
+                        gsm[m] = fmaf(h4[m], dz5, gsm[m]);                  // d out/weights
+                        gsm[NP + m] += dz4[m];                              // d fc4/biases
                     }
-                    gs[3 * NP] += dz5;                                      // d out/biases
                 }
+                gsm[3 * NP] += dz5;                                         // d out/biases
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
                     float s = 0.f;
@@ -666,10 +671,9 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                         if (m < n4 && j < n3) s = fmaf(dz4[m], wf[L.w4 + j * n4 + m], s);
                     dz3[j] = (j < n3 && z3[j] > 0.f) ? s * m3[j] * inv_keep : 0.f;
                 }
-                if (h == 0) {
 #pragma unroll
-                    for (int j = 0; j < NP; ++j) gs[2 * NP + j] += dz3[j];   // d fc3/biases
-                }
+                for (int j = 0; j < NP; ++j)
+                    if (j < n3) gsm[2 * NP + j] += dz3[j];                  // d fc3/biases
                 // d fc4/weights: row n3+h (state part) on every lane, row h (h3 part) on lanes h < n3
 #pragma unroll
                 for (int m = 0; m < NP; ++m) gw4pi[m] = fmaf(pi_h, dz4[m], gw4pi[m]);
@@ -857,6 +861,10 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     for (int m = 0; m < NP; ++m) {
         ga[(46 + m) * kRnetThreads + tid] = gw4pi[m];
         ga[(46 + NP + m) * kRnetThreads + tid] = gw4h[m];
+    }
+    if (h == 0) {
+#pragma unroll
+        for (int i = 0; i < 3 * NP + 1; ++i) smem[S.gsmall + grp * SM::NSMALL + i] = gsm[i];
     }
     __syncthreads();
     // conv slots: sum over all threads (warp w takes slots w, w+8, ...)
