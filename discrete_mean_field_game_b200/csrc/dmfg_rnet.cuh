@@ -283,6 +283,24 @@ __device__ __forceinline__ float group_sum_f(float v) {
     for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
     return v;
 }
+// Lane mapping of the reward-net kernels.  G = 32: a warp is one transition, lane = row.  G = 16: the TWO transitions of a
+// warp are INTERLEAVED -- lane l serves row l / 2 of transition l % 2 -- so that the two lanes reading the same fc3 row block
+// sit in the same half warp: a 128-bit shared load is served half warp by half warp, and 16 lanes reading 8 distinct
+// 16-byte chunks cost one wavefront instead of two (the row-block reads were 42 % of the kernel's shared-memory traffic).
+template <int G>
+struct RnetLanes {
+    static __device__ __forceinline__ int row(int tid) { return G == 16 ? (tid & 31) >> 1 : tid % G; }
+    static __device__ __forceinline__ int group(int tid) { return G == 16 ? ((tid >> 5) << 1) | (tid & 1) : tid / G; }
+    static __device__ __forceinline__ int thread_of(int grp, int h) { return G == 16 ? ((grp >> 1) << 5) | (h << 1) | (grp & 1) : grp * G + h; }
+    static __device__ __forceinline__ float sum(float v) {       // all-reduce over the lanes of one transition
+        if (G == 16) {
+#pragma unroll
+            for (int o = 16; o > 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            return v;
+        }
+        return group_sum_f<G>(v);
+    }
+};
 
 // keep masks of the two dropout layers for transition `sample` (Philox mode): unit j of layer l keeps
 // iff u01(word) < keep_prob, words drawn 4 at a time from counter (sample, l*64 + j/4, DROPOUT)
@@ -336,7 +354,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     const int d = DS ? DS : p.d, n3 = N3S ? N3S : p.n3, n4 = N4S ? N4S : p.n4;
     const RnetLayout L = rnet_layout(d, n3, n4);
     const SM S(d, L.total);
-    const int tid = threadIdx.x, h = tid % G, grp = tid / G;
+    const int tid = threadIdx.x, h = RnetLanes<G>::row(tid), grp = RnetLanes<G>::group(tid);
     float* wf = smem + S.wflat;
     float* w3s = smem + S.w3s;
     float* At = smem + S.tiles + grp * S.tile_stride;
@@ -549,7 +567,11 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
             // times the matching weight pair is ONE packed FFMA2 per unit; the two halves are added once at the end;
             // then all-reduce over the group ----
             float z3[NP];
-            const float* wrow = w3s + (row_ok ? h : 0) * S.w3stride;
+            // idle lanes (h >= d) must re-read a row block of their OWN quarter warp: a 128-bit shared load is served in
+            // quarter-warp phases, and lane 15 re-reading block 0 collided with lane 8 (same banks, another address) --
+            // 6 wavefronts per LDS.128 instead of 4, 17 % of the kernel's shared-memory traffic (ncu, round 2)
+            const int h_idle = ((h & ~7) < d) ? (h & ~7) : 0;
+            const float* wrow = w3s + (row_ok ? h : h_idle) * S.w3stride;
             {
                 float2 z3v[NP];
 #pragma unroll
@@ -605,7 +627,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
             float h3[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
-                z3[j] = group_sum_f<G>(z3[j]) + (j < n3 ? wf[L.b3 + j] : 0.f);
+                z3[j] = RnetLanes<G>::sum(z3[j]) + (j < n3 ? wf[L.b3 + j] : 0.f);
                 h3[j] = j < n3 ? fmaxf(z3[j], 0.f) * m3[j] * inv_keep : 0.f;
             }
             // ---- fc4 over [h3, pi] ----------------------------------------------------------------
@@ -613,7 +635,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
 #pragma unroll
             for (int m = 0; m < NP; ++m) {
                 float part = (row_ok && m < n4) ? pi_h * wf[L.w4 + (n3 + h) * n4 + m] : 0.f;
-                part = group_sum_f<G>(part);
+                part = RnetLanes<G>::sum(part);
                 if (m < n4) {
                     float z = wf[L.b4 + m] + part;
 #pragma unroll
@@ -891,7 +913,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
         const int slot = row < n3 ? 46 + NP + m : 46 + m;
         const int lane_h = row < n3 ? row : row - n3;
         float v = 0.f;
-        for (int g = 0; g < GPB; ++g) v += ga[slot * kRnetThreads + g * G + lane_h];
+        for (int g = 0; g < GPB; ++g) v += ga[slot * kRnetThreads + RnetLanes<G>::thread_of(g, lane_h)];
         out[L.w4 + i] = v;
     }
     // small per-group sums
