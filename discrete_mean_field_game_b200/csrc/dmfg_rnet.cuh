@@ -33,6 +33,9 @@ constexpr int kK1 = 5, kK2 = 3;
 #ifndef DMFG_RNET_TMEM_ACC
 #define DMFG_RNET_TMEM_ACC 1
 #endif
+#ifndef DMFG_RNET_KREG
+#define DMFG_RNET_KREG 1
+#endif
 #ifndef DMFG_RNET_PREFETCH
 #define DMFG_RNET_PREFETCH 3      // 0: none, 1 / 2: L2 / L1 prefetch hints for the next tile, 3: register-pipelined loads
 #endif
@@ -94,7 +97,9 @@ struct RnetSmem {
     // the lane's row of conv2 activations, h: lane), K = the GPB transitions of the tile
     static constexpr int GM = (DT + 7) & ~7;                   // rows per activation slot t (a multiple of the 8-row group)
     static constexpr int MT = (2 * DT * GM + 127) / 128, KG = GPB / 8;
-    using W3G = umma::W3Grad<MT, KG>;
+    static constexpr bool HS = (G == 16);                      // rows h >= 8 in the upper half of the M tiles (dmfg_umma.cuh)
+    using W3G = umma::W3Grad<MT, KG, HS>;
+    static_assert(!HS || (GM == 16 && MT == 4), "half split: 16-row slots, 2 x 256 rows");
     static_assert(GPB % 8 == 0 && NP <= 8, "tile = whole groups of 8 transitions; fc3 width <= 8");
     int wflat, w3s, w3stride, tiles, tile_stride, umA, umB, gacc, gsmall, total;
     __host__ __device__ RnetSmem(int d, int ptotal) {
@@ -423,6 +428,16 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
         for (int i = 0; i < kK2 * kK2 + 1; ++i) gk2v[i] = make_float2(0.f, 0.f);
     }
 #endif
+    // backward: conv kernels in registers for the whole kernel (61 uniform shared loads per transition less; the forward
+    // kernel runs two CTAs per SM at 128 registers and measured 13 % slower with them)
+    constexpr bool KREG = DMFG_RNET_KREG && BWD;
+    float k1r[kK1 * kK1], k2r[kK2 * kK2 * 2];
+    if (KREG) {
+#pragma unroll
+        for (int i = 0; i < kK1 * kK1; ++i) k1r[i] = wf[L.k1 + i];
+#pragma unroll
+        for (int i = 0; i < kK2 * kK2 * 2; ++i) k2r[i] = wf[L.k2 + i];
+    }
     // tensor-core hand-off state (uniform over the CTA)
     uint32_t mma_phase = 0;
     bool mma_pending = false, mma_first = true;
@@ -430,7 +445,10 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     const uint32_t um_b_hi = smem_u32(smem + S.umB), um_b_lo = um_b_hi + W3G::kBytesB;
     // this thread's store addresses into the A tile (row h of chunk group 0, column grp), pinned to ordinary registers:
     // left to itself the compiler splits them into a uniform part it rematerialises (ULEA from SR_CgaCtaId) per store
-    uint32_t a_st_hi = um_a_hi + W3G::off(h, grp), a_st_lo = um_a_lo + W3G::off(h, grp);
+    // row of activation slot 0 / K column of this thread's transition (half split: rows h >= 8 start at row 256, column n ^ 2)
+    const int a_row0 = SM::HS ? ((h >> 3) * (SM::MT * 64) + (h & 7)) : h;
+    const int a_col = (SM::HS && h >= 8) ? (grp ^ 2) : grp;
+    uint32_t a_st_hi = um_a_hi + W3G::off(a_row0, a_col), a_st_lo = um_a_lo + W3G::off(a_row0, a_col);
     asm volatile("mov.u32 %0, %0;\n\tmov.u32 %1, %1;" : "+r"(a_st_hi), "+r"(a_st_lo));
     const long long ntiles = TRAJ ? p.traj_M : (p.N + GPB - 1) / GPB;
     // transition served by this group in tile `tl` (dead groups shadow a live one: warp-wide syncs stay convergent)
@@ -513,7 +531,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                     const float* row = At + (hs + dh) * SA;
                     float k[kK1];
 #pragma unroll
-                    for (int dw = 0; dw < kK1; ++dw) k[dw] = wf[L.k1 + dh * kK1 + dw];
+                    for (int dw = 0; dw < kK1; ++dw) k[dw] = KREG ? k1r[dh * kK1 + dw] : wf[L.k1 + dh * kK1 + dw];
 #pragma unroll
                     for (int wp = 0; wp < W + 4; ++wp) {
                         const float v = row[wp];
@@ -543,7 +561,8 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                     float2 k[kK2];                                   // (channel 0, channel 1) weights of tap (dh, dw)
 #pragma unroll
                     for (int dw = 0; dw < kK2; ++dw)
-                        k[dw] = make_float2(wf[L.k2 + (dh * kK2 + dw) * 2], wf[L.k2 + (dh * kK2 + dw) * 2 + 1]);
+                        k[dw] = KREG ? make_float2(k2r[(dh * kK2 + dw) * 2], k2r[(dh * kK2 + dw) * 2 + 1])
+                                               : make_float2(wf[L.k2 + (dh * kK2 + dw) * 2], wf[L.k2 + (dh * kK2 + dw) * 2 + 1]);
 #pragma unroll
                     for (int wp = 0; wp < W + 2; ++wp) {
                         const float v = row[wp];
@@ -604,7 +623,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                             for (int c = 0; c < 2; ++c) {
                                 float hi, lo;
                                 umma::split_tf32(c ? c2v[w].y : c2v[w].x, hi, lo);
-                                constexpr uint32_t kRowStep = (uint32_t)(SM::GM / 8) * W3G::kSbo;
+                                constexpr uint32_t kRowStep = (SM::HS ? 1u : (uint32_t)(SM::GM / 8)) * W3G::kSbo;
                                 umma::sts_f32(a_st_hi + (uint32_t)(2 * w + c) * kRowStep, hi);
                                 umma::sts_f32(a_st_lo + (uint32_t)(2 * w + c) * kRowStep, lo);
                             }
@@ -774,7 +793,8 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                         float2 k[kK2];
 #pragma unroll
                         for (int f = 0; f < kK2; ++f)
-                            k[f] = make_float2(wf[L.k2 + ((2 - e) * kK2 + (2 - f)) * 2], wf[L.k2 + ((2 - e) * kK2 + (2 - f)) * 2 + 1]);
+                            k[f] = KREG ? make_float2(k2r[((2 - e) * kK2 + (2 - f)) * 2], k2r[((2 - e) * kK2 + (2 - f)) * 2 + 1])
+                                                  : make_float2(wf[L.k2 + ((2 - e) * kK2 + (2 - f)) * 2], wf[L.k2 + ((2 - e) * kK2 + (2 - f)) * 2 + 1]);
 #pragma unroll
                         for (int wp = 0; wp < W + 2; ++wp) {
                             const float2 v = make_float2(row0[wp], row1[wp]);
@@ -825,6 +845,10 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                     umma::split_tf32(dz3[j], hi, lo);
                     umma::sts_f32(um_b_hi + W3G::off(j, grp), hi);
                     umma::sts_f32(um_b_lo + W3G::off(j, grp), lo);
+                    if (SM::HS) {                                          // the copy the upper-half tiles multiply with
+                        umma::sts_f32(um_b_hi + 2u * W3G::kSbo + W3G::off(j, grp ^ 2), hi);
+                        umma::sts_f32(um_b_lo + 2u * W3G::kSbo + W3G::off(j, grp ^ 2), lo);
+                    }
                 }
             }
             umma::fence_proxy_async();                                 // generic-proxy stores -> visible to the tensor core
@@ -849,7 +873,8 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
             float v[8];
             umma::tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 16u * (uint32_t)mt, v);
             const int m = 128 * mt + 32 * (warp & 3) + lane;
-            const int t = m / SM::GM, hh = m % SM::GM;
+            const int t = SM::HS ? (m % (SM::MT * 64)) >> 3 : m / SM::GM;
+            const int hh = SM::HS ? ((m / (SM::MT * 64)) << 3) | (m & 7) : m % SM::GM;
             if (hh < d && t < 2 * d) {
                 const int k = hh * 2 * d + t;
 #pragma unroll

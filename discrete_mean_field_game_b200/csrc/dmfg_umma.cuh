@@ -125,10 +125,15 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // with SBO = 256 KG (the 2 KG chunks of a row group are adjacent).  The order of the M rows is free -- the caller maps
 // activation index -> m so that its stores need no address arithmetic, and un-permutes when it reads D back.
 // ---------------------------------------------------------------------------------------------------
-template <int MT, int KG>
+// HS ("half split", 16-row activation slots): the staging stores of a warp go to rows (t, h) of ONE K column per
+// transition, and rows h and h + 8 of a slot fall on the same banks (bank = 4 (m % 8) + n % 4) -- a 2-way conflict on every
+// store.  With HS the rows of the upper half (h >= 8) live in the upper half of the M tiles and use K column n ^ 2, i.e. the
+// two free banks of each quad; their MMAs read a second copy of B with the columns permuted the same way (b2).
+template <int MT, int KG, bool HS = false>
 struct W3Grad {
     static constexpr uint32_t kLbo = 128, kSbo = 256u * KG;
-    static constexpr uint32_t kBytesA = (uint32_t)MT * 16u * kSbo, kBytesB = 2u * kSbo;              // one of (hi, lo)
+    static constexpr uint32_t kBytesA = (uint32_t)MT * 16u * kSbo, kBytesB = (HS ? 4u : 2u) * kSbo;  // one of (hi, lo); HS: B then B permuted
+    static constexpr bool kHalfSplit = HS;
     static constexpr uint32_t kTmemCols = MT * 16 <= 32 ? 32 : MT * 16 <= 64 ? 64 : MT * 16 <= 128 ? 128 : 256;      // MT M-tiles x N = 16
     static __device__ __forceinline__ uint32_t off(int row, int n) {
         return (uint32_t)(row >> 3) * kSbo + (uint32_t)(n >> 2) * kLbo + (uint32_t)(row & 7) * 16u + (uint32_t)(n & 3) * 4u;
@@ -144,7 +149,8 @@ struct W3Grad {
             for (int ks = 0; ks < KG; ++ks) {
                 const uint32_t ao = (uint32_t)m * 16u * kSbo + (uint32_t)ks * 2u * kLbo, bo = (uint32_t)ks * 2u * kLbo;
                 const uint64_t ah = smem_desc(a_hi + ao, kLbo, kSbo), al = smem_desc(a_lo + ao, kLbo, kSbo);
-                const uint64_t bh = smem_desc(b_hi + bo, kLbo, kSbo), bl = smem_desc(b_lo + bo, kLbo, kSbo);
+                const uint32_t bsel = (HS && m >= MT / 2) ? 2u * kSbo : 0u;      // upper-half tiles: the permuted copy of B
+                const uint64_t bh = smem_desc(b_hi + bsel + bo, kLbo, kSbo), bl = smem_desc(b_lo + bsel + bo, kLbo, kSbo);
                 const uint32_t d = tmem_base + 16u * (uint32_t)m;
                 mma_tf32(d, ah, bh, idesc, (first && ks == 0) ? 0u : 1u);
                 mma_tf32(d, al, bh, idesc, 1u);
