@@ -565,7 +565,8 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                                                : make_float2(wf[L.k2 + (dh * kK2 + dw) * 2], wf[L.k2 + (dh * kK2 + dw) * 2 + 1]);
 #pragma unroll
                     for (int wp = 0; wp < W + 2; ++wp) {
-                        const float v = row[wp];
+                        // the centre row (dh = 1) is this lane's own conv1 row: still in registers, no shared load
+                        const float v = dh == 1 ? ((wp >= 1 && wp <= W) ? c1[wp >= 1 && wp <= W ? wp - 1 : 0] : 0.f) : row[wp];
 #pragma unroll
                         for (int dw = 0; dw < kK2; ++dw) {
                             const int w = wp - dw;
@@ -797,7 +798,9 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                                                   : make_float2(wf[L.k2 + ((2 - e) * kK2 + (2 - f)) * 2], wf[L.k2 + ((2 - e) * kK2 + (2 - f)) * 2 + 1]);
 #pragma unroll
                         for (int wp = 0; wp < W + 2; ++wp) {
-                            const float2 v = make_float2(row0[wp], row1[wp]);
+                            // the centre row (e = 1) is this lane's own dz2 row: registers, no shared loads
+                            const float2 v = e == 1 ? ((wp >= 1 && wp <= W) ? dz2v[wp >= 1 && wp <= W ? wp - 1 : 0] : make_float2(0.f, 0.f))
+                                                    : make_float2(row0[wp], row1[wp]);
 #pragma unroll
                             for (int f = 0; f < kK2; ++f) {
                                 const int w = wp - f;

@@ -55,5 +55,22 @@ for one_pass in (True, False):            # generated half in one launch (rnet_k
     irl.one_pass_reward_update = one_pass
     irl.update_reward_batch(ds[:15].reshape(-1, 15), da.reshape(-1, 15, 15), gs[:15].reshape(-1, 15),
                             ga.reshape(-1, 15, 15), 24, "time_major", group=False)
+# ---- round 2: the fused per-step launch (dmfg_ac_step), AC_IRL.train as one kernel (dmfg_irl_learners), the reward net at
+# d = 16 (generic instantiation) and d = 21 (32 lanes per transition), TMEM-parked accumulators, tensor-core fc3 gradient
+from discrete_mean_field_game_b200 import mfg_ac2
+from oracle import mfg_oracle as O
+mat = O.synthetic_start_states(n_rows=21, n_cols=30, d=15, seed=4)
+with contextlib.redirect_stdout(sys.stderr):
+    ac = mfg_ac2.actor_critic(theta=8.0, shift=0.16, alpha_scale=12000, d=15, mat_pi0=mat, dtype="float32", seed=21)
+    ac.train_batch(np.float32(rng.dirichlet(np.ones(15), size=77)), num_episodes=1, T=3, lr_critic=0.1, lr_actor=0.01,
+                   update="per_step")
+    irl.train(max_episodes=3, stop_criteria=-1, verbose=False, use_graph=False)
+    for dd in (16, 21):
+        gg = rng.standard_gamma(1.0, size=(8, dd))
+        irl2 = AC_IRL(theta=8.64, shift=0, alpha_scale=1e4, d=dd, reg="none", n_fc3=6, n_fc4=3,
+                      mat_pi0=gg / gg.sum(1, keepdims=True), demonstrations=[], device=dev, seed=1, net_seed=2)
+        s2, a2 = irl2.generate_batch(20)
+        irl2.update_reward_batch(s2[:15].reshape(-1, dd), a2.reshape(-1, dd, dd), s2[:15].reshape(-1, dd),
+                                 a2.reshape(-1, dd, dd), 20, "time_major", group=False)
 torch.cuda.synchronize()
 print("sanitize_small: done")
