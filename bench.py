@@ -428,8 +428,10 @@ def run_ours(args):
                     "ok": bool(float(err) < 1e-9)}
 
     # ---- the other two modes of config 3 (single GPU numbers, for the roofline discussion)
+    # (single-GPU side numbers: measured in the N = 1 run only -- rank 0 alone would otherwise sit in them while the other
+    # ranks wait at the barrier, and nothing in here may touch a collective)
     modes = {}
-    if rank == 0:
+    if rank == 0 and world == 1:
         def timed(fn, n=3):
             fn(); torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -63,6 +63,8 @@ class AC_IRL(_actor_critic):
         self.summarize = summarize
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.dtype = torch.float32                       # the TF graph is float32 (ac_irl.py:239-246)
+        self.group = None                                # process group of update_reward's all-reduce (None: the default
+                                                         # group when torch.distributed is initialised; False: never)
         self.theta = theta
         self.theta_initial = theta
         self.shift = shift
@@ -756,7 +758,8 @@ class AC_IRL(_actor_critic):
             gen_sampled = self.list_generated[:]
         ds, da = self._pack(demo_sampled)
         gs, ga = self._pack(gen_sampled)
-        loss = self.update_reward_batch(ds, da, gs, ga, self.num_demo_samples, "trajectory_major").cpu().numpy()
+        loss = self.update_reward_batch(ds, da, gs, ga, self.num_demo_samples, "trajectory_major",
+                                        group=self.group).cpu().numpy()
         self.loss_val, self.first_term_val, self.second_term_val = float(loss[0]), float(loss[1]), float(loss[2])
 
     def reward_iteration(self, max_iterations=500, stop_criteria=0.01, iter_check=10, verbose=True):
