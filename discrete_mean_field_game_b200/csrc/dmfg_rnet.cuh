@@ -4,19 +4,27 @@
 //   conv 5x5 (1->1) + ReLU -> conv 3x3 (1->2) + ReLU -> NHWC flatten -> fc3 (2d^2 -> n3) + ReLU [dropout]
 //   -> concat state -> fc4 (n3+d -> n4) + ReLU [dropout] -> out (n4 -> 1) + tanh
 //
-// Mapping: a group of G lanes (16 for d <= 16) owns one transition; lane h owns ROW h of the d x d action:
-// it evaluates row h of conv1 and of both conv2 channels with the outputs in registers (the 5 / 3 input
-// rows come from a zero-haloed shared-memory tile, odd row stride => conflict free), multiplies its 2d
-// conv2 activations into fc3 from a per-row block of W3 (row-block stride = 4 mod 8 words => the LDS.128
-// of a quarter warp hit 8 distinct bank quads), and the group all-reduces the n3 partial sums with
-// shuffles.  Nothing intermediate leaves the SM.  The packed parameter vector (15 KB at d = 15) is staged
-// ONCE per persistent CTA by a TMA bulk copy (cp.async.bulk + mbarrier).
+// Mapping: G lanes own one transition (G = 16 for d <= 16: two transitions per warp, INTERLEAVED across the lanes --
+// lane l = row l / 2 of transition l % 2, see RnetLanes; G = 32 for d = 20 / 21); lane h owns ROW h of the d x d action:
+// it evaluates row h of conv1 and of both conv2 channels (packed FFMA2, channel pair = register pair) with the outputs
+// in registers (the 5 / 3 input rows come from a zero-haloed shared-memory tile, odd row stride => conflict free; the
+// centre row of conv2 is the lane's own conv1 row, still in registers), multiplies its 2d conv2 activations into fc3
+// from a per-row block of W3 laid out [column][unit][channel] (row-block stride = 4 mod 8 words => the LDS.128 of a
+// quarter warp hit 8 distinct bank quads; idle lanes re-read a block of their own quarter warp), and the group
+// all-reduces the n3 partial sums with shuffles.  Nothing intermediate leaves the SM.  The packed parameter vector
+// (15 KB at d = 15) is staged ONCE per persistent CTA by a TMA bulk copy (cp.async.bulk + mbarrier).
 //
-// Backward recomputes the forward in the same kernel (activations are 2.7 KB per transition against a
-// 960 B input: recomputing beats caching), backpropagates through every layer and accumulates parameter
-// gradients without atomics: conv / fc4 gradients in per-thread slots, the fc3 gradient -- the only big
-// one, [2d^2, n3] -- as a CTA-wide outer-product over a tile of 16 transitions with thread-owned (k, n)
-// accumulators in registers.  Per-CTA partials are then summed in fixed order (deterministic).
+// Backward recomputes the forward in the same kernel (activations are 2.7 KB per transition against a 960 B input:
+// recomputing beats caching), keeps the ReLU patterns as bit masks, backpropagates through every layer and accumulates
+// parameter gradients without atomics:
+//   * the fc3 gradient -- the only big one, [2d^2, n3] = sum over transitions of h^T dz3 -- on the tensor cores: per
+//     tile of 16 transitions the activations are staged as a 3xTF32 operand tile, tcgen05.mma (kind::tf32) accumulates
+//     in tensor memory for the whole kernel (dmfg_umma.cuh);
+//   * the conv-weight gradients in per-thread accumulators that are PARKED in the thread's private strip of tensor
+//     memory between the two phases that update them (tcgen05.ld / .st), the fc4 / head gradients in registers;
+//   * per-CTA partials are then summed in fixed order (deterministic).
+// What bounds it (profiles/r2_rnet_ncu_summary.md): shared-memory wavefronts and instruction issue at one 256-thread
+// CTA per SM -- every shared load of the kernel is at its ideal wavefront count.
 #pragma once
 #include "dmfg_math.cuh"
 #include "dmfg_umma.cuh"
