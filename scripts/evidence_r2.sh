@@ -9,5 +9,5 @@ ncu --set full --clock-control none --import-source on -k regex:rollout_v2 -s 1 
 ncu --set full --clock-control none --import-source on -k regex:rollout_v2 -s 1 -c 1 -o gpurun_out/r2_v2_record -f python scripts/prof_rollout.py --log2-pops 18 --mode record > gpurun_out/r2_v2_record.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rnet_kernel -s 4 -c 2 -o gpurun_out/r2_rnet_bwd_final -f python scripts/prof_irl.py 2 > gpurun_out/r2_rnet_bwd_final.log 2>&1
 python scripts/time_irl_update.py 2>/dev/null | tail -1 > gpurun_out/r2_irl_time_final.log; cat gpurun_out/r2_irl_time_final.log
-python scripts/parity_maxerr.py > gpurun_out/r2_parity_maxerr.md 2> gpurun_out/r2_parity_maxerr.err; tail -3 gpurun_out/r2_parity_maxerr.md
+python tests/parity_maxerr.py > gpurun_out/r2_parity_maxerr.md 2> gpurun_out/r2_parity_maxerr.err; tail -3 gpurun_out/r2_parity_maxerr.md
 scripts/sanitize_run.sh | tail -12

@@ -58,8 +58,8 @@ for one_pass in (True, False):            # generated half in one launch (rnet_k
 # ---- round 2: the fused per-step launch (dmfg_ac_step), AC_IRL.train as one kernel (dmfg_irl_learners), the reward net at
 # d = 16 (generic instantiation) and d = 21 (32 lanes per transition), TMEM-parked accumulators, tensor-core fc3 gradient
 from discrete_mean_field_game_b200 import mfg_ac2
-from oracle import mfg_oracle as O
-mat = O.synthetic_start_states(n_rows=21, n_cols=30, d=15, seed=4)
+gm = rng.standard_gamma(1.0, size=(21, 15))
+mat = gm / gm.sum(1, keepdims=True)
 with contextlib.redirect_stdout(sys.stderr):
     ac = mfg_ac2.actor_critic(theta=8.0, shift=0.16, alpha_scale=12000, d=15, mat_pi0=mat, dtype="float32", seed=21)
     ac.train_batch(np.float32(rng.dirichlet(np.ones(15), size=77)), num_episodes=1, T=3, lr_critic=0.1, lr_actor=0.01,

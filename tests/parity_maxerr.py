@@ -2,7 +2,7 @@
 the golden train trace (the reference's own draws), a config-2-shaped batch (AC_IRL defaults, 4096 populations x 15
 steps) and a 2^16-population sample of config 3 (16 steps), processed in chunks.  Writes a markdown table.
 
-    python scripts/parity_maxerr.py [--out gpurun_out/r2_parity_maxerr.md] [--log2-big 16]
+    python tests/parity_maxerr.py [--out gpurun_out/r2_parity_maxerr.md] [--log2-big 16]
 """
 import argparse
 import os
