@@ -674,11 +674,48 @@ class AC_IRL(_actor_critic):
         return [[(S[t, j], A[t, j]) for t in range(T_STEPS)] for j in range(n)]
 
     # ------------------------------------------------------------- a11/a12: reward update
+    def _pack_host(self, trajectories):
+        """list of trajectories -> trajectory-major float32 arrays states [n*15, d], actions [n*15, d, d].  A trajectory
+        (a list of (state, action) pairs) is stacked ONCE and remembered: update_reward resamples the same few dozen
+        trajectories hundreds of times (ac_irl.py:804-846) and the per-pair np.asarray was a third of its wall time.
+        The memo is keyed by the list's id and validated by the identity of its first and last pair (which the entry
+        keeps alive, so a recycled id cannot alias); arrays inside a trajectory are not expected to be edited in place
+        (the reference never does)."""
+        memo = self.__dict__.setdefault("_pack_memo", {})
+        ss, aa = [], []
+        for traj in trajectories:
+            n = len(traj)
+            hit = memo.get(id(traj))
+            if hit is None or hit[0] != n or hit[1] is not traj[0] or hit[2] is not traj[-1]:
+                if len(memo) >= 8192:
+                    memo.clear()
+                s = np.asarray([pair[0] for pair in traj], dtype=np.float32).reshape(n, self.d)
+                a = np.asarray([pair[1] for pair in traj], dtype=np.float32).reshape(n, self.d, self.d)
+                hit = memo[id(traj)] = (n, traj[0], traj[-1], s, a)
+            ss.append(hit[3])
+            aa.append(hit[4])
+        if not ss:
+            return np.zeros((0, self.d), np.float32), np.zeros((0, self.d, self.d), np.float32)
+        return np.concatenate(ss), np.concatenate(aa)
+
     def _pack(self, trajectories):
         """list of trajectories -> trajectory-major device tensors states [n*15,d], actions [n*15,d,d]."""
-        s = np.asarray([pair[0] for traj in trajectories for pair in traj], dtype=np.float32).reshape(-1, self.d)
-        a = np.asarray([pair[1] for traj in trajectories for pair in traj], dtype=np.float32).reshape(-1, self.d, self.d)
+        s, a = self._pack_host(trajectories)
         return self._dev(s, torch.float32), self._dev(a, torch.float32)
+
+    def _pack_pair(self, demo, gen):
+        """both halves of a reward minibatch through ONE host-to-device copy: (demo states, demo actions, generated
+        states, generated actions) as views of one device buffer"""
+        parts = list(self._pack_host(demo)) + list(self._pack_host(gen))
+        offs, o = [], 0
+        for p in parts:                                     # every part starts on a 16-byte boundary
+            offs.append(o)
+            o += (p.size + 3) // 4 * 4
+        flat = np.zeros(o, dtype=np.float32)
+        for p, b in zip(parts, offs):
+            flat[b:b + p.size] = p.reshape(-1)
+        buf = self._dev(flat, torch.float32)
+        return [buf[b:b + p.size].view(p.shape) for p, b in zip(parts, offs)]
 
     def update_reward_batch(self, demo_states, demo_actions, gen_states, gen_actions, num_demo_traj, layout,
                             group=None, masks=None):
@@ -756,8 +793,7 @@ class AC_IRL(_actor_critic):
             gen_sampled = random.sample(self.list_generated, self.num_gen_samples)
         else:
             gen_sampled = self.list_generated[:]
-        ds, da = self._pack(demo_sampled)
-        gs, ga = self._pack(gen_sampled)
+        ds, da, gs, ga = self._pack_pair(demo_sampled, gen_sampled)
         loss = self.update_reward_batch(ds, da, gs, ga, self.num_demo_samples, "trajectory_major",
                                         group=self.group).cpu().numpy()
         self.loss_val, self.first_term_val, self.second_term_val = float(loss[0]), float(loss[1]), float(loss[2])
