@@ -386,16 +386,17 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     if (BWD) { umma::fence_after_sync(); tmem_base = tmem_slot; }
     if (tid == 0 && bulk_floats) tma_bulk_load(wf, p.params, bulk_floats * 4u, &mbar);
     for (int i = bulk_floats + tid; i < L.total; i += kRnetThreads) wf[i] = p.params[i];
-    for (int i = tid; i < GPB * S.tile_stride; i += kRnetThreads) smem[S.tiles + i] = 0.f;    // zero halos
-    if (BWD) {
-        for (int i = tid; i < 2 * (int)((W3G::kBytesA + W3G::kBytesB) / 4); i += kRnetThreads) smem[S.umA + i] = 0.f;
-        for (int i = tid; i < GPB * SM::NSMALL; i += kRnetThreads) smem[S.gsmall + i] = 0.f;
+    // everything behind the flat parameters -- fc3 row blocks (padded columns), tiles (halos), operand tiles, small sums --
+    // starts from zero: one pass of 16-byte stores while the bulk copy is in flight
+    {
+        float4* z4 = reinterpret_cast<float4*>(smem + S.w3s);
+        const int n4z = (S.total - S.w3s) / 4;
+        for (int i = tid; i < n4z; i += kRnetThreads) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = S.w3s + 4 * n4z + tid; i < S.total; i += kRnetThreads) smem[i] = 0.f;
     }
     if (bulk_floats) mbar_wait(&mbar, 0);
     __syncthreads();
-    // fc3 weights into per-row blocks [h][2d][NP] (zero padded columns), conflict-free stride
-    for (int i = tid; i < d * S.w3stride; i += kRnetThreads) w3s[i] = 0.f;
-    __syncthreads();
+    // fc3 weights into per-row blocks [h][column][unit][channel], conflict-free stride
     for (int i = tid; i < 2 * d * d * n3; i += kRnetThreads) {
         const int k = i / n3, n = i - k * n3;
         const int row = k / (2 * d), kk = k - row * 2 * d;
