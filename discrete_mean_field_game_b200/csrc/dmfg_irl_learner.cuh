@@ -38,6 +38,11 @@ struct IrlLearnerSmem {
     static constexpr int pis = c1t + 18 * SC;               // [16] state
     static constexpr int z3p = pis + 16;                    // [4 warps][8]
     static constexpr int w3a = (z3p + 32 + 3) & ~3;         // [2 d^2][8] fc3 weights, 16-byte aligned rows (zero padded columns)
+    // row r of W3 sits at 8 r + 4 (r / 4): thread (i, jp) reads rows 30 i + 4 jp + u, so without the skew the 8 lanes of
+    // a quarter warp (one i, jp = 0..7) are 32 words apart -- the same banks, an 8-way conflict on every LDS.128 (ncu:
+    // 26-30 wavefronts per load, 16 % of the kernel's samples); with it they are 36 words apart: 8 distinct bank quads
+    static __host__ __device__ constexpr int w3row(int r) { return 8 * r + 4 * (r >> 2); }
+    static constexpr int w3size = (w3row(2 * D * D - 1) + 8 + 3) & ~3;
     static_assert(D <= 16, "one 128-thread CTA covers d <= 16");
 };
 
@@ -62,13 +67,13 @@ irl_learner_cta_kernel(const LearnerParams<float> p, const PhiloxKeys rk, const 
     float* pis = ism + SMp::pis;
     float* z3p = ism + SMp::z3p;
     float* w3a = ism + SMp::w3a;
-    float* wf = w3a + 2 * D * D * 8;                        // the flat parameter vector
+    float* wf = w3a + SMp::w3size;                          // the flat parameter vector
     for (int k = tid; k < SMp::w3a; k += 128) ism[k] = 0.f;  // tiles (halos stay zero for the whole kernel)
     for (int k = tid; k < L.total; k += 128) wf[k] = net.params[k];
     __syncthreads();
     for (int k = tid; k < 2 * D * D * 8; k += 128) {
         const int row = k >> 3, j = k & 7;
-        w3a[k] = j < n3 ? wf[L.w3 + row * n3 + j] : 0.f;
+        w3a[SMp::w3row(row) + j] = j < n3 ? wf[L.w3 + row * n3 + j] : 0.f;
     }
     const float inv_keep = net.dropout ? 1.0f / net.keep_prob : 1.0f;
     // conv weights of this thread's use in registers
@@ -217,8 +222,8 @@ irl_learner_cta_kernel(const LearnerParams<float> p, const PhiloxKeys rk, const 
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (u < 2 || ok_b) {
-                        const float4 wlo = *reinterpret_cast<const float4*>(w3a + (kbase + u) * 8);
-                        const float4 whi = *reinterpret_cast<const float4*>(w3a + (kbase + u) * 8 + 4);
+                        const float4 wlo = *reinterpret_cast<const float4*>(w3a + SMp::w3row(kbase + u));
+                        const float4 whi = *reinterpret_cast<const float4*>(w3a + SMp::w3row(kbase + u) + 4);
                         z3[0] = fmaf(act[u], wlo.x, z3[0]); z3[1] = fmaf(act[u], wlo.y, z3[1]);
                         z3[2] = fmaf(act[u], wlo.z, z3[2]); z3[3] = fmaf(act[u], wlo.w, z3[3]);
                         z3[4] = fmaf(act[u], whi.x, z3[4]); z3[5] = fmaf(act[u], whi.y, z3[5]);

@@ -83,7 +83,7 @@ int rnet_grid(const dmfg_rnet_args* a, int* grid, size_t* smem_bytes, long long 
 template <int D>
 int launch_irl_learner(const LearnerParams<float>& p, const IrlLearnerNet& net, int noise_kind, cudaStream_t st) {
     const RnetLayout L = rnet_layout(D, net.n3, net.n4);
-    const size_t smem = (size_t)(IrlLearnerSmem<D>::w3a + 2 * D * D * 8 + L.total) * sizeof(float);
+    const size_t smem = (size_t)(IrlLearnerSmem<D>::w3a + IrlLearnerSmem<D>::w3size + L.total) * sizeof(float);
     if (noise_kind == DMFG_NOISE_PHILOX) {
         DMFG_CUDA(cudaFuncSetAttribute(irl_learner_cta_kernel<D, DMFG_NOISE_PHILOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         irl_learner_cta_kernel<D, DMFG_NOISE_PHILOX><<<(unsigned)p.L, 128, smem, st>>>(p, make_philox_keys(p.seed), net);
