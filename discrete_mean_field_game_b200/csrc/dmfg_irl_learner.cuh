@@ -9,10 +9,10 @@
 //     conv 5x5 + ReLU: thread (i, jp) computes outputs (i, 2jp), (i, 2jp+1)      -> second tile
 //     conv 3x3 (2 channels) + ReLU: the same two positions, both channels          (registers)
 //     fc3: each thread's 4 activations x its 4 rows of W3, block reduction of the n3 sums
-//     fc4 over [h3, pi] + ReLU, out + tanh: lanes 0..7 of warp 0; dropout masks from Philox keyed by the transition id,
+//     fc4 over [h3, pi] + ReLU, out + tanh: lanes 0..7 of every warp; dropout masks from Philox keyed by the transition id,
 //     exactly as rnet_kernel draws them (the reference's dropout is active at inference too, networks.py:70)
-// The reward enters the TD error through thread 0's partial of the block reduction.  Weights (15 KB) are staged in shared
-// memory once per CTA.  4 __syncthreads per transition.  Cumulative discount gamma^t on V(pi') and episodes counted from
+// The TD partial sums that do not depend on r cross the same barrier as the fc3 partial sums and every warp evaluates
+// the head itself.  Weights (15 KB) are staged in shared memory once per CTA.  3 __syncthreads per transition.  Cumulative discount gamma^t on V(pi') and episodes counted from
 // 1 are the caller's choice (discount_kind / episode0), as in the other learner kernels.
 // float streams, d <= 16 (d = 15 is AC_IRL's default), n_fc3, n_fc4 <= 8.
 #pragma once
@@ -35,8 +35,9 @@ struct IrlLearnerSmem {
     static constexpr int SP = 21, SC = 19;                 // odd row strides of the two zero-haloed tiles
     static constexpr int pt = 0;                            // [D+4][SP] action tile (halo 2)
     static constexpr int c1t = pt + 20 * SP;                // [D+2][SC] conv1 tile (halo 1)
-    static constexpr int pis = c1t + 18 * SC;               // [16] state
-    static constexpr int z3p = pis + 16;                    // [4 warps][8]
+    static constexpr int pis = c1t + 18 * SC;               // [2][16] state, double-buffered by step parity (the head reads it
+                                                            // after the last barrier of a step; the next step rewrites it)
+    static constexpr int z3p = pis + 32;                    // [4 warps][8]
     static constexpr int w3a = (z3p + 32 + 3) & ~3;         // [2 d^2][8] fc3 weights, 16-byte aligned rows (zero padded columns)
     // row r of W3 sits at 8 r + 4 (r / 4): thread (i, jp) reads rows 30 i + 4 jp + u, so without the skew the 8 lanes of
     // a quarter warp (one i, jp = 0..7) are 32 words apart -- the same banks, an 8-way conflict on every LDS.128 (ncu:
@@ -95,6 +96,7 @@ irl_learner_cta_kernel(const LearnerParams<float> p, const PhiloxKeys rk, const 
     const float scale = (float)(p.alpha_scale ? p.alpha_scale[l] : p.alpha_scale_scalar);
     const NoiseKey nk = make_noise_key(p.seed, (unsigned long long)(p.learner_offset + l));
     double pi_i = 0.0, pi_a = 0.0, pi_b = 0.0;
+    int par = 0;                                            // parity of the running step count (state double buffer)
     __syncthreads();
     for (int e = 0; e < p.E; ++e) {
         const int episode = p.episode0 + e;
@@ -161,7 +163,7 @@ irl_learner_cta_kernel(const LearnerParams<float> p, const PhiloxKeys rk, const 
                     Pt[(i + 2) * SP + ja + 2] = (float)yd0 * inv_f;
                     if (ok_b) Pt[(i + 2) * SP + jb + 2] = (float)yd1 * inv_f;
                 }
-                if (head) pis[i] = (float)pi_i;                       // rows >= D hold 0
+                if (head) pis[par * 16 + i] = (float)pi_i;        // rows >= D hold 0
             }
             // ---------------------------------------------------------------- pi'_j = sum_i q_i y_ij
             double ca = q * yd0, cb = q * yd1;
@@ -172,6 +174,20 @@ irl_learner_cta_kernel(const LearnerParams<float> p, const PhiloxKeys rk, const 
             }
             if (lane < PS) { colpart[warp][ja] = ca; colpart[warp][jb] = cb; }
             __syncthreads();                                                      // (1) P tile, pi, column partials
+            // dropout masks of this transition (lane m of every warp = unit m): drawn here, two barriers ahead of the head that
+            // uses them, so the two Philox chains run under the shared-memory latency of the conv phases
+            float m3 = 1.f, m4 = 1.f;
+            if (net.dropout == DMFG_DROPOUT_PHILOX) {
+                const int m = lane & 7;
+                const unsigned long long sid = net.sample_offset + (unsigned long long)et;
+                const uint32_t k0 = (uint32_t)net.seed, k1s = (uint32_t)(net.seed >> 32);
+                const uint4 wa = philox4x32_10((uint32_t)sid, (uint32_t)(sid >> 32), (uint32_t)(m >> 2), DMFG_CTR_DROPOUT, k0, k1s);
+                const uint4 wb = philox4x32_10((uint32_t)sid, (uint32_t)(sid >> 32), 64u + (uint32_t)(m >> 2), DMFG_CTR_DROPOUT, k0, k1s);
+                const uint32_t sa = (m & 3) == 0 ? wa.x : (m & 3) == 1 ? wa.y : (m & 3) == 2 ? wa.z : wa.w;
+                const uint32_t sb = (m & 3) == 0 ? wb.x : (m & 3) == 1 ? wb.y : (m & 3) == 2 ? wb.z : wb.w;
+                m3 = u01(sa) < net.keep_prob ? 1.f : 0.f;
+                m4 = u01(sb) < net.keep_prob ? 1.f : 0.f;
+            }
             double nx_i = 0.0, nx_a = 0.0, nx_b = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
@@ -240,22 +256,29 @@ irl_learner_cta_kernel(const LearnerParams<float> p, const PhiloxKeys rk, const 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) z3p[warp * 8 + j] = z3[j];
             }
-            __syncthreads();                                                      // (3) fc3 partial sums
-            // ---------------------------------------------------------------- fc4, out, tanh: lanes 0..7 of warp 0 (lane = unit)
-            float r = 0.f;
-            if (warp == 0) {
-                const int m = lane & 7;
-                float m3 = 1.f, m4 = 1.f;
-                if (net.dropout == DMFG_DROPOUT_PHILOX) {
-                    const unsigned long long sid = net.sample_offset + (unsigned long long)et;
-                    const uint32_t k0 = (uint32_t)net.seed, k1s = (uint32_t)(net.seed >> 32);
-                    const uint4 wa = philox4x32_10((uint32_t)sid, (uint32_t)(sid >> 32), (uint32_t)(m >> 2), DMFG_CTR_DROPOUT, k0, k1s);
-                    const uint4 wb = philox4x32_10((uint32_t)sid, (uint32_t)(sid >> 32), 64u + (uint32_t)(m >> 2), DMFG_CTR_DROPOUT, k0, k1s);
-                    const uint32_t sa = (m & 3) == 0 ? wa.x : (m & 3) == 1 ? wa.y : (m & 3) == 2 ? wa.z : wa.w;
-                    const uint32_t sb = (m & 3) == 0 ? wb.x : (m & 3) == 1 ? wb.y : (m & 3) == 2 ? wb.z : wb.w;
-                    m3 = u01(sa) < net.keep_prob ? 1.f : 0.f;
-                    m4 = u01(sb) < net.keep_prob ? 1.f : 0.f;
+            // ---------------------------------------------------------------- TD error with the CURRENT w: everything but r
+            // (gamma V(pi') - V(pi) and d log F / d theta do not depend on the reward net: their warp sums travel through the
+            // same barrier as the fc3 partial sums, and every warp then evaluates the small head itself -- no fourth barrier,
+            // no warp waiting for warp 0)
+            {
+                double vn = nx_i * fma(w_a, nx_a, w_b * nx_b);
+                double vc = pi_i * fma(w_a, pi_a, w_b * pi_b);
+                if (head) { vn = fma(w_lin, nx_i, vn); vc = fma(w_lin, pi_i, vc); }
+                if (tid == 0) { vn += w_bias; vc += w_bias; }
+                const double gfac = p.discount_kind == DMFG_DISCOUNT_STEP ? p.gamma : disc;
+                double dpart = fma(gfac, vn, -vc), gpart = glane;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    dpart += __shfl_xor_sync(0xffffffffu, dpart, o);
+                    gpart += __shfl_xor_sync(0xffffffffu, gpart, o);
                 }
+                if (lane == 0) { red[warp][0] = dpart; red[warp][1] = gpart; }
+            }
+            __syncthreads();                                                      // (3) fc3 partial sums, TD partial sums
+            // ---------------------------------------------------------------- fc4, out, tanh: every warp, lane % 8 = unit
+            float r = 0.f;
+            {
+                const int m = lane & 7;
                 // lane m holds h3[m]
                 float h3 = 0.f;
                 if (m < n3) {
@@ -263,37 +286,25 @@ irl_learner_cta_kernel(const LearnerParams<float> p, const PhiloxKeys rk, const 
                     h3 = fmaxf(z, 0.f) * m3 * inv_keep;
                 }
                 // lane m computes z4[m] = b4 + sum_j h3[j] W4[j][m] + sum_k pi_k W4[n3+k][m]
-                float z4 = m < n4 ? wf[L.b4 + m] : 0.f;
+                // (two independent chains: the h3 part and the state part; the state part does not wait for fc3)
+                float z4 = m < n4 ? wf[L.b4 + m] : 0.f, z4s = 0.f;
+                if (m < n4) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) z4s = fmaf(pis[par * 16 + k], wf[L.w4 + (n3 + k) * n4 + m], z4s);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float hj = __shfl_sync(0xffffffffu, h3, j);
                     if (j < n3 && m < n4) z4 = fmaf(hj, wf[L.w4 + j * n4 + m], z4);
                 }
-                if (m < n4) {
-#pragma unroll
-                    for (int k = 0; k < D; ++k) z4 = fmaf(pis[k], wf[L.w4 + (n3 + k) * n4 + m], z4);
-                }
+                z4 += z4s;
                 float part = m < n4 ? fmaxf(z4, 0.f) * m4 * inv_keep * wf[L.w5 + m] : 0.f;
                 part += __shfl_xor_sync(0xffffffffu, part, 1);
                 part += __shfl_xor_sync(0xffffffffu, part, 2);
                 part += __shfl_xor_sync(0xffffffffu, part, 4);
                 r = tanhf(part + wf[L.b5]);
             }
-            // ---------------------------------------------------------------- TD error with the CURRENT w
-            double vn = nx_i * fma(w_a, nx_a, w_b * nx_b);
-            double vc = pi_i * fma(w_a, pi_a, w_b * pi_b);
-            if (head) { vn = fma(w_lin, nx_i, vn); vc = fma(w_lin, pi_i, vc); }
-            if (tid == 0) { vn += w_bias; vc += w_bias; }
-            const double gfac = p.discount_kind == DMFG_DISCOUNT_STEP ? p.gamma : disc;
-            double dpart = fma(gfac, vn, -vc) + (tid == 0 ? (double)r : 0.0), gpart = glane;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                dpart += __shfl_xor_sync(0xffffffffu, dpart, o);
-                gpart += __shfl_xor_sync(0xffffffffu, gpart, o);
-            }
-            if (lane == 0) { red[warp][0] = dpart; red[warp][1] = gpart; }
-            __syncthreads();                                                      // (4) delta, grad
-            double delta = 0.0, grad = 0.0;
+            double delta = (double)r, grad = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) { delta += red[w][0]; grad += red[w][1]; }
             // critic first, then actor, both with the same delta (ac_irl.py:691-708)
@@ -311,6 +322,7 @@ irl_learner_cta_kernel(const LearnerParams<float> p, const PhiloxKeys rk, const 
                 total += (double)r;
             }
             disc *= p.gamma;
+            par ^= 1;
             pi_i = nx_i; pi_a = nx_a; pi_b = nx_b;
         }
         if (p.total_reward && tid == 0) p.total_reward[l * p.E + e] = total;

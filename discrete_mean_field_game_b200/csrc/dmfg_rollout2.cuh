@@ -512,7 +512,11 @@ struct LearnersV2Smem {
     static constexpr int qv = pid + 2 * GPB * G;
     static constexpr int pif = qv + GPB * G;                         // [2][GPB][G] floats
     static constexpr int wl = pif + GPB * G;                         // [GPB][NSLOT][G] doubles
-    static constexpr int total = wl + GPB * NSLOT * G;
+    // block of one learner; for G = 16 it is padded so that the two learners of a warp sit 16 (mod 32) words apart: with
+    // NSLOT * G doubles = 0 (mod 32) words both groups of a warp updated their slots through the SAME banks (ncu: 2
+    // wavefronts per STS.64 instead of 1, 9 % of the kernel's shared-memory traffic)
+    static constexpr int WLB = NSLOT * G + ((G == 16 && (NSLOT * G * 2) % 32 == 0) ? 8 : 0);
+    static constexpr int total = wl + GPB * WLB;
 };
 
 template <int D, int G, int NOISE>
@@ -530,13 +534,13 @@ learners_v2_kernel(const LearnerParams<float> p, const PhiloxKeys rk) {
     const uint32_t a_pid = sb + 8u * (S::pid + grp * G);
     const uint32_t a_pif = sb + 8u * S::pif + 4u * (grp * G);
     const uint32_t a_q = sb + 8u * (S::qv + grp * G);
-    const uint32_t a_wl_r = sb + 8u * (S::wl + grp * NSLOT * G + r);
+    const uint32_t a_wl_r = sb + 8u * (S::wl + grp * S::WLB + r);
     constexpr uint32_t kBufD = 8u * GPB * G, kBufF = 4u * GPB * G;
     const bool row_ok = r < D;
     long long l = (long long)blockIdx.x * GPB + grp;
     const bool live = l < p.L;
     if (!live) l = p.L - 1;
-    stage_critic_slots<D>(smem + S::wl + grp * NSLOT * G + r, G, p.w + l * F, r);      // lane r only ever reads its own column
+    stage_critic_slots<D>(smem + S::wl + grp * S::WLB + r, G, p.w + l * F, r);      // lane r only ever reads its own column
     double theta = p.theta[l];
     const float shift = (float)(p.shift ? p.shift[l] : p.shift_scalar);
     const float scale = (float)(p.alpha_scale ? p.alpha_scale[l] : p.alpha_scale_scalar);
@@ -644,7 +648,7 @@ learners_v2_kernel(const LearnerParams<float> p, const PhiloxKeys rk) {
     // write the private critic weights back in the reference's feature order
     constexpr int Q = D * (D + 1) / 2;
     double* wout = p.w + l * F;
-    const double* wl = smem + S::wl + grp * NSLOT * G + r;
+    const double* wl = smem + S::wl + grp * S::WLB + r;
     if (row_ok) {
 #pragma unroll
         for (int k = 0; k < D; ++k)
