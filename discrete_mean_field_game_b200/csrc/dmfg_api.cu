@@ -11,6 +11,7 @@
 #include "dmfg_error.h"
 #include "dmfg_rollout2.cuh"
 #include "dmfg_td_dmma.cuh"
+#include "dmfg_td_small.cuh"
 #include "dmfg_learner_cta.cuh"
 
 using namespace dmfg;
@@ -332,7 +333,18 @@ int run_td(const TdParams<R>& p0, double* acc, double* partials, cudaStream_t st
             DMFG_LAUNCHED();
         }
     }
-    if (!plan.use) {
+    bool small_done = false;
+    if constexpr (std::is_same<R, float>::value) {
+        if (!plan.use && (p.d == 15 || p.d == 16)) {
+            // small d: a thread per population, critic weights in shared memory (dmfg_td_small.cuh)
+            const unsigned grid = (unsigned)((p.B + kTdSmallThreads - 1) / kTdSmallThreads);
+            if (p.d == 15) td_delta_small_kernel<15><<<grid, kTdSmallThreads, 0, st>>>(p);
+            else td_delta_small_kernel<16><<<grid, kTdSmallThreads, 0, st>>>(p);
+            DMFG_LAUNCHED();
+            small_done = true;
+        }
+    }
+    if (!plan.use && !small_done) {
         const long long warps_needed = p.B;
         long long grid = (warps_needed + 3) / 4;
         if (grid > (long long)sms * 16) grid = (long long)sms * 16;
