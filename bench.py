@@ -541,6 +541,10 @@ def run_ours(args):
                     fn = lambda n=Bw: engine.rollout(piw[:n], THETA, SHIFT, ALPHA_SCALE, T, w=wd, seed=5, outputs=(),
                                                      want_acc=True)
                     fn(1 << 12); torch.cuda.synchronize()
+                    if dw <= 64:
+                        fn(); torch.cuda.synchronize()         # full-size warm-up: the first call allocates the 4.5 GB record
+                                                               # (cudaMalloc inside the timed region made this number jump
+                                                               # between 440 and 650 ms from run to run)
                     a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a_.record(); fn(); b_.record(); torch.cuda.synchronize()
                     ms = a_.elapsed_time(b_)
@@ -561,6 +565,8 @@ def run_ours(args):
                 dsd, dad = dsd[:15].reshape(-1, D).contiguous(), dad.reshape(-1, D, D)
                 with contextlib.redirect_stdout(sys.stderr):
                     irl.irl_step_batch(pii[:1 << 12], dsd, dad, Md, episode=1)
+                    torch.cuda.synchronize()
+                    irl.irl_step_batch(pii, dsd, dad, Md, episode=1)      # full-size warm-up: allocates the 15 GB record once
                     torch.cuda.synchronize()
                     a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a_.record(); irl.irl_step_batch(pii, dsd, dad, Md, episode=2); b_.record(); torch.cuda.synchronize()
