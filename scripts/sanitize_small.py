@@ -65,6 +65,10 @@ with contextlib.redirect_stdout(sys.stderr):
     ac.train_batch(np.float32(rng.dirichlet(np.ones(15), size=77)), num_episodes=1, T=3, lr_critic=0.1, lr_actor=0.01,
                    update="per_step")
     irl.train(max_episodes=3, stop_criteria=-1, verbose=False, use_graph=False)
+    # the record-based TD pass at d = 15 (td_delta_small_kernel + td_gw_kernel) through one data-parallel IRL step
+    irl_nd = AC_IRL(theta=8.64, shift=0, alpha_scale=1e4, d=15, reg="none", n_fc3=8, n_fc4=4,
+                    mat_pi0=g / g.sum(1, keepdims=True), demonstrations=[], device=dev, seed=1, net_seed=2)
+    irl_nd.irl_step_batch(np.float32(rng.dirichlet(np.ones(15), size=133)), ds[:15].reshape(-1, 15), da.reshape(-1, 15, 15), 24)
     for dd in (16, 21):
         gg = rng.standard_gamma(1.0, size=(8, dd))
         irl2 = AC_IRL(theta=8.64, shift=0, alpha_scale=1e4, d=dd, reg="none", n_fc3=6, n_fc4=3,
