@@ -520,6 +520,36 @@ def test_td_pass_on_fp64_tensor_cores_matches_numpy(dev, d, B, T, discount):
     np.testing.assert_allclose(N_(full["deltas"]), N_(td["deltas"]), rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("d,B,T", [(15, 1, 1), (15, 133, 15), (16, 257, 16), (15, 4097, 3)])
+@pytest.mark.parametrize("discount", ["step", "cumulative"])
+def test_td_pass_of_a_record_at_small_d_matches_numpy(dev, d, B, T, discount):
+    """dmfg_td_accumulate on a float32 record at d = 15 / 16 (td_delta_small_kernel: a thread per population, critic
+    weights in shared memory; then td_gw_kernel) against the float64 formulas of mfg_ac2.py:290-344, 505-514 / the
+    external rewards of ac_irl.py:683-700; ragged batch sizes, both discount conventions."""
+    rng = np.random.RandomState(7 * d + B)
+    F = O.num_features(d)
+    w = rng.randn(F)
+    pi0 = T_(rng.dirichlet(np.ones(d), size=B), dev, torch.float32)
+    rec = eng.rollout(pi0, 8.0, 0.1, 1e4, T, reward="none", seed=3, outputs=("states", "grads"))
+    r_ext = torch.as_tensor(rng.rand(T, B) - 0.5, dtype=torch.float32, device=dev)      # rewards as a reward net would give
+    gamma = 0.9
+    wd = torch.as_tensor(w, dtype=torch.float64, device=dev)
+    td = eng.td_accumulate(rec["states"], r_ext, rec["grads"], wd, gamma=gamma, discount=discount)
+    S, r, g = N_(rec["states"]), N_(r_ext), N_(rec["grads"])
+    phi = O.features(S)
+    V = phi @ w
+    gf = np.full(T, gamma) if discount == "step" else gamma ** np.arange(T)
+    delta = r + gf[:, None] * V[1:] - V[:-1]
+    vs = np.abs(V[1:]) + np.abs(V[:-1]) + np.abs(r)
+    assert np.all(np.abs(N_(td["deltas"]) - delta) <= 1e-6 * vs + 1e-12)       # deltas are stored in float
+    acc = N_(td["acc"])
+    G_w = np.einsum("tb,tbf->f", delta, phi[:-1])
+    scale = np.einsum("tb,tbf->f", np.abs(delta), np.abs(phi[:-1]))
+    assert np.all(np.abs(acc[1:1 + F] - G_w) <= 1e-10 * scale + 1e-15)
+    np.testing.assert_allclose(acc[0], np.sum(delta * g), rtol=1e-10)
+    np.testing.assert_allclose(acc[1 + F], np.sum(r), rtol=1e-12)
+
+
 @pytest.mark.parametrize("d", [21, 100, 200, 256])
 def test_wide_kernel_vs_oracle(dev, d):
     """rollout_wide_kernel (float streams, any d; 1 / 2 / 4 column pairs per lane, odd and maximum d) with injected
