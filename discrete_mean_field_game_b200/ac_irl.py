@@ -812,10 +812,9 @@ class AC_IRL(_actor_critic):
             if verbose:
                 print("Reward iteration %d" % it)
             self.update_reward(summary=False, iteration=self.reward_update_count)
-            ds = self._dev(np.asarray([p[0] for p in self.list_eval_demo_transitions], dtype=np.float32), torch.float32)
-            da = self._dev(np.asarray([p[1] for p in self.list_eval_demo_transitions], dtype=np.float32), torch.float32)
-            gs = self._dev(np.asarray([p[0] for p in self.list_eval_gen_transitions], dtype=np.float32), torch.float32)
-            ga = self._dev(np.asarray([p[1] for p in self.list_eval_gen_transitions], dtype=np.float32), torch.float32)
+            # (the flat transition lists are packed once and remembered, like the trajectories of update_reward)
+            ds, da = self._pack([self.list_eval_demo_transitions])
+            gs, ga = self._pack([self.list_eval_gen_transitions])
             reward_demo_avg = float(self._reward(ds, da).double().sum()) / len(self.list_eval_demo_transitions)
             reward_gen_avg = float(self._reward(gs, ga).double().sum()) / len(self.list_eval_gen_transitions)
             if verbose:
