@@ -114,6 +114,14 @@ class IrlGenArgs(C.Structure):
     ]
 
 
+class IrlStepArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("l1l2", C.c_int32), ("params", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+        ("step", C.c_int64), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+        ("reg_loss_out", C.c_void_p),
+    ]
+
+
 # every symbol include/dmfg.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("dmfg_version", C.c_int, []),
@@ -147,6 +155,8 @@ SYMBOLS = [
     ("dmfg_irl_loss_workspace_bytes", C.c_uint64, [C.c_int64]),
     ("dmfg_irl_loss_grad", C.c_int, [C.POINTER(IrlLossArgs), C.c_void_p]),
     ("dmfg_rnet_backward_gen", C.c_int, [C.POINTER(RnetArgs), C.POINTER(IrlGenArgs), C.c_void_p]),
+    ("dmfg_irl_reward_step", C.c_int, [C.POINTER(RnetArgs), C.POINTER(RnetArgs), C.POINTER(IrlGenArgs),
+                                       C.POINTER(IrlStepArgs), C.c_void_p]),
     ("dmfg_irl_dp_finalize", C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dmfg_adam_tf", C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64,
                                C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,

@@ -63,6 +63,7 @@ class AC_IRL(_actor_critic):
         self.summarize = summarize
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.dtype = torch.float32                       # the TF graph is float32 (ac_irl.py:239-246)
+        self.fused_reward_step = True                    # single-rank reward update through ONE C call (dmfg_irl_reward_step)
         self.group = None                                # process group of update_reward's all-reduce (None: the default
                                                          # group when torch.distributed is initialised; False: never)
         self.theta = theta
@@ -751,6 +752,20 @@ class AC_IRL(_actor_critic):
             return loss
         n_demo = demo_states.shape[0]
         d_const = self._demo_weight(n_demo, -1.0 / float(num_demo_traj))
+        if world == 1 and masks is None and not self.use_z and self.one_pass_reward_update and self.d <= 16 \
+                and n_demo > 0 and self.fused_reward_step:
+            # the whole update through one C call (dmfg_irl_reward_step): the same three launches chains as below
+            p.step += 1
+            grad, loss, reg = engine.irl_reward_step(
+                p.flat, p.m, p.v, p.step, self.lr_reward, demo_states, demo_actions, d_const, gen_states, gen_actions,
+                p.n_fc3, p.n_fc4, T_STEPS, num_demo_traj, layout=layout, keep_prob=networks.KEEP_PROB,
+                demo_seed=kd.get("seed"), demo_sample_offset=kd.get("sample_offset", 0),
+                gen_seed=kg.get("seed"), gen_sample_offset=kg.get("sample_offset", 0),
+                l1l2=self._l1l2, want_reg_loss=self._l1l2)
+            if reg is not None:
+                loss[0] += reg[0]
+            self._last_grad = grad
+            return loss
         grad, r_demo = engine.rnet_backward(p.flat, demo_states, demo_actions, d_const, p.n_fc3, p.n_fc4,
                                             keep_prob=networks.KEEP_PROB, want_rewards=True, **kd)
         if not self.use_z and self.one_pass_reward_update and self.d <= 16:

@@ -380,6 +380,36 @@ int dmfg_adam_tf(int64_t n, float* params, float* m, float* v, const float* grad
     return DMFG_OK;
 }
 
+int dmfg_irl_reward_step(const dmfg_rnet_args* demo, const dmfg_rnet_args* gen, const dmfg_irl_gen_args* g,
+                         const dmfg_irl_step_args* s, void* stream) {
+    if (!demo || !gen || !g || !s) return fail(DMFG_ERR_INVALID, "dmfg_irl_reward_step: NULL argument");
+    if (s->struct_size != sizeof(dmfg_irl_step_args)) return fail(DMFG_ERR_INVALID, "dmfg_irl_step_args.struct_size mismatch");
+    if (demo->struct_size != sizeof(dmfg_rnet_args) || gen->struct_size != sizeof(dmfg_rnet_args))
+        return fail(DMFG_ERR_INVALID, "dmfg_rnet_args.struct_size mismatch");
+    if (g->struct_size != sizeof(dmfg_irl_gen_args)) return fail(DMFG_ERR_INVALID, "dmfg_irl_gen_args.struct_size mismatch");
+    if (!s->params || s->params != demo->params || s->params != gen->params)
+        return fail(DMFG_ERR_INVALID, "dmfg_irl_reward_step: step->params, demo->params and gen->params must be one vector");
+    if (demo->d != gen->d || demo->n_fc3 != gen->n_fc3 || demo->n_fc4 != gen->n_fc4)
+        return fail(DMFG_ERR_INVALID, "dmfg_irl_reward_step: demo and gen describe different networks");
+    if (demo->N > 0 && !demo->rewards) return fail(DMFG_ERR_INVALID, "dmfg_irl_reward_step: demo->rewards (r_demo out) is required");
+    if (!demo->grad) return fail(DMFG_ERR_INVALID, "dmfg_irl_reward_step: demo->grad is required");
+    dmfg_rnet_args dm = *demo;
+    dm.accumulate = 0;
+    if (int rc = dmfg_rnet_backward(&dm, stream)) return rc;
+    dmfg_rnet_args gn = *gen;
+    gn.grad = demo->grad;
+    gn.accumulate = 1;
+    gn.workspace = demo->workspace;
+    gn.workspace_bytes = demo->workspace_bytes;
+    dmfg_irl_gen_args gg = *g;
+    gg.r_demo = demo->rewards;
+    gg.n_demo = demo->N;
+    if (int rc = dmfg_rnet_backward_gen(&gn, &gg, stream)) return rc;
+    const int64_t total = rnet_layout(demo->d, demo->n_fc3, demo->n_fc4).total;
+    return dmfg_adam_tf(total, s->params, s->m, s->v, demo->grad, 1.0, s->step, s->lr, s->beta1, s->beta2, s->eps, s->l1l2,
+                        demo->d, demo->n_fc3, demo->n_fc4, s->reg_loss_out, stream);
+}
+
 int dmfg_dirichlet_logq(int32_t d, int64_t N, int32_t K, const float* states, const float* actions,
                         const double* thetas, double shift, double* logq, void* stream) {
     if (d < 1 || d > DMFG_MAX_D || N < 0 || K < 1) return fail(DMFG_ERR_INVALID, "dmfg_dirichlet_logq: bad d/N/K");

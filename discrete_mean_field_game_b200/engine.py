@@ -714,6 +714,54 @@ def adam_tf(params, m, v, grad, step, lr, *, beta1=0.9, beta2=0.999, eps=1e-8, g
     return reg
 
 
+def irl_reward_step(params, m, v, step, lr, demo_states, demo_actions, demo_weight, gen_states, gen_actions, n_fc3, n_fc4, T,
+                    num_demo_traj, *, layout="time_major", keep_prob=0.4, demo_seed=None, demo_sample_offset=0,
+                    gen_seed=None, gen_sample_offset=0, beta1=0.9, beta2=0.999, eps=1e-8, l1l2=False, want_reg_loss=False):
+    """One whole reward update on one rank (AC_IRL.update_reward, ac_irl.py:804-846, z_j = 1) through ONE C call:
+    rnet_backward(demonstrations, dL/dr = demo_weight) -> rnet_backward_gen(generated) -> adam_tf, the same launches in the
+    same order as the three calls.  Returns (grad [P] float32, loss [4] float64 device, reg [1] float64 device or None)."""
+    from ._lib import IrlGenArgs, IrlStepArgs
+    lib = _lib.load()
+    device = demo_states.device
+    a, P = _rnet_args(params, demo_states, demo_actions, n_fc3, n_fc4, None, None, keep_prob, demo_seed, demo_sample_offset)
+    b, _ = _rnet_args(params, gen_states, gen_actions, n_fc3, n_fc4, None, None, keep_prob, gen_seed, gen_sample_offset)
+    n_demo, n_gen = demo_states.shape[0], gen_states.shape[0]
+    M = n_gen // int(T)
+    if M * int(T) != n_gen:
+        raise ValueError("%d transitions are not a multiple of T=%d" % (n_gen, T))
+    g = IrlGenArgs()
+    g.struct_size = C.sizeof(IrlGenArgs)
+    g.T, g.M = int(T), M
+    if layout == "time_major":
+        g.gen_t_stride, g.gen_j_stride = M, 1
+    elif layout == "trajectory_major":
+        g.gen_t_stride, g.gen_j_stride = 1, int(T)
+    else:
+        raise ValueError("layout must be 'time_major' or 'trajectory_major'")
+    g.num_demo_traj = float(num_demo_traj)
+    st = IrlStepArgs()
+    st.struct_size = C.sizeof(IrlStepArgs)
+    st.l1l2 = 1 if l1l2 else 0
+    for name, t in (("m", m), ("v", v)):
+        _require(t, name, device, torch.float32, (P,))
+    st.params, st.m, st.v = a.params, _ptr(m), _ptr(v)
+    st.step, st.lr, st.beta1, st.beta2, st.eps = int(step), float(lr), float(beta1), float(beta2), float(eps)
+    with _on(device):
+        grad = torch.empty(P, dtype=torch.float32, device=device)
+        r_demo = torch.empty(n_demo, dtype=torch.float32, device=device)
+        loss = torch.empty(4, dtype=torch.float64, device=device)
+        reg = torch.empty(1, dtype=torch.float64, device=device) if want_reg_loss else None
+        a.grad, a.rewards = _ptr(grad), _ptr(r_demo)
+        a.drewards = _ptr(_require(demo_weight, "demo_weight", device, torch.float32, (n_demo,)))
+        g.loss_out = _ptr(loss)
+        st.reg_loss_out = _ptr(reg)
+        ws = _workspace(device, lib.dmfg_rnet_workspace_bytes(C.byref(a)))
+        if ws is not None:
+            a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        check(lib.dmfg_irl_reward_step(C.byref(a), C.byref(b), C.byref(g), C.byref(st), _stream_ptr(device)))
+    return grad, loss, reg
+
+
 def dirichlet_logq(states, actions, thetas, shift):
     """logq[n,k] = sum_i ln Dir(a_n[i,:]; max(alpha_{theta_k}(s_n)[i,:], 1+1e-6))  (ac_irl.py:344-361)."""
     lib = _lib.load()

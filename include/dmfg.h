@@ -403,6 +403,29 @@ int dmfg_adam_tf(int64_t n, float* params, float* m, float* v, const float* grad
                  int64_t step, double lr, double beta1, double beta2, double eps,
                  int32_t l1l2, int32_t d, int32_t n_fc3, int32_t n_fc4, double* reg_loss_out, void* stream);
 
+/* ---- a12: ONE reward update in one call ------------------------------------ *
+ * AC_IRL.update_reward (ac_irl.py:804-846 -> :382-418) on one rank with z_j = 1: the chain
+ *   dmfg_rnet_backward(demo)  ->  dmfg_rnet_backward_gen(gen, g)  ->  dmfg_adam_tf(...)
+ * behind one entry point -- the same launches in the same order (bit-identical results), one trip through the host
+ * binding instead of three (a 5 + 5 trajectory update is host-bound: its two reward-net launches take 16 us each).
+ * demo: N demonstration transitions, drewards = the constant -1/num_demo_traj, rewards = r_demo out (required),
+ * grad = the gradient buffer of the whole step, workspace as for dmfg_rnet_backward.  gen: the generated
+ * transitions (its grad / accumulate / workspace fields are ignored: the step's buffers are used).  g: as for
+ * dmfg_rnet_backward_gen (r_demo / n_demo are taken from `demo`).  step: the Adam state; params must be the vector
+ * both `demo` and `gen` point at (it is updated in place AFTER the two reward-net launches). */
+typedef struct dmfg_irl_step_args {
+    uint32_t struct_size;
+    int32_t  l1l2;
+    float*   params;              /* in/out */
+    float*   m;
+    float*   v;
+    int64_t  step;                /* counts from 1 */
+    double   lr, beta1, beta2, eps;
+    double*  reg_loss_out;        /* optional (device double) */
+} dmfg_irl_step_args;
+int dmfg_irl_reward_step(const dmfg_rnet_args* demo, const dmfg_rnet_args* gen, const dmfg_irl_gen_args* g,
+                         const dmfg_irl_step_args* step, void* stream);
+
 /* ---- a13: Dirichlet log-density of recorded actions under K policies ------ *
  * calc_pdf_action / calc_z (ac_irl.py:270-379), in log space and without the `c`
  * normaliser: logq[n][k] = sum_i ln Dir(a_n[i,:]; max(alpha_{theta_k}(s_n)[i,:], 1+1e-6)).  */

@@ -505,3 +505,29 @@ def test_ac_irl_runs_at_d21_on_20x20_style_data(tmp_path, monkeypatch):
         assert np.abs(g - g_ref[2]).max() <= 3e-5 * np.abs(g_ref[2]).max() + 1e-6
         ac.train(max_episodes=2, stop_criteria=-1, lr_critic=0.1, lr_actor=0.01, verbose=False)
         assert np.isfinite(ac.theta) and ac.theta != 6.5 and np.isfinite(ac.w).all()
+
+
+@pytest.mark.parametrize("reg", ["none", "dropout_l1l2"])
+def test_reward_update_through_one_c_call_equals_the_three_call_chain(data, reg):
+    """update_reward on one rank goes through dmfg_irl_reward_step (rnet_backward -> rnet_backward_gen -> adam_tf behind one
+    entry point): the same launches in the same order as the three separate calls -- parameters, Adam moments, loss terms and
+    the gradient agree bit for bit over several updates, with and without the dropout / l1l2 regulariser."""
+    import random
+    outs = []
+    for fused in (True, False):
+        ac = make(data, reg=reg)
+        ac.fused_reward_step = fused
+        ac.list_generated = ac.generate_trajectories(12)
+        random.seed(7)
+        losses = []
+        for _ in range(4):
+            ac.update_reward()
+            losses.append((ac.loss_val, ac.first_term_val, ac.second_term_val))
+        p = ac.reward_params
+        outs.append((p.flat.clone(), p.m.clone(), p.v.clone(), ac._last_grad.clone(), losses, p.step))
+    a, b = outs
+    assert a[5] == b[5] == 4
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x, y)
+    assert a[4] == b[4]
+    assert not torch.equal(a[0], make(data, reg=reg).reward_params.flat)          # the parameters did move
