@@ -809,9 +809,26 @@ class AC_IRL(_actor_critic):
         else:
             gen_sampled = self.list_generated[:]
         ds, da, gs, ga = self._pack_pair(demo_sampled, gen_sampled)
-        loss = self.update_reward_batch(ds, da, gs, ga, self.num_demo_samples, "trajectory_major",
-                                        group=self.group).cpu().numpy()
-        self.loss_val, self.first_term_val, self.second_term_val = float(loss[0]), float(loss[1]), float(loss[2])
+        # the loss terms stay on the device until someone reads loss_val / first_term_val / second_term_val (the reference
+        # prints them every iter_check updates): no device-to-host synchronisation per update
+        self._loss_dev = self.update_reward_batch(ds, da, gs, ga, self.num_demo_samples, "trajectory_major", group=self.group)
+
+    def _loss_terms(self):
+        dev = self.__dict__.get("_loss_dev")
+        if dev is not None:
+            h = dev.cpu().numpy()
+            self._loss_host = (float(h[0]), float(h[1]), float(h[2]))
+            self._loss_dev = None
+        return self.__dict__.get("_loss_host", (float("nan"),) * 3)
+
+    def _set_loss_term(self, k, value):
+        t = list(self._loss_terms())
+        t[k] = float(value)
+        self._loss_host = tuple(t)
+
+    loss_val = property(lambda self: self._loss_terms()[0], lambda self, v: self._set_loss_term(0, v))
+    first_term_val = property(lambda self: self._loss_terms()[1], lambda self, v: self._set_loss_term(1, v))
+    second_term_val = property(lambda self: self._loss_terms()[2], lambda self, v: self._set_loss_term(2, v))
 
     def reward_iteration(self, max_iterations=500, stop_criteria=0.01, iter_check=10, verbose=True):
         """Reward updates with an evaluation / early-stop check every iter_check (ac_irl.py:849-897)."""
