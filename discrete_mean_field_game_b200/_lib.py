@@ -155,6 +155,7 @@ SYMBOLS = [
     ("dmfg_irl_loss_workspace_bytes", C.c_uint64, [C.c_int64]),
     ("dmfg_irl_loss_grad", C.c_int, [C.POINTER(IrlLossArgs), C.c_void_p]),
     ("dmfg_rnet_backward_gen", C.c_int, [C.POINTER(RnetArgs), C.POINTER(IrlGenArgs), C.c_void_p]),
+    ("dmfg_irl_reward_step_workspace_bytes", C.c_uint64, [C.POINTER(RnetArgs)]),
     ("dmfg_irl_reward_step", C.c_int, [C.POINTER(RnetArgs), C.POINTER(RnetArgs), C.POINTER(IrlGenArgs),
                                        C.POINTER(IrlStepArgs), C.c_void_p]),
     ("dmfg_irl_dp_finalize", C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -754,14 +754,15 @@ class AC_IRL(_actor_critic):
         d_const = self._demo_weight(n_demo, -1.0 / float(num_demo_traj))
         if world == 1 and masks is None and not self.use_z and self.one_pass_reward_update and self.d <= 16 \
                 and n_demo > 0 and self.fused_reward_step:
-            # the whole update through one C call (dmfg_irl_reward_step): the same three launches chains as below
+            # the whole update through one C call (dmfg_irl_reward_step): the two backward launches and ONE finishing launch
+            # (reductions, loss terms, Adam); fused_reward_step = "chain" keeps the six launches of the calls below
             p.step += 1
             grad, loss, reg = engine.irl_reward_step(
                 p.flat, p.m, p.v, p.step, self.lr_reward, demo_states, demo_actions, d_const, gen_states, gen_actions,
                 p.n_fc3, p.n_fc4, T_STEPS, num_demo_traj, layout=layout, keep_prob=networks.KEEP_PROB,
                 demo_seed=kd.get("seed"), demo_sample_offset=kd.get("sample_offset", 0),
                 gen_seed=kg.get("seed"), gen_sample_offset=kg.get("sample_offset", 0),
-                l1l2=self._l1l2, want_reg_loss=self._l1l2)
+                l1l2=self._l1l2, want_reg_loss=self._l1l2, finishing_launch=self.fused_reward_step != "chain")
             if reg is not None:
                 loss[0] += reg[0]
             self._last_grad = grad

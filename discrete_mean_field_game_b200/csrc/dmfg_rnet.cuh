@@ -88,6 +88,7 @@ struct RnetParams {
     long long traj_M, t_stride, j_stride;
     int traj_T;
     double* zpart;            // [grid] per-CTA sum_j exp(R_j)
+    double* rpart;            // [grid] per-CTA sum of the rewards it wrote (backward, not TRAJ), or null
 };
 
 // shared-memory map (in floats), identical on host and device
@@ -349,6 +350,8 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     static_assert(!TRAJ || BWD, "trajectory mode is a backward mode");
     __shared__ float rtraj[kRnetThreads / G];
     __shared__ double zsum;
+    __shared__ double rgrp[kRnetThreads / G];
+    double rsum = 0.0;                                        // this group's sum of rewards (p.rpart)
     using SM = RnetSmem<G, NP, BWD, DS>;
     constexpr int GPB = SM::GPB, SA = SM::SA, SC = SM::SC, RA = SM::RA, RC = SM::RC;
     constexpr int W = SM::DT;                                   // columns walked by the unrolled row loops (d <= W)
@@ -683,6 +686,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                 if (m < n4) z5 = fmaf(h4[m], wf[L.w5 + m], z5);
             const float r = tanhf(z5);
             if (p.rewards != nullptr && h == 0 && live) p.rewards[n] = r;
+            if (BWD && !TRAJ && p.rpart != nullptr && live) rsum += (double)r;
 
             if (BWD) {
                 float* Dt = Ct + RC * SC;                    // dz2 tile, 2 channels
@@ -924,8 +928,14 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     if (h == 0) {
 #pragma unroll
         for (int i = 0; i < 3 * NP + 1; ++i) smem[S.gsmall + grp * SM::NSMALL + i] = gsm[i];
+        rgrp[grp] = rsum;
     }
     __syncthreads();
+    if (!TRAJ && p.rpart != nullptr && tid == 0) {                     // groups in order: a fixed summation order
+        double s = 0.0;
+        for (int g = 0; g < GPB; ++g) s += rgrp[g];
+        p.rpart[blockIdx.x] = s;
+    }
     // conv slots: sum over all threads (warp w takes slots w, w+8, ...)
     {
         const int warp = tid >> 5, lane = tid & 31;
@@ -992,8 +1002,8 @@ rnet_reduce_partials_kernel(const float* __restrict__ partials, int ncta, int n,
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < kReduceSlices; ++k) s += sh[k][x];
-        if (scale != nullptr) s *= *scale;
-        grad[i] = accumulate ? grad[i] + s : s;
+        if (scale != nullptr) s = __fmul_rn(s, *scale);                // (explicit roundings: irl_step_finish_kernel repeats them)
+        grad[i] = accumulate ? __fadd_rn(grad[i], s) : s;
     }
 }
 
@@ -1169,20 +1179,93 @@ __global__ void __launch_bounds__(256) irl_loss_stage3_kernel(const IrlLossParam
 // caller from the step count; optional l1_l2 regulariser gradient sign(w) + w on [reg_begin, reg_end)
 // ranges (fc3 and fc4 weights, networks.py:69,74); grad_scale folds the 1/world of a data-parallel mean.
 // ---------------------------------------------------------------------------------------------------
-__global__ void adam_tf_kernel(int n, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                               const float* __restrict__ g, float grad_scale, float lr_t, float beta1, float beta2,
-                               float omb1, float omb2, float eps, int reg0_begin, int reg0_end, int reg1_begin, int reg1_end) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+struct AdamConsts {
+    float grad_scale, lr_t, beta1, beta2, omb1, omb2, eps;       // omb = 1 - beta rounded once from double
+    int reg0_begin, reg0_end, reg1_begin, reg1_end;
+};
+__device__ __forceinline__ void adam_tf_update(int i, float g, float* __restrict__ p, float* __restrict__ m,
+                                               float* __restrict__ v, const AdamConsts& c) {
     const float w = p[i];
-    float gi = g[i] * grad_scale;
-    if ((i >= reg0_begin && i < reg0_end) || (i >= reg1_begin && i < reg1_end))
-        gi += (w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f)) + w;
-    const float mi = beta1 * m[i] + omb1 * gi;       // omb = 1 - beta rounded once from double
-    const float vi = beta2 * v[i] + omb2 * gi * gi;
+    float gi = __fmul_rn(g, c.grad_scale);
+    if ((i >= c.reg0_begin && i < c.reg0_end) || (i >= c.reg1_begin && i < c.reg1_end))
+        gi = __fadd_rn(gi, __fadd_rn(w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f), w));
+    // every rounding spelled out: the stand-alone kernel and irl_step_finish_kernel must agree bit for bit
+    const float mi = __fadd_rn(__fmul_rn(c.beta1, m[i]), __fmul_rn(c.omb1, gi));
+    const float vi = __fadd_rn(__fmul_rn(c.beta2, v[i]), __fmul_rn(__fmul_rn(c.omb2, gi), gi));
     m[i] = mi;
     v[i] = vi;
-    p[i] = w - lr_t * mi / (sqrtf(vi) + eps);
+    p[i] = __fsub_rn(w, __fdiv_rn(__fmul_rn(c.lr_t, mi), __fadd_rn(sqrtf(vi), c.eps)));
+}
+__global__ void adam_tf_kernel(int n, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                               const float* __restrict__ g, const AdamConsts c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    adam_tf_update(i, g[i], p, m, v, c);
+}
+// Everything behind the two backward launches of a one-rank reward update (dmfg_irl_reward_step) in ONE launch: Z and the
+// demonstrations' reward sum from the per-CTA values, the loss terms (block 0), grad = sum_cta demo + (sum_cta gen) / Z and
+// the Adam step.  Block = 32 parameters x 8 slices; summation order and roundings are those of the chain
+//   rnet_reduce_partials (demo) -> irl_gen_finalize -> rnet_reduce_partials (gen, 1/Z, accumulate) -> adam_tf
+// so parameters, moments and gradient come out bit-identical to it; the first loss term sums per-CTA reward sums instead
+// of walking r_demo and agrees to the last bits of a double only.  ncta_d, ncta_g <= 32 * kReduceSlices.
+__global__ void __launch_bounds__(32 * kReduceSlices)
+irl_step_finish_kernel(const float* __restrict__ pd, int ncta_d, const float* __restrict__ pg, int ncta_g, int n,
+                       const double* __restrict__ zpart, const double* __restrict__ rpart, double num_demo_traj,
+                       long long M, double* __restrict__ loss_out, float* __restrict__ grad, float* __restrict__ p,
+                       float* __restrict__ m, float* __restrict__ v, const AdamConsts c) {
+    __shared__ float shd[kReduceSlices][33], shg[kReduceSlices][33];
+    __shared__ double shz[kReduceSlices], shr[kReduceSlices];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + x;
+    float d0 = 0.f, d1 = 0.f, g0 = 0.f, g1 = 0.f;
+    if (i < n) {
+        int k = y;
+        for (; k + kReduceSlices < ncta_d; k += 2 * kReduceSlices) {
+            d0 += pd[(long long)k * n + i];
+            d1 += pd[(long long)(k + kReduceSlices) * n + i];
+        }
+        if (k < ncta_d) d0 += pd[(long long)k * n + i];
+        k = y;
+        for (; k + kReduceSlices < ncta_g; k += 2 * kReduceSlices) {
+            g0 += pg[(long long)k * n + i];
+            g1 += pg[(long long)(k + kReduceSlices) * n + i];
+        }
+        if (k < ncta_g) g0 += pg[(long long)k * n + i];
+    }
+    shd[y][x] = d0 + d1;
+    shg[y][x] = g0 + g1;
+    double z = (int)threadIdx.x < ncta_g ? zpart[threadIdx.x] : 0.0;
+    double r = (int)threadIdx.x < ncta_d ? rpart[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        z += __shfl_xor_sync(0xffffffffu, z, o);
+        r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    if (x == 0) { shz[y] = z; shr[y] = r; }
+    __syncthreads();
+    if (y != 0) return;
+    double Z = 0.0;
+#pragma unroll
+    for (int k = 0; k < kReduceSlices; ++k) Z += shz[k];
+    if (i < n) {
+        float sd = 0.f, sg = 0.f;
+#pragma unroll
+        for (int k = 0; k < kReduceSlices; ++k) { sd += shd[k][x]; sg += shg[k][x]; }
+        const float gi = __fadd_rn(sd, __fmul_rn(sg, (float)(1.0 / Z)));
+        grad[i] = gi;
+        adam_tf_update(i, gi, p, m, v, c);
+    }
+    if (blockIdx.x == 0 && x == 0) {
+        double sr = 0.0;
+        for (int k = 0; k < kReduceSlices; ++k) sr += shr[k];
+        const double first = -sr / num_demo_traj;
+        const double lse = log(Z);
+        const double second = lse - log((double)M);
+        loss_out[0] = first + second;
+        loss_out[1] = first;
+        loss_out[2] = second;
+        loss_out[3] = lse;
+    }
 }
 // sum |w| + w^2/2 over the two regularised ranges -> out[0] (double); single block
 __global__ void __launch_bounds__(256) reg_loss_kernel(const float* __restrict__ p, int b0, int e0, int b1, int e1,

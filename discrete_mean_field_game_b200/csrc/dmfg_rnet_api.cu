@@ -53,7 +53,7 @@ RnetParams make_params(const dmfg_rnet_args* a) {
     p.dropout = a->dropout; p.keep_prob = a->keep_prob; p.mask3 = a->mask3; p.mask4 = a->mask4;
     p.seed = a->seed; p.sample_offset = a->sample_offset;
     p.rewards = a->rewards; p.drewards = a->drewards; p.partials = nullptr;
-    p.traj_M = 0; p.t_stride = 0; p.j_stride = 0; p.traj_T = 0; p.zpart = nullptr;
+    p.traj_M = 0; p.t_stride = 0; p.j_stride = 0; p.traj_T = 0; p.zpart = nullptr; p.rpart = nullptr;
     return p;
 }
 
@@ -101,6 +101,88 @@ void reg_ranges(int l1l2, int d, int n3, int n4, int* b0, int* e0, int* b1, int*
     const RnetLayout L = rnet_layout(d, n3, n4);
     *b0 = L.w3; *e0 = L.b3;
     *b1 = L.w4; *e1 = L.b4;
+}
+
+// the backward launch for the shape of `a` (demonstration form: dL/dr from p.drewards)
+int launch_rnet_backward(const dmfg_rnet_args* a, const RnetParams& p, cudaStream_t st, int* grid_out) {
+    int grid = 0;
+    size_t smem = 0;
+    // the reference's default shape (d = 15, n_fc3 = 8, n_fc4 = 4) with every size a compile-time constant (fits the
+    // 255 registers without spills since the fc3 weight gradient moved to the tensor cores); d = 15 with other widths;
+    // everything else from the arguments
+    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) {
+        if (int rc = rnet_grid<true, 15, 8, 4>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, true, 15, 8, 4><<<grid, kRnetThreads, smem, st>>>(p);
+    } else if (a->d == 15) {
+        if (int rc = rnet_grid<true, 15, 0, 0>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, true, 15, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
+    } else if (a->d <= kG) {
+        if (int rc = rnet_grid<true, 0, 0, 0>(a, &grid, &smem)) return rc;
+        rnet_kernel<kG, kNP, true, 0, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
+    } else if (a->d == 20) {
+        if (int rc = rnet_grid<true, 20, 0, 0, false, 32>(a, &grid, &smem)) return rc;
+        rnet_kernel<32, kNP, true, 20, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
+    } else {
+        if (int rc = rnet_grid<true, 21, 0, 0, false, 32>(a, &grid, &smem)) return rc;
+        rnet_kernel<32, kNP, true, 21, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
+    }
+    DMFG_LAUNCHED();
+    *grid_out = grid;
+    return DMFG_OK;
+}
+
+// the trajectory-mode backward launch (generated half of the one-pass update, d <= 16)
+int launch_rnet_backward_gen(const dmfg_rnet_args* a, const RnetParams& p, long long M, cudaStream_t st, int* grid_out) {
+    int grid = 0;
+    size_t smem = 0;
+    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) {
+        if (int rc = rnet_grid<true, 15, 8, 4, true>(a, &grid, &smem, M)) return rc;
+        rnet_kernel<kG, kNP, true, 15, 8, 4, true><<<grid, kRnetThreads, smem, st>>>(p);
+    } else if (a->d == 15) {
+        if (int rc = rnet_grid<true, 15, 0, 0, true>(a, &grid, &smem, M)) return rc;
+        rnet_kernel<kG, kNP, true, 15, 0, 0, true><<<grid, kRnetThreads, smem, st>>>(p);
+    } else {
+        if (int rc = rnet_grid<true, 0, 0, 0, true>(a, &grid, &smem, M)) return rc;
+        rnet_kernel<kG, kNP, true, 0, 0, 0, true><<<grid, kRnetThreads, smem, st>>>(p);
+    }
+    DMFG_LAUNCHED();
+    *grid_out = grid;
+    return DMFG_OK;
+}
+
+int check_gen(const dmfg_rnet_args* a, const dmfg_irl_gen_args* g) {
+    if (!g) return fail(DMFG_ERR_INVALID, "gen args is NULL");
+    if (g->struct_size != sizeof(dmfg_irl_gen_args)) return fail(DMFG_ERR_INVALID, "dmfg_irl_gen_args.struct_size mismatch");
+    if (!a || a->struct_size != sizeof(dmfg_rnet_args)) return fail(DMFG_ERR_INVALID, "dmfg_rnet_args missing / struct_size mismatch");
+    if (g->T < 1 || g->T > kRnetThreads / kG)
+        return fail(DMFG_ERR_UNSUPPORTED, "the one-pass update holds a trajectory of T <= %d transitions per CTA (T = %d)",
+                    kRnetThreads / kG, g->T);
+    if (a && a->d > kG)
+        return fail(DMFG_ERR_UNSUPPORTED, "the one-pass update is built for d <= %d (16 lanes per transition, a trajectory per CTA): "
+                    "use dmfg_rnet_forward -> dmfg_irl_loss_grad -> dmfg_rnet_backward at d = %d", kG, a->d);
+    if (g->M < 1 || g->n_demo < 0 || !(g->num_demo_traj > 0)) return fail(DMFG_ERR_INVALID, "bad M/n_demo/num_demo_traj");
+    if (a->N != g->M * (int64_t)g->T) return fail(DMFG_ERR_INVALID, "N must be M*T");
+    if (!((g->gen_t_stride == g->M && g->gen_j_stride == 1) || (g->gen_t_stride == 1 && g->gen_j_stride == g->T)))
+        return fail(DMFG_ERR_INVALID, "strides must be (M,1) time-major or (1,T) trajectory-major");
+    if (!g->loss_out || (g->n_demo > 0 && !g->r_demo)) return fail(DMFG_ERR_INVALID, "loss_out / r_demo are required");
+    return check_rnet(a, true, /*need_drewards=*/false);      // dL/dr is formed in the kernel
+}
+
+int adam_consts(int64_t n, int64_t step, double lr, double beta1, double beta2, double eps, int32_t l1l2, int32_t d,
+                int32_t n_fc3, int32_t n_fc4, bool want_reg_loss, AdamConsts* c, int* rb) {
+    if (step < 1) return fail(DMFG_ERR_INVALID, "dmfg_adam_tf: step counts from 1");
+    if (n > INT32_MAX) return fail(DMFG_ERR_UNSUPPORTED, "dmfg_adam_tf: n too large");
+    if (l1l2 || want_reg_loss) {
+        if (d < 1 || n_fc3 < 1 || n_fc4 < 1 || rnet_layout(d, n_fc3, n_fc4).total != n)
+            return fail(DMFG_ERR_INVALID, "dmfg_adam_tf: l1l2 needs (d, n_fc3, n_fc4) matching n");
+    }
+    reg_ranges(l1l2 || want_reg_loss, d, n_fc3, n_fc4, &rb[0], &rb[1], &rb[2], &rb[3]);      // the regulariser value's ranges
+    const double lr_t = lr * std::sqrt(1.0 - std::pow(beta2, (double)step)) / (1.0 - std::pow(beta1, (double)step));
+    c->grad_scale = 1.f; c->lr_t = (float)lr_t; c->beta1 = (float)beta1; c->beta2 = (float)beta2;
+    c->omb1 = (float)(1.0 - beta1); c->omb2 = (float)(1.0 - beta2); c->eps = (float)eps;
+    c->reg0_begin = l1l2 ? rb[0] : 0; c->reg0_end = l1l2 ? rb[1] : 0;
+    c->reg1_begin = l1l2 ? rb[2] : 0; c->reg1_end = l1l2 ? rb[3] : 0;
+    return DMFG_OK;
 }
 
 }  // namespace
@@ -171,50 +253,16 @@ int dmfg_rnet_backward(const dmfg_rnet_args* a, void* stream) {
         return fail(DMFG_ERR_WORKSPACE, "workspace of %llu bytes needed, %llu given", (unsigned long long)need,
                     (unsigned long long)(a->workspace ? a->workspace_bytes : 0));
     int grid = 0;
-    size_t smem = 0;
     RnetParams p = make_params(a);
     p.partials = (float*)a->workspace;
-    // the reference's default shape (d = 15, n_fc3 = 8, n_fc4 = 4) with every size a compile-time constant (fits the
-    // 255 registers without spills since the fc3 weight gradient moved to the tensor cores); d = 15 with other widths;
-    // everything else from the arguments
-    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) {
-        if (int rc = rnet_grid<true, 15, 8, 4>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, true, 15, 8, 4><<<grid, kRnetThreads, smem, st>>>(p);
-    } else if (a->d == 15) {
-        if (int rc = rnet_grid<true, 15, 0, 0>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, true, 15, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
-    } else if (a->d <= kG) {
-        if (int rc = rnet_grid<true, 0, 0, 0>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, true, 0, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
-    } else if (a->d == 20) {
-        if (int rc = rnet_grid<true, 20, 0, 0, false, 32>(a, &grid, &smem)) return rc;
-        rnet_kernel<32, kNP, true, 20, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
-    } else {
-        if (int rc = rnet_grid<true, 21, 0, 0, false, 32>(a, &grid, &smem)) return rc;
-        rnet_kernel<32, kNP, true, 21, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
-    }
-    DMFG_LAUNCHED();
+    if (int rc = launch_rnet_backward(a, p, st, &grid)) return rc;
     rnet_reduce_partials_kernel<<<(total + 31) / 32, 32 * kReduceSlices, 0, st>>>(p.partials, grid, total, a->accumulate, a->grad);
     DMFG_LAUNCHED();
     return DMFG_OK;
 }
 
 int dmfg_rnet_backward_gen(const dmfg_rnet_args* a, const dmfg_irl_gen_args* g, void* stream) {
-    if (!g) return fail(DMFG_ERR_INVALID, "gen args is NULL");
-    if (g->struct_size != sizeof(dmfg_irl_gen_args)) return fail(DMFG_ERR_INVALID, "dmfg_irl_gen_args.struct_size mismatch");
-    if (!a || a->struct_size != sizeof(dmfg_rnet_args)) return fail(DMFG_ERR_INVALID, "dmfg_rnet_args missing / struct_size mismatch");
-    if (g->T < 1 || g->T > kRnetThreads / kG)
-        return fail(DMFG_ERR_UNSUPPORTED, "the one-pass update holds a trajectory of T <= %d transitions per CTA (T = %d)",
-                    kRnetThreads / kG, g->T);
-    if (a && a->d > kG)
-        return fail(DMFG_ERR_UNSUPPORTED, "the one-pass update is built for d <= %d (16 lanes per transition, a trajectory per CTA): "
-                    "use dmfg_rnet_forward -> dmfg_irl_loss_grad -> dmfg_rnet_backward at d = %d", kG, a->d);
-    if (g->M < 1 || g->n_demo < 0 || !(g->num_demo_traj > 0)) return fail(DMFG_ERR_INVALID, "bad M/n_demo/num_demo_traj");
-    if (a->N != g->M * (int64_t)g->T) return fail(DMFG_ERR_INVALID, "N must be M*T");
-    if (!((g->gen_t_stride == g->M && g->gen_j_stride == 1) || (g->gen_t_stride == 1 && g->gen_j_stride == g->T)))
-        return fail(DMFG_ERR_INVALID, "strides must be (M,1) time-major or (1,T) trajectory-major");
-    if (!g->loss_out || (g->n_demo > 0 && !g->r_demo)) return fail(DMFG_ERR_INVALID, "loss_out / r_demo are required");
-    if (int rc = check_rnet(a, true, /*need_drewards=*/false)) return rc;      // dL/dr is formed in the kernel
+    if (int rc = check_gen(a, g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int total = rnet_layout(a->d, a->n_fc3, a->n_fc4).total;
     const uint64_t need = dmfg_rnet_workspace_bytes(a);
@@ -228,18 +276,7 @@ int dmfg_rnet_backward_gen(const dmfg_rnet_args* a, const dmfg_irl_gen_args* g, 
     float* inv_z = (float*)(tail + align_up((uint64_t)kMaxRnetCtas * 8));
     p.traj_M = g->M; p.traj_T = g->T; p.t_stride = g->gen_t_stride; p.j_stride = g->gen_j_stride;
     int grid = 0;
-    size_t smem = 0;
-    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) {
-        if (int rc = rnet_grid<true, 15, 8, 4, true>(a, &grid, &smem, g->M)) return rc;
-        rnet_kernel<kG, kNP, true, 15, 8, 4, true><<<grid, kRnetThreads, smem, st>>>(p);
-    } else if (a->d == 15) {
-        if (int rc = rnet_grid<true, 15, 0, 0, true>(a, &grid, &smem, g->M)) return rc;
-        rnet_kernel<kG, kNP, true, 15, 0, 0, true><<<grid, kRnetThreads, smem, st>>>(p);
-    } else {
-        if (int rc = rnet_grid<true, 0, 0, 0, true>(a, &grid, &smem, g->M)) return rc;
-        rnet_kernel<kG, kNP, true, 0, 0, 0, true><<<grid, kRnetThreads, smem, st>>>(p);
-    }
-    DMFG_LAUNCHED();
+    if (int rc = launch_rnet_backward_gen(a, p, g->M, st, &grid)) return rc;
     irl_gen_finalize_kernel<<<1, 1024, 0, st>>>(p.zpart, grid, g->r_demo, g->n_demo, g->num_demo_traj, g->M, g->loss_out, inv_z,
                                                 g->local_sums ? 0 : 1);
     DMFG_LAUNCHED();
@@ -357,27 +394,27 @@ int dmfg_adam_tf(int64_t n, float* params, float* m, float* v, const float* grad
                  double lr, double beta1, double beta2, double eps, int32_t l1l2, int32_t d, int32_t n_fc3,
                  int32_t n_fc4, double* reg_loss_out, void* stream) {
     if (n < 0 || (n > 0 && (!params || !m || !v || !grad))) return fail(DMFG_ERR_INVALID, "dmfg_adam_tf: bad argument");
-    if (step < 1) return fail(DMFG_ERR_INVALID, "dmfg_adam_tf: step counts from 1");
-    if (n > INT32_MAX) return fail(DMFG_ERR_UNSUPPORTED, "dmfg_adam_tf: n too large");
-    int b0, e0, b1, e1;
-    if (l1l2 || reg_loss_out) {
-        if (d < 1 || n_fc3 < 1 || n_fc4 < 1 || rnet_layout(d, n_fc3, n_fc4).total != n)
-            return fail(DMFG_ERR_INVALID, "dmfg_adam_tf: l1l2 needs (d, n_fc3, n_fc4) matching n");
-    }
-    reg_ranges(l1l2 || reg_loss_out, d, n_fc3, n_fc4, &b0, &e0, &b1, &e1);
+    AdamConsts c;
+    int rb[4];
+    if (int rc = adam_consts(n, step, lr, beta1, beta2, eps, l1l2, d, n_fc3, n_fc4, reg_loss_out != nullptr, &c, rb)) return rc;
+    c.grad_scale = (float)grad_scale;
     cudaStream_t st = (cudaStream_t)stream;
     if (reg_loss_out) {
-        reg_loss_kernel<<<1, 256, 0, st>>>(params, b0, e0, b1, e1, reg_loss_out);
+        reg_loss_kernel<<<1, 256, 0, st>>>(params, rb[0], rb[1], rb[2], rb[3], reg_loss_out);
         DMFG_LAUNCHED();
     }
-    if (!l1l2) b0 = e0 = b1 = e1 = 0;
     if (n == 0) return DMFG_OK;
-    const double lr_t = lr * std::sqrt(1.0 - std::pow(beta2, (double)step)) / (1.0 - std::pow(beta1, (double)step));
-    adam_tf_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>((int)n, params, m, v, grad, (float)grad_scale, (float)lr_t,
-                                                        (float)beta1, (float)beta2, (float)(1.0 - beta1),
-                                                        (float)(1.0 - beta2), (float)eps, b0, e0, b1, e1);
+    adam_tf_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>((int)n, params, m, v, grad, c);
     DMFG_LAUNCHED();
     return DMFG_OK;
+}
+
+uint64_t dmfg_irl_reward_step_workspace_bytes(const dmfg_rnet_args* a) {
+    const uint64_t one = dmfg_rnet_workspace_bytes(a);
+    if (!one) return 0;
+    // two sets of per-CTA partial gradients (demonstrations, generated), per-CTA sums of exp(R_j) and of r_demo
+    return one + align_up((uint64_t)kMaxRnetCtas * (uint64_t)rnet_layout(a->d, a->n_fc3, a->n_fc4).total * sizeof(float)) +
+           align_up((uint64_t)kMaxRnetCtas * 8);
 }
 
 int dmfg_irl_reward_step(const dmfg_rnet_args* demo, const dmfg_rnet_args* gen, const dmfg_irl_gen_args* g,
@@ -393,6 +430,60 @@ int dmfg_irl_reward_step(const dmfg_rnet_args* demo, const dmfg_rnet_args* gen, 
         return fail(DMFG_ERR_INVALID, "dmfg_irl_reward_step: demo and gen describe different networks");
     if (demo->N > 0 && !demo->rewards) return fail(DMFG_ERR_INVALID, "dmfg_irl_reward_step: demo->rewards (r_demo out) is required");
     if (!demo->grad) return fail(DMFG_ERR_INVALID, "dmfg_irl_reward_step: demo->grad is required");
+    const int64_t total = rnet_layout(demo->d, demo->n_fc3, demo->n_fc4).total;
+    cudaStream_t st = (cudaStream_t)stream;
+    // Fast form (both halves non-empty, a workspace of dmfg_irl_reward_step_workspace_bytes): the two backward launches
+    // write their per-CTA partial gradients side by side and ONE launch does what the chain's two reductions, the loss
+    // kernel and the Adam kernel do (irl_step_finish_kernel) -- same summation order and roundings, six launches -> three.
+    if (demo->N > 0 && demo->workspace && demo->workspace_bytes >= dmfg_irl_reward_step_workspace_bytes(demo) &&
+        !g->local_sums) {
+        if (int rc = check_rnet(demo, true)) return rc;
+        dmfg_irl_gen_args gg = *g;
+        gg.r_demo = demo->rewards;
+        gg.n_demo = demo->N;
+        dmfg_rnet_args gn = *gen;
+        gn.grad = demo->grad;
+        if (int rc = check_gen(&gn, &gg)) return rc;
+        AdamConsts c;
+        int rb[4];
+        if (int rc = adam_consts(total, s->step, s->lr, s->beta1, s->beta2, s->eps, s->l1l2, demo->d, demo->n_fc3,
+                                 demo->n_fc4, s->reg_loss_out != nullptr, &c, rb)) return rc;
+        if (!s->m || !s->v) return fail(DMFG_ERR_INVALID, "dmfg_irl_reward_step: m / v are NULL");
+        const uint64_t part_bytes = align_up((uint64_t)kMaxRnetCtas * (uint64_t)total * sizeof(float));
+        char* ws = (char*)demo->workspace;
+        RnetParams pd = make_params(demo);
+        pd.partials = (float*)ws;
+        pd.rpart = (double*)(ws + 2 * part_bytes + align_up((uint64_t)kMaxRnetCtas * 8));
+        RnetParams pg = make_params(&gn);
+        pg.partials = (float*)(ws + part_bytes);
+        pg.zpart = (double*)(ws + 2 * part_bytes);
+        pg.traj_M = gg.M; pg.traj_T = gg.T; pg.t_stride = gg.gen_t_stride; pg.j_stride = gg.gen_j_stride;
+        if (s->reg_loss_out) {                                 // the regulariser value BEFORE the step
+            reg_loss_kernel<<<1, 256, 0, st>>>(s->params, rb[0], rb[1], rb[2], rb[3], s->reg_loss_out);
+            DMFG_LAUNCHED();
+        }
+        int grid_d = 0, grid_g = 0;
+        if (int rc = launch_rnet_backward(demo, pd, st, &grid_d)) return rc;
+        if (int rc = launch_rnet_backward_gen(&gn, pg, gg.M, st, &grid_g)) return rc;
+        if (grid_d <= 32 * kReduceSlices && grid_g <= 32 * kReduceSlices) {
+            irl_step_finish_kernel<<<(int)((total + 31) / 32), 32 * kReduceSlices, 0, st>>>(
+                pd.partials, grid_d, pg.partials, grid_g, (int)total, pg.zpart, pd.rpart, gg.num_demo_traj, gg.M, gg.loss_out,
+                demo->grad, s->params, s->m, s->v, c);
+            DMFG_LAUNCHED();
+            return DMFG_OK;
+        }
+        // (more CTAs than the finishing block has threads: finish with the chain's own kernels)
+        float* inv_z = (float*)(ws + 2 * part_bytes + 2 * align_up((uint64_t)kMaxRnetCtas * 8));
+        rnet_reduce_partials_kernel<<<(int)((total + 31) / 32), 32 * kReduceSlices, 0, st>>>(pd.partials, grid_d, (int)total, 0, demo->grad);
+        DMFG_LAUNCHED();
+        irl_gen_finalize_kernel<<<1, 1024, 0, st>>>(pg.zpart, grid_g, gg.r_demo, gg.n_demo, gg.num_demo_traj, gg.M, gg.loss_out, inv_z, 1);
+        DMFG_LAUNCHED();
+        rnet_reduce_partials_kernel<<<(int)((total + 31) / 32), 32 * kReduceSlices, 0, st>>>(pg.partials, grid_g, (int)total, 1, demo->grad, inv_z);
+        DMFG_LAUNCHED();
+        adam_tf_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>((int)total, s->params, s->m, s->v, demo->grad, c);
+        DMFG_LAUNCHED();
+        return DMFG_OK;
+    }
     dmfg_rnet_args dm = *demo;
     dm.accumulate = 0;
     if (int rc = dmfg_rnet_backward(&dm, stream)) return rc;
@@ -405,7 +496,6 @@ int dmfg_irl_reward_step(const dmfg_rnet_args* demo, const dmfg_rnet_args* gen, 
     gg.r_demo = demo->rewards;
     gg.n_demo = demo->N;
     if (int rc = dmfg_rnet_backward_gen(&gn, &gg, stream)) return rc;
-    const int64_t total = rnet_layout(demo->d, demo->n_fc3, demo->n_fc4).total;
     return dmfg_adam_tf(total, s->params, s->m, s->v, demo->grad, 1.0, s->step, s->lr, s->beta1, s->beta2, s->eps, s->l1l2,
                         demo->d, demo->n_fc3, demo->n_fc4, s->reg_loss_out, stream);
 }

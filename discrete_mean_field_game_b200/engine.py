@@ -716,10 +716,11 @@ def adam_tf(params, m, v, grad, step, lr, *, beta1=0.9, beta2=0.999, eps=1e-8, g
 
 def irl_reward_step(params, m, v, step, lr, demo_states, demo_actions, demo_weight, gen_states, gen_actions, n_fc3, n_fc4, T,
                     num_demo_traj, *, layout="time_major", keep_prob=0.4, demo_seed=None, demo_sample_offset=0,
-                    gen_seed=None, gen_sample_offset=0, beta1=0.9, beta2=0.999, eps=1e-8, l1l2=False, want_reg_loss=False):
+                    gen_seed=None, gen_sample_offset=0, beta1=0.9, beta2=0.999, eps=1e-8, l1l2=False, want_reg_loss=False,
+                    finishing_launch=True):
     """One whole reward update on one rank (AC_IRL.update_reward, ac_irl.py:804-846, z_j = 1) through ONE C call:
-    rnet_backward(demonstrations, dL/dr = demo_weight) -> rnet_backward_gen(generated) -> adam_tf, the same launches in the
-    same order as the three calls.  Returns (grad [P] float32, loss [4] float64 device, reg [1] float64 device or None)."""
+    rnet_backward(demonstrations, dL/dr = demo_weight) -> rnet_backward_gen(generated) -> adam_tf, with everything behind the
+    two backward launches (reductions, loss terms, Adam) in one finishing launch; bit-identical parameters.  Returns (grad [P] float32, loss [4] float64 device, reg [1] float64 device or None)."""
     from ._lib import IrlGenArgs, IrlStepArgs
     lib = _lib.load()
     device = demo_states.device
@@ -755,9 +756,12 @@ def irl_reward_step(params, m, v, step, lr, demo_states, demo_actions, demo_weig
         a.drewards = _ptr(_require(demo_weight, "demo_weight", device, torch.float32, (n_demo,)))
         g.loss_out = _ptr(loss)
         st.reg_loss_out = _ptr(reg)
-        ws = _workspace(device, lib.dmfg_rnet_workspace_bytes(C.byref(a)))
+        # (finishing_launch=False hands over the smaller workspace of one backward call: the entry point then runs the
+        # chain's own six launches -- kept reachable for the parity test of the two forms)
+        need = (lib.dmfg_irl_reward_step_workspace_bytes if finishing_launch else lib.dmfg_rnet_workspace_bytes)(C.byref(a))
+        ws = _workspace(device, need)
         if ws is not None:
-            a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+            a.workspace, a.workspace_bytes = _ptr(ws), need
         check(lib.dmfg_irl_reward_step(C.byref(a), C.byref(b), C.byref(g), C.byref(st), _stream_ptr(device)))
     return grad, loss, reg
 

@@ -406,8 +406,12 @@ int dmfg_adam_tf(int64_t n, float* params, float* m, float* v, const float* grad
 /* ---- a12: ONE reward update in one call ------------------------------------ *
  * AC_IRL.update_reward (ac_irl.py:804-846 -> :382-418) on one rank with z_j = 1: the chain
  *   dmfg_rnet_backward(demo)  ->  dmfg_rnet_backward_gen(gen, g)  ->  dmfg_adam_tf(...)
- * behind one entry point -- the same launches in the same order (bit-identical results), one trip through the host
- * binding instead of three (a 5 + 5 trajectory update is host-bound: its two reward-net launches take 16 us each).
+ * behind one entry point: one trip through the host binding instead of three (a 5 + 5 trajectory update is host-bound:
+ * its two reward-net launches take 16 us each).  With a workspace of dmfg_irl_reward_step_workspace_bytes(demo) the two
+ * reductions, the loss kernel and the Adam kernel of the chain run as ONE launch behind the two backward launches
+ * (six launches -> three); with the smaller dmfg_rnet_workspace_bytes it is the chain's own launches in order.  Either
+ * way parameters, moments and gradient are bit-identical to the chain; the fast form's first loss term is summed per
+ * CTA and agrees with the chain's to the last bits of a double.
  * demo: N demonstration transitions, drewards = the constant -1/num_demo_traj, rewards = r_demo out (required),
  * grad = the gradient buffer of the whole step, workspace as for dmfg_rnet_backward.  gen: the generated
  * transitions (its grad / accumulate / workspace fields are ignored: the step's buffers are used).  g: as for
@@ -423,6 +427,7 @@ typedef struct dmfg_irl_step_args {
     double   lr, beta1, beta2, eps;
     double*  reg_loss_out;        /* optional (device double) */
 } dmfg_irl_step_args;
+uint64_t dmfg_irl_reward_step_workspace_bytes(const dmfg_rnet_args* demo);
 int dmfg_irl_reward_step(const dmfg_rnet_args* demo, const dmfg_rnet_args* gen, const dmfg_irl_gen_args* g,
                          const dmfg_irl_step_args* step, void* stream);
 

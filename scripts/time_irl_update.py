@@ -29,9 +29,12 @@ def timed(fn, n=20):
     return float(np.median([a.elapsed_time(b) for a, b in ev])) * 1e3
 
 t_upd = timed(lambda: irl.update_reward_batch(ds, da, gs, ga, M, "time_major", group=False))
+irl.fused_reward_step = "chain"
+t_chain = timed(lambda: irl.update_reward_batch(ds, da, gs, ga, M, "time_major", group=False))
+irl.fused_reward_step = True
 t_bwd = timed(lambda: engine.rnet_backward(p.flat, ds, da, dconst, 8, 4))
 t_fwd = timed(lambda: engine.rnet_forward(p.flat, ds, da, 8, 4))
 r_demo = engine.rnet_forward(p.flat, ds, da, 8, 4)
 t_gen = timed(lambda: engine.rnet_backward_gen(p.flat, gs, ga, 8, 4, 15, r_demo, M))
-print("%s: update %.1f us (%.0f it/s) | backward %.1f us | backward_gen %.1f us | forward %.1f us | %d transitions per launch" % (
-    os.environ.get("DMFG_LIB_PATH", "default"), t_upd, 1e6 / t_upd, t_bwd, t_gen, t_fwd, ds.shape[0]))
+print("%s: update %.1f us (%.0f it/s; six-launch chain %.1f us) | backward %.1f us | backward_gen %.1f us | forward %.1f us | %d transitions per launch" % (
+    os.environ.get("DMFG_LIB_PATH", "default"), t_upd, 1e6 / t_upd, t_chain, t_bwd, t_gen, t_fwd, ds.shape[0]))

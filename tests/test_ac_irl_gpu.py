@@ -510,11 +510,13 @@ def test_ac_irl_runs_at_d21_on_20x20_style_data(tmp_path, monkeypatch):
 @pytest.mark.parametrize("reg", ["none", "dropout_l1l2"])
 def test_reward_update_through_one_c_call_equals_the_three_call_chain(data, reg):
     """update_reward on one rank goes through dmfg_irl_reward_step (rnet_backward -> rnet_backward_gen -> adam_tf behind one
-    entry point): the same launches in the same order as the three separate calls -- parameters, Adam moments, loss terms and
-    the gradient agree bit for bit over several updates, with and without the dropout / l1l2 regulariser."""
+    entry point, the reductions / loss terms / Adam step behind the two backward launches in ONE finishing launch): same
+    summation order and roundings as the three separate calls -- parameters, Adam moments and the gradient agree bit for
+    bit over several updates, with and without the dropout / l1l2 regulariser; the loss terms to the last bits of a double
+    (the finishing launch sums per-CTA reward sums, the chain walks r_demo)."""
     import random
     outs = []
-    for fused in (True, False):
+    for fused in (True, False, "chain"):
         ac = make(data, reg=reg)
         ac.fused_reward_step = fused
         ac.list_generated = ac.generate_trajectories(12)
@@ -525,9 +527,10 @@ def test_reward_update_through_one_c_call_equals_the_three_call_chain(data, reg)
             losses.append((ac.loss_val, ac.first_term_val, ac.second_term_val))
         p = ac.reward_params
         outs.append((p.flat.clone(), p.m.clone(), p.v.clone(), ac._last_grad.clone(), losses, p.step))
-    a, b = outs
-    assert a[5] == b[5] == 4
-    for x, y in zip(a[:4], b[:4]):
-        assert torch.equal(x, y)
-    assert a[4] == b[4]
+    a, b, c = outs
+    assert a[5] == b[5] == c[5] == 4
+    for x, y, z in zip(a[:4], b[:4], c[:4]):
+        assert torch.equal(x, y) and torch.equal(y, z)
+    assert b[4] == c[4]                                   # the same launches in the same order
+    np.testing.assert_allclose(np.array(a[4]), np.array(b[4]), rtol=1e-13, atol=1e-14)
     assert not torch.equal(a[0], make(data, reg=reg).reward_params.flat)          # the parameters did move
