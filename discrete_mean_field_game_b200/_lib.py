@@ -84,7 +84,11 @@ class RnetArgs(C.Structure):
         ("seed", C.c_uint64), ("sample_offset", C.c_uint64), ("rewards", C.c_void_p),
         ("drewards", C.c_void_p), ("grad", C.c_void_p), ("accumulate", C.c_int32), ("reserved", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+        ("gather_T", C.c_int32), ("reserved2", C.c_int32), ("gather_slots", C.c_int32 * 32),
     ]
+
+
+MAX_GATHER = 32
 
 
 class IrlNetArgs(C.Structure):

@@ -64,6 +64,7 @@ class AC_IRL(_actor_critic):
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.dtype = torch.float32                       # the TF graph is float32 (ac_irl.py:239-246)
         self.fused_reward_step = True                    # single-rank reward update through ONE C call (dmfg_irl_reward_step)
+        self.resident_trajectories = True                # update_reward: sampled trajectories live in a device pool
         self.group = None                                # process group of update_reward's all-reduce (None: the default
                                                          # group when torch.distributed is initialised; False: never)
         self.theta = theta
@@ -718,6 +719,88 @@ class AC_IRL(_actor_critic):
         buf = self._dev(flat, torch.float32)
         return [buf[b:b + p.size].view(p.shape) for p, b in zip(parts, offs)]
 
+    # ---- trajectories resident in device memory ---------------------------------------------------------------------
+    # update_reward (ac_irl.py:804-846) draws 5 + 5 trajectories out of the same few dozen, hundreds of times per outer
+    # iteration.  Each trajectory is uploaded ONCE into a pool ([slot * 15 + t] rows of states / actions) and a minibatch
+    # is then just its slot numbers, which travel by value with the launch (dmfg_rnet_args.gather_*).
+    _POOL_LIMIT = 1 << 14                                # slots (236 MB at d = 15) before the pool starts over
+
+    def _resident_ok(self, demo, gen):
+        from . import parallel
+        from ._lib import MAX_GATHER
+        if not (self.resident_trajectories and self.fused_reward_step and self.one_pass_reward_update) or self.use_z \
+                or self.rank_invariant_reward_step or self.d > 16:
+            return False
+        if not (0 < len(demo) <= MAX_GATHER and 0 < len(gen) <= MAX_GATHER):
+            return False
+        if parallel.world_info(self.group)[1] != 1:
+            return False
+        return all(len(t) == T_STEPS for t in demo) and all(len(t) == T_STEPS for t in gen)
+
+    def _resident_slots(self, trajectories):
+        pool = self.__dict__.get("_pool")
+        if pool is None:
+            pool = self._pool = {"index": {}, "used": 0, "states": None, "actions": None}
+        index = pool["index"]
+        if pool["used"] + len(trajectories) > self._POOL_LIMIT:
+            index.clear()
+            pool["used"] = 0
+        out = []
+        for traj in trajectories:
+            hit = index.get(id(traj))
+            # (an entry keeps its first and last pair alive, so a recycled id() cannot alias another trajectory)
+            if hit is None or hit[1] is not traj[0] or hit[2] is not traj[-1]:
+                hit = index[id(traj)] = (self._pool_add(pool, traj), traj[0], traj[-1])
+            out.append(hit[0])
+        return out
+
+    def _pool_add(self, pool, traj):
+        T = T_STEPS
+        slot = pool["used"]
+        cap = 0 if pool["states"] is None else pool["states"].shape[0] // T
+        if slot == cap:                                    # grow by doubling; slot numbers stay valid
+            new_cap = max(64, 2 * cap)
+            with torch.cuda.device(self.device):
+                st = torch.empty((new_cap * T, self.d), dtype=torch.float32, device=self.device)
+                ac = torch.empty((new_cap * T, self.d, self.d), dtype=torch.float32, device=self.device)
+                if cap:
+                    st[:cap * T].copy_(pool["states"])
+                    ac[:cap * T].copy_(pool["actions"])
+            pool["states"], pool["actions"] = st, ac
+        s, a = self._pack_host([traj])
+        pool["states"][slot * T:(slot + 1) * T].copy_(torch.from_numpy(s))
+        pool["actions"][slot * T:(slot + 1) * T].copy_(torch.from_numpy(a))
+        pool["used"] = slot + 1
+        return slot
+
+    def _update_reward_resident(self, demo, gen):
+        """update_reward_batch's one-call branch on pool slots instead of stacked device arrays (same kernels, same
+        order, same dropout offsets: bit-identical to it)."""
+        p = self.reward_params
+        T = T_STEPS
+        slots = self._resident_slots(list(demo) + list(gen))             # one pass: a pool reset cannot split the batch
+        ds, gs = slots[:len(demo)], slots[len(demo):]
+        pool = self._pool
+        n_demo, n_gen = len(ds) * T, len(gs) * T
+        seed_d = seed_g = None
+        off_d = off_g = 0
+        if self._dropout:
+            seed_d = seed_g = self.seed ^ 0x5DEECE66D
+            off_d = self._next_dropout_offset(n_demo)
+            off_g = self._next_dropout_offset(n_gen)
+        d_const = self._demo_weight(n_demo, -1.0 / float(self.num_demo_samples))
+        p.step += 1
+        grad, loss, reg = engine.irl_reward_step(
+            p.flat, p.m, p.v, p.step, self.lr_reward, pool["states"], pool["actions"], d_const, pool["states"],
+            pool["actions"], p.n_fc3, p.n_fc4, T, self.num_demo_samples, layout="trajectory_major",
+            keep_prob=networks.KEEP_PROB, demo_seed=seed_d, demo_sample_offset=off_d, gen_seed=seed_g,
+            gen_sample_offset=off_g, l1l2=self._l1l2, want_reg_loss=self._l1l2,
+            finishing_launch=self.fused_reward_step != "chain", demo_gather=(T, ds), gen_gather=(T, gs))
+        if reg is not None:
+            loss[0] += reg[0]
+        self._last_grad = grad
+        return loss
+
     def update_reward_batch(self, demo_states, demo_actions, gen_states, gen_actions, num_demo_traj, layout,
                             group=None, masks=None):
         """One gradient step on the reward net from device tensors (the kernel chain of update_reward):
@@ -809,6 +892,11 @@ class AC_IRL(_actor_critic):
             gen_sampled = random.sample(self.list_generated, self.num_gen_samples)
         else:
             gen_sampled = self.list_generated[:]
+        if self._resident_ok(demo_sampled, gen_sampled):
+            # the sampled trajectories are already in device memory (uploaded the first time they were drawn): the update
+            # is one C call with the ten pool slots by value -- no stacking, no host-to-device copy
+            self._loss_dev = self._update_reward_resident(demo_sampled, gen_sampled)
+            return
         ds, da, gs, ga = self._pack_pair(demo_sampled, gen_sampled)
         # the loss terms stay on the device until someone reads loss_val / first_term_val / second_term_val (the reference
         # prints them every iter_check updates): no device-to-host synchronisation per update

@@ -70,6 +70,7 @@ __host__ __device__ inline RnetLayout rnet_layout(int d, int n3, int n4) {
     return L;
 }
 
+constexpr int kRnetMaxGather = 32;
 struct RnetParams {
     int d, n3, n4;
     long long N;
@@ -89,6 +90,10 @@ struct RnetParams {
     int traj_T;
     double* zpart;            // [grid] per-CTA sum_j exp(R_j)
     double* rpart;            // [grid] per-CTA sum of the rewards it wrote (backward, not TRAJ), or null
+    // gather (gather_T > 0): states / actions are a pool of trajectories of gather_T transitions; transition n of the
+    // batch is read from pool row gather[n / gather_T] * gather_T + n % gather_T (everything else is indexed by n)
+    int gather_T;
+    int gather[kRnetMaxGather];
 };
 
 // shared-memory map (in floats), identical on host and device
@@ -345,7 +350,8 @@ __device__ __forceinline__ void dropout_masks_philox(unsigned long long seed, un
 // Z = sum_j u_j is linear in the weight, so 1/Z is applied once to the reduced gradient (rnet_reduce_partials_kernel)
 // and the separate forward launch, the three loss kernels and the dL/dr stream disappear.  |r| < 1 (tanh) bounds
 // u_j by e^16: no max shift is needed.
-template <int G, int NP, bool BWD, int DS, int N3S, int N4S, bool TRAJ = false>
+// GATHER: the batch is slot numbers into a pool of resident trajectories (RnetParams::gather*); its own instantiation.
+template <int G, int NP, bool BWD, int DS, int N3S, int N4S, bool TRAJ = false, bool GATHER = false>
 __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const RnetParams p) {
     static_assert(!TRAJ || BWD, "trajectory mode is a backward mode");
     __shared__ float rtraj[kRnetThreads / G];
@@ -469,6 +475,12 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
         const long long nn = tl * GPB + grp;
         return nn < p.N ? nn : p.N - 1;
     };
+    // row of the states / actions arrays a transition of the batch is read from (the pool of resident trajectories)
+    auto source_of = [&](long long nn) -> long long {
+        if (!GATHER) return nn;
+        const int ni = (int)nn, j = ni / p.gather_T;              // (a gathered batch has <= 32 * gather_T transitions)
+        return (long long)p.gather[j] * p.gather_T + (ni - j * p.gather_T);
+    };
 #if DMFG_RNET_PREFETCH == 3
     // software pipeline over tiles: this lane's column of the NEXT transition's action (d global loads), its state entry
     // and dL/dr travel to registers while the current tile computes -- with one CTA per SM there is nothing else to hide
@@ -476,10 +488,11 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
     float a_next[W], pi_next = 0.f, dr_next = 0.f;
     auto fetch = [&](long long tl) {
         const long long nn = transition_of(tl);
-        const float* a = p.actions + nn * d * d;
+        const long long src = source_of(nn);
+        const float* a = p.actions + src * d * d;
 #pragma unroll
         for (int i = 0; i < W; ++i) a_next[i] = (row_ok && i < d) ? a[i * d + h] : 0.f;
-        pi_next = row_ok ? p.states[nn * d + h] : 0.f;
+        pi_next = row_ok ? p.states[src * d + h] : 0.f;
         if (BWD && !TRAJ) dr_next = p.drewards[nn];
     };
     if ((long long)blockIdx.x < ntiles) fetch(blockIdx.x);
@@ -506,10 +519,11 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
             const float dr_in = dr_next;
             if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);
 #else
-            const float* a = p.actions + n * d * d;
+            const long long src = source_of(n);
+            const float* a = p.actions + src * d * d;
             if (row_ok)
                 for (int i = 0; i < d; ++i) At[(i + 2) * SA + h + 2] = a[i * d + h];
-            const float pi_h = row_ok ? p.states[n * d + h] : 0.f;
+            const float pi_h = row_ok ? p.states[src * d + h] : 0.f;
             const float dr_in = (BWD && !TRAJ) ? p.drewards[n] : 0.f;
 #endif
 #if DMFG_RNET_PREFETCH == 1 || DMFG_RNET_PREFETCH == 2
@@ -522,7 +536,7 @@ __global__ void __launch_bounds__(kRnetThreads, BWD ? 1 : 2) rnet_kernel(const R
                     long long nn;
                     if (TRAJ) nn = (grp < p.traj_T ? grp : 0) * p.t_stride + tn * p.j_stride;
                     else { nn = tn * GPB + grp; if (nn >= p.N) nn = p.N - 1; }
-                    const char* nx = reinterpret_cast<const char*>(p.actions + nn * d * d);
+                    const char* nx = reinterpret_cast<const char*>(p.actions + source_of(nn) * d * d);
 #if DMFG_RNET_PREFETCH == 2
                     if (h * 128 < d * d * 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + h * 128));
 #else

@@ -38,6 +38,15 @@ int check_rnet(const dmfg_rnet_args* a, bool bwd, bool need_drewards = true) {
         return fail(DMFG_ERR_INVALID, "keep_prob must be in (0,1]");
     if (a->dropout == DMFG_DROPOUT_MASKS && a->N > 0 && (!a->mask3 || !a->mask4))
         return fail(DMFG_ERR_INVALID, "dropout=MASKS needs mask3 and mask4");
+    if (a->gather_T < 0) return fail(DMFG_ERR_INVALID, "gather_T < 0");
+    if (a->gather_T > 0) {
+        static_assert(DMFG_MAX_GATHER == kRnetMaxGather, "header and kernel disagree on the gather capacity");
+        if (a->N > (int64_t)DMFG_MAX_GATHER * a->gather_T)
+            return fail(DMFG_ERR_UNSUPPORTED, "a gathered batch holds <= %d trajectories (N = %lld, gather_T = %d)", DMFG_MAX_GATHER,
+                        (long long)a->N, a->gather_T);
+        for (int64_t j = 0; j * a->gather_T < a->N; ++j)
+            if (a->gather_slots[j] < 0) return fail(DMFG_ERR_INVALID, "gather_slots[%lld] < 0", (long long)j);
+    }
     if (!bwd && a->N > 0 && !a->rewards) return fail(DMFG_ERR_INVALID, "rewards is NULL");
     if (bwd) {
         if (!a->grad) return fail(DMFG_ERR_INVALID, "grad is NULL");
@@ -54,12 +63,14 @@ RnetParams make_params(const dmfg_rnet_args* a) {
     p.seed = a->seed; p.sample_offset = a->sample_offset;
     p.rewards = a->rewards; p.drewards = a->drewards; p.partials = nullptr;
     p.traj_M = 0; p.t_stride = 0; p.j_stride = 0; p.traj_T = 0; p.zpart = nullptr; p.rpart = nullptr;
+    p.gather_T = a->gather_T;
+    for (int i = 0; i < kRnetMaxGather; ++i) p.gather[i] = a->gather_T > 0 ? a->gather_slots[i] : 0;
     return p;
 }
 
-template <bool BWD, int DS, int N3S, int N4S, bool TRAJ = false, int G = kG>
+template <bool BWD, int DS, int N3S, int N4S, bool TRAJ = false, int G = kG, bool GATHER = false>
 int rnet_grid(const dmfg_rnet_args* a, int* grid, size_t* smem_bytes, long long traj_M = 0) {
-    auto kern = rnet_kernel<G, kNP, BWD, DS, N3S, N4S, TRAJ>;
+    auto kern = rnet_kernel<G, kNP, BWD, DS, N3S, N4S, TRAJ, GATHER>;
     const RnetLayout L = rnet_layout(a->d, a->n_fc3, a->n_fc4);
     const RnetSmem<G, kNP, BWD, DS> S(a->d, L.total);
     const size_t smem = (size_t)S.total * sizeof(float);
@@ -77,6 +88,29 @@ int rnet_grid(const dmfg_rnet_args* a, int* grid, size_t* smem_bytes, long long 
     if (g < 1) g = 1;
     *grid = (int)g;
     *smem_bytes = smem;
+    return DMFG_OK;
+}
+
+// grid + launch of one instantiation.  The gather form (dmfg_rnet_args.gather_T > 0: the batch is slot numbers into a
+// pool of resident trajectories) is its own instantiation of the 16-lane kernels, so the address arithmetic of the
+// plain form -- the one the large batches run -- carries no trace of it.
+template <bool BWD, int DS, int N3S, int N4S, bool TRAJ = false, int G = kG>
+int rnet_launch(const dmfg_rnet_args* a, const RnetParams& p, cudaStream_t st, int* grid_out, long long traj_M = 0) {
+    int grid = 0;
+    size_t smem = 0;
+    if (a->gather_T > 0) {
+        if constexpr (G == kG) {
+            if (int rc = rnet_grid<BWD, DS, N3S, N4S, TRAJ, G, true>(a, &grid, &smem, traj_M)) return rc;
+            rnet_kernel<G, kNP, BWD, DS, N3S, N4S, TRAJ, true><<<grid, kRnetThreads, smem, st>>>(p);
+        } else {
+            return fail(DMFG_ERR_UNSUPPORTED, "gathered batches are built for d <= %d (got %d)", kG, a->d);
+        }
+    } else {
+        if (int rc = rnet_grid<BWD, DS, N3S, N4S, TRAJ, G, false>(a, &grid, &smem, traj_M)) return rc;
+        rnet_kernel<G, kNP, BWD, DS, N3S, N4S, TRAJ, false><<<grid, kRnetThreads, smem, st>>>(p);
+    }
+    DMFG_LAUNCHED();
+    if (grid_out) *grid_out = grid;
     return DMFG_OK;
 }
 
@@ -105,49 +139,21 @@ void reg_ranges(int l1l2, int d, int n3, int n4, int* b0, int* e0, int* b1, int*
 
 // the backward launch for the shape of `a` (demonstration form: dL/dr from p.drewards)
 int launch_rnet_backward(const dmfg_rnet_args* a, const RnetParams& p, cudaStream_t st, int* grid_out) {
-    int grid = 0;
-    size_t smem = 0;
     // the reference's default shape (d = 15, n_fc3 = 8, n_fc4 = 4) with every size a compile-time constant (fits the
     // 255 registers without spills since the fc3 weight gradient moved to the tensor cores); d = 15 with other widths;
     // everything else from the arguments
-    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) {
-        if (int rc = rnet_grid<true, 15, 8, 4>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, true, 15, 8, 4><<<grid, kRnetThreads, smem, st>>>(p);
-    } else if (a->d == 15) {
-        if (int rc = rnet_grid<true, 15, 0, 0>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, true, 15, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
-    } else if (a->d <= kG) {
-        if (int rc = rnet_grid<true, 0, 0, 0>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, true, 0, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
-    } else if (a->d == 20) {
-        if (int rc = rnet_grid<true, 20, 0, 0, false, 32>(a, &grid, &smem)) return rc;
-        rnet_kernel<32, kNP, true, 20, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
-    } else {
-        if (int rc = rnet_grid<true, 21, 0, 0, false, 32>(a, &grid, &smem)) return rc;
-        rnet_kernel<32, kNP, true, 21, 0, 0><<<grid, kRnetThreads, smem, st>>>(p);
-    }
-    DMFG_LAUNCHED();
-    *grid_out = grid;
-    return DMFG_OK;
+    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) return rnet_launch<true, 15, 8, 4>(a, p, st, grid_out);
+    if (a->d == 15) return rnet_launch<true, 15, 0, 0>(a, p, st, grid_out);
+    if (a->d <= kG) return rnet_launch<true, 0, 0, 0>(a, p, st, grid_out);
+    if (a->d == 20) return rnet_launch<true, 20, 0, 0, false, 32>(a, p, st, grid_out);
+    return rnet_launch<true, 21, 0, 0, false, 32>(a, p, st, grid_out);
 }
 
 // the trajectory-mode backward launch (generated half of the one-pass update, d <= 16)
 int launch_rnet_backward_gen(const dmfg_rnet_args* a, const RnetParams& p, long long M, cudaStream_t st, int* grid_out) {
-    int grid = 0;
-    size_t smem = 0;
-    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) {
-        if (int rc = rnet_grid<true, 15, 8, 4, true>(a, &grid, &smem, M)) return rc;
-        rnet_kernel<kG, kNP, true, 15, 8, 4, true><<<grid, kRnetThreads, smem, st>>>(p);
-    } else if (a->d == 15) {
-        if (int rc = rnet_grid<true, 15, 0, 0, true>(a, &grid, &smem, M)) return rc;
-        rnet_kernel<kG, kNP, true, 15, 0, 0, true><<<grid, kRnetThreads, smem, st>>>(p);
-    } else {
-        if (int rc = rnet_grid<true, 0, 0, 0, true>(a, &grid, &smem, M)) return rc;
-        rnet_kernel<kG, kNP, true, 0, 0, 0, true><<<grid, kRnetThreads, smem, st>>>(p);
-    }
-    DMFG_LAUNCHED();
-    *grid_out = grid;
-    return DMFG_OK;
+    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) return rnet_launch<true, 15, 8, 4, true>(a, p, st, grid_out, M);
+    if (a->d == 15) return rnet_launch<true, 15, 0, 0, true>(a, p, st, grid_out, M);
+    return rnet_launch<true, 0, 0, 0, true>(a, p, st, grid_out, M);
 }
 
 int check_gen(const dmfg_rnet_args* a, const dmfg_irl_gen_args* g) {
@@ -165,6 +171,8 @@ int check_gen(const dmfg_rnet_args* a, const dmfg_irl_gen_args* g) {
     if (!((g->gen_t_stride == g->M && g->gen_j_stride == 1) || (g->gen_t_stride == 1 && g->gen_j_stride == g->T)))
         return fail(DMFG_ERR_INVALID, "strides must be (M,1) time-major or (1,T) trajectory-major");
     if (!g->loss_out || (g->n_demo > 0 && !g->r_demo)) return fail(DMFG_ERR_INVALID, "loss_out / r_demo are required");
+    if (a->gather_T > 0 && !(a->gather_T == g->T && g->gen_t_stride == 1))
+        return fail(DMFG_ERR_INVALID, "a gathered generated batch is trajectory-major with gather_T = T");
     return check_rnet(a, true, /*need_drewards=*/false);      // dL/dr is formed in the kernel
 }
 
@@ -213,31 +221,16 @@ uint64_t dmfg_rnet_workspace_bytes(const dmfg_rnet_args* a) {
 int dmfg_rnet_forward(const dmfg_rnet_args* a, void* stream) {
     if (int rc = check_rnet(a, false)) return rc;
     if (a->N == 0) return DMFG_OK;
-    int grid = 0;
-    size_t smem = 0;
     // the reference's default shape (d = 15, n_fc3 = 8, n_fc4 = 4) and d = 15 with other widths are compiled with
     // those sizes as constants; everything else takes them from the arguments
-    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) {
-        if (int rc = rnet_grid<false, 15, 8, 4>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, false, 15, 8, 4><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
-    } else if (a->d == 15) {
-        if (int rc = rnet_grid<false, 15, 0, 0>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, false, 15, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
-    } else if (a->d <= kG) {
-        if (int rc = rnet_grid<false, 0, 0, 0>(a, &grid, &smem)) return rc;
-        rnet_kernel<kG, kNP, false, 0, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
-    } else if (a->d == 20) {      // the reference's action files are 20 x 20 (ac_irl.py:164-200)
-        if (int rc = rnet_grid<false, 20, 0, 0, false, 32>(a, &grid, &smem)) return rc;
-        rnet_kernel<32, kNP, false, 20, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
-    } else if (a->d == 21) {      // mfg_ac2.py:25 default d
-        if (int rc = rnet_grid<false, 21, 0, 0, false, 32>(a, &grid, &smem)) return rc;
-        rnet_kernel<32, kNP, false, 21, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
-    } else {                      // 16 < d <= 32: 32 lanes per transition, sizes from the arguments
-        if (int rc = rnet_grid<false, 0, 0, 0, false, 32>(a, &grid, &smem)) return rc;
-        rnet_kernel<32, kNP, false, 0, 0, 0><<<grid, kRnetThreads, smem, (cudaStream_t)stream>>>(make_params(a));
-    }
-    DMFG_LAUNCHED();
-    return DMFG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const RnetParams p = make_params(a);
+    if (a->d == 15 && a->n_fc3 == 8 && a->n_fc4 == 4) return rnet_launch<false, 15, 8, 4>(a, p, st, nullptr);
+    if (a->d == 15) return rnet_launch<false, 15, 0, 0>(a, p, st, nullptr);
+    if (a->d <= kG) return rnet_launch<false, 0, 0, 0>(a, p, st, nullptr);
+    if (a->d == 20) return rnet_launch<false, 20, 0, 0, false, 32>(a, p, st, nullptr);      // the reference's action files are 20 x 20 (ac_irl.py:164-200)
+    if (a->d == 21) return rnet_launch<false, 21, 0, 0, false, 32>(a, p, st, nullptr);      // mfg_ac2.py:25 default d
+    return rnet_launch<false, 0, 0, 0, false, 32>(a, p, st, nullptr);                       // 16 < d <= 32: sizes from the arguments
 }
 
 int dmfg_rnet_backward(const dmfg_rnet_args* a, void* stream) {

@@ -530,17 +530,29 @@ def rnet_param_offsets(d, n_fc3, n_fc4):
     return [int(x) for x in o]
 
 
-def _rnet_args(params, states, actions, n_fc3, n_fc4, mask3, mask4, keep_prob, seed, sample_offset):
-    from ._lib import DROPOUT_MASKS, DROPOUT_NONE, DROPOUT_PHILOX, RnetArgs
+def _rnet_args(params, states, actions, n_fc3, n_fc4, mask3, mask4, keep_prob, seed, sample_offset, gather=None):
+    """gather = (T, slots): states / actions are a pool of trajectories of T transitions each (rows [s*T, (s+1)*T) = slot s)
+    and the batch is the trajectories `slots` in that order, N = len(slots) * T transitions (dmfg_rnet_args.gather_*)."""
+    from ._lib import DROPOUT_MASKS, DROPOUT_NONE, DROPOUT_PHILOX, MAX_GATHER, RnetArgs
     device = states.device
     N, d = states.shape
     P = rnet_param_count(d, n_fc3, n_fc4)
     a = RnetArgs()
     a.struct_size = C.sizeof(RnetArgs)
-    a.d, a.n_fc3, a.n_fc4, a.N = d, int(n_fc3), int(n_fc4), N
     a.params = _ptr(_require(params, "params", device, torch.float32, (P,)))
     a.states = _ptr(_require(states, "states", device, torch.float32, (N, d)))
     a.actions = _ptr(_require(actions, "actions", device, torch.float32, (N, d, d)))
+    if gather is not None:
+        T, slots = int(gather[0]), gather[1]
+        if T < 1 or len(slots) > MAX_GATHER:
+            raise ValueError("a gathered batch holds at most %d trajectories (got %d)" % (MAX_GATHER, len(slots)))
+        if len(slots) and not (0 <= min(slots) and (max(slots) + 1) * T <= N):
+            raise ValueError("gather slots outside the pool of %d rows" % N)
+        a.gather_T = T
+        for i, sl in enumerate(slots):
+            a.gather_slots[i] = sl
+        N = len(slots) * T
+    a.d, a.n_fc3, a.n_fc4, a.N = d, int(n_fc3), int(n_fc4), N
     if mask3 is not None or mask4 is not None:
         a.dropout = DROPOUT_MASKS
         a.mask3 = _ptr(_require(mask3, "mask3", device, torch.uint8, (N, n_fc3)))
@@ -555,13 +567,13 @@ def _rnet_args(params, states, actions, n_fc3, n_fc4, mask3, mask4, keep_prob, s
 
 
 def rnet_forward(params, states, actions, n_fc3, n_fc4, *, mask3=None, mask4=None, keep_prob=0.4, seed=None,
-                 sample_offset=0, out=None):
+                 sample_offset=0, out=None, gather=None):
     """r_net(state, action) for N transitions (networks.py:13-157).  states [N,d], actions [N,d,d] float32.
     Dropout: mask3/mask4 uint8 keep masks (parity), or `seed` for in-kernel Philox masks, or neither."""
     lib = _lib.load()
-    a, _ = _rnet_args(params, states, actions, n_fc3, n_fc4, mask3, mask4, keep_prob, seed, sample_offset)
+    a, _ = _rnet_args(params, states, actions, n_fc3, n_fc4, mask3, mask4, keep_prob, seed, sample_offset, gather)
     device = states.device
-    N = states.shape[0]
+    N = a.N
     with _on(device):
         r = out if out is not None else torch.empty(N, dtype=torch.float32, device=device)
         a.rewards = _ptr(_require(r, "rewards", device, torch.float32, (N,)))
@@ -570,12 +582,12 @@ def rnet_forward(params, states, actions, n_fc3, n_fc4, *, mask3=None, mask4=Non
 
 
 def rnet_backward(params, states, actions, drewards, n_fc3, n_fc4, *, grad=None, accumulate=False, mask3=None,
-                  mask4=None, keep_prob=0.4, seed=None, sample_offset=0, want_rewards=False):
+                  mask4=None, keep_prob=0.4, seed=None, sample_offset=0, want_rewards=False, gather=None):
     """Flat gradient of sum_n drewards[n]*r[n] w.r.t. the parameters (forward recomputed in-kernel)."""
     lib = _lib.load()
-    a, P = _rnet_args(params, states, actions, n_fc3, n_fc4, mask3, mask4, keep_prob, seed, sample_offset)
+    a, P = _rnet_args(params, states, actions, n_fc3, n_fc4, mask3, mask4, keep_prob, seed, sample_offset, gather)
     device = states.device
-    N = states.shape[0]
+    N = a.N
     with _on(device):
         if grad is None:
             accumulate = False                               # every entry is written by the reduction
@@ -717,16 +729,18 @@ def adam_tf(params, m, v, grad, step, lr, *, beta1=0.9, beta2=0.999, eps=1e-8, g
 def irl_reward_step(params, m, v, step, lr, demo_states, demo_actions, demo_weight, gen_states, gen_actions, n_fc3, n_fc4, T,
                     num_demo_traj, *, layout="time_major", keep_prob=0.4, demo_seed=None, demo_sample_offset=0,
                     gen_seed=None, gen_sample_offset=0, beta1=0.9, beta2=0.999, eps=1e-8, l1l2=False, want_reg_loss=False,
-                    finishing_launch=True):
+                    finishing_launch=True, demo_gather=None, gen_gather=None):
     """One whole reward update on one rank (AC_IRL.update_reward, ac_irl.py:804-846, z_j = 1) through ONE C call:
     rnet_backward(demonstrations, dL/dr = demo_weight) -> rnet_backward_gen(generated) -> adam_tf, with everything behind the
     two backward launches (reductions, loss terms, Adam) in one finishing launch; bit-identical parameters.  Returns (grad [P] float32, loss [4] float64 device, reg [1] float64 device or None)."""
     from ._lib import IrlGenArgs, IrlStepArgs
     lib = _lib.load()
     device = demo_states.device
-    a, P = _rnet_args(params, demo_states, demo_actions, n_fc3, n_fc4, None, None, keep_prob, demo_seed, demo_sample_offset)
-    b, _ = _rnet_args(params, gen_states, gen_actions, n_fc3, n_fc4, None, None, keep_prob, gen_seed, gen_sample_offset)
-    n_demo, n_gen = demo_states.shape[0], gen_states.shape[0]
+    a, P = _rnet_args(params, demo_states, demo_actions, n_fc3, n_fc4, None, None, keep_prob, demo_seed, demo_sample_offset,
+                      demo_gather)
+    b, _ = _rnet_args(params, gen_states, gen_actions, n_fc3, n_fc4, None, None, keep_prob, gen_seed, gen_sample_offset,
+                      gen_gather)
+    n_demo, n_gen = a.N, b.N
     M = n_gen // int(T)
     if M * int(T) != n_gen:
         raise ValueError("%d transitions are not a multiple of T=%d" % (n_gen, T))

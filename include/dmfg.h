@@ -326,7 +326,19 @@ typedef struct dmfg_rnet_args {
     int32_t  reserved;
     void*    workspace;           /* backward: per-CTA partial gradients */
     uint64_t workspace_bytes;     /* >= dmfg_rnet_workspace_bytes(args) */
+    /* Optional gather from a pool of trajectories resident in device memory (gather_T = 0: off).  states / actions
+     * are then the POOL -- slot s holds the gather_T transitions of one trajectory in rows [s*gather_T, (s+1)*gather_T)
+     * -- and transition n of the batch is read from row gather_slots[n / gather_T] * gather_T + n % gather_T.
+     * Everything else (rewards, drewards, masks, the Philox dropout offset) stays indexed by n, so a gathered batch
+     * gives bit for bit what the same trajectories stacked into [N][d] arrays give.  N <= DMFG_MAX_GATHER * gather_T;
+     * dmfg_rnet_backward_gen / dmfg_irl_reward_step: trajectory-major, gather_T = T.  The slots travel by value with
+     * the launch: update_reward (ac_irl.py:804-846) resamples 5 + 5 of the same few dozen trajectories per update and
+     * needs no host-to-device copy this way. */
+    int32_t  gather_T;
+    int32_t  reserved2;
+    int32_t  gather_slots[32];    /* DMFG_MAX_GATHER */
 } dmfg_rnet_args;
+#define DMFG_MAX_GATHER 32
 uint64_t dmfg_rnet_workspace_bytes(const dmfg_rnet_args* args);
 /* sess.run(reward_gen / reward_demo) (ac_irl.py:683,882) */
 int dmfg_rnet_forward(const dmfg_rnet_args* args, void* stream);

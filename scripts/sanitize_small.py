@@ -76,5 +76,15 @@ with contextlib.redirect_stdout(sys.stderr):
         s2, a2 = irl2.generate_batch(20)
         irl2.update_reward_batch(s2[:15].reshape(-1, dd), a2.reshape(-1, dd, dd), s2[:15].reshape(-1, dd),
                                  a2.reshape(-1, dd, dd), 20, "time_major", group=False)
+    # update_reward on trajectories resident in the device pool (gathered batches: rnet_kernel<..., GATHER> in both backward
+    # forms + irl_step_finish_kernel), with pool growth, and the gathered forward
+    irl.one_pass_reward_update = True
+    irl.list_demonstrations = irl.generate_trajectories(7)
+    irl.list_generated = irl.generate_trajectories(70)
+    for _ in range(16):
+        irl.update_reward()
+    pool = irl._pool
+    from discrete_mean_field_game_b200 import engine
+    engine.rnet_forward(irl.reward_params.flat, pool["states"], pool["actions"], 8, 4, gather=(15, [3, 0, 5]))
 torch.cuda.synchronize()
 print("sanitize_small: done")

@@ -534,3 +534,50 @@ def test_reward_update_through_one_c_call_equals_the_three_call_chain(data, reg)
     assert b[4] == c[4]                                   # the same launches in the same order
     np.testing.assert_allclose(np.array(a[4]), np.array(b[4]), rtol=1e-13, atol=1e-14)
     assert not torch.equal(a[0], make(data, reg=reg).reward_params.flat)          # the parameters did move
+
+
+@pytest.mark.parametrize("reg", ["none", "dropout_l1l2"])
+def test_reward_update_on_resident_trajectories_equals_the_stacked_update(data, reg):
+    """update_reward with the sampled trajectories resident in a device pool (uploaded once, the minibatch = slot numbers
+    by value with the launch) against the same updates on freshly stacked and copied arrays: bit-identical parameters,
+    moments, gradient and loss terms -- across pool growth (more trajectories than the first 64 slots) and with
+    trajectories appended to list_generated between updates."""
+    outs = []
+    for resident in (True, False):
+        ac = make(data, reg=reg)
+        ac.resident_trajectories = resident
+        ac.list_generated = ac.generate_trajectories(70)
+        random.seed(11)
+        losses = []
+        for k in range(30):
+            ac.update_reward()
+            losses.append((ac.loss_val, ac.first_term_val, ac.second_term_val))
+            if k == 12:
+                ac.list_generated = ac.list_generated + ac.generate_trajectories(30)
+        p = ac.reward_params
+        outs.append((p.flat.clone(), p.m.clone(), p.v.clone(), ac._last_grad.clone(), losses))
+        if resident:
+            pool = ac._pool
+            assert 64 < pool["used"] <= 108 and pool["states"].shape[0] == 128 * T      # grew once
+            assert len(pool["index"]) == pool["used"]
+        else:
+            assert "_pool" not in ac.__dict__
+    a, b = outs
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x, y)
+    assert a[4] == b[4]
+
+
+def test_resident_pool_starts_over_when_full(data):
+    ac = make(data)
+    ac._POOL_LIMIT = 12
+    ac.list_generated = ac.generate_trajectories(20)
+    ref = make(data)
+    ref.resident_trajectories = False
+    ref.list_generated = ac.list_generated
+    ref.list_demonstrations = ac.list_demonstrations
+    for seed in range(8):
+        random.seed(seed); ac.update_reward()
+        random.seed(seed); ref.update_reward()
+        assert ac._pool["used"] <= 12
+    assert torch.equal(ac.reward_params.flat, ref.reward_params.flat)

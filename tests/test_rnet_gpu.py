@@ -313,3 +313,30 @@ def test_reward_net_forward_generic_wide_d_and_limits(dev):
         engine.rnet_forward(T_(f32(R.xavier_init(d, 6, 3, rng)), dev), T_(f32(rng.dirichlet(np.ones(d), size=2)), dev),
                             T_(f32(rng.dirichlet(np.ones(d), size=(2, d))), dev), 6, 3)
     assert e.value.code == ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("d,n3,n4", [(15, 8, 4), (4, 6, 8), (16, 8, 8)])
+def test_gathered_batch_equals_the_stacked_batch(dev, d, n3, n4):
+    """dmfg_rnet_args.gather_*: the batch as slot numbers into a pool of resident trajectories gives bit for bit what the
+    same trajectories stacked into [N, d] / [N, d, d] arrays give -- forward, backward (gradient and rewards), with the
+    Philox dropout offsets following the position in the batch, not in the pool."""
+    from discrete_mean_field_game_b200 import engine
+    rng = np.random.RandomState(3 * d + n3)
+    Tt, slots_total = 15, 40
+    p, s, a = make(rng, slots_total * Tt, d, n3, n4, scale=0.2)
+    P, S, A = T_(p, dev), T_(s, dev), T_(a, dev)
+    slots = [int(x) for x in rng.permutation(slots_total)[:11]] + [7, 7]        # repeats are allowed
+    rows = np.concatenate([np.arange(sl * Tt, (sl + 1) * Tt) for sl in slots])
+    Ss, As = S[torch.as_tensor(rows, device=dev)].contiguous(), A[torch.as_tensor(rows, device=dev)].contiguous()
+    dr = T_(f32(rng.randn(len(rows))), dev)
+    for kw in ({}, dict(seed=11, sample_offset=1000)):
+        r0 = engine.rnet_forward(P, Ss, As, n3, n4, **kw)
+        r1 = engine.rnet_forward(P, S, A, n3, n4, gather=(Tt, slots), **kw)
+        assert torch.equal(r0, r1)
+        g0, q0 = engine.rnet_backward(P, Ss, As, dr, n3, n4, want_rewards=True, **kw)
+        g1, q1 = engine.rnet_backward(P, S, A, dr, n3, n4, want_rewards=True, gather=(Tt, slots), **kw)
+        assert torch.equal(g0, g1) and torch.equal(q0, q1)
+    with pytest.raises(ValueError):
+        engine.rnet_forward(P, S, A, n3, n4, gather=(Tt, [slots_total]))          # outside the pool
+    with pytest.raises(ValueError):
+        engine.rnet_forward(P, S, A, n3, n4, gather=(Tt, list(range(33))))        # more than DMFG_MAX_GATHER
