@@ -705,6 +705,20 @@ class AC_IRL(_actor_critic):
         s, a = self._pack_host(trajectories)
         return self._dev(s, torch.float32), self._dev(a, torch.float32)
 
+    def _pack_resident(self, transitions):
+        """_pack([transitions]) whose device tensors are remembered: the evaluation lists of reward_iteration
+        (ac_irl.py:877-884) are the same objects for a whole outer iteration and were stacked and copied every tenth update.
+        Keyed like the host memo (id of the list, validated by length and the identity of its first and last pair)."""
+        memo = self.__dict__.setdefault("_dev_memo", {})
+        n = len(transitions)
+        hit = memo.get(id(transitions))
+        if hit is None or hit[0] != n or n == 0 or hit[1] is not transitions[0] or hit[2] is not transitions[-1]:
+            if len(memo) >= 8:
+                memo.clear()
+            s, a = self._pack([transitions])
+            hit = memo[id(transitions)] = (n, transitions[0] if n else None, transitions[-1] if n else None, s, a)
+        return hit[3], hit[4]
+
     def _pack_pair(self, demo, gen):
         """both halves of a reward minibatch through ONE host-to-device copy: (demo states, demo actions, generated
         states, generated actions) as views of one device buffer"""
@@ -934,10 +948,11 @@ class AC_IRL(_actor_critic):
                 print("Reward iteration %d" % it)
             self.update_reward(summary=False, iteration=self.reward_update_count)
             # (the flat transition lists are packed once and remembered, like the trajectories of update_reward)
-            ds, da = self._pack([self.list_eval_demo_transitions])
-            gs, ga = self._pack([self.list_eval_gen_transitions])
-            reward_demo_avg = float(self._reward(ds, da).double().sum()) / len(self.list_eval_demo_transitions)
-            reward_gen_avg = float(self._reward(gs, ga).double().sum()) / len(self.list_eval_gen_transitions)
+            ds, da = self._pack_resident(self.list_eval_demo_transitions)
+            gs, ga = self._pack_resident(self.list_eval_gen_transitions)
+            sums = torch.stack([self._reward(ds, da).double().sum(), self._reward(gs, ga).double().sum()]).cpu()
+            reward_demo_avg = float(sums[0]) / len(self.list_eval_demo_transitions)      # (one read-back for both)
+            reward_gen_avg = float(sums[1]) / len(self.list_eval_gen_transitions)
             if verbose:
                 print("Reward demo avg %f | Reward gen avg %f" % (reward_demo_avg, reward_gen_avg))
                 print("First %f | Second %f | Loss %f" % (self.first_term_val, self.second_term_val, self.loss_val))
