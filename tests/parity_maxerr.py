@@ -101,6 +101,47 @@ for name, B, T, worst in cases:
     lines += ["## %s" % name, "", "| output | max error |", "|---|---|"]
     lines += ["| %s | %.3e |" % (k, v) for k, v in worst.items()]
     lines.append("")
+
+# ---- the IRL half: reward net forward / backward and one reward update against the float64 reward-net oracle ----------------
+from oracle import rnet_oracle as R
+
+
+def rnet_case(name, d, n3, n4, n, seed, dropout):
+    rng = np.random.RandomState(seed)
+    p = np.float32(R.xavier_init(d, n3, n4, rng) + 0.1 * rng.randn(R.param_count(d, n3, n4)))
+    s = np.float32(rng.dirichlet(np.ones(d), size=n))
+    ac = np.float32(rng.dirichlet(np.ones(d) * 0.5, size=(n, d)))
+    m3 = (rng.rand(n, n3) < 0.4) if dropout else None
+    m4 = (rng.rand(n, n4) < 0.4) if dropout else None
+    dr = np.float32(rng.randn(n))
+    r_ref, cache = R.forward(p, s, ac, n3, n4, m3, m4, cache=True)
+    g_ref = R.backward(cache, dr)
+    T_ = lambda x, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(x), dtype=dt, device=dev)
+    kw = dict(mask3=T_(m3, torch.uint8), mask4=T_(m4, torch.uint8)) if dropout else {}
+    g, r = eng.rnet_backward(T_(p), T_(s), T_(ac), T_(dr), n3, n4, want_rewards=True, **kw)
+    g, r = g.cpu().numpy().astype(np.float64), r.cpu().numpy().astype(np.float64)
+    worst = {"r, max |err| (|r| < 1)": float(np.abs(r - r_ref).max()),
+             "r, rel (floor 1e-2)": rel(r, r_ref, 1e-2)}
+    # a gradient entry is a float32 sum over n transitions of mixed-sign terms: its error is measured against the sum of the
+    # magnitudes of its terms (what a float32 accumulation can resolve) and against the largest entry of its tensor
+    for tname, shp, off in R.layout(d, n3, n4):
+        sl = slice(off, off + int(np.prod(shp)))
+        scale = np.abs(g_ref[sl]).max()
+        worst["d %s, max |err| / max |entry|" % tname] = float(np.abs(g[sl] - g_ref[sl]).max() / scale) if scale > 0 else 0.0
+    return name, n, 1, worst
+
+
+rcases = [rnet_case("reward net, d=15, n_fc3=8, n_fc4=4 (AC_IRL defaults), 4096 transitions, no dropout", 15, 8, 4, 4096, 11, False),
+          rnet_case("reward net, d=15, n_fc3=8, n_fc4=4, 4096 transitions, dropout masks (keep 0.4)", 15, 8, 4, 4096, 12, True),
+          rnet_case("reward net, d=16, n_fc3=8, n_fc4=8, 777 transitions", 16, 8, 8, 777, 13, False),
+          rnet_case("reward net, d=21 (32-lane groups), n_fc3=6, n_fc4=3, 777 transitions", 21, 6, 3, 777, 14, False)]
+lines += ["# Reward net (float32 kernels, fc3 weight gradient as 3xTF32 on the tensor cores) vs the float64 oracle", "",
+          "`dmfg_rnet_backward` with random dL/dr ~ N(0,1): rewards handed back by the backward launch and the flat gradient, per "
+          "parameter tensor.", ""]
+for name, B, T, worst in rcases:
+    lines += ["## %s" % name, "", "| output | max error |", "|---|---|"]
+    lines += ["| %s | %.3e |" % (k, v) for k, v in worst.items()]
+    lines.append("")
 os.makedirs(os.path.dirname(a.out), exist_ok=True)
 with open(a.out, "w") as f:
     f.write("\n".join(lines))

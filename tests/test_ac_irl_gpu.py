@@ -56,7 +56,7 @@ def test_constructor_surface_and_session_shim(data):
     r = ac.sess.run(ac.reward_gen, feed_dict={ac.gen_states: s, ac.gen_actions: a})
     assert r.shape == (T, 1)
     ref = R.forward(ac.reward_params.flat.cpu().numpy(), np.float32(s), np.float32(a), N3, N4)
-    np.testing.assert_allclose(r[:, 0], ref, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(r[:, 0], ref, rtol=1e-5, atol=1e-6)
     rd, rg = ac.sess.run([ac.reward_demo, ac.reward_gen], feed_dict={ac.demo_states: s, ac.demo_actions: a,
                                                                     ac.gen_states: s[:3], ac.gen_actions: a[:3]})
     np.testing.assert_allclose(rd, r, rtol=1e-6)
@@ -110,8 +110,8 @@ def test_train_matches_serial_oracle_with_reward_net(data):
                                  reward_fn=reward_fn, noise=Noise(), num_steps=T)
     ac.train(max_episodes=E, stop_criteria=-1, lr_critic=0.1, lr_actor=0.001, start_rows=rows, noise_y=ys,
              verbose=False)
-    np.testing.assert_allclose(ac.theta, th, rtol=2e-5)
-    np.testing.assert_allclose(ac.w.ravel(), w, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(ac.theta, th, rtol=1e-5)
+    np.testing.assert_allclose(ac.w.ravel(), w, rtol=1e-5, atol=1e-6)
     assert ac.list_policies[-1] == ac.theta and len(ac.list_policies) == 10
 
 
@@ -132,10 +132,10 @@ def test_update_reward_matches_oracle(data, reg):
         gs = np.float32([p[0] for tr in gen for p in tr]); ga = np.float32([p[1] for tr in gen for p in tr])
         loss, (first, second), grad = R.loss_and_grad(p0, ds, da, gs, ga, N3, N4, 5, T, reg=reg)
         np.testing.assert_allclose([ac.loss_val, ac.first_term_val, ac.second_term_val], [loss, first, second],
-                                   rtol=2e-5, atol=2e-6)
+                                   rtol=1e-5, atol=1e-6)
         g_dev = ac._last_grad.cpu().numpy()
         g_data = grad - (R.reg_grad(p0, D, N3, N4) if reg == "l1l2" else 0)
-        assert np.abs(g_dev - g_data).max() <= 3e-5 * np.abs(g_data).max() + 1e-6
+        assert np.abs(g_dev - g_data).max() <= 1e-5 * np.abs(g_data).max() + 1e-6
         p0, m, v = R.adam_tf(p0, m, v, grad, step, 1e-4)
         # Adam normalises the step to ~lr, so a tiny gradient error can flip a coordinate early on:
         # compare the parameters at the scale of one step
@@ -162,7 +162,7 @@ def test_one_pass_reward_update_equals_the_three_launch_chain(data, reg):
         outs.append((loss.cpu().numpy(), irl._last_grad.cpu().numpy(), irl.reward_params.flat.cpu().numpy()))
     (l1, g1, p1), (l0, g0, p0) = outs
     np.testing.assert_allclose(l1[:3], l0[:3], rtol=1e-5, atol=3e-5)
-    assert np.abs(g1 - g0).max() <= 2e-5 * np.abs(g0).max() + 1e-7
+    assert np.abs(g1 - g0).max() <= 1e-5 * np.abs(g0).max() + 1e-7
     np.testing.assert_allclose(p1, p0, rtol=0, atol=2.1e-4)      # one Adam step moves every weight by <= lr = 1e-4
     assert np.mean(np.abs(p1 - p0) <= 1e-6) > 0.99                # (sign flips of ~0 gradients aside)
 
@@ -191,7 +191,7 @@ def test_irl_step_batch_equals_train_batch_then_update_reward_batch(data):
     np.testing.assert_allclose(t1, t0, rtol=1e-9)
     np.testing.assert_allclose(w1, w0, rtol=1e-7, atol=1e-10)
     np.testing.assert_allclose(l1[:3], l0[:3], rtol=1e-5, atol=3e-5)
-    assert np.abs(g1 - g0).max() <= 2e-5 * np.abs(g0).max() + 1e-7
+    assert np.abs(g1 - g0).max() <= 1e-5 * np.abs(g0).max() + 1e-7
     assert np.mean(np.abs(p1 - p0) <= 1e-6) > 0.99 and np.abs(p1 - p0).max() <= 4.2e-4     # two Adam steps of 1e-4
 
 
@@ -224,7 +224,7 @@ def test_data_parallel_reward_step_is_rank_count_invariant(data):
         assert float(total[2 * P + 2]) == 37 and float(total[2 * P + 3]) == 53
         np.testing.assert_allclose(loss.cpu().numpy()[:3], loss_ref[:3], rtol=1e-6, atol=1e-6)
         err = np.abs(grad.cpu().numpy() - g_ref).max()
-        assert err <= 2e-5 * np.abs(g_ref).max() + 1e-8, (err, np.abs(g_ref).max())     # float32 summation order only
+        assert err <= 1e-5 * np.abs(g_ref).max() + 1e-8, (err, np.abs(g_ref).max())     # float32 summation order only
     # the forced single-rank form of the public call takes the same path and lands on the same parameters
     irl2 = make(data, reg="none")
     irl2.rank_invariant_reward_step = True
@@ -270,7 +270,7 @@ def test_update_reward_with_importance_weights(data):
     loss, (first, second), grad = R.loss_and_grad(p0, ds, da, gs, ga, N3, N4, 5, T, log_z=lz)
     np.testing.assert_allclose(ac.second_term_val, second, rtol=1e-5)
     g_dev = ac._last_grad.cpu().numpy()
-    assert np.abs(g_dev - grad).max() <= 1e-4 * np.abs(grad).max() + 1e-6
+    assert np.abs(g_dev - grad).max() <= 1e-5 * np.abs(grad).max() + 1e-6
 
 
 def test_dropout_variant_runs_and_is_stochastic(data):

@@ -34,7 +34,7 @@ def test_r_net_variants_share_variables_in_a_scope(dev):
     r = gen().cpu().numpy()
     assert r.shape == (9, 1)
     ref = R.forward(demo.params.flat.cpu().numpy(), s, a, 6, 8)
-    np.testing.assert_allclose(r[:, 0], ref, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(r[:, 0], ref, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(demo(s, a).cpu().numpy(), r, rtol=0, atol=0)
     with pytest.raises(ValueError):
         demo()                                                        # placeholder not fed
@@ -61,7 +61,7 @@ def test_dropout_variants_flag_and_masks(dev):
     m4 = torch.as_tensor(rng.rand(33, 4) < 0.4, dtype=torch.uint8, device=dev)
     r = net(mask3=m3, mask4=m4).cpu().numpy()[:, 0]
     ref = R.forward(net.params.flat.cpu().numpy(), s, a, 8, 4, m3.cpu().numpy(), m4.cpu().numpy())
-    np.testing.assert_allclose(r, ref, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(r, ref, rtol=1e-5, atol=1e-6)
     assert not np.array_equal(net(seed=1).cpu().numpy(), net(seed=2).cpu().numpy())
 
 
