@@ -394,7 +394,7 @@ def run_ours(args):
     ac.w = rng.rand(F, 1)
     # every step copies its start states from pinned host memory (double-buffered under the previous step's
     # kernel) and reads (theta, w, mean reward) of THAT step back into pinned host memory (history=True)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 40))               # (the first copy of the double-buffered pipeline is not hidden)
     ac.train_batch(pi0_host, num_episodes=2, T=T, lr_critic=LR_CRITIC, lr_actor=LR_ACTOR, pop_offset=pop_offset,
                    history=True)
     barrier()
